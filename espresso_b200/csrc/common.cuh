@@ -1,0 +1,89 @@
+// espresso_b200 -- shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing for the C ABI (no exceptions cross the boundary) -------------------------
+void esp_set_error(const char* fmt, ...);
+#define ESP_CHECK(cond, ...)                 \
+  do {                                       \
+    if (!(cond)) {                           \
+      esp_set_error(__VA_ARGS__);            \
+      return -1;                             \
+    }                                        \
+  } while (0)
+#define ESP_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      esp_set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+#define ESP_LAUNCH_CHECK() ESP_CUDA(cudaGetLastError())
+
+int esp_num_sms();
+
+// ---- small device helpers --------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t p, float& lo, float& hi) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&p);
+  lo = __low2float(t);
+  hi = __high2float(t);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// d/dx [x*sigmoid(x)]
+__device__ __forceinline__ float silu_gradf_(float x) {
+  float s = sigmoidf_(x);
+  return s * (1.f + x * (1.f - s));
+}
+
+// ---- counter-based RNG for dropout: one 32-bit hash per element ------------------------------
+// Stateless: the backward pass regenerates the identical mask from (seed, element index), so
+// dropout masks are never stored in HBM.  (Philox-like mixing; murmur3 finaliser over a 64-bit
+// counter keyed by the seed.)
+__device__ __forceinline__ uint32_t esp_hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// keep-decision: keep iff hash >= p * 2^32
+__device__ __forceinline__ bool esp_dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+  return esp_hash_u32(seed, idx) >= thresh;
+}
+static inline uint32_t esp_dropout_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}

@@ -1,0 +1,555 @@
+// espresso_b200 -- persistent warp-specialised bf16 GEMM for sm_100a.
+//
+//   C[b][M,N] = epilogue( op(A[b])[M,K] * op(B[b])[N,K]^T )        fp32 accumulate in TMEM
+//
+// * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a multi-stage smem ring,
+// * tcgen05.mma (cta_group::1, kind::f16, 128 x BN x 16) issued by one elected thread,
+// * accumulators double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of i+1,
+// * epilogue warps read TMEM with tcgen05.ld and fuse bias / activation (+grad) / dropout /
+//   scaled residual / relative-position skew, writing bf16 or fp32 straight to HBM.
+//
+// This one kernel replaces every dense contraction on the Espresso hot path:
+//   Linear layers                fairseq/modules/conformer_layer.py:134-146 (FFN), :79-101 (pw convs)
+//   q/k/v/out/pos projections    fairseq/modules/multihead_attention.py:650-653,799-814,899-907
+//   QK^T, (q+v)P^T, PV           fairseq/modules/multihead_attention.py:788,815-823,897
+//   fc0 / fc_out                 espresso/models/transformer/speech_transformer_encoder.py:341-343,
+//                                .../speech_transformer_encoder_model.py:207-208
+// and their dgrad / wgrad counterparts (operand majors are template flags: K-major or MN-major
+// smem descriptors, so no transposes are ever materialised).
+#include "common.cuh"
+#include "espresso_b200.h"
+#include <cuda.h>
+
+void esp_count_launch(int n);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kAccStages = 2;
+
+struct EpiParams {
+  void* C;
+  bf16* C2;
+  const bf16* bias;
+  const bf16* aux;
+  const void* R;
+  long ldc, ld_aux, ldr;
+  long sC1, sC2, sAux1, sAux2, sR1, sR2;
+  int c_f32, r_f32, act, drop_mode, skew_r;
+  float alpha, beta, drop_scale;
+  uint32_t drop_thresh;
+  unsigned long long seed;
+};
+
+struct KParams {
+  int M, N, K, nb1, nb2;
+  int a_b1, a_b2, b_b1, b_b2;  // 0 => operand is broadcast along that batch dim
+  EpiParams ep;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    // A protocol bug must surface as a launch failure, never as a hung GPU.
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B).  Field layout: cute/arch/mma_sm100_desc.hpp
+// (SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
+// layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes,
+                                               uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ float apply_act(float v, float u, int act) {
+  switch (act) {
+    case ESP_ACT_RELU: return fmaxf(v, 0.f);
+    case ESP_ACT_SILU: return siluf_(v);
+    case ESP_ACT_RELU_BWD: return u > 0.f ? v : 0.f;
+    case ESP_ACT_SILU_BWD: return v * silu_gradf_(u);
+    default: return v;
+  }
+}
+
+template <int BN, bool A_K, bool B_K>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
+};
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const KParams p) {
+  using L = SmemLayout<BN, A_K, B_K>;
+  constexpr int S = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + L::kBarOffset);
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * S + kAccStages + s); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int nbatch = p.nb1 * p.nb2;
+  const int total_tiles = tiles_m * tiles_n * nbatch;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    constexpr int kCols = kAccStages * BN;  // 128 / 256 / 512: all powers of two >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % tiles_m;
+        const int rest = tile / tiles_m;
+        const int nt = rest % tiles_n;
+        const int bt = rest / tiles_n;
+        const int b1 = bt % p.nb1, b2 = bt / p.nb1;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), L::kStageBytes);
+          const uint32_t sa = smem_base + s * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+          if (A_K) {
+            tma_load_4d(sa, &tmA, full_bar(s), kb * BK, mt * BM, b1 * p.a_b1, b2 * p.a_b2);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(s), mt * BM + 64 * j, kb * BK,
+                          b1 * p.a_b1, b2 * p.a_b2);
+          }
+          if (B_K) {
+            tma_load_4d(sb, &tmB, full_bar(s), kb * BK, nt * BN, b1 * p.b_b1, b2 * p.b_b2);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), nt * BN + 64 * j, kb * BK,
+                          b1 * p.b_b1, b2 * p.b_b2);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =======================================
+    if (lane == 0) {
+      // Instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=bf16.
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_K ? 0u : 1u) << 15) |
+                             ((B_K ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int as = ti % kAccStages;
+        const uint32_t aph = (ti / kAccStages) & 1;
+        mbar_wait(tempty_bar(as), aph ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + s * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 8-row groups are 1024 B apart (SBO); a 16-element K step is +32 B.
+            // MN-major: 64-element MN chunks are BK*128 B apart (LBO); 8-k groups 1024 B apart
+            //           (SBO); a 16-element K step is 16 rows * 128 B.
+            const uint64_t da = A_K ? make_sdesc(sa + k * 32, 16, 1024)
+                                    : make_sdesc(sa + k * 2048, BK * 128, 1024);
+            const uint64_t db = B_K ? make_sdesc(sb + k * 32, 16, 1024)
+                                    : make_sdesc(sb + k * 2048, BK * 128, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+        }
+        tcgen05_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue =========================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const EpiParams& e = p.ep;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int mt = tile % tiles_m;
+      const int rest = tile / tiles_m;
+      const int nt = rest % tiles_n;
+      const int bt = rest / tiles_n;
+      const int b1 = bt % p.nb1, b2 = bt / p.nb1;
+      const int as = ti % kAccStages;
+      const uint32_t aph = (ti / kAccStages) & 1;
+      mbar_wait(tfull_bar(as), aph);
+      tcgen05_fence_after();
+
+      const int m = mt * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const long c_off = (long)b1 * e.sC1 + (long)b2 * e.sC2 + (long)m * e.ldc;
+      const long aux_off = (long)b1 * e.sAux1 + (long)b2 * e.sAux2 + (long)m * e.ld_aux;
+      const long r_off = (long)b1 * e.sR1 + (long)b2 * e.sR2 + (long)m * e.ldr;
+      const unsigned long long rng_row = ((unsigned long long)bt * p.M + m) * (unsigned long long)p.N;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nt * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = (n0 + 32 <= p.N);
+          if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || n0 + j < p.N) v[j] += bf2f(e.bias[n0 + j]);
+          }
+          if (e.C2) {
+            bf16* c2 = e.C2 + c_off + n0;
+            if (full && ((e.ldc & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]);
+                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(c2 + j) = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) c2[j] = f2bf(v[j]);
+            }
+          }
+          if (e.drop_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = esp_dropout_keep(e.seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+          }
+          if (e.act != ESP_ACT_NONE) {
+            if (e.act >= ESP_ACT_RELU_BWD) {
+              const bf16* ax = e.aux + aux_off + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float u = (full || n0 + j < p.N) ? bf2f(ax[j]) : 0.f;
+                v[j] = apply_act(v[j], u, e.act);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], 0.f, e.act);
+            }
+          }
+          if (e.drop_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = esp_dropout_keep(e.seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+          if (e.R) {
+            if (e.skew_r) {
+              // Transformer-XL skew fused into the score GEMM: R is BD_full[row m, (skew_r-1)-m+n]
+              // (fairseq/modules/multihead_attention.py:824-830 as_strided trick).
+              const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) v[j] += e.beta * bf2f(rr[j]);
+            } else if (e.r_f32) {
+              const float* rr = (const float*)e.R + r_off + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || n0 + j < p.N) v[j] += e.beta * rr[j];
+            } else {
+              const bf16* rr = (const bf16*)e.R + r_off + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || n0 + j < p.N) v[j] += e.beta * bf2f(rr[j]);
+            }
+          }
+          if (e.c_f32) {
+            float* cp = (float*)e.C + c_off + n0;
+            if (full && ((e.ldc & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) cp[j] = v[j];
+            }
+          } else {
+            bf16* cp = (bf16*)e.C + c_off + n0;
+            if (full && ((e.ldc & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]);
+                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) cp[j] = f2bf(v[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    constexpr int kCols = kAccStages * BN;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// rows x inner (inner contiguous), two batch dims.  box = {box_inner(64), box_rows}.
+int make_tmap(CUtensorMap* tm, const void* base, long inner, long rows, long ld, int nb1, long s1,
+              int nb2, long s2, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  ESP_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  ESP_CHECK(((uintptr_t)base & 15) == 0, "GEMM operand base must be 16-byte aligned");
+  ESP_CHECK((ld % 8) == 0, "GEMM operand leading dimension (%ld) must be a multiple of 8 elements", ld);
+  // Broadcast / singleton batch dims get size 1 (coordinate forced to 0 by the kernel) and a
+  // dummy legal stride.
+  long dummy = ((rows * ld + 7) / 8) * 8;
+  if (nb1 <= 1 || s1 == 0) { nb1 = 1; s1 = dummy; }
+  if (nb2 <= 1 || s2 == 0) { nb2 = 1; s2 = dummy * (nb1 > 1 ? nb1 : 1); }
+  ESP_CHECK((s1 % 8) == 0 && (s2 % 8) == 0, "GEMM batch strides must be multiples of 8 elements");
+  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ESP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%ld rows=%ld ld=%ld", (int)r,
+            inner, rows, ld);
+  return 0;
+}
+
+template <int BN, bool A_K, bool B_K>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t st) {
+  using L = SmemLayout<BN, A_K, B_K>;
+  static bool configured = false;
+  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K>;
+  if (!configured) {
+    ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ((kp.M + BM - 1) / BM) * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2;
+  int grid = tiles < esp_num_sms() ? tiles : esp_num_sms();
+  if (grid < 1) return 0;
+  kfn<<<grid, kThreads, L::kTotal, st>>>(ta, tb, kp);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+template <int BN>
+int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp,
+                   cudaStream_t st) {
+  if (ak && bk) return launch<BN, true, true>(ta, tb, kp, st);
+  if (ak && !bk) return launch<BN, true, false>(ta, tb, kp, st);
+  if (!ak && bk) return launch<BN, false, true>(ta, tb, kp, st);
+  return launch<BN, false, false>(ta, tb, kp, st);
+}
+
+}  // namespace
+
+extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ESP_CHECK(g != nullptr, "null gemm descriptor");
+  ESP_CHECK(g->M >= 0 && g->N >= 0 && g->K > 0, "bad GEMM shape %ld x %ld x %ld", (long)g->M, (long)g->N,
+            (long)g->K);
+  if (g->M == 0 || g->N == 0) return 0;
+  const int nb1 = g->nb1 > 0 ? g->nb1 : 1, nb2 = g->nb2 > 0 ? g->nb2 : 1;
+  CUtensorMap ta, tb;
+  const bool ak = g->a_kmajor != 0, bk = g->b_kmajor != 0;
+  // tile width: wide tiles for wide N (better smem-bandwidth ratio), narrow when N is small or the
+  // tile count would not fill the machine.
+  int bn = 128;
+  {
+    long t128 = ((g->M + 127) / 128) * ((g->N + 127) / 128) * (long)nb1 * nb2;
+    if (g->N <= 64) bn = 64;
+    else if (g->N >= 256 && ((g->M + 127) / 128) * ((g->N + 255) / 256) * (long)nb1 * nb2 >= 2L * esp_num_sms()) bn = 256;
+    else if (t128 < esp_num_sms() && g->N > 64) bn = 64;
+    if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) bn = g->tile_n;
+  }
+  int rc;
+  if (ak) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, nb1, g->sA1, nb2, g->sA2, BM);
+  else    rc = make_tmap(&ta, g->A, g->M, g->K, g->lda, nb1, g->sA1, nb2, g->sA2, BK);
+  if (rc) return rc;
+  if (bk) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, nb1, g->sB1, nb2, g->sB2, bn);
+  else    rc = make_tmap(&tb, g->B, g->N, g->K, g->ldb, nb1, g->sB1, nb2, g->sB2, BK);
+  if (rc) return rc;
+
+  KParams kp;
+  kp.M = (int)g->M; kp.N = (int)g->N; kp.K = (int)g->K; kp.nb1 = nb1; kp.nb2 = nb2;
+  kp.a_b1 = (nb1 > 1 && g->sA1 != 0) ? 1 : 0;
+  kp.a_b2 = (nb2 > 1 && g->sA2 != 0) ? 1 : 0;
+  kp.b_b1 = (nb1 > 1 && g->sB1 != 0) ? 1 : 0;
+  kp.b_b2 = (nb2 > 1 && g->sB2 != 0) ? 1 : 0;
+  EpiParams& e = kp.ep;
+  e.C = g->C; e.C2 = (bf16*)g->C2; e.bias = (const bf16*)g->bias; e.aux = (const bf16*)g->aux; e.R = g->R;
+  e.ldc = g->ldc; e.ld_aux = g->ld_aux; e.ldr = g->ldr;
+  e.sC1 = g->sC1; e.sC2 = g->sC2; e.sAux1 = g->sAux1; e.sAux2 = g->sAux2; e.sR1 = g->sR1; e.sR2 = g->sR2;
+  e.c_f32 = g->c_f32; e.r_f32 = g->r_f32; e.act = g->act; e.skew_r = g->skew_r;
+  e.drop_mode = (g->drop_p > 0.f) ? g->drop_mode : 0;
+  e.alpha = g->alpha; e.beta = g->beta;
+  e.drop_thresh = esp_dropout_thresh(g->drop_p);
+  e.drop_scale = g->drop_p > 0.f ? 1.f / (1.f - g->drop_p) : 1.f;
+  e.seed = g->seed;
+  ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
+  ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
+  if (bn == 64) return dispatch_major<64>(ak, bk, ta, tb, kp, st);
+  if (bn == 256) return dispatch_major<256>(ak, bk, ta, tb, kp, st);
+  return dispatch_major<128>(ak, bk, ta, tb, kp, st);
+}

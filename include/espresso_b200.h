@@ -1,0 +1,111 @@
+/* espresso_b200 -- C ABI of the B200-native Espresso hot path (libespresso_b200.so).
+ *
+ * Conventions (SURVEY.md §8b "What the C-ABI replacement exports"):
+ *  - plain C: raw DEVICE pointers, explicit sizes/strides (in ELEMENTS unless noted), no torch types;
+ *  - the caller owns all memory (the library never allocates or frees device memory);
+ *  - every entry point launches asynchronously on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, negative on error; esp_last_error() returns a thread-local message;
+ *  - no global mutable state apart from cached device attributes / kernel attributes.
+ *
+ * Each entry point cites the reference call site it replaces (paths relative to the
+ * freewym/espresso tree).  The reference reaches native code through pybind11 torch extensions
+ * (fairseq/clib/cuda/ngram_repeat_block_cuda.cpp:22-55); INTEGRATION.md shows the ctypes stub a
+ * maintainer would add instead.
+ */
+#ifndef ESPRESSO_B200_H_
+#define ESPRESSO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* esp_last_error(void);
+int esp_version(void);
+/* number of kernel launches issued through this library since load (for bench gpu_launches) */
+int64_t esp_launch_count(void);
+
+/* ---- dense contraction: C = epi(op(A) * op(B)^T), bf16 in, fp32 accumulate (tcgen05 + TMA) -----
+ * replaces torch.nn.functional.linear / torch.bmm call sites:
+ *   fairseq/modules/conformer_layer.py:134-146,79-101; fairseq/modules/multihead_attention.py:650-653,
+ *   788,799-823,897-907; espresso/models/transformer/speech_transformer_encoder.py:341-343;
+ *   espresso/models/transformer/speech_transformer_encoder_model.py:207-208.
+ * A is logically [M,K]: a_kmajor=1 -> A[m*lda+k]; a_kmajor=0 -> A[k*lda+m].
+ * B is logically [N,K]: b_kmajor=1 -> B[n*ldb+k]; b_kmajor=0 -> B[k*ldb+n].
+ * Two batch dims (nb1 fastest) with per-operand strides; stride 0 broadcasts the operand.
+ * Epilogue, in order: +bias[n]; C2=bf16(pre-activation); dropout(mode 2); activation
+ * (ESP_ACT_*; *_BWD multiply by act'(aux)); dropout(mode 1); *alpha; +beta*R (R optionally read with
+ * the Transformer-XL skew R[m,(skew_r-1)-m+n]); store bf16 or fp32.
+ * Dropout is a stateless counter RNG keyed by (seed, logical element index): the backward pass
+ * regenerates the forward mask, nothing is stored. */
+enum { ESP_ACT_NONE = 0, ESP_ACT_RELU = 1, ESP_ACT_SILU = 2, ESP_ACT_RELU_BWD = 3, ESP_ACT_SILU_BWD = 4 };
+
+typedef struct EspGemm {
+  const void* A;
+  const void* B;
+  void* C;
+  void* C2;          /* optional bf16 [M,N] (same ld/strides as C): value before activation */
+  const void* bias;  /* optional bf16 [N] */
+  const void* aux;   /* bf16, saved pre-activation for *_BWD */
+  const void* R;     /* optional residual, bf16 or fp32 (r_f32) */
+  int64_t M, N, K;
+  int64_t lda, ldb, ldc, ld_aux, ldr;
+  int64_t sA1, sA2, sB1, sB2, sC1, sC2, sAux1, sAux2, sR1, sR2;
+  int32_t a_kmajor, b_kmajor;
+  int32_t nb1, nb2;
+  int32_t c_f32, r_f32;
+  int32_t act;
+  int32_t drop_mode; /* 0 none, 1 after activation (forward), 2 before activation (backward) */
+  int32_t skew_r;    /* 0, or T: read R with relative-position skew */
+  int32_t tile_n;    /* 0 auto, or 64/128/256 */
+  float alpha, beta, drop_p;
+  uint64_t seed;
+} EspGemm;
+
+int esp_gemm_bf16(const EspGemm* g, void* stream);
+
+/* ---- fused front end: framing -> DC removal -> pre-emphasis -> Povey window -> 512-pt rFFT ->
+ *      power -> 80 mel -> log -> global CMVN -> adaptive SpecAugment, batched on device ---------
+ * replaces espresso/data/feat_text_dataset.py:128-161 (per-utterance CPU path):
+ *   espresso/tools/utils.py:426-454 -> torchaudio/compliance/kaldi.py:514-646 (fbank defaults),
+ *   fairseq/data/audio/feature_transforms/global_cmvn.py:26-29,
+ *   espresso/data/feature_transforms/adaptive_specaugment.py:77-136 (mask draws stay on the host
+ *   with the reference's NumPy RNG; only the descriptors are uploaded).
+ * wave: [B, wave_ld] samples in int16 range (fp32, or int16 if wave_i16), right padded.
+ * n_samples[b]: valid samples.  frames m_b = 1 + (n-400)/160 (0 if n < 400).
+ * cmvn_mean/cmvn_std: fp32[80] or NULL (no CMVN).
+ * freq_masks: int32 [B, n_freq_masks, 2] = (f0, f); time_masks: int32 [B, max_time_masks, 2] = (t0, t);
+ *   a mask with width 0 is a no-op.  Fill value = mean of the utterance's CMVN'd features
+ *   (adaptive_specaugment.py:83-86).  Pass NULL / 0 for no SpecAugment (validation / decoding).
+ * out: [B, t_max, 80] (bf16, or fp32 if out_f32), frames >= m_b are zero (collate pad value 0.0,
+ *   espresso/tools/utils.py:97-113).  out_lens: int32[B] = m_b.
+ * workspace: >= B*16 bytes, zero-initialised by the caller is NOT required (the kernel resets it). */
+int esp_frontend_fbank(const void* wave, int32_t wave_i16, int64_t wave_ld, const int32_t* n_samples,
+                       int32_t B, const float* cmvn_mean, const float* cmvn_std,
+                       const int32_t* freq_masks, int32_t n_freq_masks, const int32_t* time_masks,
+                       int32_t max_time_masks, void* out, int32_t out_f32, int32_t t_max,
+                       int32_t* out_lens, void* workspace, void* stream);
+int64_t esp_frontend_workspace_bytes(int32_t B);
+
+/* ---- CTC loss forward+backward fused with the fp32 log-softmax ---------------------------------
+ * replaces espresso/criterions/ctc_loss.py:59-103 = get_normalized_probs (fp32 log_softmax,
+ *   espresso/models/transformer/speech_transformer_encoder_model.py:141-150) + F.ctc_loss(reduction
+ *   ="sum", zero_infinity) with cuDNN disabled, and their autograd backward.
+ * logits: bf16 [.., V] addressed as logits[b*stride_b + t*stride_t + v]; in_lens int32[B];
+ * targets: int32 [B, u_max] (pad ignored beyond tgt_lens[b]); blank index.
+ * loss: fp32[B] per-utterance negative log-likelihood (0 where infinite and zero_infinity);
+ * grad: bf16, same addressing as logits; = grad_scale * d(sum_b loss_b)/d logits; rows t>=in_lens[b]
+ *   and padded columns [V, ld) are written as zero.  Pass grad=NULL for loss only.
+ * workspace: esp_ctc_workspace_bytes(B, t_max, u_max). */
+int64_t esp_ctc_workspace_bytes(int32_t B, int32_t t_max, int32_t u_max);
+int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride_t, int32_t V, int32_t B,
+                 int32_t t_max, const int32_t* in_lens, const int32_t* targets, int32_t u_max,
+                 const int32_t* tgt_lens, int32_t blank, int32_t zero_infinity, float grad_scale,
+                 float* loss, void* grad, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESPRESSO_B200_H_ */

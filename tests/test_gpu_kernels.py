@@ -1,0 +1,241 @@
+"""GPU parity tests (through the C ABI): front end, CTC, tcgen05 GEMM vs the oracle / golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------ front end
+def _run_frontend(dev, waves, mean, std, fms, tms, out_dtype=torch.float32, i16=False):
+    from espresso_b200 import ops
+    from espresso_b200.data import specaugment as SA
+
+    B = len(waves)
+    n = np.array([len(w) for w in waves], dtype=np.int32)
+    wv = np.zeros((B, max(int(n.max()), 400)), dtype=np.float32)
+    for b, w in enumerate(waves):
+        wv[b, : len(w)] = w
+    wt = torch.from_numpy(wv).to(dev)
+    if i16:
+        wt = wt.to(torch.int16)
+    fm = tm = None
+    if fms is not None:
+        fmp, tmp = SA.pack_masks(fms, tms)
+        fm, tm = torch.from_numpy(fmp).to(dev), torch.from_numpy(tmp).to(dev)
+    mt = None if mean is None else torch.from_numpy(mean.astype(np.float32)).to(dev)
+    st = None if std is None else torch.from_numpy(std.astype(np.float32)).to(dev)
+    out, lens = ops.frontend_fbank(wt, torch.from_numpy(n).to(dev), mt, st, fm, tm, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    return out.float().cpu().numpy(), lens.cpu().numpy()
+
+
+def test_frontend_vs_reference_fixture(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend.npz"))
+    ids = [i for i in range(len(g["durs"])) if "wave_%d" % i in g]
+    waves = [g["wave_%d" % i] for i in ids]
+    # plain fbank (no CMVN, no masks) vs torchaudio's output recorded from the reference
+    out, lens = _run_frontend(dev, waves, None, None, None, None)
+    for b, i in enumerate(ids):
+        ref = g["fbank_%d" % i]
+        assert lens[b] == ref.shape[0]
+        assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3  # fp32 FFT rounding; see test_oracle_golden
+        assert not out[b, lens[b]:].any()
+    # full chain with the reference's recorded mask descriptors: masks identical, values within tolerance
+    fms = [[tuple(x) for x in g["fmask_%d" % i]] for i in ids]
+    tms = [[tuple(x) for x in g["tmask_%d" % i]] for i in ids]
+    out, lens = _run_frontend(dev, waves, g["cmvn_mean"], g["cmvn_std"], fms, tms)
+    for b, i in enumerate(ids):
+        ref = g["final_%d" % i]
+        assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3
+        assert not out[b, lens[b]:].any()
+    # run twice: the SpecAugment workspace must be left clean by the kernel
+    out2, _ = _run_frontend(dev, waves, g["cmvn_mean"], g["cmvn_std"], fms, tms)
+    assert np.array_equal(out, out2)
+
+
+def test_frontend_vs_oracle_ragged_and_int16(dev):
+    from oracle import frontend as O
+
+    durs = [0.02, 0.025, 1.003, 2.5, 0.7, 4.01]  # includes < 1 frame and exactly 1 frame
+    waves = [O.synth_waveform(20 + i, d) for i, d in enumerate(durs)]
+    out, lens = _run_frontend(dev, waves, None, None, None, None, i16=True)
+    for b, w in enumerate(waves):
+        ref = O.kaldi_fbank(w)
+        assert lens[b] == ref.shape[0]
+        if ref.shape[0]:
+            assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3
+        assert not out[b, lens[b]:].any()
+    outb, _ = _run_frontend(dev, waves, None, None, None, None, out_dtype=torch.bfloat16)
+    assert np.abs(outb - out).max() < 0.1  # bf16 rounding of values ~ 20
+
+
+def test_frontend_full_size_properties(dev):
+    """LibriSpeech-shape batch (24 x up to 35 s): linearity-free properties -- determinism, padding zero,
+    per-utterance independence from batch composition."""
+    from oracle import frontend as O
+
+    rs = np.random.RandomState(7)
+    durs = np.clip(rs.gamma(6.1, 2.0, size=24), 1.0, 35.0)
+    waves = [O.synth_waveform(100 + i, d) for i, d in enumerate(durs)]
+    out, lens = _run_frontend(dev, waves, None, None, None, None)
+    solo, l1 = _run_frontend(dev, [waves[5]], None, None, None, None)
+    assert l1[0] == lens[5] and np.array_equal(solo[0, : l1[0]], out[5, : lens[5]])
+    ref = O.kaldi_fbank(waves[5])
+    assert np.abs(out[5, : lens[5]] - ref).max() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------ CTC
+def test_ctc_vs_reference_fixture(dev, golden_dir):
+    from espresso_b200 import ops
+
+    g = np.load(os.path.join(golden_dir, "ctc.npz"))
+    logits = torch.from_numpy(g["logits"]).bfloat16()
+    B, T, V = logits.shape
+    ld = (V + 7) // 8 * 8
+    buf = torch.full((B, T, ld), 5.0, dtype=torch.bfloat16)
+    buf[:, :, :V] = logits
+    loss, grad = ops.ctc_loss(buf.to(dev), V, torch.from_numpy(g["in_lens"]).to(dev), torch.from_numpy(g["targets"]).to(dev),
+                              torch.from_numpy(g["tgt_lens"]).to(dev), int(g["blank"]))
+    torch.cuda.synchronize()
+    assert np.allclose(loss.cpu().numpy(), g["loss"], rtol=1e-5, atol=1e-4)
+    gr = grad.float().cpu().numpy()
+    assert np.abs(gr[:, :, :V] - g["grad"]).max() < 5e-3  # bf16 storage of the gradient
+    assert not gr[:, :, V:].any()
+
+
+@pytest.mark.parametrize("V,T,U", [(50, 40, 12), (5004, 60, 20), (300, 200, 90), (64, 30, 0)])
+def test_ctc_vs_oracle(dev, V, T, U):
+    from espresso_b200 import ops
+    from oracle import ctc as O
+
+    rs = np.random.RandomState(V + T)
+    B = 3
+    ld = (V + 7) // 8 * 8
+    x = (rs.randn(B, T, ld) * 1.5).astype(np.float32)
+    xt = torch.from_numpy(x).bfloat16()
+    in_lens = np.array([T, max(1, T - 7), max(1, T // 2)], dtype=np.int32)
+    tl = np.array([U, max(0, U - 3), U // 2], dtype=np.int32)
+    tg = rs.randint(1, V, size=(B, max(U, 1))).astype(np.int32)
+    if U > 3:
+        tg[:, 2] = tg[:, 1]
+    loss, grad = ops.ctc_loss(xt.to(dev), V, torch.from_numpy(in_lens).to(dev), torch.from_numpy(tg).to(dev),
+                              torch.from_numpy(tl).to(dev), 0, grad_scale=0.5)
+    torch.cuda.synchronize()
+    gr = grad.float().cpu().numpy()
+    for b in range(B):
+        nll, g = O.ctc_loss_and_grad(xt[b, :, :V].float().numpy(), in_lens[b], tg[b, : tl[b]], 0)
+        assert abs(loss[b].item() - nll) <= 1e-5 * max(1.0, abs(nll)) + 1e-4, (b, loss[b].item(), nll)
+        assert np.abs(gr[b, :, :V] - 0.5 * g).max() < 4e-3
+        assert not gr[b, in_lens[b]:].any()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def _ref_mm(a, b):
+    return a.float() @ b.float().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 72, 96), (1000, 512, 512), (333, 2048, 520), (6500, 5008, 512),
+                                   (77, 40, 2560), (1, 8, 8)])
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 256])
+def test_gemm_kmajor(dev, M, N, K, tile_n):
+    from espresso_b200 import ops
+
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    c = ops.linear(a, b, out_dtype=torch.float32, tile_n=tile_n)
+    ref = _ref_mm(a, b)
+    assert (c - ref).abs().max().item() <= 2e-3 * K ** 0.5 + 1e-3
+    cb = ops.linear(a, b, tile_n=tile_n)
+    assert (cb.float() - ref).abs().max().item() <= 0.02 * ref.abs().max().item() + 1e-2
+
+
+@pytest.mark.parametrize("ak,bk", [(True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+def test_gemm_mn_major(dev, ak, bk, tile_n):
+    from espresso_b200 import ops
+
+    M, N, K = 300, 328, 200
+    torch.manual_seed(5)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    A = a if ak else a.t().contiguous()   # [K, M] when MN-major
+    Bm = b if bk else b.t().contiguous()  # [K, N]
+    c = torch.empty(M, N, device=dev, dtype=torch.float32)
+    ops.gemm(A, Bm, c, M, N, K, A.stride(0), Bm.stride(0), N, a_kmajor=ak, b_kmajor=bk, tile_n=tile_n)
+    assert (c - _ref_mm(a, b)).abs().max().item() < 0.05
+
+
+def test_gemm_epilogues(dev):
+    from espresso_b200 import ops
+
+    torch.manual_seed(1)
+    M, N, K = 400, 264, 136
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.2).bfloat16()
+    bias = torch.randn(N, device=dev).bfloat16()
+    res = torch.randn(M, N, device=dev).bfloat16()
+    pre = _ref_mm(a, w) + bias.float()
+    # bias + SiLU, pre-activation side output, scaled residual
+    c2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    y = ops.linear(a, w, bias, act=ops.ACT_SILU, C2=c2, R=res, ldr=N, alpha=0.5, beta=1.0)
+    ref = 0.5 * torch.nn.functional.silu(pre) + res.float()
+    assert (y.float() - ref).abs().max().item() < 0.06
+    assert (c2.float() - pre).abs().max().item() < 0.06
+    # relu
+    y = ops.linear(a, w, bias, act=ops.ACT_RELU, out_dtype=torch.float32)
+    assert (y - torch.relu(pre)).abs().max().item() < 0.02
+    # silu backward: acc * silu'(aux)
+    aux = torch.randn(M, N, device=dev).bfloat16()
+    y = ops.linear(a, w, None, act=ops.ACT_SILU_BWD, aux=aux, ld_aux=N, out_dtype=torch.float32)
+    u = aux.float()
+    s = torch.sigmoid(u)
+    assert (y - _ref_mm(a, w) * (s * (1 + u * (1 - s)))).abs().max().item() < 0.02
+    # dropout: deterministic in (seed, index), forward mask == backward mask, keep rate ~ 1-p
+    y1 = ops.linear(a, w, None, out_dtype=torch.float32, drop_p=0.25, drop_mode=1, seed=1234)
+    y2 = ops.linear(a, w, None, out_dtype=torch.float32, drop_p=0.25, drop_mode=2, seed=1234)
+    y3 = ops.linear(a, w, None, out_dtype=torch.float32, drop_p=0.25, drop_mode=1, seed=99)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    keep = (y1 != 0).float().mean().item()
+    assert abs(keep - 0.75) < 0.01
+    full = _ref_mm(a, w)
+    m = y1 != 0
+    assert (y1[m] - full[m] / 0.75).abs().max().item() < 0.02
+
+
+def test_gemm_batched_and_skew(dev):
+    """Attention-shaped use: batch dims (head, batch) with broadcast B operand and the rel-pos skew read."""
+    from espresso_b200 import ops
+
+    torch.manual_seed(2)
+    T, H, Bz, hd = 37, 4, 3, 64
+    d = H * hd
+    q = torch.randn(Bz, T, d, device=dev).bfloat16()
+    k = torch.randn(Bz, T, d, device=dev).bfloat16()
+    p = torch.randn(2 * T - 1, d, device=dev).bfloat16()  # projected positions, shared over batch
+    ldp = (2 * T - 1 + 7) // 8 * 8
+    bd = torch.zeros(H, Bz, T, ldp, device=dev, dtype=torch.bfloat16)
+    # BD_full[h,b] = q[b,:,h] @ p[:,h]^T   (B operand broadcast over the batch dim)
+    ops.gemm(q, p, bd, T, 2 * T - 1, hd, d, d, ldp, nb1=H, nb2=Bz, sA=(hd, T * d), sB=(hd, 0),
+             sC=(Bz * T * ldp, T * ldp))
+    ref_bd = torch.einsum("bthd,rhd->hbtr", q.float().view(Bz, T, H, hd), p.float().view(-1, H, hd))
+    assert (bd[..., : 2 * T - 1].float() - ref_bd).abs().max().item() < 0.25
+    # scores = q k^T * scale + skew(BD)
+    ldt = (T + 7) // 8 * 8
+    sc = torch.zeros(H, Bz, T, ldt, device=dev, dtype=torch.float32)
+    ops.gemm(q, k, sc, T, T, hd, d, d, ldt, nb1=H, nb2=Bz, sA=(hd, T * d), sB=(hd, T * d), sC=(Bz * T * ldt, T * ldt),
+             R=bd, ldr=ldp, sR=(Bz * T * ldp, T * ldp), skew_r=T, alpha=0.125, beta=1.0)
+    ac = torch.einsum("bihd,bjhd->hbij", q.float().view(Bz, T, H, hd), k.float().view(Bz, T, H, hd)) * 0.125
+    i = torch.arange(T, device=dev)[:, None]
+    j = torch.arange(T, device=dev)[None, :]
+    skew = bd[..., : 2 * T - 1].float().gather(-1, ((T - 1) - i + j).expand(H, Bz, T, T))
+    assert (sc[..., :T] - (ac + skew)).abs().max().item() < 0.05

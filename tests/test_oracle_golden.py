@@ -1,0 +1,68 @@
+"""CPU: the oracle restatements reproduce the fixtures generated from the real reference
+(oracle/pin_against_reference.py), and the host mask-drawing logic consumes the RNG like the reference."""
+import os
+
+import numpy as np
+
+from espresso_b200.data import specaugment as SA
+from oracle import ctc as octc
+from oracle import frontend as ofe
+
+
+def test_frontend_oracle_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend.npz"))
+    mean, std = g["cmvn_mean"], g["cmvn_std"]
+    for i in range(len(g["durs"])):
+        if "wave_%d" % i not in g:
+            continue
+        w = g["wave_%d" % i]
+        fb = ofe.kaldi_fbank(w)
+        assert fb.shape == g["fbank_%d" % i].shape
+        # two fp32 FFT implementations (numpy pocketfft vs torch) differ by a few 1e-4 on log-mel
+        assert np.abs(fb - g["fbank_%d" % i]).max() < 2e-3
+        # ... and both sit that close to the float64 evaluation of the same formula
+        fb64 = ofe.kaldi_fbank(w, dtype=np.float64)
+        assert np.abs(fb64 - g["fbank_%d" % i]).max() < 2e-3
+        with ofe.numpy_seed(1, 1, i):
+            out, fm, tm = ofe.adaptive_specaugment(ofe.global_cmvn(fb, mean, std), return_masks=True)
+        assert np.abs(out - g["final_%d" % i]).max() < 2e-3
+        assert np.array_equal(np.array(fm, dtype=np.int32).reshape(-1, 2), g["fmask_%d" % i])
+        assert np.array_equal(np.array(tm, dtype=np.int32).reshape(-1, 2), g["tmask_%d" % i])
+
+
+def test_host_mask_draws_match_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend.npz"))
+    cfg = SA.AdaptiveSpecAugmentConfig.from_config_dict(
+        {"time_warp_W": 0, "freq_mask_F": 27, "freq_mask_N": 2, "time_mask_pm": 0.04, "time_mask_ps": 0.04})
+    for i in range(len(g["durs"])):
+        if "wave_%d" % i not in g:
+            continue
+        m = g["fbank_%d" % i].shape[0]
+        with SA.numpy_seed(1, 1, i):
+            fm, tm = SA.draw_masks(cfg, m, 80)
+        assert np.array_equal(np.array(fm, dtype=np.int32).reshape(-1, 2), g["fmask_%d" % i])
+        assert np.array_equal(np.array(tm, dtype=np.int32).reshape(-1, 2), g["tmask_%d" % i])
+    fmp, tmp = SA.pack_masks([[(1, 2)], []], [[], [(3, 4), (5, 6)]])
+    assert fmp.shape == (2, 1, 2) and tmp.shape == (2, 2, 2) and tmp[0].sum() == 0
+
+
+def test_num_frames_edges():
+    assert ofe.num_frames(399) == 0 and ofe.num_frames(400) == 1 and ofe.num_frames(559) == 1
+    assert ofe.num_frames(560) == 2 and ofe.num_frames(160000) == 998
+
+
+def test_ctc_oracle_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ctc.npz"))
+    for b in range(g["logits"].shape[0]):
+        tgt = g["targets"][b, : g["tgt_lens"][b]]
+        nll, grad = octc.ctc_loss_and_grad(g["logits"][b], g["in_lens"][b], tgt, int(g["blank"]))
+        assert abs(nll - g["loss"][b]) < 1e-4 * max(1.0, abs(g["loss"][b]))
+        assert np.abs(grad - g["grad"][b]).max() < 1e-5
+
+
+def test_ctc_oracle_edge_cases():
+    x = np.zeros((4, 3))
+    nll, grad = octc.ctc_loss_and_grad(x, 4, [], 0)  # empty target: all-blank path
+    assert abs(nll - 4 * np.log(3.0)) < 1e-9
+    nll, grad = octc.ctc_loss_and_grad(x, 1, [1, 2], 0)  # infeasible -> zero_infinity
+    assert nll == 0.0 and not grad.any()
