@@ -1,0 +1,858 @@
+// espresso_b200 -- HBM-bound kernels of the Conformer/Transformer block, forward and backward.
+//
+//   LayerNorm                fairseq/modules/layer_norm.py (torch.nn.LayerNorm), used at
+//                            fairseq/modules/conformer_layer.py:79-81,134-136 and
+//                            espresso/modules/conformer_with_relative_positional_embedding_encoder_layer.py:118,143
+//   GLU + depthwise conv k   fairseq/modules/conformer_layer.py:88-93   (+ BatchNorm batch statistics)
+//   BatchNorm1d + SiLU       fairseq/modules/conformer_layer.py:95-96   (batch stats incl. padded frames)
+//   rel-pos softmax          fairseq/modules/multihead_attention.py:841-867 (key-padding -inf, fp32 softmax, dropout)
+//   (q+u)*s, (q+v)*s         fairseq/modules/multihead_attention.py:679-688
+//   dropout                  torch.nn.Dropout call sites of the modules above (stateless counter RNG)
+//   column sums              bias / pos_bias gradients
+// All tensors are batch-major [B, T, C] bf16 with fp32 statistics; every kernel reads each input
+// element once and writes each output element once (vectorised 16-byte accesses).
+#include "common.cuh"
+#include "espresso_b200.h"
+#include <math.h>
+
+void esp_count_launch(int n);
+
+namespace {
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(q.x, v[0], v[1]);
+  unpack_bf16x2(q.y, v[2], v[3]);
+  unpack_bf16x2(q.z, v[4], v[5]);
+  unpack_bf16x2(q.w, v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+inline int grid_for(long work_items, int per_block, int max_waves = 8) {
+  long g = (work_items + per_block - 1) / per_block;
+  long cap = (long)esp_num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ================================================================================================
+// LayerNorm: one warp per row, row cached in registers (d <= 2048, d % 8 == 0)
+// ================================================================================================
+constexpr int kLnMaxVec = 8;  // uint4 per lane (template parameter NV <= kLnMaxVec)
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
+              long R, int d, bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = d >> 3;
+  const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long r = warp0; r < R; r += nwarps) {
+    const bf16* xr = x + r * d;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        load8(xr + vi * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float c = v[i][j] - mean;
+          ss += c * c;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+    // optional: zero padded rows (t >= len_b) -- speech_transformer_encoder.py:354-357
+    bool zero_row = false;
+    if (lens) {
+      const int b = (int)(r / T), t = (int)(r % T);
+      zero_row = t >= lens[b];
+    }
+    bf16* yr = y + r * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float g[8], bb[8], o[8];
+        load8(gamma + vi * 8, g);
+        load8(beta + vi * 8, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = (v[i][j] - mean) * rstd * g[j] + bb[j];
+          if (drop_p > 0.f)
+            t = esp_dropout_keep(seed, (unsigned long long)r * d + vi * 8 + j, drop_thresh) ? t * drop_scale : 0.f;
+          o[j] = zero_row ? 0.f : t;
+        }
+        store8(yr + vi * 8, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat*mean(g*dy*xhat)) [+ dres];  dgamma += dy*xhat; dbeta += dy
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, const bf16* __restrict__ dres, long R,
+              int d, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed) {
+  extern __shared__ float sm_red[];  // [2][d]
+  const int lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;
+  const long warp0 = (long)blockIdx.x * nw + (threadIdx.x >> 5);
+  const long nwarps = (long)gridDim.x * nw;
+  const int nvec = d >> 3;
+  const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm_red[i] = 0.f;
+  __syncthreads();
+  for (long r = warp0; r < R; r += nwarps) {
+    bool zero_row = false;
+    if (lens) {
+      const int b = (int)(r / T), t = (int)(r % T);
+      zero_row = t >= lens[b];
+    }
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float gdy[NV][8], xh[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float a[8], xv[8], g[8];
+        load8(dy + r * d + vi * 8, a);
+        load8(x + r * d + vi * 8, xv);
+        load8(gamma + vi * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dyv = a[j];
+          if (zero_row) dyv = 0.f;
+          else if (drop_p > 0.f)
+            dyv = esp_dropout_keep(seed, (unsigned long long)r * d + vi * 8 + j, drop_thresh) ? dyv * drop_scale : 0.f;
+          const float h = (xv[j] - mean) * rstd;
+          xh[i][j] = h;
+          gdy[i][j] = dyv * g[j];
+          ag[i][j] += dyv * h;
+          ab[i][j] += dyv;
+          s1 += gdy[i][j];
+          s2 += gdy[i][j] * h;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+        float rr[8];
+        if (dres) load8(dres + r * d + vi * 8, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rstd * (gdy[i][j] - s1 - xh[i][j] * s2);
+          if (dres) o[j] += rr[j];
+        }
+        store8(dx + r * d + vi * 8, o);
+      }
+    }
+  }
+  // block reduce of the per-column partial sums, then one atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm_red[vi * 8 + j], ag[i][j]);
+        atomicAdd(&sm_red[d + vi * 8 + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[i], sm_red[i]);
+    if (dbeta) atomicAdd(&dbeta[i], sm_red[d + i]);
+  }
+}
+
+// ================================================================================================
+// generic elementwise / reductions over [R, N] bf16 (N % 8 == 0, row stride ld)
+// ================================================================================================
+// out[n] += scale * sum_r x[r, n]     (fp32 accumulate, atomics across CTAs)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, long R, int N, long ld, float scale, float* __restrict__ out) {
+  // block = 32 column-vectors x 8 row lanes
+  const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  __shared__ float red[8][32][8];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cv * 8 < N) {
+    for (long r = (long)blockIdx.y * 8 + rl; r < R; r += (long)gridDim.y * 8) {
+      float v[8];
+      load8(x + r * ld + cv * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][threadIdx.x & 31][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && cv * 8 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x & 31][j];
+      atomicAdd(&out[cv * 8 + j], s * scale);
+    }
+  }
+}
+
+// y = dropout(x) * scale  (same counter RNG as the GEMM epilogue: index = r*N + n)
+__global__ void __launch_bounds__(256)
+dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, float scale, float drop_p,
+               uint32_t thresh, unsigned long long seed, bf16* __restrict__ y) {
+  const long nvec = R * (N >> 3);
+  const float ds = drop_p > 0.f ? scale / (1.f - drop_p) : scale;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (N >> 3);
+    const int c = (int)(i % (N >> 3)) * 8;
+    float v[8];
+    load8(x + r * ldx + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool keep = drop_p > 0.f ? esp_dropout_keep(seed, (unsigned long long)r * N + c + j, thresh) : true;
+      v[j] = keep ? v[j] * ds : 0.f;
+    }
+    store8(y + r * ldy + c, v);
+  }
+}
+
+// zero rows t >= lens[b] of x [B, T, N]
+__global__ void __launch_bounds__(256)
+mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ lens, int B, int T, int N) {
+  const long nvec = (long)B * T * (N >> 3);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (N >> 3);
+    const int b = (int)(r / T), t = (int)(r % T);
+    if (t >= lens[b]) *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// q_u = (q + u) * s ; q_v = (q + v) * s          (multihead_attention.py:679-688)
+__global__ void __launch_bounds__(256)
+qprep_fwd_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ u, const bf16* __restrict__ v, float s,
+                 long R, int d, bf16* __restrict__ qu, bf16* __restrict__ qv) {
+  const long nvec = R * (d >> 3);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (d >> 3);
+    const int c = (int)(i % (d >> 3)) * 8;
+    float a[8], bu[8], bv[8], o1[8], o2[8];
+    load8(q + r * ldq + c, a);
+    load8(u + c, bu);
+    load8(v + c, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // the reference rounds (q + bias) to bf16 before scaling; mirror that
+      o1[j] = bf2f(f2bf(a[j] + bu[j])) * s;
+      o2[j] = bf2f(f2bf(a[j] + bv[j])) * s;
+    }
+    store8(qu + r * d + c, o1);
+    store8(qv + r * d + c, o2);
+  }
+}
+// dq = s * (dqu + dqv)  -> written with row stride ld_out
+__global__ void __launch_bounds__(256)
+qprep_bwd_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, float s, long R, int d,
+                 bf16* __restrict__ dq, long ld_out) {
+  const long nvec = R * (d >> 3);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / (d >> 3);
+    const int c = (int)(i % (d >> 3)) * 8;
+    float a[8], b[8], o[8];
+    load8(dqu + r * d + c, a);
+    load8(dqv + r * d + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = s * (a[j] + b[j]);
+    store8(dq + r * ld_out + c, o);
+  }
+}
+
+// ================================================================================================
+// attention softmax over keys with key-padding mask; one warp per (head, batch, query) row
+// scores layout [H, B, T, ld] bf16.  T <= 32*kSmMax.
+// ================================================================================================
+constexpr int kSmMax = 36;  // up to 1152 keys per row (36 s of audio after 4x subsampling = 900)
+
+__global__ void __launch_bounds__(256)
+attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int ld, const int* __restrict__ lens,
+                        bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
+                        unsigned long long seed) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long rows = (long)H * B * T;
+  if (row >= rows) return;
+  const int b = (int)((row / T) % B);
+  const int klen = lens ? lens[b] : T;
+  const bf16* sr = s_in + row * ld;
+  float v[kSmMax];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmMax; ++i) {
+    const int j = lane + i * 32;
+    v[i] = (j < klen && j < T) ? bf2f(sr[j]) : -INFINITY;  // key_padding_mask -> -inf (:848-854)
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmMax; ++i) {
+    v[i] = (v[i] == -INFINITY) ? 0.f : __expf(v[i] - mx);
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+#pragma unroll
+  for (int i = 0; i < kSmMax; ++i) {
+    const int j = lane + i * 32;
+    if (j < ld) {
+      // softmax in fp32, result cast to the model dtype (fairseq/utils.py:514-525 + .type_as)
+      const bf16 pb = f2bf(j < T ? v[i] * inv : 0.f);
+      p_out[row * ld + j] = pb;
+      if (pd_out) {
+        const bool keep = esp_dropout_keep(seed, (unsigned long long)row * T + j, thresh);
+        pd_out[row * ld + j] = (j < T && keep) ? f2bf(bf2f(pb) * ds) : f2bf(0.f);
+      }
+    }
+  }
+}
+
+// dS = P * (dP - sum_j dP*P), dP = dropmask * dPd / (1-p);  also scatters dS into the skewed
+// relative-position layout dBD[row, (T-1) - i + j]  (zeros elsewhere).
+__global__ void __launch_bounds__(256)
+attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int T, int ld,
+                        bf16* __restrict__ ds_out, bf16* __restrict__ dbd_out, int ldp, float drop_p,
+                        uint32_t thresh, unsigned long long seed) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long rows = (long)H * B * T;
+  if (row >= rows) return;
+  const int qi = (int)(row % T);
+  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float pv[kSmMax], dv[kSmMax];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmMax; ++i) {
+    const int j = lane + i * 32;
+    pv[i] = 0.f;
+    dv[i] = 0.f;
+    if (j < T) {
+      pv[i] = bf2f(p_in[row * ld + j]);
+      float g = bf2f(dpd[row * ld + j]);
+      if (drop_p > 0.f) g = esp_dropout_keep(seed, (unsigned long long)row * T + j, thresh) ? g * dscale : 0.f;
+      dv[i] = g;
+      dot += g * pv[i];
+    }
+  }
+  dot = warp_sum(dot);
+  bf16* dbd = dbd_out ? dbd_out + row * ldp : nullptr;
+  if (dbd) {
+    // zero the parts of the skewed row that no (i, j) maps to
+    const int lo = (T - 1) - qi;  // r of j = 0
+    for (int r = lane; r < ldp; r += 32)
+      if (r < lo || r >= lo + T) dbd[r] = f2bf(0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < kSmMax; ++i) {
+    const int j = lane + i * 32;
+    if (j < ld) {
+      const bf16 o = f2bf(j < T ? pv[i] * (dv[i] - dot) : 0.f);
+      ds_out[row * ld + j] = o;
+      if (dbd && j < T) dbd[(T - 1) - qi + j] = o;
+    }
+  }
+}
+
+// ================================================================================================
+// Conformer convolution module body: GLU -> depthwise conv (k odd, 'same' zero padding over the
+// padded batch length T) -> BatchNorm1d statistics.   conformer_layer.py:88-95
+//   g [B, T, 2C] bf16 ; w [C, k] bf16 ; y [B, T, C] bf16 ; stats double [2, C] (sum, sum of squares)
+// CTA tile: 64 time steps x 64 channels.
+// ================================================================================================
+constexpr int kDwT = 64, kDwC = 64, kDwMaxK = 31;
+
+__global__ void __launch_bounds__(256)
+glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, int B, int T, int Cn, int ksz,
+                      bf16* __restrict__ y, double* __restrict__ stats) {
+  __shared__ float tile[kDwT + kDwMaxK - 1][kDwC + 1];
+  __shared__ float wsm[kDwC][kDwMaxK + 1];
+  __shared__ float red[2][4][kDwC];
+  const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
+  const int half = ksz >> 1;
+  const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 time groups
+  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i / ksz][i % ksz] = bf2f(w[(long)(c0 + i / ksz) * ksz + i % ksz]);
+  for (int r = tg; r < kDwT + ksz - 1; r += 4) {
+    const int t = t0 + r - half;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const bf16* row = g + ((long)b * T + t) * 2 * Cn;
+      const float a = bf2f(row[c0 + cl]);
+      const float gate = bf2f(row[Cn + c0 + cl]);
+      v = bf2f(f2bf(a * sigmoidf_(gate)));  // GLU output is a bf16 tensor in the reference
+    }
+    tile[r][cl] = v;
+  }
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int tt = tg; tt < kDwT; tt += 4) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    float acc = 0.f;
+    for (int k = 0; k < ksz; ++k) acc = fmaf(tile[tt + k][cl], wsm[cl][k], acc);
+    const bf16 ob = f2bf(acc);
+    y[((long)b * T + t) * Cn + c0 + cl] = ob;
+    const float of = bf2f(ob);
+    s1 += of;
+    s2 += of * of;
+  }
+  red[0][tg][cl] = s1;
+  red[1][tg][cl] = s2;
+  __syncthreads();
+  if (stats && tg == 0) {
+    const float a = red[0][0][cl] + red[0][1][cl] + red[0][2][cl] + red[0][3][cl];
+    const float q = red[1][0][cl] + red[1][1][cl] + red[1][2][cl] + red[1][3][cl];
+    atomicAdd(&stats[c0 + cl], (double)a);
+    atomicAdd(&stats[Cn + c0 + cl], (double)q);
+  }
+}
+
+// backward of GLU + depthwise conv:
+//   dglu[t,c] = sum_k w[c,k] * dy[t - k + half, c]
+//   dw[c,k]  += sum_t dy[t,c] * glu[t + k - half, c]
+//   dg[:, :C] = dglu * sigmoid(gate) ; dg[:, C:] = dglu * a * sigmoid(gate) * (1 - sigmoid(gate))
+__global__ void __launch_bounds__(256)
+glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, const bf16* __restrict__ w, int B,
+                      int T, int Cn, int ksz, bf16* __restrict__ dg, float* __restrict__ dw) {
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  typedef float TileT[kDwC + 1];
+  typedef float WT[kDwMaxK + 1];
+  TileT* dyt = reinterpret_cast<TileT*>(dw_smem);                       // dy at t0-half .. t0+63+half
+  TileT* glt = dyt + (kDwT + kDwMaxK - 1);                              // glu at the same times
+  WT* wsm = reinterpret_cast<WT*>(glt + (kDwT + kDwMaxK - 1));          // [kDwC][kDwMaxK+1]
+  typedef float RedT[kDwC][kDwMaxK + 1];
+  RedT* dwred = reinterpret_cast<RedT*>(wsm + kDwC);                    // [4][kDwC][kDwMaxK+1]
+  const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
+  const int half = ksz >> 1;
+  const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i / ksz][i % ksz] = bf2f(w[(long)(c0 + i / ksz) * ksz + i % ksz]);
+  for (int r = tg; r < kDwT + ksz - 1; r += 4) {
+    const int t = t0 + r - half;
+    float dv = 0.f, gl = 0.f;
+    if (t >= 0 && t < T) {
+      dv = bf2f(dy[((long)b * T + t) * Cn + c0 + cl]);
+      const bf16* row = g + ((long)b * T + t) * 2 * Cn;
+      gl = bf2f(f2bf(bf2f(row[c0 + cl]) * sigmoidf_(bf2f(row[Cn + c0 + cl]))));
+    }
+    dyt[r][cl] = dv;
+    glt[r][cl] = gl;
+  }
+  __syncthreads();
+  // input gradient
+  for (int tt = tg; tt < kDwT; tt += 4) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    float acc = 0.f;
+    for (int k = 0; k < ksz; ++k) acc = fmaf(dyt[tt + 2 * half - k][cl], wsm[cl][k], acc);  // dy[t - k + half]
+    const bf16* row = g + ((long)b * T + t) * 2 * Cn;
+    const float a = bf2f(row[c0 + cl]);
+    const float sg = sigmoidf_(bf2f(row[Cn + c0 + cl]));
+    bf16* orow = dg + ((long)b * T + t) * 2 * Cn;
+    orow[c0 + cl] = f2bf(acc * sg);
+    orow[Cn + c0 + cl] = f2bf(acc * a * sg * (1.f - sg));
+  }
+  // weight gradient: this CTA owns dy[t0 .. t0+63]; glu halo is already staged
+  for (int k = 0; k < ksz; ++k) {
+    float acc = 0.f;
+    for (int tt = tg; tt < kDwT; tt += 4) {
+      if (t0 + tt >= T) break;
+      acc = fmaf(dyt[tt + half][cl], glt[tt + k][cl], acc);  // dy[t] * glu[t + k - half]
+    }
+    dwred[tg][cl][k] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) {
+    const int c = i / ksz, k = i % ksz;
+    const float s = dwred[0][c][k] + dwred[1][c][k] + dwred[2][c][k] + dwred[3][c][k];
+    atomicAdd(&dw[(long)(c0 + c) * ksz + k], s);
+  }
+}
+
+// mean/rstd per channel from the double (sum, sumsq) accumulators (training) or the running stats
+// (eval); also the running-stat update  rm = (1-m) rm + m mean ; rv = (1-m) rv + m * unbiased var
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long R, int Cn, float eps, float momentum,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var, int training,
+                                   float* __restrict__ mr) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  if (training) {
+    const double m = stats[c] / (double)R;
+    double var = stats[Cn + c] / (double)R - m * m;
+    if (var < 0) var = 0;
+    mr[c] = (float)m;
+    mr[Cn + c] = rsqrtf((float)var + eps);
+    if (run_mean && run_var) {
+      const double unb = R > 1 ? var * (double)R / (double)(R - 1) : var;
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mr[c] = run_mean[c];
+    mr[Cn + c] = rsqrtf(run_var[c] + eps);
+  }
+}
+
+// z = silu(bn(y))
+__global__ void __launch_bounds__(256)
+bn_silu_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __restrict__ mr,
+                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ z) {
+  const long nvec = R * (Cn >> 3);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (Cn >> 3)) * 8;
+    float v[8], gm[8], bt[8];
+    load8(y + i * 8, v);
+    load8(gamma + c, gm);
+    load8(beta + c, bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bn = bf2f(f2bf((v[j] - mr[c + j]) * mr[Cn + c + j] * gm[j] + bt[j]));  // BN output is bf16
+      v[j] = siluf_(bn);
+    }
+    store8(z + i * 8, v);
+  }
+}
+
+// pass 1 of BN+SiLU backward: s1[c] = sum dbn, s2[c] = sum dbn * xhat   (dbn = dz * silu'(bn))
+__global__ void __launch_bounds__(256)
+bn_silu_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+                          const float* __restrict__ mr, const bf16* __restrict__ gamma,
+                          const bf16* __restrict__ beta, double* __restrict__ sums) {
+  const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  __shared__ float red[2][8][32][8];
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cv * 8 < Cn) {
+    const int c = cv * 8;
+    float gm[8], bt[8];
+    load8(gamma + c, gm);
+    load8(beta + c, bt);
+    for (long r = (long)blockIdx.y * 8 + rl; r < R; r += (long)gridDim.y * 8) {
+      float d[8], v[8];
+      load8(dz + r * Cn + c, d);
+      load8(y + r * Cn + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[j] - mr[c + j]) * mr[Cn + c + j];
+        const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
+        const float dbn = d[j] * silu_gradf_(bn);
+        a1[j] += dbn;
+        a2[j] += dbn * xh;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][rl][threadIdx.x & 31][j] = a1[j];
+    red[1][rl][threadIdx.x & 31][j] = a2[j];
+  }
+  __syncthreads();
+  if (rl == 0 && cv * 8 < Cn) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        s1 += red[0][k][threadIdx.x & 31][j];
+        s2 += red[1][k][threadIdx.x & 31][j];
+      }
+      atomicAdd(&sums[cv * 8 + j], (double)s1);
+      atomicAdd(&sums[Cn + cv * 8 + j], (double)s2);
+    }
+  }
+}
+
+// pass 2: dy = gamma * rstd * (dbn - s1/n - xhat * s2/n)
+__global__ void __launch_bounds__(256)
+bn_silu_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+                         const float* __restrict__ mr, const double* __restrict__ sums,
+                         const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ dy) {
+  const long nvec = R * (Cn >> 3);
+  const float invn = 1.f / (float)R;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (Cn >> 3)) * 8;
+    float d[8], v[8], gm[8], bt[8], o[8];
+    load8(dz + i * 8, d);
+    load8(y + i * 8, v);
+    load8(gamma + c, gm);
+    load8(beta + c, bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rstd = mr[Cn + c + j];
+      const float xh = (v[j] - mr[c + j]) * rstd;
+      const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
+      const float dbn = d[j] * silu_gradf_(bn);
+      const float m1 = (float)sums[c + j] * invn, m2 = (float)sums[Cn + c + j] * invn;
+      o[j] = gm[j] * rstd * (dbn - m1 - xh * m2);
+    }
+    store8(dy + i * 8, o);
+  }
+}
+// dgamma += s2 ; dbeta += s1
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int Cn, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  atomicAdd(&dgamma[c], (float)sums[Cn + c]);
+  atomicAdd(&dbeta[c], (float)sums[c]);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define ESP_ST cudaStream_t st = (cudaStream_t)stream
+
+extern "C" int esp_layer_norm_fwd(const void* x, const void* gamma, const void* beta, float eps, int64_t R, int32_t d,
+                                  void* y, float* mean, float* rstd, const int32_t* lens, int32_t T, float drop_p,
+                                  uint64_t seed, void* stream) {
+  ESP_ST;
+  ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported (need d%%8==0, d<=2048)", d);
+  if (R == 0) return 0;
+#define ESP_LN_FWD(NV)                                                                                              \
+  ln_fwd_kernel<NV><<<grid_for(R, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, eps, R, d, \
+                                                     (bf16*)y, mean, rstd, lens, T, drop_p, esp_dropout_thresh(drop_p), seed)
+  if (d <= 512) ESP_LN_FWD(2);
+  else if (d <= 1024) ESP_LN_FWD(4);
+  else ESP_LN_FWD(8);
+#undef ESP_LN_FWD
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                  const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
+                                  const int32_t* lens, int32_t T, float drop_p, uint64_t seed, void* stream) {
+  ESP_ST;
+  ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported", d);
+  if (R == 0) return 0;
+#define ESP_LN_BWD(NV)                                                                                             \
+  ln_bwd_kernel<NV><<<grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st>>>(                                          \
+      (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
+      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed)
+  if (d <= 512) ESP_LN_BWD(2);
+  else if (d <= 1024) ESP_LN_BWD(4);
+  else ESP_LN_BWD(8);
+#undef ESP_LN_BWD
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream) {
+  ESP_ST;
+  ESP_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum needs N and ld multiples of 8");
+  if (R == 0 || N == 0) return 0;
+  dim3 grid((N / 8 + 31) / 32, (unsigned)((R + 8 * 32 - 1) / (8 * 32) > 2048 ? 2048 : (R + 8 * 32 - 1) / (8 * 32)));
+  if (grid.y < 1) grid.y = 1;
+  colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, R, N, ld, scale, out);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
+                           uint64_t seed, void* y, void* stream) {
+  ESP_ST;
+  ESP_CHECK(N % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dropout needs N/ld multiples of 8");
+  if (R == 0 || N == 0) return 0;
+  dropout_kernel<<<grid_for(R * (N / 8), 256), 256, 0, st>>>((const bf16*)x, R, N, ldx, ldy, scale, drop_p,
+                                                             esp_dropout_thresh(drop_p), seed, (bf16*)y);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_mask_rows(void* x, const int32_t* lens, int32_t B, int32_t T, int32_t N, void* stream) {
+  ESP_ST;
+  ESP_CHECK(N % 8 == 0, "mask_rows needs N %% 8 == 0");
+  if ((long)B * T * N == 0) return 0;
+  mask_rows_kernel<<<grid_for((long)B * T * (N / 8), 256), 256, 0, st>>>((bf16*)x, lens, B, T, N);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_qprep_fwd(const void* q, int64_t ldq, const void* u, const void* v, float scale, int64_t R, int32_t d,
+                             void* qu, void* qv, void* stream) {
+  ESP_ST;
+  ESP_CHECK(d % 8 == 0 && ldq % 8 == 0, "qprep needs d/ld multiples of 8");
+  if (R == 0) return 0;
+  qprep_fwd_kernel<<<grid_for(R * (d / 8), 256), 256, 0, st>>>((const bf16*)q, ldq, (const bf16*)u, (const bf16*)v,
+                                                               scale, R, d, (bf16*)qu, (bf16*)qv);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int64_t R, int32_t d, void* dq, int64_t ld_out,
+                             void* stream) {
+  ESP_ST;
+  ESP_CHECK(d % 8 == 0 && ld_out % 8 == 0, "qprep needs d/ld multiples of 8");
+  if (R == 0) return 0;
+  qprep_bwd_kernel<<<grid_for(R * (d / 8), 256), 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, scale, R, d,
+                                                               (bf16*)dq, ld_out);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
+                                    void* p, void* p_drop, float drop_p, uint64_t seed, void* stream) {
+  ESP_ST;
+  ESP_CHECK(T <= 32 * kSmMax, "attention length %d exceeds the register softmax limit %d", T, 32 * kSmMax);
+  ESP_CHECK(ld >= T && ld <= 32 * kSmMax, "bad score row stride");
+  ESP_CHECK(drop_p <= 0.f || p_drop != nullptr, "dropout requested but p_drop is null");
+  const long rows = (long)H * B * T;
+  if (rows == 0) return 0;
+  attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)scores, H, B, T, ld, lens, (bf16*)p,
+                                                                      drop_p > 0.f ? (bf16*)p_drop : nullptr, drop_p,
+                                                                      esp_dropout_thresh(drop_p), seed);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
+                                    void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, void* stream) {
+  ESP_ST;
+  ESP_CHECK(T <= 32 * kSmMax && ld >= T && ld <= 32 * kSmMax, "bad attention softmax-bwd shape");
+  ESP_CHECK(dbd == nullptr || ldp >= 2 * T - 1, "dBD row stride too small");
+  const long rows = (long)H * B * T;
+  if (rows == 0) return 0;
+  attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, T, ld,
+                                                                      (bf16*)ds, (bf16*)dbd, ldp, drop_p,
+                                                                      esp_dropout_thresh(drop_p), seed);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_glu_dwconv_fwd(const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz, void* y,
+                                  double* stats, void* stream) {
+  ESP_ST;
+  ESP_CHECK(C % kDwC == 0, "depthwise conv channels must be a multiple of %d", kDwC);
+  ESP_CHECK((ksz & 1) && ksz <= kDwMaxK, "depthwise kernel size must be odd and <= %d", kDwMaxK);
+  if ((long)B * T == 0) return 0;
+  dim3 grid((T + kDwT - 1) / kDwT, C / kDwC, B);
+  glu_dwconv_fwd_kernel<<<grid, 256, 0, st>>>((const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)y, stats);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_glu_dwconv_bwd(const void* dy, const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz,
+                                  void* dg, float* dw, void* stream) {
+  ESP_ST;
+  ESP_CHECK(C % kDwC == 0 && (ksz & 1) && ksz <= kDwMaxK, "unsupported depthwise conv shape");
+  if ((long)B * T == 0) return 0;
+  dim3 grid((T + kDwT - 1) / kDwT, C / kDwC, B);
+  constexpr size_t kSmem = sizeof(float) * (2 * (kDwT + kDwMaxK - 1) * (kDwC + 1) + 5 * kDwC * (kDwMaxK + 1));
+  static bool cfg = false;
+  if (!cfg) {
+    ESP_CUDA(cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    cfg = true;
+  }
+  glu_dwconv_bwd_kernel<<<grid, 256, kSmem, st>>>((const bf16*)dy, (const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)dg, dw);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float eps, float momentum, float* run_mean,
+                               float* run_var, int32_t training, float* mr, void* stream) {
+  ESP_ST;
+  ESP_CHECK(mr != nullptr, "bn_finalize: null output");
+  ESP_CHECK(training ? stats != nullptr : (run_mean && run_var), "bn_finalize: missing statistics");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, R, C, eps, momentum, run_mean, run_var, training, mr);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_bn_silu_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
+                               void* z, void* stream) {
+  ESP_ST;
+  ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
+  if (R == 0) return 0;
+  bn_silu_fwd_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)y, R, C, mr, (const bf16*)gamma,
+                                                                 (const bf16*)beta, (bf16*)z);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_bn_silu_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
+                               const void* beta, double* sums, void* dy, float* dgamma, float* dbeta, void* stream) {
+  ESP_ST;
+  ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
+  if (R == 0) return 0;
+  ESP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+  dim3 grid((C / 8 + 31) / 32, (unsigned)((R + 255) / 256 > 1024 ? 1024 : (R + 255) / 256));
+  if (grid.y < 1) grid.y = 1;
+  bn_silu_bwd_reduce_kernel<<<grid, 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, (const bf16*)gamma,
+                                                  (const bf16*)beta, sums);
+  ESP_LAUNCH_CHECK();
+  bn_silu_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, sums,
+                                                                       (const bf16*)gamma, (const bf16*)beta, (bf16*)dy);
+  ESP_LAUNCH_CHECK();
+  int n = 2;
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+    ESP_LAUNCH_CHECK();
+    ++n;
+  }
+  esp_count_launch(n);
+  return 0;
+}

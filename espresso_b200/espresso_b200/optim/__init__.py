@@ -1,0 +1,1 @@
+from .lr_scheduler import NoamLRScheduler, TriStageLRScheduler  # noqa: F401

@@ -1,0 +1,5 @@
+from .speech_transformer_config import SpeechTransformerConfig  # noqa: F401
+from .speech_transformer_encoder_model import (  # noqa: F401
+    SpeechTransformerEncoderForPrediction,
+    SpeechTransformerEncoderModel,
+)

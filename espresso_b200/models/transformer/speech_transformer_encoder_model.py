@@ -1,0 +1,372 @@
+"""`speech_transformer_encoder_model` (CTC / encoder-only Transformer or Conformer), B200-native.
+
+Mirrors the reference's public surface so criterions/decoders written for it keep working:
+  espresso/models/transformer/speech_transformer_encoder_model.py:35-210
+      SpeechTransformerEncoderModel.build_model / forward / get_normalized_probs / output_lengths
+      SpeechTransformerEncoderForPrediction (encoder + fc_out)
+  espresso/models/transformer/speech_transformer_encoder.py:48-409  (SpeechTransformerEncoderBase)
+  espresso/modules/speech_convolutions.py:20-102                      (ConvBNReLU)
+Parameter names (state_dict keys) are identical to the reference's, so checkpoints interchange.
+The modules below are *containers*: they own parameters (re-homed into one flat bf16 buffer by
+`finalize_()`), while the arithmetic runs in `EncoderEngine` over libespresso_b200.so.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops as _ops
+from ...flat import FlatParams
+from ...modules.encoder_engine import EncoderEngine
+from ...registry import register_model
+from .speech_transformer_config import DEFAULT_MAX_SOURCE_POSITIONS, SpeechTransformerConfig, eval_str_nested_list_or_tuple
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers (names == reference)
+# ---------------------------------------------------------------------------------------------------
+def _xavier(t, gain=1.0):
+    nn.init.xavier_uniform_(t, gain=gain)
+    return t
+
+
+class _Affine(nn.Module):  # LayerNorm container
+    def __init__(self, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.bias = nn.Parameter(torch.zeros(d))
+
+
+class _Linear(nn.Module):
+    def __init__(self, i, o, bias=True, xavier=None):
+        super().__init__()
+        lin = nn.Linear(i, o, bias=bias)  # default torch init (fairseq/modules/conformer_layer.py:128-129)
+        if xavier is not None:            # fairseq Linear helper / MHA init (multihead_attention.py:190-212)
+            _xavier(lin.weight, xavier)
+            if bias:
+                nn.init.constant_(lin.bias, 0.0)
+        self.weight = lin.weight
+        if bias:
+            self.bias = lin.bias
+
+
+class _PosEmbStub(nn.Module):
+    """Keeps the reference's `positional_embedding._float_tensor` buffer key."""
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("_float_tensor", torch.zeros(1))
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, d, H):
+        super().__init__()
+        g = 1 / math.sqrt(2)
+        self.pos_bias_u = nn.Parameter(torch.empty(d))
+        self.pos_bias_v = nn.Parameter(torch.empty(d))
+        nn.init.xavier_uniform_(self.pos_bias_u.data.view(H, -1))
+        nn.init.xavier_uniform_(self.pos_bias_v.data.view(H, -1))
+        self.k_proj = _Linear(d, d, xavier=g)
+        self.v_proj = _Linear(d, d, xavier=g)
+        self.q_proj = _Linear(d, d, xavier=g)
+        self.out_proj = _Linear(d, d, xavier=1.0)
+        self.positional_embedding = _PosEmbStub()
+        self.pos_proj = _Linear(d, d, bias=False, xavier=g)
+
+
+class _FFN(nn.Module):
+    def __init__(self, d, ffn):
+        super().__init__()
+        self.layer_norm = _Affine(d)
+        self.w_1 = _Linear(d, ffn)
+        self.w_2 = _Linear(ffn, d)
+
+
+class _BN(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _ConvModule(nn.Module):
+    def __init__(self, d, k):
+        super().__init__()
+        self.layer_norm = _Affine(d)
+        self.pointwise_conv1 = nn.Conv1d(d, 2 * d, 1, bias=False)
+        self.depthwise_conv = nn.Conv1d(d, d, k, padding=(k - 1) // 2, groups=d, bias=False)
+        self.batch_norm = _BN(d)
+        self.pointwise_conv2 = nn.Conv1d(d, d, 1, bias=False)
+
+
+class _ConformerLayer(nn.Module):
+    def __init__(self, d, ffn, H, k):
+        super().__init__()
+        self.ffn1 = _FFN(d, ffn)
+        self.self_attn = _SelfAttn(d, H)
+        self.self_attn_layer_norm = _Affine(d)
+        self.conv_module = _ConvModule(d, k)
+        self.ffn2 = _FFN(d, ffn)
+        self.final_layer_norm = _Affine(d)
+
+
+class _TransformerLayer(nn.Module):
+    def __init__(self, d, ffn, H):
+        super().__init__()
+        self.self_attn = _SelfAttn(d, H)
+        self.self_attn_layer_norm = _Affine(d)
+        self.fc1 = _Linear(d, ffn, xavier=1.0)
+        self.fc2 = _Linear(ffn, d, xavier=1.0)
+        self.final_layer_norm = _Affine(d)
+
+
+class ConvBNReLU(nn.Module):
+    """espresso/modules/speech_convolutions.py:20-102.  (Conv2d 3x3 -> BatchNorm2d -> ReLU) x N, then
+    [B, C, T', F'] -> [B, T', C*F'] with padded frames zeroed.  Round 1: this 3%-of-FLOPs stack still calls
+    cuDNN through torch (see DESIGN.md "not yet native"); everything after it is espresso_b200 kernels."""
+
+    def __init__(self, out_channels, kernel_sizes, strides, in_channels=1):
+        super().__init__()
+        self.out_channels, self.kernel_sizes, self.strides, self.in_channels = out_channels, kernel_sizes, strides, in_channels
+        self.convolutions = nn.ModuleList()
+        self.batchnorms = nn.ModuleList()
+        cin = in_channels
+        for c, k, s in zip(out_channels, kernel_sizes, strides):
+            k = tuple(k) if isinstance(k, (list, tuple)) else (k, k)
+            s = tuple(s) if isinstance(s, (list, tuple)) else (s, s)
+            self.convolutions.append(nn.Conv2d(cin, c, k, stride=s, padding=((k[0] - 1) // 2, (k[1] - 1) // 2)))
+            self.batchnorms.append(nn.BatchNorm2d(c))
+            cin = c
+
+    def output_lengths(self, in_lengths):
+        out = in_lengths
+        for s in self.strides:
+            s0 = s[0] if isinstance(s, (list, tuple)) else s
+            out = torch.div(out + s0 - 1, s0, rounding_mode="floor") if torch.is_tensor(out) else (out + s0 - 1) // s0
+        return out
+
+    def forward(self, src, src_lengths):
+        x = src.view(src.size(0), src.size(1), self.in_channels, src.size(2) // self.in_channels).transpose(1, 2)
+        for conv, bn in zip(self.convolutions, self.batchnorms):
+            x = F.relu(bn(conv(x)))
+        x = x.transpose(1, 2).contiguous()
+        x = x.view(x.size(0), x.size(1), x.size(2) * x.size(3))
+        x_lengths = self.output_lengths(src_lengths)
+        return x, x_lengths
+
+
+class _EncoderFn(torch.autograd.Function):
+    """One autograd node for the whole encoder stack: forward/backward are the hand-written engine passes;
+    parameter gradients go straight into the flat fp32 buffer (nothing is returned for them)."""
+
+    @staticmethod
+    def forward(ctx, xc, anchor, engine, lens, has_pads):
+        ctx.engine = engine
+        return engine.forward(xc, lens, has_pads, save=torch.is_grad_enabled() or True)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dxc = ctx.engine.backward(dout.contiguous())
+        return dxc, None, None, None, None
+
+
+class SpeechTransformerEncoderForPrediction(nn.Module):
+    """Encoder (+ optional fc_out).  forward returns the reference's dict of lists
+    (speech_transformer_encoder.py:399-409) with `encoder_out` = T' x B x V."""
+
+    def __init__(self, cfg: SpeechTransformerConfig, pre_encoder=None, input_size=83, vocab_size=None):
+        super().__init__()
+        self.cfg = cfg
+        e = cfg.encoder
+        if not e.relative_positional_embeddings or e.learned_pos:
+            raise NotImplementedError("B200 encoder: sinusoidal relative positions only (recipes transformer_ctc / "
+                                      "conformer_transducer); learned tables are a next-round item")
+        if not e.normalize_before:
+            raise NotImplementedError("post-LN encoder layers are not on the recipes' path")
+        self.register_buffer("version", torch.Tensor([3]))
+        self.pre_encoder = pre_encoder
+        d = e.embed_dim
+        self.max_source_positions = cfg.max_source_positions
+        self.fc0 = _Linear(input_size, d, xavier=1.0)
+        self.layernorm_embedding = _Affine(d) if cfg.layernorm_embedding else None
+        if e.layer_type == "conformer":
+            self.layers = nn.ModuleList([_ConformerLayer(d, e.ffn_embed_dim, e.attention_heads, e.depthwise_conv_kernel_size)
+                                         for _ in range(e.layers)])
+            self.layer_norm = None
+        elif e.layer_type == "transformer":
+            self.layers = nn.ModuleList([_TransformerLayer(d, e.ffn_embed_dim, e.attention_heads) for _ in range(e.layers)])
+            self.layer_norm = _Affine(d)
+        else:
+            raise NotImplementedError(e.layer_type)
+        self.vocab_size = vocab_size
+        self.fc_out = _Linear(d, vocab_size, xavier=1.0) if vocab_size is not None else None
+        self.num_updates = 0
+        self.flat = None
+        self.engine = None
+        self._anchor = None
+        self.dropout_seed = 1
+
+    # ---- B200 wiring ----------------------------------------------------------------------------
+    def finalize_(self, device):
+        """Cast to bf16 on `device`, re-home all parameters into the flat buffers and build the engine.
+        Call once after construction / load_state_dict (fairseq does the equivalent cast in
+        fairseq/trainer.py:105-107)."""
+        self.to(device)
+        groups = []
+        for i in range(len(self.layers)):
+            groups.append(["layers.%d.self_attn.%s_proj.weight" % (i, c) for c in "qkv"])
+            groups.append(["layers.%d.self_attn.%s_proj.bias" % (i, c) for c in "qkv"])
+        self.flat = FlatParams(self, groups=groups, device=device)
+        for m in self.modules():  # floating buffers of the torch conv front follow the model dtype (model.bfloat16())
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.data = m.running_mean.data.to(torch.bfloat16)
+                m.running_var.data = m.running_var.data.to(torch.bfloat16)
+        e = self.cfg.encoder
+        ecfg = dict(embed_dim=e.embed_dim, ffn_dim=e.ffn_embed_dim, heads=e.attention_heads, layers=e.layers,
+                    layer_type=e.layer_type, dw_kernel=e.depthwise_conv_kernel_size, dropout=self.cfg.dropout,
+                    attention_dropout=self.cfg.attention_dropout, activation_dropout=self.cfg.activation_dropout,
+                    layernorm_embedding=self.cfg.layernorm_embedding, final_layer_norm=self.layer_norm is not None,
+                    vocab=self.vocab_size)
+        self.engine = EncoderEngine(self.flat, "", ecfg)
+        if e.layer_type == "conformer":
+            self.engine.bn_state = {i: (l.conv_module.batch_norm.running_mean, l.conv_module.batch_norm.running_var)
+                                    for i, l in enumerate(self.layers)}
+            for l in self.layers:
+                bn = l.conv_module.batch_norm
+                bn.running_mean.data = bn.running_mean.data.float()
+                bn.running_var.data = bn.running_var.data.float()
+        self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        return self
+
+    def sync_torch_grads_(self):
+        """Fold the gradients of the torch-executed conv front (bf16 .grad) into the flat fp32 buffer."""
+        if self.pre_encoder is None:
+            return
+        for n, p in self.pre_encoder.named_parameters():
+            if p.grad is not None:
+                self.flat.grad("pre_encoder." + n).add_(p.grad.float())
+                p.grad = None
+
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+
+    def output_lengths(self, in_lengths):
+        return in_lengths if self.pre_encoder is None else self.pre_encoder.output_lengths(in_lengths)
+
+    def max_positions(self):
+        return self.max_source_positions
+
+    def forward(self, src_tokens, src_lengths, return_all_hiddens: bool = False, src_lengths_cpu=None):
+        if self.engine is None:
+            raise RuntimeError("call finalize_(device) before running the B200 encoder")
+        x = src_tokens
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)  # fairseq/trainer.py:1279-1297 casts float samples under --bf16
+        if self.pre_encoder is not None:
+            x, out_lens = self.pre_encoder(x, src_lengths)
+        else:
+            out_lens = src_lengths
+        B, T, _ = x.shape
+        lens_cpu = src_lengths_cpu if src_lengths_cpu is not None else src_lengths.cpu()
+        out_lens_cpu = self.output_lengths(lens_cpu)
+        has_pads = bool((out_lens_cpu < T).any())
+        lens_i32 = out_lens.to(torch.int32)
+        eng = self.engine
+        eng.training = self.training
+        eng.seed = self.dropout_seed * 7919 + self.num_updates
+        if self.training:
+            for l in self.layers:
+                if hasattr(l, "conv_module"):
+                    l.conv_module.batch_norm.num_batches_tracked += 1
+        if torch.is_grad_enabled() and self.training:
+            out = _EncoderFn.apply(x.contiguous(), self._anchor, eng, lens_i32, has_pads)
+        else:
+            out = eng.forward(x.contiguous(), lens_i32, has_pads, save=False)
+        V = self.vocab_size
+        pad_mask = torch.arange(T, device=x.device)[None, :] >= out_lens[:, None]
+        enc_out = out[:, :, :V] if V is not None else out
+        return {
+            "encoder_out": [enc_out.transpose(0, 1)],  # T x B x C (a view of the batch-major buffer)
+            "encoder_padding_mask": [pad_mask] if has_pads else [],
+            "encoder_embedding": [],
+            "encoder_states": [],
+            "fc_results": [],
+            "src_tokens": [],
+            "src_lengths": [out_lens],
+            "b200_out": out,  # batch-major [B, T', ld] buffer the B200 criterions consume directly
+        }
+
+
+@register_model("speech_transformer_encoder_model", dataclass=SpeechTransformerConfig)
+class SpeechTransformerEncoderModel(nn.Module):
+    def __init__(self, cfg, encoder):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = encoder
+        self.num_updates = 0
+        self.frontend = None  # optional espresso_b200.data.frontend.OnTheFlyFbank (not a submodule: no parameters)
+
+    @classmethod
+    def build_model(cls, cfg, task):
+        """speech_transformer_encoder_model.py:50-117: needs task.feat_dim, task.feat_in_channels,
+        task.target_dictionary."""
+        if cfg.max_source_positions is None:
+            cfg.max_source_positions = DEFAULT_MAX_SOURCE_POSITIONS
+        e = cfg.encoder
+        out_channels = eval_str_nested_list_or_tuple(e.conv_channels)
+        kernel_sizes = eval_str_nested_list_or_tuple(e.conv_kernel_sizes)
+        strides = eval_str_nested_list_or_tuple(e.conv_strides)
+        assert task.feat_dim % task.feat_in_channels == 0
+        conv_layers = ConvBNReLU(out_channels, kernel_sizes, strides, in_channels=task.feat_in_channels) \
+            if out_channels is not None else None
+        size = task.feat_dim // task.feat_in_channels
+        if conv_layers is not None:
+            for s in strides:
+                s1 = (s[1] if len(s) > 1 else s[0]) if isinstance(s, (list, tuple)) else s
+                size = (size + s1 - 1) // s1
+            size *= out_channels[-1]
+        else:
+            size = task.feat_dim
+        vocab = len(task.target_dictionary) if task.target_dictionary is not None else None
+        encoder = SpeechTransformerEncoderForPrediction(cfg, pre_encoder=conv_layers, input_size=size, vocab_size=vocab)
+        return cls(cfg, encoder)
+
+    def finalize_(self, device):
+        self.encoder.finalize_(device)
+        return self
+
+    @property
+    def flat(self):
+        return self.encoder.flat
+
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+        self.encoder.set_num_updates(num_updates)
+
+    def output_lengths(self, in_lengths):
+        return self.encoder.output_lengths(in_lengths)
+
+    def max_positions(self):
+        return self.encoder.max_positions()
+
+    def forward(self, src_tokens, src_lengths, freq_masks=None, time_masks=None, src_lengths_cpu=None, **kwargs):
+        """src_tokens: features [B, T, F] (reference layout) or, with the on-device front end, raw waveforms
+        [B, N] in int16 range with src_lengths = sample counts (+ host-drawn SpecAugment descriptors)."""
+        if src_tokens.dim() == 2:
+            if self.frontend is None:
+                raise RuntimeError("raw waveform input needs model.frontend (espresso_b200.data.frontend.OnTheFlyFbank)")
+            n_cpu = src_lengths_cpu
+            src_tokens, src_lengths = self.frontend(src_tokens, src_lengths, freq_masks if self.training else None,
+                                                    time_masks if self.training else None)
+            if n_cpu is not None:
+                src_lengths_cpu = torch.where(n_cpu >= 400, 1 + (n_cpu - 400) // 160, torch.zeros_like(n_cpu))
+        return self.encoder(src_tokens, src_lengths, src_lengths_cpu=src_lengths_cpu)
+
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        """fp32 (log-)softmax over the vocabulary (speech_transformer_encoder_model.py:141-150).  Used by the
+        validation decoders; the B200 CTC criterion never materialises this tensor."""
+        logits = net_output["encoder_out"][0].float()
+        return F.log_softmax(logits, dim=-1) if log_probs else F.softmax(logits, dim=-1)

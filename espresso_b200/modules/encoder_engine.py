@@ -1,0 +1,362 @@
+"""Forward / backward orchestration of the speech Transformer/Conformer encoder over the sm_100a kernels.
+
+This is the host-side mirror of (paths in the reference tree):
+  espresso/models/transformer/speech_transformer_encoder.py:298-409   (fc0, layernorm_embedding, layer loop)
+  espresso/modules/conformer_with_relative_positional_embedding_encoder_layer.py:81-145   (Conformer block)
+  fairseq/modules/conformer_layer.py:79-101,134-146                     (conv module, feed-forward module)
+  fairseq/modules/multihead_attention.py:639-917                        (relative-position self-attention)
+  fairseq/modules/transformer_layer.py:163-226                          (pre-LN Transformer block)
+  espresso/models/transformer/speech_transformer_encoder_model.py:177-210 (fc_out)
+Activations are batch-major [B*T, d] bf16.  Every arithmetic step is one call into libespresso_b200.so
+(`ops`); this file only sequences them, owns the saved-for-backward tensors and hands the kernels views
+of the flat parameter / gradient buffers.  The backward pass is written by hand (no autograd tape): each
+module's backward mirrors its forward line by line and accumulates parameter gradients directly into
+the flat fp32 gradient buffer.
+"""
+import math
+
+import torch
+
+from .. import ops as _ops
+from ..lib import ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_SILU, ACT_SILU_BWD
+
+LN_EPS = 1e-5
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+def sinusoidal_relative_table(T, d, device, dtype=torch.bfloat16):
+    """Rows for relative positions -(T-1)..(T-1), scaled by d^-0.5 (scale_embedding=True), sin | cos halves.
+
+    espresso/modules/sinusoidal_relative_positional_embedding.py:46-71,73-124 and
+    espresso/modules/relative_positional_embedding.py:28-34.  Computed in fp32 then cast to the model
+    dtype exactly like `self.weight.to(self._float_tensor)`."""
+    half = d // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    pos = torch.arange(-(T - 1), T, dtype=torch.float32)[:, None] * freq[None, :]
+    emb = torch.cat([torch.sin(pos), torch.cos(pos)], dim=1)
+    if d % 2 == 1:
+        emb = torch.cat([emb, torch.zeros(emb.shape[0], 1)], dim=1)
+    return (emb * d ** -0.5).to(device=device, dtype=dtype).contiguous()
+
+
+class EncoderEngine:
+    def __init__(self, flat, prefix, cfg):
+        """cfg keys: embed_dim, ffn_dim, heads, layers, layer_type ('conformer'|'transformer'), dw_kernel,
+        dropout, attention_dropout, activation_dropout, layernorm_embedding, final_layer_norm, vocab (or None),
+        learned_rel_pos (False only for now)."""
+        self.flat = flat
+        self.pre = prefix
+        self.cfg = dict(cfg)
+        self.d = cfg["embed_dim"]
+        self.H = cfg["heads"]
+        self.hd = self.d // self.H
+        self.scaling = self.hd ** -0.5
+        self._pe = {}
+        self.bn_state = None  # {layer: (running_mean fp32, running_var fp32)} provided by the module
+        self.training = True
+        self.seed = 0
+
+    # ------------------------------------------------------------------------------------------
+    def P(self, name):
+        return self.flat.param(self.pre + name)
+
+    def G(self, name):
+        return self.flat.grad(self.pre + name)
+
+    def _qkv(self, lp):
+        names = [self.pre + lp + "self_attn.%s_proj.weight" % c for c in "qkv"]
+        bn = [self.pre + lp + "self_attn.%s_proj.bias" % c for c in "qkv"]
+        d = self.d
+        return (self.flat.span(self.flat.p16, names, (3 * d, d)), self.flat.span(self.flat.p16, bn, (3 * d,)),
+                self.flat.span(self.flat.g32, names, (3 * d, d)), self.flat.span(self.flat.g32, bn, (3 * d,)))
+
+    def pe(self, T, device):
+        key = (T, str(device))
+        if key not in self._pe:
+            self._pe[key] = sinusoidal_relative_table(T, self.d, device)
+        return self._pe[key]
+
+    def _drop(self, kind):
+        if not self.training:
+            return 0.0
+        return float(self.cfg.get(kind, 0.0))
+
+    def _seed(self, layer, op):
+        return (self.seed * 1000003 + layer * 64 + op) & 0x7FFFFFFFFFFFFFFF
+
+    # ---- GEMM helpers ---------------------------------------------------------------------------
+    @staticmethod
+    def _dgrad(dy, W, **kw):
+        """dx[M,K] = dy[M,N] @ W[N,K]"""
+        M, N = dy.shape
+        K = W.shape[1]
+        out = torch.empty(M, K, device=dy.device, dtype=torch.bfloat16)
+        return _ops.gemm(dy, W, out, M, K, N, dy.stride(0), W.stride(0), K, b_kmajor=False, **kw)
+
+    @staticmethod
+    def _wgrad(dy, x, gW):
+        """gW[N,K] += dy[M,N]^T @ x[M,K]   (fp32 accumulate into the flat gradient buffer)"""
+        M, N = dy.shape
+        K = x.shape[1]
+        gW2 = gW.view(N, K)
+        _ops.gemm(dy, x, gW2, N, K, M, dy.stride(0), x.stride(0), K, a_kmajor=False, b_kmajor=False, R=gW2, ldr=K, beta=1.0)
+
+    # ---- feed-forward module ----------------------------------------------------------------------
+    def ffn_fwd(self, x, lp, names, act, alpha, li, opbase):
+        ln_n, w1_n, w2_n = names
+        ln, mean, rstd = _ops.layer_norm_fwd(x, self.P(lp + ln_n + ".weight"), self.P(lp + ln_n + ".bias"), LN_EPS)
+        W1, W2 = self.P(lp + w1_n + ".weight"), self.P(lp + w2_n + ".weight")
+        R = x.shape[0]
+        U = torch.empty(R, W1.shape[0], device=x.device, dtype=torch.bfloat16)
+        Hh = _ops.linear(ln, W1, self.P(lp + w1_n + ".bias"), act=act, C2=U, drop_p=self._drop("activation_dropout"),
+                         drop_mode=1, seed=self._seed(li, opbase))
+        y = _ops.linear(Hh, W2, self.P(lp + w2_n + ".bias"), drop_p=self._drop("dropout"), drop_mode=1,
+                        seed=self._seed(li, opbase + 1), alpha=alpha, R=x, ldr=x.stride(0), beta=1.0)
+        return y, (x, mean, rstd, ln, U, Hh)
+
+    def ffn_bwd(self, dy, saved, lp, names, act_bwd, alpha, li, opbase):
+        ln_n, w1_n, w2_n = names
+        x, mean, rstd, ln, U, Hh = saved
+        W1, W2 = self.P(lp + w1_n + ".weight"), self.P(lp + w2_n + ".weight")
+        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha)
+        self._wgrad(dZ, Hh, self.G(lp + w2_n + ".weight"))
+        _ops.colsum(dZ, self.G(lp + w2_n + ".bias"))
+        dU = self._dgrad(dZ, W2, act=act_bwd, aux=U, ld_aux=U.stride(0), drop_p=self._drop("activation_dropout"),
+                         drop_mode=2, seed=self._seed(li, opbase))
+        self._wgrad(dU, ln, self.G(lp + w1_n + ".weight"))
+        _ops.colsum(dU, self.G(lp + w1_n + ".bias"))
+        dln = self._dgrad(dU, W1)
+        return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + ln_n + ".weight"), self.G(lp + ln_n + ".weight"),
+                                   self.G(lp + ln_n + ".bias"), dres=dy)
+
+    # ---- relative-position multi-head self-attention ---------------------------------------------
+    def mha_fwd(self, x, lp, B, T, lens, li):
+        d, H, hd = self.d, self.H, self.hd
+        R = B * T
+        ln, mean, rstd = _ops.layer_norm_fwd(x, self.P(lp + "self_attn_layer_norm.weight"),
+                                             self.P(lp + "self_attn_layer_norm.bias"), LN_EPS)
+        Wqkv, bqkv, _, _ = self._qkv(lp)
+        qkv = _ops.linear(ln, Wqkv, bqkv)
+        q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        qu, qv = _ops.qprep_fwd(q, self.P(lp + "self_attn.pos_bias_u"), self.P(lp + "self_attn.pos_bias_v"), self.scaling)
+        pe = self.pe(T, x.device)
+        Pp = _ops.linear(pe, self.P(lp + "self_attn.pos_proj.weight"))  # [2T-1, d], batch independent
+        ldt, ldp = _r8(T), _r8(2 * T - 1)
+        BD = torch.empty(H, B, T, ldp, device=x.device, dtype=torch.bfloat16)
+        _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, d, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, 0),
+                  sC=(B * T * ldp, T * ldp))
+        S = torch.empty(H, B, T, ldt, device=x.device, dtype=torch.bfloat16)
+        _ops.gemm(qu, k, S, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
+                  sC=(B * T * ldt, T * ldt), R=BD, ldr=ldp, sR=(B * T * ldp, T * ldp), skew_r=T)
+        Pr, Pd = _ops.attn_softmax_fwd(S, T, lens, self._drop("attention_dropout"), self._seed(li, 10))
+        ctx = torch.empty(R, d, device=x.device, dtype=torch.bfloat16)
+        _ops.gemm(Pd, v, ctx, T, hd, T, ldt, 3 * d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
+                  sB=(hd, T * 3 * d), sC=(hd, T * d))
+        y = _ops.linear(ctx, self.P(lp + "self_attn.out_proj.weight"), self.P(lp + "self_attn.out_proj.bias"),
+                        drop_p=self._drop("dropout"), drop_mode=1, seed=self._seed(li, 11), R=x, ldr=x.stride(0), beta=1.0)
+        return y, (x, mean, rstd, ln, qkv, qu, qv, Pp, Pr, Pd, ctx)
+
+    def mha_bwd(self, dy, saved, lp, B, T, li):
+        d, H, hd = self.d, self.H, self.hd
+        R = B * T
+        x, mean, rstd, ln, qkv, qu, qv, Pp, Pr, Pd, ctx = saved
+        k, v = qkv[:, d:2 * d], qkv[:, 2 * d:]
+        ldt, ldp = _r8(T), _r8(2 * T - 1)
+        dev = dy.device
+        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
+        self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"))
+        _ops.colsum(dO, self.G(lp + "self_attn.out_proj.bias"))
+        dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
+        dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
+        _ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
+                  sC=(B * T * ldt, T * ldt))
+        dqkv = torch.empty(R, 3 * d, device=dev, dtype=torch.bfloat16)
+        # dV = Pd^T dctx
+        _ops.gemm(Pd, dctx, dqkv[:, 2 * d:], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+                  sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+        dS, dBD = _ops.attn_softmax_bwd(Pr, dPd, T, ldp, self._drop("attention_dropout"), self._seed(li, 10))
+        # dq_u = dS k ; dK = dS^T q_u
+        dqu = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+        _ops.gemm(dS, k, dqu, T, hd, T, ldt, 3 * d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
+                  sB=(hd, T * 3 * d), sC=(hd, T * d))
+        _ops.gemm(dS, qu, dqkv[:, d:2 * d], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+                  sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+        # dq_v = dBD P ; dP = sum_b dBD^T q_v
+        dqv = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+        _ops.gemm(dBD, Pp, dqv, T, hd, 2 * T - 1, ldp, d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldp, T * ldp),
+                  sB=(hd, 0), sC=(hd, T * d))
+        dPp = torch.empty(2 * T - 1, d, device=dev, dtype=torch.bfloat16)
+        _ops.gemm(dBD, qv, dPp, 2 * T - 1, hd, B * T, ldp, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=1,
+                  sA=(B * T * ldp, 0), sB=(hd, 0), sC=(hd, 0))
+        self._wgrad(dPp, self.pe(T, dev), self.G(lp + "self_attn.pos_proj.weight"))
+        _ops.qprep_bwd(dqu, dqv, self.scaling, dqkv[:, :d])
+        _ops.colsum(dqu, self.G(lp + "self_attn.pos_bias_u"), scale=self.scaling)
+        _ops.colsum(dqv, self.G(lp + "self_attn.pos_bias_v"), scale=self.scaling)
+        Wqkv, _, gW, gb = self._qkv(lp)
+        self._wgrad(dqkv, ln, gW)
+        _ops.colsum(dqkv, gb)
+        dln = self._dgrad(dqkv, Wqkv)
+        return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + "self_attn_layer_norm.weight"),
+                                   self.G(lp + "self_attn_layer_norm.weight"), self.G(lp + "self_attn_layer_norm.bias"),
+                                   dres=dy)
+
+    # ---- convolution module -----------------------------------------------------------------------
+    def conv_fwd(self, x, lp, B, T, li):
+        d = self.d
+        cp = lp + "conv_module."
+        ln, mean, rstd = _ops.layer_norm_fwd(x, self.P(cp + "layer_norm.weight"), self.P(cp + "layer_norm.bias"), LN_EPS)
+        W1 = self.P(cp + "pointwise_conv1.weight").view(2 * d, d)
+        Gg = _ops.linear(ln, W1)
+        Wd = self.P(cp + "depthwise_conv.weight")
+        ksz = Wd.shape[-1]
+        Y, stats = _ops.glu_dwconv_fwd(Gg.view(B, T, 2 * d), Wd.view(d, ksz))
+        rm, rv = self.bn_state[li]
+        mr = _ops.bn_finalize(stats, B * T, d, BN_EPS, BN_MOMENTUM, rm, rv, self.training)
+        Z = _ops.bn_silu_fwd(Y, mr, self.P(cp + "batch_norm.weight"), self.P(cp + "batch_norm.bias"))
+        y = _ops.linear(Z.view(B * T, d), self.P(cp + "pointwise_conv2.weight").view(d, d), None,
+                        drop_p=self._drop("dropout"), drop_mode=1, seed=self._seed(li, 20), R=x, ldr=x.stride(0), beta=1.0)
+        return y, (x, mean, rstd, ln, Gg, Y, mr, Z)
+
+    def conv_bwd(self, dy, saved, lp, B, T, li):
+        d = self.d
+        cp = lp + "conv_module."
+        x, mean, rstd, ln, Gg, Y, mr, Z = saved
+        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 20))
+        W2 = self.P(cp + "pointwise_conv2.weight").view(d, d)
+        self._wgrad(dO, Z.view(B * T, d), self.G(cp + "pointwise_conv2.weight"))
+        dZ = self._dgrad(dO, W2)
+        dY = _ops.bn_silu_bwd(dZ.view(B, T, d), Y, mr, self.P(cp + "batch_norm.weight"), self.P(cp + "batch_norm.bias"),
+                              self.G(cp + "batch_norm.weight"), self.G(cp + "batch_norm.bias"))
+        Wd = self.P(cp + "depthwise_conv.weight")
+        ksz = Wd.shape[-1]
+        dG = _ops.glu_dwconv_bwd(dY, Gg.view(B, T, 2 * d), Wd.view(d, ksz), self.G(cp + "depthwise_conv.weight").view(d, ksz))
+        dG2 = dG.view(B * T, 2 * d)
+        self._wgrad(dG2, ln, self.G(cp + "pointwise_conv1.weight"))
+        dln = self._dgrad(dG2, self.P(cp + "pointwise_conv1.weight").view(2 * d, d))
+        return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(cp + "layer_norm.weight"), self.G(cp + "layer_norm.weight"),
+                                   self.G(cp + "layer_norm.bias"), dres=dy)
+
+    # ---- layers -----------------------------------------------------------------------------------
+    _CONF_FFN1 = ("ffn1.layer_norm", "ffn1.w_1", "ffn1.w_2")
+    _CONF_FFN2 = ("ffn2.layer_norm", "ffn2.w_1", "ffn2.w_2")
+    _TR_FFN = ("final_layer_norm", "fc1", "fc2")
+
+    def layer_fwd(self, x, li, B, T, lens):
+        lp = "layers.%d." % li
+        st = {}
+        if self.cfg["layer_type"] == "conformer":
+            x, st["ffn1"] = self.ffn_fwd(x, lp, self._CONF_FFN1, ACT_SILU, 0.5, li, 0)
+            x, st["mha"] = self.mha_fwd(x, lp, B, T, lens, li)
+            x, st["conv"] = self.conv_fwd(x, lp, B, T, li)
+            x, st["ffn2"] = self.ffn_fwd(x, lp, self._CONF_FFN2, ACT_SILU, 0.5, li, 2)
+            y, mean, rstd = _ops.layer_norm_fwd(x, self.P(lp + "final_layer_norm.weight"), self.P(lp + "final_layer_norm.bias"), LN_EPS)
+            st["final"] = (x, mean, rstd)
+            return y, st
+        # pre-LN Transformer block (normalize_before=True; fairseq/modules/transformer_layer.py:163-226)
+        x, st["mha"] = self.mha_fwd(x, lp, B, T, lens, li)
+        x, st["ffn"] = self.ffn_fwd(x, lp, self._TR_FFN, ACT_RELU, 1.0, li, 0)
+        return x, st
+
+    def layer_bwd(self, dy, st, li, B, T):
+        lp = "layers.%d." % li
+        if self.cfg["layer_type"] == "conformer":
+            x, mean, rstd = st["final"]
+            dx = _ops.layer_norm_bwd(dy, x, mean, rstd, self.P(lp + "final_layer_norm.weight"),
+                                     self.G(lp + "final_layer_norm.weight"), self.G(lp + "final_layer_norm.bias"))
+            dx = self.ffn_bwd(dx, st["ffn2"], lp, self._CONF_FFN2, ACT_SILU_BWD, 0.5, li, 2)
+            dx = self.conv_bwd(dx, st["conv"], lp, B, T, li)
+            dx = self.mha_bwd(dx, st["mha"], lp, B, T, li)
+            return self.ffn_bwd(dx, st["ffn1"], lp, self._CONF_FFN1, ACT_SILU_BWD, 0.5, li, 0)
+        dx = self.ffn_bwd(dy, st["ffn"], lp, self._TR_FFN, ACT_RELU_BWD, 1.0, li, 0)
+        return self.mha_bwd(dx, st["mha"], lp, B, T, li)
+
+    # ---- whole encoder ----------------------------------------------------------------------------
+    def forward(self, xc, lens, has_pads, save=True):
+        """xc [B, T, F] bf16 (output of the conv front), lens int32 [B] (device).  Returns logits [B, T, ldV]
+        (or encoder states [B, T, d] when there is no output layer) and keeps what backward needs."""
+        B, T, Fin = xc.shape
+        R = B * T
+        cfg = self.cfg
+        lens_k = lens if has_pads else None
+        pdrop = self._drop("dropout")
+        xin = xc.reshape(R, Fin)
+        if pdrop > 0:
+            xin = _ops.dropout(xin, pdrop, self._seed(999, 0))
+        e = _ops.linear(xin, self.P("fc0.weight"), self.P("fc0.bias"))
+        if cfg.get("layernorm_embedding", False):
+            x, mean0, rstd0 = _ops.layer_norm_fwd(e, self.P("layernorm_embedding.weight"), self.P("layernorm_embedding.bias"),
+                                                  LN_EPS, lens=lens_k, T=T, drop_p=pdrop, seed=self._seed(999, 1))
+        else:
+            x = _ops.dropout(e, pdrop, self._seed(999, 1)) if pdrop > 0 else e.clone()
+            if lens_k is not None:
+                _ops.mask_rows_(x.view(B, T, -1), lens_k)
+            mean0 = rstd0 = None
+        states = []
+        for li in range(cfg["layers"]):
+            x, st = self.layer_fwd(x, li, B, T, lens_k)
+            states.append(st)
+        fin = None
+        if cfg.get("final_layer_norm", False):
+            xf = x
+            x, mf, rf = _ops.layer_norm_fwd(xf, self.P("layer_norm.weight"), self.P("layer_norm.bias"), LN_EPS)
+            fin = (xf, mf, rf)
+        out = x.view(B, T, self.d)
+        V = cfg.get("vocab")
+        if V:
+            ldV = _r8(V)
+            logits = torch.zeros(R, ldV, device=x.device, dtype=torch.bfloat16) if ldV != V else \
+                torch.empty(R, ldV, device=x.device, dtype=torch.bfloat16)
+            _ops.gemm(x, self.P("fc_out.weight"), logits, R, V, self.d, x.stride(0), self.d, ldV, bias=self.P("fc_out.bias"))
+            out = logits.view(B, T, ldV)
+        if save:
+            self.saved = dict(B=B, T=T, xin=xin, e=e, mean0=mean0, rstd0=rstd0, lens=lens_k, states=states, fin=fin,
+                              xL=x, Fin=Fin)
+        return out
+
+    def backward(self, dout):
+        """dout: gradient of the forward output ([B, T, ldV] logits or [B, T, d]).  Returns d(xc) [B, T, F]."""
+        s = self.saved
+        B, T = s["B"], s["T"]
+        R = B * T
+        cfg = self.cfg
+        V = cfg.get("vocab")
+        if V:
+            ldV = _r8(V)
+            dlog = dout.reshape(R, ldV)
+            dl = dlog[:, :V] if ldV != V else dlog
+            self._wgrad(dl, s["xL"], self.G("fc_out.weight"))
+            tmp = torch.zeros(ldV, device=dlog.device, dtype=torch.float32)
+            _ops.colsum(dlog, tmp)
+            self.G("fc_out.bias").add_(tmp[:V])
+            dx = self._dgrad(dl, self.P("fc_out.weight"))
+        else:
+            dx = dout.reshape(R, self.d).contiguous()
+        if s["fin"] is not None:
+            xf, mf, rf = s["fin"]
+            dx = _ops.layer_norm_bwd(dx, xf, mf, rf, self.P("layer_norm.weight"), self.G("layer_norm.weight"),
+                                     self.G("layer_norm.bias"))
+        for li in reversed(range(cfg["layers"])):
+            dx = self.layer_bwd(dx, s["states"][li], li, B, T)
+        pdrop = self._drop("dropout")
+        if cfg.get("layernorm_embedding", False):
+            de = _ops.layer_norm_bwd(dx, s["e"], s["mean0"], s["rstd0"], self.P("layernorm_embedding.weight"),
+                                     self.G("layernorm_embedding.weight"), self.G("layernorm_embedding.bias"),
+                                     lens=s["lens"], T=T, drop_p=pdrop, seed=self._seed(999, 1))
+        else:
+            de = dx
+            if s["lens"] is not None:
+                de = _ops.mask_rows_(de.clone().view(B, T, -1), s["lens"]).view(R, -1)
+            if pdrop > 0:
+                de = _ops.dropout(de, pdrop, self._seed(999, 1))
+        self._wgrad(de, s["xin"], self.G("fc0.weight"))
+        _ops.colsum(de, self.G("fc0.bias"))
+        dxin = self._dgrad(de, self.P("fc0.weight"))
+        if pdrop > 0:
+            dxin = _ops.dropout(dxin, pdrop, self._seed(999, 0))
+        self.saved = None
+        return dxin.view(B, T, s["Fin"])

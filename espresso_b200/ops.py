@@ -131,3 +131,201 @@ def ctc_loss(logits, V, in_lens, targets, tgt_lens, blank, zero_infinity=True, g
                               _ptr(targets.contiguous()), u_max, _ptr(tgt_lens), blank, int(zero_infinity),
                               float(grad_scale), _ptr(loss), _ptr(grad), _ptr(ws), _stream()))
     return loss, grad
+
+
+# ----------------------------------------------------------------------------------------------
+# HBM-bound block kernels.  Conventions: activations bf16, row-major [rows, channels]; "acc" outputs are
+# fp32 tensors that the kernel ACCUMULATES into (they are views of the flat gradient buffer).
+# ----------------------------------------------------------------------------------------------
+def _bf(*ts):
+    for t in ts:
+        assert t is None or t.dtype == torch.bfloat16
+
+
+def layer_norm_fwd(x, gamma, beta, eps=1e-5, lens=None, T=0, drop_p=0.0, seed=0):
+    """x [R, d] contiguous.  Returns (y, mean[R], rstd[R]).  lens/T: zero rows t >= lens[b] (rows are [B,T])."""
+    _need_cuda(x, gamma, beta, lens)
+    _bf(x, gamma, beta)
+    assert x.is_contiguous()
+    R, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(R, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(R, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().esp_layer_norm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), eps, R, d, _ptr(y), _ptr(mean), _ptr(rstd),
+                                              _ptr(lens), T, drop_p, seed, _stream()))
+    return y, mean, rstd
+
+
+def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0):
+    _need_cuda(dy, x, gamma, dres)
+    _bf(dy, x, gamma, dres)
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    assert dgamma_acc.dtype == torch.float32 and dbeta_acc.dtype == torch.float32
+    R, d = x.shape
+    dx = torch.empty_like(x)
+    _lib.check(_lib.load().esp_layer_norm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), R, d,
+                                              _ptr(dx), _ptr(dgamma_acc), _ptr(dbeta_acc), _ptr(lens), T, drop_p, seed,
+                                              _stream()))
+    return dx
+
+
+def colsum(x, out_acc, scale=1.0):
+    """out_acc[n] += scale * sum_r x[r, n]; x may be a column-slice view (row stride = x.stride(0))."""
+    _need_cuda(x, out_acc)
+    _bf(x)
+    assert out_acc.dtype == torch.float32 and x.stride(1) == 1
+    R, N = x.shape
+    _lib.check(_lib.load().esp_colsum(_ptr(x), R, N, x.stride(0), scale, _ptr(out_acc), _stream()))
+
+
+def dropout(x, p, seed, scale=1.0, out=None):
+    """y = dropout_p(x) * scale with the GEMM-epilogue RNG (index r*N+n)."""
+    _need_cuda(x)
+    _bf(x)
+    assert x.stride(1) == 1
+    R, N = x.shape
+    if out is None:
+        out = torch.empty(R, N, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_dropout(_ptr(x), R, N, x.stride(0), out.stride(0), scale, p, seed, _ptr(out), _stream()))
+    return out
+
+
+def mask_rows_(x, lens):
+    """In place: zero x[b, t >= lens[b], :] for x [B, T, N]."""
+    _need_cuda(x, lens)
+    _bf(x)
+    assert x.is_contiguous()
+    B, T, N = x.shape
+    _lib.check(_lib.load().esp_mask_rows(_ptr(x), _ptr(lens), B, T, N, _stream()))
+    return x
+
+
+def qprep_fwd(q, u, v, scale):
+    """q [R, d] view (row stride q.stride(0)); returns (q_u, q_v) = ((q+u)*s, (q+v)*s), contiguous."""
+    _need_cuda(q, u, v)
+    _bf(q, u, v)
+    R, d = q.shape
+    qu = torch.empty(R, d, device=q.device, dtype=torch.bfloat16)
+    qv = torch.empty(R, d, device=q.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_qprep_fwd(_ptr(q), q.stride(0), _ptr(u), _ptr(v), scale, R, d, _ptr(qu), _ptr(qv), _stream()))
+    return qu, qv
+
+
+def qprep_bwd(dqu, dqv, scale, dq_out):
+    """dq_out[R, d] view (row stride) = scale * (dqu + dqv)."""
+    _need_cuda(dqu, dqv, dq_out)
+    _bf(dqu, dqv, dq_out)
+    R, d = dqu.shape
+    _lib.check(_lib.load().esp_qprep_bwd(_ptr(dqu), _ptr(dqv), scale, R, d, _ptr(dq_out), dq_out.stride(0), _stream()))
+
+
+def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
+    """scores [H, B, T, ld] bf16 -> (p, p_drop) same shape; p_drop is p when drop_p == 0."""
+    _need_cuda(scores, lens)
+    _bf(scores)
+    H, B, T_, ld = scores.shape
+    assert T_ == T and scores.is_contiguous()
+    p = torch.empty_like(scores)
+    pd = torch.empty_like(scores) if drop_p > 0 else None
+    _lib.check(_lib.load().esp_attn_softmax_fwd(_ptr(scores), H, B, T, ld, _ptr(lens), _ptr(p), _ptr(pd), drop_p, seed, _stream()))
+    return p, (pd if pd is not None else p)
+
+
+def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
+    """Returns (dS [H,B,T,ld], dBD [H,B,T,ldp] in skewed relative-position layout or None)."""
+    _need_cuda(p, dp_drop)
+    _bf(p, dp_drop)
+    H, B, T_, ld = p.shape
+    ds = torch.empty_like(p)
+    dbd = torch.empty(H, B, T, ldp, device=p.device, dtype=torch.bfloat16) if want_dbd else None
+    _lib.check(_lib.load().esp_attn_softmax_bwd(_ptr(p), _ptr(dp_drop), H, B, T, ld, _ptr(ds), _ptr(dbd), ldp, drop_p, seed, _stream()))
+    return ds, dbd
+
+
+def glu_dwconv_fwd(g, w):
+    """g [B, T, 2C], w [C, k] -> (y [B, T, C], stats double [2, C] = per-channel sum / sum of squares of y)."""
+    _need_cuda(g, w)
+    _bf(g, w)
+    assert g.is_contiguous() and w.is_contiguous()
+    B, T, C2 = g.shape
+    Cn, k = w.shape
+    assert C2 == 2 * Cn
+    y = torch.empty(B, T, Cn, device=g.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2, Cn, device=g.device, dtype=torch.float64)
+    _lib.check(_lib.load().esp_glu_dwconv_fwd(_ptr(g), _ptr(w), B, T, Cn, k, _ptr(y), _ptr(stats), _stream()))
+    return y, stats
+
+
+def glu_dwconv_bwd(dy, g, w, dw_acc):
+    """Returns dg [B, T, 2C]; accumulates dw into dw_acc fp32 [C, k]."""
+    _need_cuda(dy, g, w, dw_acc)
+    _bf(dy, g, w)
+    assert dy.is_contiguous() and g.is_contiguous() and dw_acc.dtype == torch.float32
+    B, T, C2 = g.shape
+    Cn, k = w.shape
+    dg = torch.empty_like(g)
+    _lib.check(_lib.load().esp_glu_dwconv_bwd(_ptr(dy), _ptr(g), _ptr(w), B, T, Cn, k, _ptr(dg), _ptr(dw_acc), _stream()))
+    return dg
+
+
+def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
+    """-> mr fp32 [2, C] (mean, rstd); in training also updates the fp32 running stats in place."""
+    _need_cuda(stats, run_mean, run_var)
+    dev = stats.device if stats is not None else run_mean.device
+    mr = torch.empty(2, C_, device=dev, dtype=torch.float32)
+    _lib.check(_lib.load().esp_bn_finalize(_ptr(stats), R, C_, eps, momentum, _ptr(run_mean), _ptr(run_var), int(training),
+                                           _ptr(mr), _stream()))
+    return mr
+
+
+def bn_silu_fwd(y, mr, gamma, beta):
+    _need_cuda(y, mr, gamma, beta)
+    _bf(y, gamma, beta)
+    assert y.is_contiguous()
+    Cn = y.shape[-1]
+    z = torch.empty_like(y)
+    _lib.check(_lib.load().esp_bn_silu_fwd(_ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(z), _stream()))
+    return z
+
+
+def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+    _need_cuda(dz, y, mr, gamma, beta)
+    _bf(dz, y, gamma, beta)
+    assert dz.is_contiguous() and y.is_contiguous()
+    Cn = y.shape[-1]
+    sums = torch.empty(2, Cn, device=y.device, dtype=torch.float64)
+    dy = torch.empty_like(y)
+    _lib.check(_lib.load().esp_bn_silu_bwd(_ptr(dz), _ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
+                                           _ptr(dy), _ptr(dgamma_acc), _ptr(dbeta_acc), _stream()))
+    return dy
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizer
+# ----------------------------------------------------------------------------------------------
+def sumsq(g, out):
+    _need_cuda(g, out)
+    assert g.dtype == torch.float32 and out.dtype == torch.float32
+    _lib.check(_lib.load().esp_sumsq_f32(_ptr(g), g.numel(), _ptr(out), _stream()))
+    return out
+
+
+def adam_step(p32, m, v, g, p16, lr, beta1, beta2, eps, weight_decay, step, sumsq_t, denom_dev=None, denom_const=1.0,
+              clip_norm=0.0, gnorm_out=None):
+    _need_cuda(p32, m, v, g, p16, sumsq_t, denom_dev, gnorm_out)
+    assert p32.dtype == m.dtype == v.dtype == g.dtype == torch.float32 and p16.dtype == torch.bfloat16
+    n = p32.numel()
+    assert m.numel() == n and v.numel() == n and p16.numel() == n and g.numel() >= n
+    _lib.check(_lib.load().esp_adam_step(_ptr(p32), _ptr(m), _ptr(v), _ptr(g), _ptr(p16), n, lr, beta1, beta2, eps, weight_decay,
+                                         step, _ptr(sumsq_t), _ptr(denom_dev), denom_const, clip_norm, _ptr(gnorm_out),
+                                         _stream()))
+
+
+def cast_f32_bf16(x, y):
+    _need_cuda(x, y)
+    _lib.check(_lib.load().esp_cast_f32_bf16(_ptr(x), x.numel(), _ptr(y), _stream()))
+
+
+def cast_bf16_f32(x, y):
+    _need_cuda(x, y)
+    _lib.check(_lib.load().esp_cast_bf16_f32(_ptr(x), x.numel(), _ptr(y), _stream()))

@@ -105,6 +105,65 @@ int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride_t, int32_t
                  const int32_t* tgt_lens, int32_t blank, int32_t zero_infinity, float grad_scale,
                  float* loss, void* grad, void* workspace, void* stream);
 
+/* ---- HBM-bound block kernels (bf16 activations [rows, channels], fp32 statistics) ----------------
+ * LayerNorm forward/backward -- torch.nn.LayerNorm call sites: fairseq/modules/conformer_layer.py:79-81,
+ *   134-136; espresso/modules/conformer_with_relative_positional_embedding_encoder_layer.py:118,143;
+ *   fairseq/modules/transformer_layer.py:163-226; speech_transformer_encoder.py:348-349.
+ * Optional fusions: zero rows t >= lens[b] (speech_transformer_encoder.py:354-357; rows are [B,T]) and a
+ * trailing dropout (:350).  Backward accumulates dgamma/dbeta (fp32, +=) and adds an optional residual
+ * gradient `dres` into dx. */
+int esp_layer_norm_fwd(const void* x, const void* gamma, const void* beta, float eps, int64_t R, int32_t d,
+                       void* y, float* mean, float* rstd, const int32_t* lens, int32_t T, float drop_p,
+                       uint64_t seed, void* stream);
+int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                       const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
+                       const int32_t* lens, int32_t T, float drop_p, uint64_t seed, void* stream);
+/* out[n] += scale * sum_r x[r,n]   (bias / pos_bias gradients) */
+int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream);
+/* y = dropout(x) * scale, same counter RNG / indexing (r*N+n) as the GEMM epilogue */
+int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
+                uint64_t seed, void* y, void* stream);
+/* zero rows t >= lens[b] of x [B,T,N] */
+int esp_mask_rows(void* x, const int32_t* lens, int32_t B, int32_t T, int32_t N, void* stream);
+/* q_u = (q+u)*s, q_v = (q+v)*s  (fairseq/modules/multihead_attention.py:679-688) and the backward sum */
+int esp_qprep_fwd(const void* q, int64_t ldq, const void* u, const void* v, float scale, int64_t R, int32_t d,
+                  void* qu, void* qv, void* stream);
+int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int64_t R, int32_t d, void* dq, int64_t ld_out,
+                  void* stream);
+/* attention softmax over keys (scores [H,B,T,ld] bf16): key-padding -> -inf, fp32 softmax, optional dropout
+ * copy (fairseq/modules/multihead_attention.py:841-876); backward also scatters dS into the skewed
+ * relative-position layout dBD[., i, (T-1)-i+j] (inverse of :824-830). */
+int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
+                         void* p, void* p_drop, float drop_p, uint64_t seed, void* stream);
+int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
+                         void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, void* stream);
+/* Conformer convolution module body (fairseq/modules/conformer_layer.py:88-96):
+ *   y = depthwise_conv_k(GLU(g)) with 'same' zero padding over the padded length T, g [B,T,2C], w [C,k];
+ *   stats (double [2,C], +=): per-channel sum and sum of squares of y for BatchNorm1d batch statistics.
+ *   bn_finalize: mean / rstd (float [2,C]) from stats (training; also updates running stats with
+ *   momentum, unbiased variance) or from the running stats (eval).  bn_silu: z = SiLU(BN(y)). */
+int esp_glu_dwconv_fwd(const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz, void* y,
+                       double* stats, void* stream);
+int esp_glu_dwconv_bwd(const void* dy, const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz,
+                       void* dg, float* dw, void* stream);
+int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float eps, float momentum, float* run_mean,
+                    float* run_var, int32_t training, float* mr, void* stream);
+int esp_bn_silu_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
+                    void* z, void* stream);
+int esp_bn_silu_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
+                    const void* beta, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
+
+/* ---- optimizer on flat buffers (fairseq/optim/fp16_optimizer.py:109-168, fairseq/optim/adam.py:150-239,
+ *      fairseq/utils.py:347-397) ---------------------------------------------------------------- */
+int esp_sumsq_f32(const float* g, int64_t n, float* out, void* stream);
+/* g_eff = g / denom * clip_coef, denom read from device memory if denom_dev != NULL (the all-reduced
+ * sample_size in the gradient buffer's tail), else denom_const.  Writes fp32 master + bf16 model params. */
+int esp_adam_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
+                  const float* denom_dev, float denom_const, float clip_norm, float* gnorm_out, void* stream);
+int esp_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream);
+int esp_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,303 @@
+"""Oracle: plain-PyTorch (CPU, fp32 math) statement of every op in espresso_b200/ops.py, same signatures.
+
+TEST INFRASTRUCTURE ONLY.  Two uses:
+  * GPU parity tests compare each CUDA kernel with the function of the same name here;
+  * CPU tests monkeypatch these in for `espresso_b200.ops` to exercise the host-side orchestration
+    (forward/backward wiring of the Conformer block, flat-buffer optimizer, trainer) against autograd of
+    oracle/conformer.py -- no GPU needed.  The product never imports this module.
+Each function names the reference computation it restates (see the kernel headers for file:line).
+Dropout uses the kernels' counter RNG and is only emulated for p == 0.
+"""
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_RELU_BWD, ACT_SILU_BWD = 0, 1, 2, 3, 4
+BF = torch.bfloat16
+
+
+def _silu_grad(u):
+    s = torch.sigmoid(u)
+    return s * (1 + u * (1 - s))
+
+
+def _view(t, nb2, nb1, rows, cols, s2, s1, ld, kmajor):
+    """Logical [nb2, nb1, rows, cols] view of a strided operand (cols is the reduction/N dim)."""
+    stride = (s2, s1, ld, 1) if kmajor else (s2, s1, 1, ld)
+    return t.as_strided((nb2, nb1, rows, cols), stride)
+
+
+def gemm(A, B, C_out, M, N, K, lda, ldb, ldc, *, a_kmajor=True, b_kmajor=True, nb1=1, nb2=1, sA=(0, 0), sB=(0, 0),
+         sC=(0, 0), bias=None, act=ACT_NONE, aux=None, ld_aux=0, sAux=(0, 0), R=None, ldr=0, sR=(0, 0), alpha=1.0,
+         beta=1.0, C2=None, drop_p=0.0, drop_mode=0, seed=0, skew_r=0, tile_n=0):
+    assert drop_p == 0.0, "oracle gemm emulates dropout only for p == 0"
+    a = _view(A, nb2, nb1, M, K, sA[1], sA[0], lda, a_kmajor).float()
+    b = _view(B, nb2, nb1, N, K, sB[1], sB[0], ldb, b_kmajor).float()
+    v = a @ b.transpose(-1, -2)
+    if bias is not None:
+        v = v + bias.float()[:N]
+    if C2 is not None:
+        _view(C2, nb2, nb1, M, N, sC[1], sC[0], ldc, True).copy_(v.to(C2.dtype))
+    if act == ACT_RELU:
+        v = torch.relu(v)
+    elif act == ACT_SILU:
+        v = F.silu(v)
+    elif act in (ACT_RELU_BWD, ACT_SILU_BWD):
+        u = _view(aux, nb2, nb1, M, N, sAux[1], sAux[0], ld_aux, True).float()
+        v = v * ((u > 0).float() if act == ACT_RELU_BWD else _silu_grad(u))
+    v = v * alpha
+    if R is not None:
+        if skew_r:
+            T = skew_r
+            full = _view(R, nb2, nb1, M, 2 * T - 1, sR[1], sR[0], ldr, True).float()
+            i = torch.arange(M)[:, None]
+            j = torch.arange(N)[None, :]
+            idx = ((T - 1) - i + j).expand(nb2, nb1, M, N)
+            v = v + beta * full.gather(-1, idx)
+        else:
+            v = v + beta * _view(R, nb2, nb1, M, N, sR[1], sR[0], ldr, True).float()
+    _view(C_out, nb2, nb1, M, N, sC[1], sC[0], ldc, True).copy_(v.to(C_out.dtype))
+    return C_out
+
+
+def linear(x, W, bias=None, *, act=ACT_NONE, out=None, out_dtype=BF, **kw):
+    M, K = x.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype)
+    return gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), out.stride(0), bias=bias, act=act, **kw)
+
+
+def layer_norm_fwd(x, gamma, beta, eps=1e-5, lens=None, T=0, drop_p=0.0, seed=0):
+    assert drop_p == 0.0
+    xf = x.float()
+    mean = xf.mean(-1)
+    var = ((xf - mean[:, None]) ** 2).mean(-1)
+    rstd = torch.rsqrt(var + eps)
+    y = (xf - mean[:, None]) * rstd[:, None] * gamma.float() + beta.float()
+    if lens is not None:
+        t = torch.arange(x.shape[0]) % T
+        b = torch.arange(x.shape[0]) // T
+        y = y * (t < lens[b]).float()[:, None]
+    return y.to(BF), mean, rstd
+
+
+def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0):
+    assert drop_p == 0.0
+    dyf = dy.float()
+    if lens is not None:
+        t = torch.arange(x.shape[0]) % T
+        b = torch.arange(x.shape[0]) // T
+        dyf = dyf * (t < lens[b]).float()[:, None]
+    xh = (x.float() - mean[:, None]) * rstd[:, None]
+    g = dyf * gamma.float()
+    dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if dres is not None:
+        dx = dx + dres.float()
+    dgamma_acc += (dyf * xh).sum(0)
+    dbeta_acc += dyf.sum(0)
+    return dx.to(BF)
+
+
+def colsum(x, out_acc, scale=1.0):
+    out_acc += scale * x.float().sum(0)
+
+
+def dropout(x, p, seed, scale=1.0, out=None):
+    assert p == 0.0
+    y = (x.float() * scale).to(BF)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def mask_rows_(x, lens):
+    B, T, _ = x.shape
+    x *= (torch.arange(T)[None, :] < lens[:, None]).to(x.dtype)[:, :, None]
+    return x
+
+
+def qprep_fwd(q, u, v, scale):
+    qf = q.float()
+    qu = ((qf + u.float()).to(BF).float() * scale).to(BF)
+    qv = ((qf + v.float()).to(BF).float() * scale).to(BF)
+    return qu, qv
+
+
+def qprep_bwd(dqu, dqv, scale, dq_out):
+    dq_out.copy_((scale * (dqu.float() + dqv.float())).to(BF))
+
+
+def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
+    assert drop_p == 0.0
+    H, B, _, ld = scores.shape
+    s = scores.float()[..., :T].clone()
+    if lens is not None:
+        km = torch.arange(T)[None, :] >= lens[:, None]  # [B, T] keys to mask
+        s = s.masked_fill(km[None, :, None, :], float("-inf"))
+    p = torch.zeros(H, B, T, ld)
+    p[..., :T] = torch.softmax(s, dim=-1)
+    p = p.to(BF)
+    return p, p
+
+
+def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
+    assert drop_p == 0.0
+    H, B, _, ld = p.shape
+    pf = p.float()[..., :T]
+    dp = dp_drop.float()[..., :T]
+    ds_ = pf * (dp - (dp * pf).sum(-1, keepdim=True))
+    ds = torch.zeros(H, B, T, ld)
+    ds[..., :T] = ds_
+    ds = ds.to(BF)
+    dbd = None
+    if want_dbd:
+        dbd = torch.zeros(H, B, T, ldp)
+        i = torch.arange(T)[:, None]
+        j = torch.arange(T)[None, :]
+        idx = ((T - 1) - i + j).expand(H, B, T, T)
+        dbd.scatter_(-1, idx, ds[..., :T].float())
+        dbd = dbd.to(BF)
+    return ds, dbd
+
+
+def _glu(g):
+    C = g.shape[-1] // 2
+    return (g[..., :C].float() * torch.sigmoid(g[..., C:].float())).to(BF).float()
+
+
+def glu_dwconv_fwd(g, w):
+    B, T, C2 = g.shape
+    C, k = w.shape
+    gl = _glu(g).transpose(1, 2)  # [B, C, T]
+    y = F.conv1d(gl, w.float()[:, None, :], padding=k // 2, groups=C).transpose(1, 2).contiguous().to(BF)
+    yf = y.double().reshape(-1, C)
+    stats = torch.stack([yf.sum(0), (yf * yf).sum(0)])
+    return y, stats
+
+
+def glu_dwconv_bwd(dy, g, w, dw_acc):
+    B, T, C2 = g.shape
+    C, k = w.shape
+    with torch.enable_grad():  # may be called from inside an autograd.Function.backward
+        a = g[..., :C].float().detach().requires_grad_(True)
+        gate = g[..., C:].float().detach().requires_grad_(True)
+        wf = w.float().detach().requires_grad_(True)
+        gl = (a * torch.sigmoid(gate))
+        y = F.conv1d(gl.transpose(1, 2), wf[:, None, :], padding=k // 2, groups=C).transpose(1, 2)
+        y.backward(dy.float())
+    dw_acc += wf.grad
+    return torch.cat([a.grad, gate.grad], dim=-1).to(BF)
+
+
+def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
+    if training:
+        m = stats[0] / R
+        var = (stats[1] / R - m * m).clamp_min(0)
+        mr = torch.stack([m.float(), torch.rsqrt(var.float() + eps)])
+        if run_mean is not None:
+            unb = var * R / (R - 1) if R > 1 else var
+            run_mean.mul_(1 - momentum).add_(momentum * m.float())
+            run_var.mul_(1 - momentum).add_(momentum * unb.float())
+        return mr
+    return torch.stack([run_mean.float(), torch.rsqrt(run_var.float() + eps)])
+
+
+def bn_silu_fwd(y, mr, gamma, beta):
+    bn = ((y.float() - mr[0]) * mr[1] * gamma.float() + beta.float()).to(BF).float()
+    return F.silu(bn).to(BF)
+
+
+def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+    Cn = y.shape[-1]
+    yf = y.float().reshape(-1, Cn)
+    xh = (yf - mr[0]) * mr[1]
+    bn = (xh * gamma.float() + beta.float()).to(BF).float()
+    dbn = dz.float().reshape(-1, Cn) * _silu_grad(bn)
+    s1, s2 = dbn.sum(0), (dbn * xh).sum(0)
+    n = yf.shape[0]
+    dy = gamma.float() * mr[1] * (dbn - s1 / n - xh * s2 / n)
+    dgamma_acc += s2
+    dbeta_acc += s1
+    return dy.to(BF).reshape(y.shape)
+
+
+def sumsq(g, out):
+    out.copy_((g.double() ** 2).sum().float().reshape(out.shape))
+    return out
+
+
+def adam_step(p32, m, v, g, p16, lr, beta1, beta2, eps, weight_decay, step, sumsq_t, denom_dev=None, denom_const=1.0,
+              clip_norm=0.0, gnorm_out=None):
+    n = p32.numel()
+    denom = float(denom_dev.item()) if denom_dev is not None else denom_const
+    gscale = 1.0 / denom if denom > 0 else 0.0
+    gnorm = float(sumsq_t.item()) ** 0.5 * gscale
+    coef = min(1.0, clip_norm / (gnorm + 1e-6)) if clip_norm > 0 else 1.0
+    if gnorm_out is not None:
+        gnorm_out.fill_(gnorm)
+    gi = g.view(-1)[:n] * (gscale * coef)
+    m.mul_(beta1).add_((1 - beta1) * gi)
+    v.mul_(beta2).add_((1 - beta2) * gi * gi)
+    b1, b2 = 1 - beta1 ** step, 1 - beta2 ** step
+    if weight_decay != 0:
+        p32.add_(p32, alpha=-weight_decay * lr)
+    p32.addcdiv_(m, v.sqrt() + eps, value=-lr * (b2 ** 0.5) / b1)
+    p16.copy_(p32.to(BF))
+
+
+def cast_f32_bf16(x, y):
+    y.copy_(x.to(BF))
+
+
+def cast_bf16_f32(x, y):
+    y.copy_(x.float())
+
+
+def frontend_fbank(wave, n_samples, cmvn_mean=None, cmvn_std=None, freq_masks=None, time_masks=None, t_max=None,
+                   out_dtype=BF, workspace=None):
+    import numpy as np
+
+    from oracle import frontend as O
+
+    B = wave.shape[0]
+    if t_max is None:
+        t_max = O.num_frames(wave.shape[1])
+    out = torch.zeros(B, t_max, 80)
+    lens = torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        n = int(n_samples[b])
+        fb = O.kaldi_fbank(wave[b, :n].float().numpy())
+        m = fb.shape[0]
+        lens[b] = m
+        if m == 0:
+            continue
+        x = fb.astype(np.float64)
+        if cmvn_mean is not None:
+            x = O.global_cmvn(fb, cmvn_mean.double().numpy(), cmvn_std.double().numpy())
+        fill = x.mean()
+        y = x.copy()
+        if freq_masks is not None:
+            for f0, f in freq_masks[b].tolist():
+                if f > 0:
+                    y[:, f0:f0 + f] = fill
+        if time_masks is not None:
+            for t0, t in time_masks[b].tolist():
+                if t > 0:
+                    y[t0:t0 + t, :] = fill
+        out[b, :m] = torch.from_numpy(y).float()
+    return out.to(out_dtype), lens
+
+
+def ctc_loss(logits, V, in_lens, targets, tgt_lens, blank, zero_infinity=True, grad_scale=1.0, want_grad=True):
+    from oracle import ctc as O
+
+    B, T, ld = logits.shape
+    loss = torch.zeros(B)
+    grad = torch.zeros(B, T, ld)
+    for b in range(B):
+        nll, g = O.ctc_loss_and_grad(logits[b, :, :V].float().numpy(), int(in_lens[b]),
+                                     targets[b, : int(tgt_lens[b])].numpy(), blank, zero_infinity)
+        loss[b] = float(nll)
+        grad[b, :, :V] = torch.from_numpy(g).float() * grad_scale
+    return loss, (grad.to(BF) if want_grad else None)

@@ -100,7 +100,118 @@ def pin_ctc():
     print("ctc pinned -> tests/golden/ctc.npz")
 
 
-SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc}
+def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50):
+    from espresso.models.transformer.speech_transformer_config import SpeechTransformerConfig
+    from espresso.models.transformer.speech_transformer_encoder_model import SpeechTransformerEncoderModel
+
+    cfg = SpeechTransformerConfig()
+    cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
+    e = cfg.encoder
+    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
+    e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
+    e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = d, ffn, layers, heads
+    e.normalize_before, e.learned_pos, e.relative_positional_embeddings = True, False, True
+    e.layer_type, e.depthwise_conv_kernel_size = layer_type, 31
+    cfg.layernorm_embedding = True
+    cfg.dropout = cfg.attention_dropout = cfg.activation_dropout = 0.0
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return 1
+
+    class _Task:
+        feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+
+    torch.manual_seed(1)
+    return SpeechTransformerEncoderModel.build_model(cfg, _Task())
+
+
+def pin_conformer():
+    """Reference model forward + CtcLossCriterion-equivalent loss/grad vs oracle/conformer.py; fixtures for both
+    layer types (conformer = cfg 3/4 encoder, transformer = cfg 2 encoder)."""
+    import torch.nn.functional as F
+
+    from oracle import conformer as O
+
+    for layer_type in ("conformer", "transformer"):
+        m = _ref_model(layer_type)
+        # make LayerNorm/BatchNorm affine params and biases non-trivial so every gradient path is exercised
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for n, p_ in m.named_parameters():
+                if p_.dim() == 1:
+                    p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+        rs = np.random.RandomState(11)
+        B, T = 3, 61
+        lens = torch.tensor([61, 50, 37])
+        feats = torch.from_numpy(rs.randn(B, T, 80).astype(np.float32))
+        for b in range(B):
+            feats[b, lens[b]:] = 0.0
+        V, pad_idx, eos_idx, blank = 50, 1, 2, 0
+        tgt = torch.full((B, 7), pad_idx, dtype=torch.long)
+        for b, u in enumerate((6, 4, 3)):
+            tgt[b, :u] = torch.from_numpy(rs.randint(4, V, size=u))
+            tgt[b, u] = eos_idx
+        cfg = dict(embed_dim=64, ffn_dim=128, heads=4, layers=2, layer_type=layer_type, dw_kernel=31, dropout=0.0,
+                   attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True,
+                   final_layer_norm=(layer_type != "conformer"), vocab=V)
+        out = {}
+        for mode in ("train", "eval"):
+            m.train(mode == "train")
+            sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+            m.zero_grad()
+            net = m(feats, lens)
+            logits = net["encoder_out"][0]                      # T' x B x V
+            olens = net["src_lengths"][0]
+            lprobs = m.get_normalized_probs(net, log_probs=True).contiguous()
+            keep = (tgt != pad_idx) & (tgt != eos_idx)
+            with torch.backends.cudnn.flags(enabled=False):
+                loss = F.ctc_loss(lprobs, tgt.masked_select(keep), olens, keep.sum(-1), blank=blank, reduction="sum",
+                                  zero_infinity=True)              # espresso/criterions/ctc_loss.py:85-94
+            # oracle on the same weights (state before this forward: BN running stats are updated in train mode)
+            sd = {k: v.clone().requires_grad_(v.is_floating_point() and k in dict(m.named_parameters()))
+                  for k, v in sd0.items()}
+            o_logits, o_lens, _ = O.encoder_forward(sd, cfg, feats, lens, training=(mode == "train"))
+            o_loss = O.ctc_criterion(o_logits, o_lens, tgt, pad_idx, eos_idx, blank)
+            d_log = (o_logits.transpose(0, 1) - logits).abs().max().item()
+            assert torch.equal(o_lens, olens)
+            assert d_log < 2e-4, (layer_type, mode, d_log)
+            assert abs(o_loss.item() - loss.item()) < 1e-3 * abs(loss.item())
+            print("%s/%s: |logits diff|=%.3g loss ref=%.6f oracle=%.6f" % (layer_type, mode, d_log, loss.item(), o_loss.item()))
+            if mode == "train":
+                loss.backward()
+                o_loss.backward()
+                worst = 0.0
+                for n, p_ in m.named_parameters():
+                    # biases feeding a BatchNorm have an analytically zero gradient (pure rounding noise): compare
+                    # against the largest gradient magnitude in the model, not the tensor's own
+                    dg = (sd[n].grad - p_.grad).abs().max().item() / max(p_.grad.abs().max().item(), 1e-3)
+                    if dg > 2e-3:
+                        print("   ", n, dg, p_.grad.abs().max().item())
+                    worst = max(worst, dg)
+                print("   worst relative grad diff %.3g" % worst)
+                assert worst < 2e-3
+                for k, v in sd0.items():
+                    out["sd." + k] = v.numpy()
+                for n, p_ in m.named_parameters():
+                    out["grad." + n] = p_.grad.numpy()
+                # BN running stats after the training forward (momentum update incl. padded frames)
+                for k, v in m.state_dict().items():
+                    if "running_" in k:
+                        out["after." + k] = v.numpy()
+                        assert (sd[k] - v).abs().max().item() < 1e-4
+            out["logits_" + mode] = logits.detach().transpose(0, 1).numpy()   # B x T' x V
+            out["loss_" + mode] = np.float64(loss.item())
+        out.update(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), out_lens=olens.numpy())
+        np.savez_compressed(os.path.join(GOLDEN, "encoder_%s.npz" % layer_type), **out)
+        print("%s encoder pinned -> tests/golden/encoder_%s.npz" % (layer_type, layer_type))
+
+
+SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer}
 
 
 def main(argv):
