@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: audio-seconds/second of Conformer-CTC training on synthetic
+LibriSpeech-shape 16 kHz waveforms (BASELINE.json configs[2]: Conformer encoder 17 x 512, conv-k31, CTC, bf16,
+on-the-fly fbank + SpecAugment, data parallel with one gradient all-reduce).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      CPU arm: the oracle port of the reference path on host cores
+
+One "step" = one full update: front end -> conv front -> 17 Conformer layers -> fc_out -> CTC -> backward ->
+gradient all-reduce -> clip + Adam.  `value` times K steps with the step's waveforms already in HBM; `e2e`
+times the same K steps from pinned HOST buffers (H2D copy of every step's inputs inside the timed region)
+and reads the step's loss back (D2H).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V = 5004  # 5000 sentencepiece units + <s>(blank) <pad> </s> <unk>   (run_torchaudio.sh:25)
+MAX_TOKENS, MAX_SENTENCES = 26000, 24  # frames / sentences per GPU batch (conformer_librispeech.yaml:29-30)
+MODEL = dict(embed_dim=512, ffn_embed_dim=2048, layers=17, attention_heads=8, normalize_before=True, learned_pos=False,
+             relative_positional_embeddings=True, layer_type="conformer", depthwise_conv_kernel_size=31)
+SPECAUG = {"time_warp_W": 0, "freq_mask_F": 27, "freq_mask_N": 2, "time_mask_pm": 0.04, "time_mask_ps": 0.04}
+
+
+def synth_wave(rs, n):
+    """noise + sine in int16 range, float32."""
+    t = np.arange(n, dtype=np.float32) / 16000.0
+    x = np.round(3000.0 * rs.standard_normal(n).astype(np.float32) + 1500.0 * np.sin(2 * np.pi * rs.uniform(80, 400) * t))
+    return np.clip(x, -32767, 32767).astype(np.float32)
+
+
+def make_batches(n_batches, world, rank, seed=7, pool=4000):
+    """LibriSpeech-shape durations Gamma(6.1, 2.0) clipped to [1, 35] s, sorted by length, packed under
+    max_tokens/max_sentences; consecutive (similar-length) batches go to consecutive ranks."""
+    from espresso_b200.data import batching, specaugment as SA
+
+    rs = np.random.RandomState(seed)
+    durs = np.clip(rs.gamma(6.1, 2.0, size=pool), 1.0, 35.0)
+    n_samples = np.round(durs * 16000).astype(np.int64)
+    frames = 1 + (n_samples - 400) // 160
+    order = batching.ordered_indices(frames)
+    batches = batching.batch_by_size(order, frames, MAX_TOKENS, MAX_SENTENCES)
+    # grouped shuffle: groups of `world` consecutive batches stay together (fairseq/data/iterators.py:537-545)
+    groups = [batches[i:i + world] for i in range(0, len(batches) - world + 1, world)]
+    np.random.RandomState(seed + 1).shuffle(groups)
+    cfg = SA.AdaptiveSpecAugmentConfig.from_config_dict(SPECAUG)
+    out = []
+    for gi in range(n_batches):
+        idx = groups[gi % len(groups)][rank]
+        idx = idx[np.argsort(-frames[idx], kind="mergesort")]  # collate: sort by length descending (asr_dataset.py:60-70)
+        B = len(idx)
+        n = n_samples[idx]
+        wave = np.zeros((B, int(n.max())), dtype=np.float32)
+        fms, tms, tgts = [], [], []
+        for b, i in enumerate(idx):
+            wrs = np.random.RandomState(1000 + int(i))
+            wave[b, : n[b]] = synth_wave(wrs, int(n[b]))
+            with SA.numpy_seed(1, 1, int(i)):
+                fm, tm = SA.draw_masks(cfg, int(frames[i]), 80)
+            fms.append(fm)
+            tms.append(tm)
+            u = max(1, int(round(4.0 * durs[i])))
+            tgts.append(np.random.RandomState(11 + int(i)).randint(4, V, size=u))
+        fmp, tmp = SA.pack_masks(fms, tms)
+        U = max(len(t) for t in tgts) + 1
+        target = np.full((B, U), 1, dtype=np.int64)
+        for b, t in enumerate(tgts):
+            target[b, : len(t)] = t
+            target[b, len(t)] = 2
+        out.append(dict(wave=wave, n_samples=n.astype(np.int32), fm=fmp, tm=tmp, target=target,
+                        audio_s=float(n.sum() / 16000.0), ntokens=int(sum(len(t) for t in tgts))))
+    return out
+
+
+class _Dict:
+    def __len__(self):
+        return V
+
+    def pad(self):
+        return 1
+
+    def eos(self):
+        return 2
+
+    def index(self, s):
+        return 0
+
+
+class _Task:
+    feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path (numpy Kaldi fbank + CMVN + SpecAugment, PyTorch fp32
+    Conformer-CTC forward/backward, Adam) on the host cores; bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import conformer as OC
+    from oracle import frontend as OF
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=17, layer_type="conformer", dw_kernel=31, dropout=0.1,
+               attention_dropout=0.1, activation_dropout=0.1, layernorm_embedding=True, final_layer_norm=False, vocab=V)
+    sd = OC.random_state_dict(cfg, seed=1)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if "running_" not in k}
+    sd.update(params)
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.98), eps=1e-8)
+    durs = [9.0, 7.0]  # bounded sample of the workload per step
+    waves = [OF.synth_waveform(i, d) for i, d in enumerate(durs)]
+    mean, std = np.zeros(80), np.ones(80) * 4.0
+    audio_s = sum(len(w) for w in waves) / 16000.0
+
+    def step(it):
+        feats = []
+        for i, w in enumerate(waves):
+            x = OF.global_cmvn(OF.kaldi_fbank(w), mean + 15.0, std)
+            with OF.numpy_seed(1, it, i):
+                x = OF.adaptive_specaugment(x)
+            feats.append(torch.from_numpy(x).float())
+        lens = torch.tensor([f.shape[0] for f in feats])
+        order = torch.argsort(lens, descending=True)
+        T = int(lens.max())
+        batch = torch.zeros(len(feats), T, 80)
+        for b, j in enumerate(order.tolist()):
+            batch[b, : feats[j].shape[0]] = feats[j]
+        lens = lens[order]
+        tgt = torch.full((len(feats), 40), 1, dtype=torch.long)
+        for b in range(len(feats)):
+            tgt[b, :30] = torch.randint(4, V, (30,))
+            tgt[b, 30] = 2
+        opt.zero_grad()
+        logits, ol, _ = OC.encoder_forward(sd, cfg, batch, lens, training=True)
+        loss = OC.ctc_criterion(logits, ol, tgt, 1, 2, 0)
+        (loss / len(feats)).backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 2.0)
+        opt.step()
+        return float(loss)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    val = audio_s * args.steps / dt
+    sample = "%d utterances (%s s) per step, fp32, %d torch threads" % (len(durs), "+".join(str(d) for d in durs), cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "training throughput (audio-seconds/second)", "value": val, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(n):
+    return {"workload": "Conformer encoder 17x512 (ffn 2048, 8 heads, conv-k31, sinusoidal rel-pos) + CTC, V=5004, on-the-fly "
+                        "fbank80+CMVN+adaptive SpecAugment from raw 16 kHz waveforms, Adam + clip 2.0, dropout 0.1",
+            "max_tokens": MAX_TOKENS, "batch_size": MAX_SENTENCES, "length_distribution": "Gamma(6.1,2.0) s clipped [1,35]",
+            "parallelism": "dp%d" % n, "l2": "per-step working set (activations+weights > 1 GB) exceeds the 126 MB L2"}
+
+
+def cpu_baseline_quick():
+    """Oracle (port) timed on the host cores on a bounded sample: 1 fwd+bwd of the same model on 1 x 6 s."""
+    from oracle import conformer as OC
+    from oracle import frontend as OF
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=17, layer_type="conformer", dw_kernel=31, dropout=0.0,
+               attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, final_layer_norm=False, vocab=V)
+    sd = OC.random_state_dict(cfg, seed=1)
+    for k, v in sd.items():
+        if "running_" not in k:
+            v.requires_grad_(True)
+    w = OF.synth_waveform(0, 6.0)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 12.0 or reps < 2:
+        x = torch.from_numpy(OF.kaldi_fbank(w))[None]
+        logits, ol, _ = OC.encoder_forward(sd, cfg, x, torch.tensor([x.shape[1]]), training=True)
+        loss = OC.ctc_criterion(logits, ol, torch.randint(4, V, (1, 20)), 1, 2, 0)
+        loss.backward()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": 6.0 * reps / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": "%d x (fbank + fwd + bwd) of one 6 s utterance, fp32, no optimizer step" % reps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--layers", type=int, default=None, help="debug only: override layer count (invalidates the number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from espresso_b200 import lib, ops
+    from espresso_b200.criterions import CtcLossCriterion
+    from espresso_b200.data.frontend import OnTheFlyFbank
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerEncoderModel
+    from espresso_b200.optim import NoamLRScheduler
+    from espresso_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "--gpus must equal WORLD_SIZE (launch N > 1 under torchrun)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    torch.manual_seed(1)
+    enc = dict(MODEL)
+    if args.layers is not None:
+        enc["layers"] = args.layers
+    cfg = SpeechTransformerConfig.from_dict(dict(dropout=0.1, attention_dropout=0.1, activation_dropout=0.1,
+                                                 layernorm_embedding=True, encoder=enc))
+    model = SpeechTransformerEncoderModel.build_model(cfg, _Task()).finalize_(dev)
+    model.frontend = OnTheFlyFbank(np.full(80, 15.0), np.full(80, 4.0))
+    trainer = Trainer(model, CtcLossCriterion(_Task()), NoamLRScheduler(5.0, 25000, 512, 1e-6), adam_betas=(0.9, 0.98),
+                      clip_norm=2.0)
+
+    n_distinct = min(8, args.steps + args.warmup)
+    host = make_batches(n_distinct, world, rank)
+    pinned = [{k: (torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in b.items()} for b in host]
+
+    def to_dev(b):
+        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+    def sample_of(d, n_cpu):
+        return {"net_input": {"src_tokens": d["wave"], "src_lengths": d["n_samples"], "freq_masks": d["fm"],
+                              "time_masks": d["tm"], "src_lengths_cpu": n_cpu},
+                "target": d["target"], "ntokens": d["ntokens"]}
+
+    resident = [to_dev(b) for b in pinned]
+    n_cpu = [b["n_samples"].clone().long() for b in pinned]
+    h2d_bytes = int(np.mean([sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v)) for b in pinned]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, from_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        audio = 0.0
+        e0.record()
+        for i in range(nsteps):
+            j = i % n_distinct
+            d = to_dev(pinned[j]) if from_host else resident[j]
+            trainer.train_step([sample_of(d, n_cpu[j])])
+            audio += pinned[j]["audio_s"]
+            if from_host:
+                _ = trainer.last_stats[3].item()  # D2H read of the step's loss
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, audio], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(mx[0]), float(t[1])
+        return float(t[0]), float(t[1])
+
+    timed(args.warmup, False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.launch_count()
+    ms, audio = timed(args.steps, False)
+    launches = lib.launch_count() - l0
+    ms_e2e, audio_e2e = timed(args.steps, True)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): one extra step with per-launch CUDA events ---------
+    roof = None
+    if rank == 0:
+        import json as _json
+        peaks = {}
+        try:
+            peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        recs = []
+        orig = ops.gemm
+
+        def prof_gemm(A, B, C_out, M, N, K, *a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(A, B, C_out, M, N, K, *a, **kw)
+            e.record()
+            recs.append((s, e, 2.0 * M * N * K * kw.get("nb1", 1) * kw.get("nb2", 1)))
+            return r
+
+        ops.gemm = prof_gemm
+        try:
+            trainer.train_step([sample_of(resident[0], n_cpu[0])])
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm = orig
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        roof = {"kernel": "gemm_tcgen05_kernel (all %d launches of one step)" % len(recs), "bound": "tensor", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "gemm_ms_per_step": tot_ms, "gemm_share_of_step": tot_ms / (ms / args.steps), "traffic": None}
+
+    if rank == 0:
+        val = audio / (ms * 1e-3)
+        out = {
+            "metric": "training throughput (audio-seconds/second)", "value": val, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world), "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": audio_e2e / (ms_e2e * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "roofline": roof,
+        }
+        if args.layers is not None:
+            out["INVALID"] = "layer count overridden for debugging"
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_quick()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,225 @@
+"""GPU parity: every HBM-bound block kernel and the optimizer vs the oracle's per-op reference
+(oracle/ops_ref.py, same signatures), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _close(a, b, tol, what=""):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs().max().item()
+    scale = max(b.abs().max().item(), 1e-3)
+    assert err <= tol * scale, "%s: err %.4g vs scale %.4g" % (what, err, scale)
+
+
+@pytest.mark.parametrize("R,d", [(37, 64), (1000, 512), (300, 256), (65, 1024)])
+def test_layer_norm(dev, R, d):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(R)
+    x = (torch.randn(R, d) * 2 + 0.5).to(BF)
+    g = (1 + 0.2 * torch.randn(d)).to(BF)
+    b = (0.2 * torch.randn(d)).to(BF)
+    T = 25 if R % 25 == 0 else R
+    lens = torch.tensor([T - 3] * (R // T), dtype=torch.int32) if R % 25 == 0 else None
+    y, mean, rstd = ops.layer_norm_fwd(x.to(dev), g.to(dev), b.to(dev), lens=None if lens is None else lens.to(dev), T=T)
+    yr, mr, rr = O.layer_norm_fwd(x, g, b, lens=lens, T=T)
+    _close(y, yr, 0.01, "ln y")
+    _close(mean, mr, 1e-4, "ln mean")
+    _close(rstd, rr, 1e-4, "ln rstd")
+    dy = torch.randn(R, d).to(BF)
+    dres = torch.randn(R, d).to(BF)
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dx = ops.layer_norm_bwd(dy.to(dev), x.to(dev), mean, rstd, g.to(dev), dg, db, dres=dres.to(dev),
+                            lens=None if lens is None else lens.to(dev), T=T)
+    dgr, dbr = torch.zeros(d), torch.zeros(d)
+    dxr = O.layer_norm_bwd(dy, x, mr, rr, g, dgr, dbr, dres=dres, lens=lens, T=T)
+    _close(dx, dxr, 0.02, "ln dx")
+    _close(dg, dgr, 0.01, "ln dgamma")
+    _close(db, dbr, 0.01, "ln dbeta")
+
+
+def test_layer_norm_dropout_consistency(dev):
+    """forward dropout mask == mask regenerated in backward (zeros line up), keep rate ~ 1-p."""
+    from espresso_b200 import ops
+
+    R, d, p = 400, 512, 0.1
+    x = torch.randn(R, d, device=dev).to(BF)
+    g = torch.ones(d, device=dev, dtype=BF)
+    b = torch.full((d,), 3.0, device=dev, dtype=BF)  # keeps y away from 0 so zeros mark dropped elements
+    y, mean, rstd = ops.layer_norm_fwd(x, g, b, drop_p=p, seed=77)
+    dropped = (y == 0)
+    assert abs(dropped.float().mean().item() - p) < 0.01
+    dy = torch.ones(R, d, device=dev, dtype=BF)
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    ops.layer_norm_bwd(dy, x, mean, rstd, g, dg, db, drop_p=p, seed=77)
+    # dbeta = sum_r mask/(1-p)  => counts of kept elements per column
+    kept = (~dropped).float().sum(0) / (1 - p)
+    assert (db - kept).abs().max().item() < 1e-2 * kept.max().item()
+
+
+def test_colsum_dropout_mask_rows_qprep(dev):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(3)
+    x = torch.randn(700, 1536).to(BF)
+    acc = torch.ones(512, device=dev)
+    ops.colsum(x.to(dev)[:, 512:1024], acc, scale=0.5)
+    accr = torch.ones(512)
+    O.colsum(x[:, 512:1024], accr, scale=0.5)
+    _close(acc, accr, 2e-3, "colsum")
+    y = ops.dropout(x.to(dev), 0.0, 1, scale=0.5)
+    _close(y, O.dropout(x, 0.0, 1, scale=0.5), 1e-2, "scale")
+    yd = ops.dropout(x.to(dev), 0.3, 5)
+    keep = (yd != 0).float().mean().item()
+    assert abs(keep - 0.7) < 0.01
+    m = yd != 0
+    _close(yd[m], (x.to(dev).float() / 0.7)[m], 1e-2, "dropout scale")
+    # same (seed, index) stream as the GEMM epilogue: dropout(I @ x) masks must coincide
+    eye = torch.eye(64, device=dev, dtype=BF)
+    xs = torch.randn(64, 64, device=dev).to(BF) + 4
+    via_gemm = ops.linear(eye, xs.t().contiguous(), drop_p=0.3, drop_mode=1, seed=5)
+    via_kernel = ops.dropout(xs, 0.3, 5)
+    assert torch.equal(via_gemm == 0, via_kernel == 0)
+    # mask rows
+    z = torch.randn(3, 20, 64).to(BF)
+    lens = torch.tensor([20, 7, 1], dtype=torch.int32)
+    zr = O.mask_rows_(z.clone(), lens)
+    zg = ops.mask_rows_(z.to(dev).clone(), lens.to(dev))
+    assert torch.equal(zg.cpu(), zr)
+    # qprep
+    q = x[:, :512]
+    u, v = torch.randn(512).to(BF), torch.randn(512).to(BF)
+    qu, qv = ops.qprep_fwd(x.to(dev)[:, :512], u.to(dev), v.to(dev), 0.125)
+    qur, qvr = O.qprep_fwd(q, u, v, 0.125)
+    _close(qu, qur, 1e-2, "qu")
+    _close(qv, qvr, 1e-2, "qv")
+    out = torch.zeros(700, 1536, device=dev, dtype=BF)
+    ops.qprep_bwd(qu, qv, 0.125, out[:, :512])
+    outr = torch.zeros(700, 1536, dtype=BF)
+    O.qprep_bwd(qur, qvr, 0.125, outr[:, :512])
+    _close(out, outr, 1e-2, "qprep bwd")
+
+
+@pytest.mark.parametrize("T", [16, 61, 250, 305])
+def test_attn_softmax(dev, T):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(T)
+    H, B = 2, 3
+    ld, ldp = (T + 7) // 8 * 8, (2 * T + 6) // 8 * 8
+    s = (torch.randn(H, B, T, ld) * 3).to(BF)
+    lens = torch.tensor([T, max(1, T - 5), max(1, T // 2)], dtype=torch.int32)
+    p, pd = ops.attn_softmax_fwd(s.to(dev), T, lens.to(dev))
+    pr, _ = O.attn_softmax_fwd(s, T, lens)
+    _close(p[..., :T], pr[..., :T], 0.01, "softmax")
+    assert not p[..., T:].any()
+    p2, _ = ops.attn_softmax_fwd(s.to(dev), T, None)
+    pr2, _ = O.attn_softmax_fwd(s, T, None)
+    _close(p2[..., :T], pr2[..., :T], 0.01, "softmax nomask")
+    dp = torch.randn(H, B, T, ld).to(BF)
+    ds, dbd = ops.attn_softmax_bwd(p, dp.to(dev), T, ldp)
+    dsr, dbdr = O.attn_softmax_bwd(p.cpu(), dp, T, ldp)
+    _close(ds[..., :T], dsr[..., :T], 0.02, "softmax bwd")
+    _close(dbd[..., : 2 * T - 1], dbdr[..., : 2 * T - 1], 0.02, "dBD scatter")
+    # dropout variant: kept fraction, and backward uses the same mask
+    p3, pd3 = ops.attn_softmax_fwd(s.to(dev), T, None, drop_p=0.2, seed=9)
+    assert torch.equal(p3, p2)
+    nz = p3[..., :T].float() > 1e-4
+    keep = ((pd3[..., :T] != 0) & nz).float().sum().item() / nz.float().sum().item()
+    assert abs(keep - 0.8) < 0.02
+    ones = torch.ones(H, B, T, ld, device=dev, dtype=BF)
+    ds3, _ = ops.attn_softmax_bwd(p3, ones, T, ldp, drop_p=0.2, seed=9)
+    mask = (pd3[..., :T] != 0).float() / 0.8
+    pf = p3[..., :T].float()
+    expect = pf * (mask - (mask * pf).sum(-1, keepdim=True))
+    sel = nz
+    assert ((ds3[..., :T].float() - expect)[sel]).abs().max().item() < 0.02
+
+
+@pytest.mark.parametrize("B,T,C,k", [(2, 50, 64, 31), (3, 200, 128, 31), (1, 7, 64, 3), (2, 65, 512, 31)])
+def test_conv_module_kernels(dev, B, T, C, k):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(T + C)
+    g = torch.randn(B, T, 2 * C).to(BF)
+    w = (torch.randn(C, k) * 0.3).to(BF)
+    y, stats = ops.glu_dwconv_fwd(g.to(dev), w.to(dev))
+    yr, statsr = O.glu_dwconv_fwd(g, w)
+    _close(y, yr, 0.02, "dwconv y")
+    _close(stats, statsr, 0.02, "bn stats")
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    mr = ops.bn_finalize(stats, B * T, C, 1e-5, 0.1, rm, rv, True)
+    rmr, rvr = torch.zeros(C), torch.ones(C)
+    mrr = O.bn_finalize(statsr, B * T, C, 1e-5, 0.1, rmr, rvr, True)
+    _close(mr, mrr, 0.02, "bn mean/rstd")
+    _close(rm, rmr, 0.02, "running mean")
+    _close(rv, rvr, 0.02, "running var")
+    gm, bt = (1 + 0.2 * torch.randn(C)).to(BF), (0.2 * torch.randn(C)).to(BF)
+    z = ops.bn_silu_fwd(y, mr, gm.to(dev), bt.to(dev))
+    zr = O.bn_silu_fwd(y.cpu(), mr.cpu(), gm, bt)
+    _close(z, zr, 0.02, "bn silu")
+    mre = ops.bn_finalize(None, B * T, C, 1e-5, 0.1, rm, rv, False)  # eval: running stats
+    _close(mre[0], rm, 1e-6, "eval mean")
+    dz = torch.randn(B, T, C).to(BF)
+    dgm, dbt = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dy = ops.bn_silu_bwd(dz.to(dev), y, mr, gm.to(dev), bt.to(dev), dgm, dbt)
+    dgmr, dbtr = torch.zeros(C), torch.zeros(C)
+    dyr = O.bn_silu_bwd(dz, y.cpu(), mr.cpu(), gm, bt, dgmr, dbtr)
+    _close(dy, dyr, 0.03, "bn bwd dy")
+    _close(dgm, dgmr, 0.02, "bn dgamma")
+    _close(dbt, dbtr, 0.02, "bn dbeta")
+    dw = torch.zeros(C, k, device=dev)
+    dg = ops.glu_dwconv_bwd(dy, g.to(dev), w.to(dev), dw)
+    dwr = torch.zeros(C, k)
+    dgr = O.glu_dwconv_bwd(dy.cpu(), g, w, dwr)
+    _close(dg, dgr, 0.03, "dwconv dg")
+    _close(dw, dwr, 0.03, "dwconv dw")
+
+
+def test_optimizer_kernels(dev):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(0)
+    n = 100003
+    p32 = torch.randn(n)
+    g = torch.randn(n + 8) * 3
+    g[n] = 4.0  # tail: sample_size
+    st = [dict(p32=p32.clone(), m=torch.zeros(n), v=torch.zeros(n), p16=torch.zeros(n, dtype=BF)) for _ in range(2)]
+    gd = {k: v.to(dev) for k, v in st[0].items()}
+    gg = g.to(dev)
+    ss, ssr = torch.zeros(1, device=dev), torch.zeros(1)
+    gn = torch.zeros(1, device=dev)
+    for step in (1, 2, 3):
+        ops.sumsq(gg[:n], ss)
+        O.sumsq(g[:n], ssr)
+        _close(ss, ssr, 1e-4, "sumsq")
+        ops.adam_step(gd["p32"], gd["m"], gd["v"], gg, gd["p16"], 1e-2, 0.9, 0.98, 1e-8, 0.01, step, ss, denom_dev=gg[n:n + 1],
+                      clip_norm=2.0, gnorm_out=gn)
+        r = st[1]
+        O.adam_step(r["p32"], r["m"], r["v"], g, r["p16"], 1e-2, 0.9, 0.98, 1e-8, 0.01, step, ssr, denom_dev=g[n:n + 1], clip_norm=2.0)
+    _close(gd["p32"], st[1]["p32"], 1e-4, "adam p32")
+    _close(gd["v"], st[1]["v"], 1e-3, "adam v")
+    assert torch.equal(gd["p16"].cpu(), gd["p32"].cpu().to(BF))
+    assert abs(gn.item() - ssr.item() ** 0.5 / 4.0) < 1e-3 * gn.item()
+    x = torch.randn(1000, device=dev)
+    y = torch.empty(1000, device=dev, dtype=BF)
+    ops.cast_f32_bf16(x, y)
+    assert torch.equal(y, x.to(BF))
+    z = torch.empty(1000, device=dev)
+    ops.cast_bf16_f32(y, z)
+    assert torch.equal(z, y.float())
