@@ -455,6 +455,14 @@ int make_tmap(CUtensorMap* tm, const void* base, long inner, long rows, long ld,
               int nb2, long s2, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   ESP_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  // cuTensorMapEncodeTiled is a DRIVER call: the calling thread needs a current context.  PyTorch's
+  // autograd engine runs backward on its own threads where only the runtime device is set, so bind the
+  // primary context once per thread (cudaFree(0) is the canonical no-op that does it).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    ESP_CUDA(cudaFree(0));
+    ctx_bound = true;
+  }
   ESP_CHECK(((uintptr_t)base & 15) == 0, "GEMM operand base must be 16-byte aligned");
   ESP_CHECK((ld % 8) == 0, "GEMM operand leading dimension (%ld) must be a multiple of 8 elements", ld);
   // Broadcast / singleton batch dims get size 1 (coordinate forced to 0 by the kernel) and a
