@@ -61,7 +61,7 @@ class CtcLossCriterion(torch.nn.Module):
         targets, tgt_lens = compact_targets(sample["target"], self.pad_idx, self.eos_idx)
         loss_b = _CtcFn.apply(out, V, in_lens, targets, tgt_lens, self.blank_idx, self.zero_infinity, self.unit_grad_output)
         loss = loss_b.sum() if reduce else loss_b
-        ntokens = sample["ntokens"] if "ntokens" in sample else tgt_lens.sum()
+        ntokens = sample["ntokens"] if "ntokens" in sample else tgt_lens.sum()  # device scalar when not given
         nsent = sample["target"].size(0)
         sample_size = nsent if self.sentence_avg else ntokens
         logging_output = {"loss": loss.detach(), "ntokens": ntokens, "nsentences": nsent, "sample_size": sample_size}

@@ -52,7 +52,9 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
               long R, int d, bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed) {
+              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed0,
+              const unsigned long long* __restrict__ seed_ptr) {
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -122,7 +124,9 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, const bf16* __restrict__ dres, long R,
               int d, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed) {
+              const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed0,
+              const unsigned long long* __restrict__ seed_ptr) {
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   extern __shared__ float sm_red[];  // [2][d]
   const int lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
@@ -242,7 +246,9 @@ colsum_kernel(const bf16* __restrict__ x, long R, int N, long ld, float scale, f
 // y = dropout(x) * scale  (same counter RNG as the GEMM epilogue: index = r*N + n)
 __global__ void __launch_bounds__(256)
 dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, float scale, float drop_p,
-               uint32_t thresh, unsigned long long seed, bf16* __restrict__ y) {
+               uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr,
+               bf16* __restrict__ y) {
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const long nvec = R * (N >> 3);
   const float ds = drop_p > 0.f ? scale / (1.f - drop_p) : scale;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
@@ -318,7 +324,8 @@ constexpr int kSmMax = 36;  // up to 1152 keys per row (36 s of audio after 4x s
 __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int ld, const int* __restrict__ lens,
                         bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
-                        unsigned long long seed) {
+                        unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long rows = (long)H * B * T;
@@ -364,7 +371,8 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int 
 __global__ void __launch_bounds__(256)
 attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int T, int ld,
                         bf16* __restrict__ ds_out, bf16* __restrict__ dbd_out, int ldp, float drop_p,
-                        uint32_t thresh, unsigned long long seed) {
+                        uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long rows = (long)H * B * T;
@@ -655,13 +663,14 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int Cn, fl
 
 extern "C" int esp_layer_norm_fwd(const void* x, const void* gamma, const void* beta, float eps, int64_t R, int32_t d,
                                   void* y, float* mean, float* rstd, const int32_t* lens, int32_t T, float drop_p,
-                                  uint64_t seed, void* stream) {
+                                  uint64_t seed, const uint64_t* seed_ptr, void* stream) {
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported (need d%%8==0, d<=2048)", d);
   if (R == 0) return 0;
 #define ESP_LN_FWD(NV)                                                                                              \
   ln_fwd_kernel<NV><<<grid_for(R, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, eps, R, d, \
-                                                     (bf16*)y, mean, rstd, lens, T, drop_p, esp_dropout_thresh(drop_p), seed)
+                                                     (bf16*)y, mean, rstd, lens, T, drop_p, esp_dropout_thresh(drop_p), seed,       \
+                                                     (const unsigned long long*)seed_ptr)
   if (d <= 512) ESP_LN_FWD(2);
   else if (d <= 1024) ESP_LN_FWD(4);
   else ESP_LN_FWD(8);
@@ -673,14 +682,15 @@ extern "C" int esp_layer_norm_fwd(const void* x, const void* gamma, const void* 
 
 extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                                   const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
-                                  const int32_t* lens, int32_t T, float drop_p, uint64_t seed, void* stream) {
+                                  const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                                  void* stream) {
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported", d);
   if (R == 0) return 0;
 #define ESP_LN_BWD(NV)                                                                                             \
   ln_bwd_kernel<NV><<<grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st>>>(                                          \
       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
-      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed)
+      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
   if (d <= 512) ESP_LN_BWD(2);
   else if (d <= 1024) ESP_LN_BWD(4);
   else ESP_LN_BWD(8);
@@ -703,12 +713,13 @@ extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float
 }
 
 extern "C" int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
-                           uint64_t seed, void* y, void* stream) {
+                           uint64_t seed, const uint64_t* seed_ptr, void* y, void* stream) {
   ESP_ST;
   ESP_CHECK(N % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dropout needs N/ld multiples of 8");
   if (R == 0 || N == 0) return 0;
   dropout_kernel<<<grid_for(R * (N / 8), 256), 256, 0, st>>>((const bf16*)x, R, N, ldx, ldy, scale, drop_p,
-                                                             esp_dropout_thresh(drop_p), seed, (bf16*)y);
+                                                             esp_dropout_thresh(drop_p), seed,
+                                                             (const unsigned long long*)seed_ptr, (bf16*)y);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -749,7 +760,8 @@ extern "C" int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int6
 }
 
 extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
-                                    void* p, void* p_drop, float drop_p, uint64_t seed, void* stream) {
+                                    void* p, void* p_drop, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                                    void* stream) {
   ESP_ST;
   ESP_CHECK(T <= 32 * kSmMax, "attention length %d exceeds the register softmax limit %d", T, 32 * kSmMax);
   ESP_CHECK(ld >= T && ld <= 32 * kSmMax, "bad score row stride");
@@ -758,14 +770,16 @@ extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, in
   if (rows == 0) return 0;
   attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)scores, H, B, T, ld, lens, (bf16*)p,
                                                                       drop_p > 0.f ? (bf16*)p_drop : nullptr, drop_p,
-                                                                      esp_dropout_thresh(drop_p), seed);
+                                                                      esp_dropout_thresh(drop_p), seed,
+                                                                      (const unsigned long long*)seed_ptr);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
 extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
-                                    void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, void* stream) {
+                                    void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                                    void* stream) {
   ESP_ST;
   ESP_CHECK(T <= 32 * kSmMax && ld >= T && ld <= 32 * kSmMax, "bad attention softmax-bwd shape");
   ESP_CHECK(dbd == nullptr || ldp >= 2 * T - 1, "dBD row stride too small");
@@ -773,7 +787,8 @@ extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t 
   if (rows == 0) return 0;
   attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, T, ld,
                                                                       (bf16*)ds, (bf16*)dbd, ldp, drop_p,
-                                                                      esp_dropout_thresh(drop_p), seed);
+                                                                      esp_dropout_thresh(drop_p), seed,
+                                                                      (const unsigned long long*)seed_ptr);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;

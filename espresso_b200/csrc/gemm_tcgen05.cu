@@ -42,6 +42,7 @@ struct EpiParams {
   float alpha, beta, drop_scale;
   uint32_t drop_thresh;
   unsigned long long seed;
+  const unsigned long long* seed_ptr;
 };
 
 struct KParams {
@@ -290,6 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================ epilogue =========================================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const EpiParams& e = p.ep;
+    const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int mt = tile % tiles_m;
@@ -345,7 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (e.drop_mode == 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              v[j] = esp_dropout_keep(e.seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+              v[j] = esp_dropout_keep(seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
           }
           if (e.act != ESP_ACT_NONE) {
             if (e.act >= ESP_ACT_RELU_BWD) {
@@ -363,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (e.drop_mode == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              v[j] = esp_dropout_keep(e.seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+              v[j] = esp_dropout_keep(seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
@@ -555,6 +557,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   e.drop_thresh = esp_dropout_thresh(g->drop_p);
   e.drop_scale = g->drop_p > 0.f ? 1.f / (1.f - g->drop_p) : 1.f;
   e.seed = g->seed;
+  e.seed_ptr = (const unsigned long long*)g->seed_ptr;
   ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
   if (bn == 64) return dispatch_major<64>(ak, bk, ta, tb, kp, st);

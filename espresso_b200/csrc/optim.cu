@@ -42,8 +42,14 @@ sumsq_kernel(const float* __restrict__ g, long n, float* __restrict__ out) {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p32, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
             bf16* __restrict__ p16, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
-            float bias1, float bias2, const float* __restrict__ sumsq, const float* __restrict__ denom_ptr,
-            float denom_const, float clip_norm, float* __restrict__ gnorm_out) {
+            float step, const float* __restrict__ sumsq, const float* __restrict__ denom_ptr,
+            float denom_const, float clip_norm, float* __restrict__ gnorm_out, const float* __restrict__ hyper) {
+  if (hyper) {  // schedule values live in device memory so a captured graph replays with fresh ones
+    lr = hyper[0];
+    step = hyper[1];
+  }
+  const float bias1 = 1.f - powf(beta1, step);
+  const float bias2 = 1.f - powf(beta2, step);
   const float denom = denom_ptr ? *denom_ptr : denom_const;
   const float gscale = denom > 0.f ? 1.f / denom : 0.f;                 // multiply_grads(world/sample_size) after the
                                                                         // pre-divided sum == 1/sum(sample_size)
@@ -100,15 +106,13 @@ extern "C" int esp_sumsq_f32(const float* g, int64_t n, float* out, void* stream
 extern "C" int esp_adam_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
                              const float* denom_dev, float denom_const, float clip_norm, float* gnorm_out,
-                             void* stream) {
+                             const float* hyper_dev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  ESP_CHECK(step >= 1, "Adam step count must start at 1");
+  ESP_CHECK(step >= 1 || hyper_dev != nullptr, "Adam step count must start at 1");
   ESP_CHECK(sumsq != nullptr, "Adam needs the squared gradient norm (esp_sumsq_f32)");
   if (n == 0) return 0;
-  const float bias1 = 1.f - powf(beta1, (float)step);
-  const float bias2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid_n(n), 256, 0, st>>>(p32, m, v, g, (bf16*)p16, n, lr, beta1, beta2, eps, weight_decay, bias1, bias2,
-                                        sumsq, denom_dev, denom_const, clip_norm, gnorm_out);
+  adam_kernel<<<grid_n(n), 256, 0, st>>>(p32, m, v, g, (bf16*)p16, n, lr, beta1, beta2, eps, weight_decay, (float)step,
+                                        sumsq, denom_dev, denom_const, clip_norm, gnorm_out, hyper_dev);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;

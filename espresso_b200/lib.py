@@ -27,6 +27,7 @@ class EspGemm(C.Structure):
         ("skew_r", C.c_int32), ("tile_n", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("drop_p", C.c_float),
         ("seed", C.c_uint64),
+        ("seed_ptr", C.c_void_p),
     ]
 
 
@@ -46,15 +47,15 @@ SIGNATURES = {
     "esp_ctc_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "esp_ctc_loss": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp,
                                _vp, _vp]),
-    "esp_layer_norm_fwd": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _u64, _vp]),
-    "esp_layer_norm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _u64, _vp]),
+    "esp_layer_norm_fwd": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
+    "esp_layer_norm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
     "esp_colsum": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp, _vp]),
-    "esp_dropout": (C.c_int, [_vp, _i64, _i32, _i64, _i64, _f32, _f32, _u64, _vp, _vp]),
+    "esp_dropout": (C.c_int, [_vp, _i64, _i32, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp]),
     "esp_mask_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "esp_qprep_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
     "esp_qprep_bwd": (C.c_int, [_vp, _vp, _f32, _i64, _i32, _vp, _i64, _vp]),
-    "esp_attn_softmax_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _u64, _vp]),
-    "esp_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _vp]),
+    "esp_attn_softmax_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _u64, _vp, _vp]),
+    "esp_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
     "esp_glu_dwconv_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_glu_dwconv_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_bn_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _i32, _vp, _vp]),
@@ -62,7 +63,7 @@ SIGNATURES = {
     "esp_bn_silu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "esp_sumsq_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "esp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _f32, _f32,
-                                _vp, _vp]),
+                                _vp, _vp, _vp]),
     "esp_cast_f32_bf16": (C.c_int, [_vp, _i64, _vp, _vp]),
     "esp_cast_bf16_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
 }

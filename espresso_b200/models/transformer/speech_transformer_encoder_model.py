@@ -276,7 +276,8 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         lens_i32 = out_lens.to(torch.int32)
         eng = self.engine
         eng.training = self.training
-        eng.seed = self.dropout_seed * 7919 + self.num_updates
+        # per-update variation comes from the device seed tensor when a trainer installed one (graph-replay safe)
+        eng.seed = self.dropout_seed if _ops._SEED_T is not None else self.dropout_seed * 7919 + self.num_updates
         if self.training:
             for l in self.layers:
                 if hasattr(l, "conv_module"):

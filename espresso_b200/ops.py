@@ -19,6 +19,21 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# Device-resident seed increment (uint64/int64 tensor of 1 element) added to every op's seed inside the
+# kernels.  The trainer bumps it once per update; because the kernels read it from memory, a captured CUDA
+# graph of the whole step replays with fresh dropout masks.
+_SEED_T = None
+
+
+def set_seed_tensor(t):
+    global _SEED_T
+    _SEED_T = t
+
+
+def _seed_ptr():
+    return None if _SEED_T is None else C.c_void_p(_SEED_T.data_ptr())
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -59,6 +74,7 @@ def gemm(A, B, C_out, M, N, K, lda, ldb, ldc, *, a_kmajor=True, b_kmajor=True, n
     g.act, g.drop_mode, g.skew_r, g.tile_n = act, drop_mode, skew_r, tile_n
     g.alpha, g.beta, g.drop_p = alpha, beta, drop_p
     g.seed = seed
+    g.seed_ptr = _SEED_T.data_ptr() if (_SEED_T is not None and drop_p > 0) else None
     _lib.check(_lib.load().esp_gemm_bf16(C.byref(g), _stream()))
     return C_out
 
@@ -152,7 +168,7 @@ def layer_norm_fwd(x, gamma, beta, eps=1e-5, lens=None, T=0, drop_p=0.0, seed=0)
     mean = torch.empty(R, device=x.device, dtype=torch.float32)
     rstd = torch.empty(R, device=x.device, dtype=torch.float32)
     _lib.check(_lib.load().esp_layer_norm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), eps, R, d, _ptr(y), _ptr(mean), _ptr(rstd),
-                                              _ptr(lens), T, drop_p, seed, _stream()))
+                                              _ptr(lens), T, drop_p, seed, _seed_ptr(), _stream()))
     return y, mean, rstd
 
 
@@ -165,7 +181,7 @@ def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, l
     dx = torch.empty_like(x)
     _lib.check(_lib.load().esp_layer_norm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), R, d,
                                               _ptr(dx), _ptr(dgamma_acc), _ptr(dbeta_acc), _ptr(lens), T, drop_p, seed,
-                                              _stream()))
+                                              _seed_ptr(), _stream()))
     return dx
 
 
@@ -186,7 +202,7 @@ def dropout(x, p, seed, scale=1.0, out=None):
     R, N = x.shape
     if out is None:
         out = torch.empty(R, N, device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.load().esp_dropout(_ptr(x), R, N, x.stride(0), out.stride(0), scale, p, seed, _ptr(out), _stream()))
+    _lib.check(_lib.load().esp_dropout(_ptr(x), R, N, x.stride(0), out.stride(0), scale, p, seed, _seed_ptr(), _ptr(out), _stream()))
     return out
 
 
@@ -227,7 +243,7 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
     assert T_ == T and scores.is_contiguous()
     p = torch.empty_like(scores)
     pd = torch.empty_like(scores) if drop_p > 0 else None
-    _lib.check(_lib.load().esp_attn_softmax_fwd(_ptr(scores), H, B, T, ld, _ptr(lens), _ptr(p), _ptr(pd), drop_p, seed, _stream()))
+    _lib.check(_lib.load().esp_attn_softmax_fwd(_ptr(scores), H, B, T, ld, _ptr(lens), _ptr(p), _ptr(pd), drop_p, seed, _seed_ptr(), _stream()))
     return p, (pd if pd is not None else p)
 
 
@@ -238,7 +254,7 @@ def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     H, B, T_, ld = p.shape
     ds = torch.empty_like(p)
     dbd = torch.empty(H, B, T, ldp, device=p.device, dtype=torch.bfloat16) if want_dbd else None
-    _lib.check(_lib.load().esp_attn_softmax_bwd(_ptr(p), _ptr(dp_drop), H, B, T, ld, _ptr(ds), _ptr(dbd), ldp, drop_p, seed, _stream()))
+    _lib.check(_lib.load().esp_attn_softmax_bwd(_ptr(p), _ptr(dp_drop), H, B, T, ld, _ptr(ds), _ptr(dbd), ldp, drop_p, seed, _seed_ptr(), _stream()))
     return ds, dbd
 
 
@@ -311,14 +327,14 @@ def sumsq(g, out):
 
 
 def adam_step(p32, m, v, g, p16, lr, beta1, beta2, eps, weight_decay, step, sumsq_t, denom_dev=None, denom_const=1.0,
-              clip_norm=0.0, gnorm_out=None):
+              clip_norm=0.0, gnorm_out=None, hyper_dev=None):
     _need_cuda(p32, m, v, g, p16, sumsq_t, denom_dev, gnorm_out)
     assert p32.dtype == m.dtype == v.dtype == g.dtype == torch.float32 and p16.dtype == torch.bfloat16
     n = p32.numel()
     assert m.numel() == n and v.numel() == n and p16.numel() == n and g.numel() >= n
     _lib.check(_lib.load().esp_adam_step(_ptr(p32), _ptr(m), _ptr(v), _ptr(g), _ptr(p16), n, lr, beta1, beta2, eps, weight_decay,
                                          step, _ptr(sumsq_t), _ptr(denom_dev), denom_const, clip_norm, _ptr(gnorm_out),
-                                         _stream()))
+                                         _ptr(hyper_dev), _stream()))
 
 
 def cast_f32_bf16(x, y):

@@ -62,6 +62,7 @@ typedef struct EspGemm {
   int32_t tile_n;    /* 0 auto, or 64/128/256 */
   float alpha, beta, drop_p;
   uint64_t seed;
+  const uint64_t* seed_ptr; /* optional DEVICE pointer: effective seed = seed + *seed_ptr (CUDA-graph replays) */
 } EspGemm;
 
 int esp_gemm_bf16(const EspGemm* g, void* stream);
@@ -114,15 +115,16 @@ int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride_t, int32_t
  * gradient `dres` into dx. */
 int esp_layer_norm_fwd(const void* x, const void* gamma, const void* beta, float eps, int64_t R, int32_t d,
                        void* y, float* mean, float* rstd, const int32_t* lens, int32_t T, float drop_p,
-                       uint64_t seed, void* stream);
+                       uint64_t seed, const uint64_t* seed_ptr, void* stream);
 int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                        const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
-                       const int32_t* lens, int32_t T, float drop_p, uint64_t seed, void* stream);
+                       const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                       void* stream);
 /* out[n] += scale * sum_r x[r,n]   (bias / pos_bias gradients) */
 int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream);
 /* y = dropout(x) * scale, same counter RNG / indexing (r*N+n) as the GEMM epilogue */
 int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
-                uint64_t seed, void* y, void* stream);
+                uint64_t seed, const uint64_t* seed_ptr, void* y, void* stream);
 /* zero rows t >= lens[b] of x [B,T,N] */
 int esp_mask_rows(void* x, const int32_t* lens, int32_t B, int32_t T, int32_t N, void* stream);
 /* q_u = (q+u)*s, q_v = (q+v)*s  (fairseq/modules/multihead_attention.py:679-688) and the backward sum */
@@ -134,9 +136,10 @@ int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int64_t R, int3
  * copy (fairseq/modules/multihead_attention.py:841-876); backward also scatters dS into the skewed
  * relative-position layout dBD[., i, (T-1)-i+j] (inverse of :824-830). */
 int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
-                         void* p, void* p_drop, float drop_p, uint64_t seed, void* stream);
+                         void* p, void* p_drop, float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
-                         void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, void* stream);
+                         void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                         void* stream);
 /* Conformer convolution module body (fairseq/modules/conformer_layer.py:88-96):
  *   y = depthwise_conv_k(GLU(g)) with 'same' zero padding over the padded length T, g [B,T,2C], w [C,k];
  *   stats (double [2,C], +=): per-channel sum and sum of squares of y for BatchNorm1d batch statistics.
@@ -157,10 +160,13 @@ int esp_bn_silu_bwd(const void* dz, const void* y, int64_t R, int32_t C, const f
  *      fairseq/utils.py:347-397) ---------------------------------------------------------------- */
 int esp_sumsq_f32(const float* g, int64_t n, float* out, void* stream);
 /* g_eff = g / denom * clip_coef, denom read from device memory if denom_dev != NULL (the all-reduced
- * sample_size in the gradient buffer's tail), else denom_const.  Writes fp32 master + bf16 model params. */
+ * sample_size in the gradient buffer's tail), else denom_const.  hyper_dev (optional DEVICE float[2] =
+ * {lr, step}) overrides the by-value lr/step so a captured CUDA graph can be replayed with a new schedule
+ * value.  Writes fp32 master + bf16 model params. */
 int esp_adam_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
-                  const float* denom_dev, float denom_const, float clip_norm, float* gnorm_out, void* stream);
+                  const float* denom_dev, float denom_const, float clip_norm, float* gnorm_out,
+                  const float* hyper_dev, void* stream);
 int esp_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream);
 int esp_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream);
 

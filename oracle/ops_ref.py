@@ -227,9 +227,15 @@ def sumsq(g, out):
     return out
 
 
+def set_seed_tensor(t):
+    pass
+
+
 def adam_step(p32, m, v, g, p16, lr, beta1, beta2, eps, weight_decay, step, sumsq_t, denom_dev=None, denom_const=1.0,
-              clip_norm=0.0, gnorm_out=None):
+              clip_norm=0.0, gnorm_out=None, hyper_dev=None):
     n = p32.numel()
+    if hyper_dev is not None:
+        lr, step = float(hyper_dev[0]), float(hyper_dev[1])
     denom = float(denom_dev.item()) if denom_dev is not None else denom_const
     gscale = 1.0 / denom if denom > 0 else 0.0
     gnorm = float(sumsq_t.item()) ** 0.5 * gscale
