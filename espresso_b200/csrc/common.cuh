@@ -66,24 +66,31 @@ __device__ __forceinline__ float silu_gradf_(float x) {
   return s * (1.f + x * (1.f - s));
 }
 
-// ---- counter-based RNG for dropout: one 32-bit hash per element ------------------------------
-// Stateless: the backward pass regenerates the identical mask from (seed, element index), so
-// dropout masks are never stored in HBM.  (Philox-like mixing; murmur3 finaliser over a 64-bit
-// counter keyed by the seed.)
-__device__ __forceinline__ uint32_t esp_hash_u32(uint64_t seed, uint64_t idx) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+// ---- counter-based RNG for dropout ---------------------------------------------------------------
+// Stateless: the backward pass regenerates the identical mask from (seed, logical element index), so
+// dropout masks are never stored in HBM.  One 64-bit hash (splitmix64 finaliser keyed by the seed) yields
+// FOUR 16-bit lanes = the keep decisions of elements 4g..4g+3, so a kernel that walks 4 (or 32)
+// consecutive elements pays one hash per 4 elements.  p is quantised to 1/65536 and the rescale uses the
+// quantised keep probability, so E[dropout(x)] = x exactly.
+__host__ __device__ __forceinline__ unsigned long long esp_hash_u64(unsigned long long seed, unsigned long long g) {
+  unsigned long long z = g + seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  return z ^ (z >> 31);
 }
-// keep-decision: keep iff hash >= p * 2^32
-__device__ __forceinline__ bool esp_dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-  return esp_hash_u32(seed, idx) >= thresh;
+// keep-decision of element idx: its 16-bit lane of the group hash must be >= thresh (= round(p * 65536))
+__host__ __device__ __forceinline__ bool esp_dropout_keep(unsigned long long seed, unsigned long long idx, uint32_t thresh) {
+  const unsigned long long h = esp_hash_u64(seed, idx >> 2);
+  return (uint32_t)((h >> (16 * (idx & 3))) & 0xFFFFull) >= thresh;
 }
 static inline uint32_t esp_dropout_thresh(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
+}
+// 1 / (quantised keep probability)
+static inline float esp_dropout_scale(float p) {
+  if (!(p > 0.f)) return 1.f;
+  return (float)(65536.0 / (65536.0 - (double)esp_dropout_thresh(p)));
 }

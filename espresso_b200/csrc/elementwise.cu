@@ -59,7 +59,7 @@ ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const 
   const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
   const int nvec = d >> 3;
-  const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float drop_scale = drop_p > 0.f ? 65536.f / (65536.f - (float)drop_thresh) : 1.f;
   for (long r = warp0; r < R; r += nwarps) {
     const bf16* xr = x + r * d;
     float v[NV][8];
@@ -133,7 +133,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
   const long warp0 = (long)blockIdx.x * nw + (threadIdx.x >> 5);
   const long nwarps = (long)gridDim.x * nw;
   const int nvec = d >> 3;
-  const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float drop_scale = drop_p > 0.f ? 65536.f / (65536.f - (float)drop_thresh) : 1.f;
   float ag[NV][8], ab[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
@@ -250,7 +250,7 @@ dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, fl
                bf16* __restrict__ y) {
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const long nvec = R * (N >> 3);
-  const float ds = drop_p > 0.f ? scale / (1.f - drop_p) : scale;
+  const float ds = drop_p > 0.f ? scale * 65536.f / (65536.f - (float)thresh) : scale;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const long r = i / (N >> 3);
     const int c = (int)(i % (N >> 3)) * 8;
@@ -350,7 +350,7 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int 
   }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float ds = drop_p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
 #pragma unroll
   for (int i = 0; i < kSmMax; ++i) {
     const int j = lane + i * 32;
@@ -378,7 +378,7 @@ attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ 
   const long rows = (long)H * B * T;
   if (row >= rows) return;
   const int qi = (int)(row % T);
-  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float dscale = drop_p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
   float pv[kSmMax], dv[kSmMax];
   float dot = 0.f;
 #pragma unroll

@@ -27,7 +27,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue (2 per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 constexpr int kAccStages = 2;
 
 struct EpiParams {
@@ -38,7 +39,7 @@ struct EpiParams {
   const void* R;
   long ldc, ld_aux, ldr;
   long sC1, sC2, sAux1, sAux2, sR1, sR2;
-  int c_f32, r_f32, act, drop_mode, skew_r;
+  int c_f32, r_f32, act, drop_mode, skew_r, atomic;
   float alpha, beta, drop_scale;
   uint32_t drop_thresh;
   unsigned long long seed;
@@ -46,7 +47,7 @@ struct EpiParams {
 };
 
 struct KParams {
-  int M, N, K, nb1, nb2;
+  int M, N, K, nb1, nb2, ksplit;
   int a_b1, a_b2, b_b1, b_b2;  // 0 => operand is broadcast along that batch dim
   EpiParams ep;
 };
@@ -140,13 +141,64 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   return d;
 }
 
-__device__ __forceinline__ float apply_act(float v, float u, int act) {
-  switch (act) {
-    case ESP_ACT_RELU: return fmaxf(v, 0.f);
-    case ESP_ACT_SILU: return siluf_(v);
-    case ESP_ACT_RELU_BWD: return u > 0.f ? v : 0.f;
-    case ESP_ACT_SILU_BWD: return v * silu_gradf_(u);
-    default: return v;
+// sigmoid through the single-MUFU tanh approximation (|err| ~ 5e-4: below bf16 output resolution)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void load8f(const bf16* p, float* v) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  unpack_bf16x2(q.x, v[0], v[1]);
+  unpack_bf16x2(q.y, v[2], v[3]);
+  unpack_bf16x2(q.z, v[4], v[5]);
+  unpack_bf16x2(q.w, v[6], v[7]);
+}
+// 32 consecutive bf16 (vectorised when 16-byte aligned and fully in range)
+__device__ __forceinline__ void load32(const bf16* p, int valid, float* v) {
+  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) load8f(p + j, v + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = j < valid ? bf2f(p[j]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store32_bf16(bf16* p, int valid, const float* v) {
+  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o;
+      o.x = pack_bf16x2(v[j], v[j + 1]);
+      o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+      o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+      o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+      *reinterpret_cast<uint4*>(p + j) = o;
+    }
+  } else {
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) p[j] = f2bf(v[j]);
+  }
+}
+// dropout over 32 consecutive logical indices starting at idx0: one hash per 4 elements when aligned
+__device__ __forceinline__ void dropout32(float* v, unsigned long long seed, unsigned long long idx0, uint32_t thresh,
+                                          float scale) {
+  if ((idx0 & 3ull) == 0) {
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+      const unsigned long long h = esp_hash_u64(seed, (idx0 >> 2) + g4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t lane16 = (uint32_t)(h >> (16 * t)) & 0xFFFFu;
+        v[g4 * 4 + t] = lane16 >= thresh ? v[g4 * 4 + t] * scale : 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = esp_dropout_keep(seed, idx0 + j, thresh) ? v[j] * scale : 0.f;
   }
 }
 
@@ -184,8 +236,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_m = (p.M + BM - 1) / BM;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int nbatch = p.nb1 * p.nb2;
-  const int total_tiles = tiles_m * tiles_n * nbatch;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb_all = (p.K + BK - 1) / BK;
+  const int kb_per = (num_kb_all + p.ksplit - 1) / p.ksplit;
+  const int total_tiles = tiles_m * tiles_n * nbatch * p.ksplit;  // work items = output tiles x K splits
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -198,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -218,13 +271,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================ TMA producer =====================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int ks = work % p.ksplit;
+        const int tile = work / p.ksplit;
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(num_kb_all, kb0 + kb_per);
+        if (kb0 >= kb1) continue;  // empty K split (all three roles skip it identically)
         const int mt = tile % tiles_m;
         const int rest = tile / tiles_m;
         const int nt = rest % tiles_n;
         const int bt = rest / tiles_n;
         const int b1 = bt % p.nb1, b2 = bt / p.nb1;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
@@ -258,13 +316,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              ((B_K ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int ks = work % p.ksplit;
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(num_kb_all, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
         const int as = ti % kAccStages;
         const uint32_t aph = (ti / kAccStages) & 1;
+        ++ti;
         mbar_wait(tempty_bar(as), aph ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(full_bar(s), ph);
@@ -280,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     : make_sdesc(sa + k * 2048, BK * 128, 1024);
             const uint64_t db = B_K ? make_sdesc(sb + k * 32, 16, 1024)
                                     : make_sdesc(sb + k * 2048, BK * 128, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           tcgen05_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
         }
@@ -289,11 +352,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue =========================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the tile's columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BN / 32;          // 32-column chunks per tile
+    constexpr int kChunksPerWarp = kChunks / 2;
     const EpiParams& e = p.ep;
     const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int ks = work % p.ksplit;
+      const int tile = work / p.ksplit;
+      const int kb0 = ks * kb_per;
+      const int kb1 = min(num_kb_all, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
       const int mt = tile % tiles_m;
       const int rest = tile / tiles_m;
       const int nt = rest % tiles_n;
@@ -301,6 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b1 = bt % p.nb1, b2 = bt / p.nb1;
       const int as = ti % kAccStages;
       const uint32_t aph = (ti / kAccStages) & 1;
+      ++ti;
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
 
@@ -312,109 +385,95 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const unsigned long long rng_row = ((unsigned long long)bt * p.M + m) * (unsigned long long)p.N;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int c = half * kChunksPerWarp + cc;
         const int n0 = nt * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
-        if (row_ok) {
-          float v[32];
+        if (!row_ok) continue;
+        const int valid = p.N - n0;  // >= 1; >= 32 for a full chunk
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = (n0 + 32 <= p.N);
-          if (e.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (e.atomic) {
+          // split-K / gradient accumulation: C (fp32) += alpha * acc, vector reductions at L2
+          float* cp = (float*)e.C + c_off + n0;
+          if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(cp + j, v[j] * e.alpha, v[j + 1] * e.alpha, v[j + 2] * e.alpha, v[j + 3] * e.alpha);
+          } else {
             for (int j = 0; j < 32; ++j)
-              if (full || n0 + j < p.N) v[j] += bf2f(e.bias[n0 + j]);
+              if (j < valid) atomicAdd(cp + j, v[j] * e.alpha);
           }
-          if (e.C2) {
-            bf16* c2 = e.C2 + c_off + n0;
-            if (full && ((e.ldc & 7) == 0)) {
+          continue;
+        }
+        if (e.bias) {
+          float bv[32];
+          load32(e.bias + n0, valid, bv);
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]);
-                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(c2 + j) = o;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) c2[j] = f2bf(v[j]);
-            }
+          for (int j = 0; j < 32; ++j) v[j] += bv[j];
+        }
+        if (e.C2) store32_bf16(e.C2 + c_off + n0, valid, v);
+        if (e.drop_mode == 2) dropout32(v, seed, rng_row + n0, e.drop_thresh, e.drop_scale);
+        if (e.act == ESP_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+        } else if (e.act == ESP_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (e.act == ESP_ACT_SILU_BWD) {
+          float u[32];
+          load32(e.aux + aux_off + n0, valid, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sg = fast_sigmoid(u[j]);
+            v[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
           }
-          if (e.drop_mode == 2) {
+        } else if (e.act == ESP_ACT_RELU_BWD) {
+          float u[32];
+          load32(e.aux + aux_off + n0, valid, u);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = esp_dropout_keep(seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
-          }
-          if (e.act != ESP_ACT_NONE) {
-            if (e.act >= ESP_ACT_RELU_BWD) {
-              const bf16* ax = e.aux + aux_off + n0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float u = (full || n0 + j < p.N) ? bf2f(ax[j]) : 0.f;
-                v[j] = apply_act(v[j], u, e.act);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], 0.f, e.act);
-            }
-          }
-          if (e.drop_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = esp_dropout_keep(seed, rng_row + n0 + j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
+        }
+        if (e.drop_mode == 1) dropout32(v, seed, rng_row + n0, e.drop_thresh, e.drop_scale);
+        if (e.alpha != 1.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
-          if (e.R) {
-            if (e.skew_r) {
-              // Transformer-XL skew fused into the score GEMM: R is BD_full[row m, (skew_r-1)-m+n]
-              // (fairseq/modules/multihead_attention.py:824-830 as_strided trick).
-              const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += e.beta * bf2f(rr[j]);
-            } else if (e.r_f32) {
-              const float* rr = (const float*)e.R + r_off + n0;
+        }
+        if (e.R) {
+          if (e.skew_r) {
+            // Transformer-XL skew fused into the score GEMM: R is BD_full[row m, (skew_r-1)-m+n]
+            // (fairseq/modules/multihead_attention.py:824-830 as_strided trick).
+            const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || n0 + j < p.N) v[j] += e.beta * rr[j];
-            } else {
-              const bf16* rr = (const bf16*)e.R + r_off + n0;
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) v[j] += e.beta * bf2f(rr[j]);
+          } else if (e.r_f32) {
+            const float* rr = (const float*)e.R + r_off + n0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || n0 + j < p.N) v[j] += e.beta * bf2f(rr[j]);
-            }
-          }
-          if (e.c_f32) {
-            float* cp = (float*)e.C + c_off + n0;
-            if (full && ((e.ldc & 3) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) cp[j] = v[j];
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) v[j] += e.beta * rr[j];
           } else {
-            bf16* cp = (bf16*)e.C + c_off + n0;
-            if (full && ((e.ldc & 7) == 0)) {
+            float rv[32];
+            load32((const bf16*)e.R + r_off + n0, valid, rv);
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]);
-                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = o;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) cp[j] = f2bf(v[j]);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(e.beta, rv[j], v[j]);
           }
+        }
+        if (e.c_f32) {
+          float* cp = (float*)e.C + c_off + n0;
+          if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) cp[j] = v[j];
+          }
+        } else {
+          store32_bf16((bf16*)e.C + c_off + n0, valid, v);
         }
       }
       tcgen05_fence_before();
@@ -494,7 +553,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cuda
     ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int tiles = ((kp.M + BM - 1) / BM) * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2;
+  const int tiles = ((kp.M + BM - 1) / BM) * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2 * kp.ksplit;
   int grid = tiles < esp_num_sms() ? tiles : esp_num_sms();
   if (grid < 1) return 0;
   kfn<<<grid, kThreads, L::kTotal, st>>>(ta, tb, kp);
@@ -523,16 +582,32 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   const int nb1 = g->nb1 > 0 ? g->nb1 : 1, nb2 = g->nb2 > 0 ? g->nb2 : 1;
   CUtensorMap ta, tb;
   const bool ak = g->a_kmajor != 0, bk = g->b_kmajor != 0;
-  // tile width: wide tiles for wide N (better smem-bandwidth ratio), narrow when N is small or the
-  // tile count would not fill the machine.
-  int bn = 128;
-  {
-    long t128 = ((g->M + 127) / 128) * ((g->N + 127) / 128) * (long)nb1 * nb2;
+  // tile width: wide tiles have the best operand-bytes per flop (a 128 x BN tile reads (128+BN)*64*2 B from L2 per
+  // 128*BN*64*2 flop); narrow ones only when N is small or the machine would be badly under-filled.
+  const int sms = esp_num_sms();
+  const long tm = (g->M + BM - 1) / BM;
+  auto tiles_for = [&](int w) { return tm * ((g->N + w - 1) / w) * (long)nb1 * nb2; };
+  int bn;
+  int ksplit = 1;
+  const int num_kb = (int)((g->K + BK - 1) / BK);
+  if (g->accumulate) {
+    // gradient GEMMs: long reduction (K = rows of the batch), small output -> split K across CTAs and
+    // accumulate with vector reductions; keep >= 4 k-blocks per split.
+    bn = g->N >= 192 ? 256 : (g->N > 64 ? 128 : 64);
+    const long t = tiles_for(bn);
+    if (t < sms) {
+      ksplit = (int)((sms + t - 1) / t);
+      const int max_split = num_kb / 4 > 0 ? num_kb / 4 : 1;
+      if (ksplit > max_split) ksplit = max_split;
+    }
+  } else {
     if (g->N <= 64) bn = 64;
-    else if (g->N >= 256 && ((g->M + 127) / 128) * ((g->N + 255) / 256) * (long)nb1 * nb2 >= 2L * esp_num_sms()) bn = 256;
-    else if (t128 < esp_num_sms() && g->N > 64) bn = 64;
-    if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) bn = g->tile_n;
+    else if (g->N >= 192 && tiles_for(256) * 10 >= (long)sms * 8) bn = 256;
+    else if (g->N > 64 && tiles_for(128) * 10 >= (long)sms * 6) bn = 128;
+    else if (g->N >= 192 && tiles_for(256) * 2 >= tiles_for(128)) bn = 128;
+    else bn = g->N > 128 ? 128 : (g->N > 64 && tiles_for(64) < sms ? 64 : 128);
   }
+  if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) bn = g->tile_n;
   int rc;
   if (ak) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, nb1, g->sA1, nb2, g->sA2, BM);
   else    rc = make_tmap(&ta, g->A, g->M, g->K, g->lda, nb1, g->sA1, nb2, g->sA2, BK);
@@ -542,7 +617,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   if (rc) return rc;
 
   KParams kp;
-  kp.M = (int)g->M; kp.N = (int)g->N; kp.K = (int)g->K; kp.nb1 = nb1; kp.nb2 = nb2;
+  kp.M = (int)g->M; kp.N = (int)g->N; kp.K = (int)g->K; kp.nb1 = nb1; kp.nb2 = nb2; kp.ksplit = ksplit;
   kp.a_b1 = (nb1 > 1 && g->sA1 != 0) ? 1 : 0;
   kp.a_b2 = (nb2 > 1 && g->sA2 != 0) ? 1 : 0;
   kp.b_b1 = (nb1 > 1 && g->sB1 != 0) ? 1 : 0;
@@ -551,14 +626,15 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   e.C = g->C; e.C2 = (bf16*)g->C2; e.bias = (const bf16*)g->bias; e.aux = (const bf16*)g->aux; e.R = g->R;
   e.ldc = g->ldc; e.ld_aux = g->ld_aux; e.ldr = g->ldr;
   e.sC1 = g->sC1; e.sC2 = g->sC2; e.sAux1 = g->sAux1; e.sAux2 = g->sAux2; e.sR1 = g->sR1; e.sR2 = g->sR2;
-  e.c_f32 = g->c_f32; e.r_f32 = g->r_f32; e.act = g->act; e.skew_r = g->skew_r;
+  e.c_f32 = g->c_f32; e.r_f32 = g->r_f32; e.act = g->act; e.skew_r = g->skew_r; e.atomic = g->accumulate ? 1 : 0;
   e.drop_mode = (g->drop_p > 0.f) ? g->drop_mode : 0;
   e.alpha = g->alpha; e.beta = g->beta;
   e.drop_thresh = esp_dropout_thresh(g->drop_p);
-  e.drop_scale = g->drop_p > 0.f ? 1.f / (1.f - g->drop_p) : 1.f;
+  e.drop_scale = esp_dropout_scale(g->drop_p);
   e.seed = g->seed;
   e.seed_ptr = (const unsigned long long*)g->seed_ptr;
   ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
+  ESP_CHECK(!g->accumulate || g->c_f32, "accumulate (atomic) output must be fp32");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
   if (bn == 64) return dispatch_major<64>(ak, bk, ta, tb, kp, st);
   if (bn == 256) return dispatch_major<256>(ak, bk, ta, tb, kp, st);

@@ -24,7 +24,7 @@ class EspGemm(C.Structure):
         ("sR1", C.c_int64), ("sR2", C.c_int64),
         ("a_kmajor", C.c_int32), ("b_kmajor", C.c_int32), ("nb1", C.c_int32), ("nb2", C.c_int32),
         ("c_f32", C.c_int32), ("r_f32", C.c_int32), ("act", C.c_int32), ("drop_mode", C.c_int32),
-        ("skew_r", C.c_int32), ("tile_n", C.c_int32),
+        ("skew_r", C.c_int32), ("tile_n", C.c_int32), ("accumulate", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("drop_p", C.c_float),
         ("seed", C.c_uint64),
         ("seed_ptr", C.c_void_p),

@@ -104,7 +104,7 @@ class EncoderEngine:
         M, N = dy.shape
         K = x.shape[1]
         gW2 = gW.view(N, K)
-        _ops.gemm(dy, x, gW2, N, K, M, dy.stride(0), x.stride(0), K, a_kmajor=False, b_kmajor=False, R=gW2, ldr=K, beta=1.0)
+        _ops.gemm(dy, x, gW2, N, K, M, dy.stride(0), x.stride(0), K, a_kmajor=False, b_kmajor=False, accumulate=True)
 
     # ---- feed-forward module ----------------------------------------------------------------------
     def ffn_fwd(self, x, lp, names, act, alpha, li, opbase):

@@ -37,7 +37,8 @@ int64_t esp_launch_count(void);
  * Two batch dims (nb1 fastest) with per-operand strides; stride 0 broadcasts the operand.
  * Epilogue, in order: +bias[n]; C2=bf16(pre-activation); dropout(mode 2); activation
  * (ESP_ACT_*; *_BWD multiply by act'(aux)); dropout(mode 1); *alpha; +beta*R (R optionally read with
- * the Transformer-XL skew R[m,(skew_r-1)-m+n]); store bf16 or fp32.
+ * the Transformer-XL skew R[m,(skew_r-1)-m+n]); store bf16 or fp32.  With `accumulate`, the epilogue is
+ * C(fp32) += alpha*acc only (atomic, split-K).
  * Dropout is a stateless counter RNG keyed by (seed, logical element index): the backward pass
  * regenerates the forward mask, nothing is stored. */
 enum { ESP_ACT_NONE = 0, ESP_ACT_RELU = 1, ESP_ACT_SILU = 2, ESP_ACT_RELU_BWD = 3, ESP_ACT_SILU_BWD = 4 };
@@ -60,6 +61,7 @@ typedef struct EspGemm {
   int32_t drop_mode; /* 0 none, 1 after activation (forward), 2 before activation (backward) */
   int32_t skew_r;    /* 0, or T: read R with relative-position skew */
   int32_t tile_n;    /* 0 auto, or 64/128/256 */
+  int32_t accumulate; /* 1: C (fp32) += alpha*acc with L2 vector reductions; enables split-K (weight gradients) */
   float alpha, beta, drop_p;
   uint64_t seed;
   const uint64_t* seed_ptr; /* optional DEVICE pointer: effective seed = seed + *seed_ptr (CUDA-graph replays) */

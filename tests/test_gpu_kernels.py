@@ -239,3 +239,19 @@ def test_gemm_batched_and_skew(dev):
     j = torch.arange(T, device=dev)[None, :]
     skew = bd[..., : 2 * T - 1].float().gather(-1, ((T - 1) - i + j).expand(H, Bz, T, T))
     assert (sc[..., :T] - (ac + skew)).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 6500), (2048, 512, 3000), (5004, 512, 1806), (512, 2560, 777), (64, 31 * 8, 4000)])
+def test_gemm_accumulate_splitk(dev, M, N, K):
+    """Weight-gradient form: C(fp32) += A^T B with both operands MN-major, split-K + vector reductions."""
+    from espresso_b200 import ops
+
+    torch.manual_seed(M + K)
+    dy = torch.randn(K, M, device=dev).bfloat16()  # [rows, N_out]  (A logical [M, K] = dy^T)
+    x = torch.randn(K, N, device=dev).bfloat16()
+    c = torch.full((M, N), 2.0, device=dev, dtype=torch.float32)
+    ops.gemm(dy, x, c, M, N, K, M if M % 8 == 0 else dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True)
+    ref = 2.0 + dy.float().t() @ x.float()
+    assert (c - ref).abs().max().item() <= 3e-3 * K ** 0.5 + 1e-2
+    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, alpha=-1.0)
+    assert (c - 2.0).abs().max().item() <= 6e-3 * K ** 0.5 + 2e-2
