@@ -319,8 +319,21 @@ qprep_bwd_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, flo
 // attention softmax over keys with key-padding mask; one warp per (head, batch, query) row
 // scores layout [H, B, T, ld] bf16.  T <= 32*kSmMax.
 // ================================================================================================
-constexpr int kSmMax = 36;  // up to 1152 keys per row (36 s of audio after 4x subsampling = 900)
+constexpr int kSmMaxT = 1280;  // keys per row (36 s of audio after 4x subsampling = 900)
 
+// keep decisions of 8 consecutive elements whose first logical index idx0 is a multiple of 4
+__device__ __forceinline__ void keep8(unsigned long long seed, unsigned long long idx0, uint32_t thresh, bool (&k)[8]) {
+  const unsigned long long h0 = esp_hash_u64(seed, idx0 >> 2), h1 = esp_hash_u64(seed, (idx0 >> 2) + 1);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    k[t] = ((uint32_t)(h0 >> (16 * t)) & 0xFFFFu) >= thresh;
+    k[4 + t] = ((uint32_t)(h1 >> (16 * t)) & 0xFFFFu) >= thresh;
+  }
+}
+
+// Each lane owns NI groups of 8 consecutive keys: j = (i*32 + lane)*8 + e.  Dropout indices are row*ld + j
+// (ld % 8 == 0, so every group is hash-aligned).
+template <int NI>
 __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int ld, const int* __restrict__ lens,
                         bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
@@ -331,36 +344,47 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int 
   const long rows = (long)H * B * T;
   if (row >= rows) return;
   const int b = (int)((row / T) % B);
-  const int klen = lens ? lens[b] : T;
+  const int klen = lens ? min(lens[b], T) : T;
   const bf16* sr = s_in + row * ld;
-  float v[kSmMax];
+  float v[NI][8];
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < kSmMax; ++i) {
-    const int j = lane + i * 32;
-    v[i] = (j < klen && j < T) ? bf2f(sr[j]) : -INFINITY;  // key_padding_mask -> -inf (:848-854)
-    mx = fmaxf(mx, v[i]);
+  for (int i = 0; i < NI; ++i) {
+    const int j = (i * 32 + lane) * 8;
+    if (j < ld) load8(sr + j, v[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[i][e] = (j + e < klen) ? v[i][e] : -INFINITY;  // key_padding_mask -> -inf (:848-854)
+      mx = fmaxf(mx, v[i][e]);
+    }
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSmMax; ++i) {
-    v[i] = (v[i] == -INFINITY) ? 0.f : __expf(v[i] - mx);
-    sum += v[i];
-  }
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[i][e] = (v[i][e] == -INFINITY) ? 0.f : __expf(v[i][e] - mx);
+      sum += v[i][e];
+    }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
   const float ds = drop_p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
 #pragma unroll
-  for (int i = 0; i < kSmMax; ++i) {
-    const int j = lane + i * 32;
+  for (int i = 0; i < NI; ++i) {
+    const int j = (i * 32 + lane) * 8;
     if (j < ld) {
       // softmax in fp32, result cast to the model dtype (fairseq/utils.py:514-525 + .type_as)
-      const bf16 pb = f2bf(j < T ? v[i] * inv : 0.f);
-      p_out[row * ld + j] = pb;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = bf2f(f2bf(v[i][e] * inv));
+      store8(p_out + row * ld + j, o);
       if (pd_out) {
-        const bool keep = esp_dropout_keep(seed, (unsigned long long)row * T + j, thresh);
-        pd_out[row * ld + j] = (j < T && keep) ? f2bf(bf2f(pb) * ds) : f2bf(0.f);
+        bool k[8];
+        keep8(seed, (unsigned long long)row * ld + j, thresh, k);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = k[e] ? o[e] * ds : 0.f;
+        store8(pd_out + row * ld + j, o);
       }
     }
   }
@@ -368,6 +392,7 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int 
 
 // dS = P * (dP - sum_j dP*P), dP = dropmask * dPd / (1-p);  also scatters dS into the skewed
 // relative-position layout dBD[row, (T-1) - i + j]  (zeros elsewhere).
+template <int NI>
 __global__ void __launch_bounds__(256)
 attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int T, int ld,
                         bf16* __restrict__ ds_out, bf16* __restrict__ dbd_out, int ldp, float drop_p,
@@ -379,36 +404,47 @@ attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ 
   if (row >= rows) return;
   const int qi = (int)(row % T);
   const float dscale = drop_p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
-  float pv[kSmMax], dv[kSmMax];
+  float pv[NI][8], dv[NI][8];
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSmMax; ++i) {
-    const int j = lane + i * 32;
-    pv[i] = 0.f;
-    dv[i] = 0.f;
-    if (j < T) {
-      pv[i] = bf2f(p_in[row * ld + j]);
-      float g = bf2f(dpd[row * ld + j]);
-      if (drop_p > 0.f) g = esp_dropout_keep(seed, (unsigned long long)row * T + j, thresh) ? g * dscale : 0.f;
-      dv[i] = g;
-      dot += g * pv[i];
+  for (int i = 0; i < NI; ++i) {
+    const int j = (i * 32 + lane) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pv[i][e] = dv[i][e] = 0.f;
+    if (j < ld) {
+      load8(p_in + row * ld + j, pv[i]);
+      load8(dpd + row * ld + j, dv[i]);
+      bool k[8];
+      if (drop_p > 0.f) keep8(seed, (unsigned long long)row * ld + j, thresh, k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (j + e >= T) { pv[i][e] = 0.f; dv[i][e] = 0.f; }
+        else if (drop_p > 0.f) dv[i][e] = k[e] ? dv[i][e] * dscale : 0.f;
+        dot += dv[i][e] * pv[i][e];
+      }
     }
   }
   dot = warp_sum(dot);
   bf16* dbd = dbd_out ? dbd_out + row * ldp : nullptr;
+  const int lo = (T - 1) - qi;  // dBD column of key j = 0
   if (dbd) {
     // zero the parts of the skewed row that no (i, j) maps to
-    const int lo = (T - 1) - qi;  // r of j = 0
     for (int r = lane; r < ldp; r += 32)
       if (r < lo || r >= lo + T) dbd[r] = f2bf(0.f);
   }
 #pragma unroll
-  for (int i = 0; i < kSmMax; ++i) {
-    const int j = lane + i * 32;
+  for (int i = 0; i < NI; ++i) {
+    const int j = (i * 32 + lane) * 8;
     if (j < ld) {
-      const bf16 o = f2bf(j < T ? pv[i] * (dv[i] - dot) : 0.f);
-      ds_out[row * ld + j] = o;
-      if (dbd && j < T) dbd[(T - 1) - qi + j] = o;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = pv[i][e] * (dv[i][e] - dot);
+      store8(ds_out + row * ld + j, o);
+      if (dbd) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (j + e < T) dbd[lo + j + e] = f2bf(o[e]);
+      }
     }
   }
 }
@@ -425,12 +461,14 @@ __global__ void __launch_bounds__(256)
 glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, int B, int T, int Cn, int ksz,
                       bf16* __restrict__ y, double* __restrict__ stats) {
   __shared__ float tile[kDwT + kDwMaxK - 1][kDwC + 1];
-  __shared__ float wsm[kDwC][kDwMaxK + 1];
   __shared__ float red[2][4][kDwC];
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 time groups
-  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i / ksz][i % ksz] = bf2f(w[(long)(c0 + i / ksz) * ksz + i % ksz]);
+  // each thread owns one channel: its taps live in registers (no shared-memory bank conflicts)
+  float wr[kDwMaxK];
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
   for (int r = tg; r < kDwT + ksz - 1; r += 4) {
     const int t = t0 + r - half;
     float v = 0.f;
@@ -448,7 +486,9 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
     const int t = t0 + tt;
     if (t >= T) break;
     float acc = 0.f;
-    for (int k = 0; k < ksz; ++k) acc = fmaf(tile[tt + k][cl], wsm[cl][k], acc);
+#pragma unroll
+    for (int k = 0; k < kDwMaxK; ++k)
+      if (k < ksz) acc = fmaf(tile[tt + k][cl], wr[k], acc);
     const bf16 ob = f2bf(acc);
     y[((long)b * T + t) * Cn + c0 + cl] = ob;
     const float of = bf2f(ob);
@@ -475,16 +515,16 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
                       int T, int Cn, int ksz, bf16* __restrict__ dg, float* __restrict__ dw) {
   extern __shared__ __align__(16) uint8_t dw_smem[];
   typedef float TileT[kDwC + 1];
-  typedef float WT[kDwMaxK + 1];
   TileT* dyt = reinterpret_cast<TileT*>(dw_smem);                       // dy at t0-half .. t0+63+half
   TileT* glt = dyt + (kDwT + kDwMaxK - 1);                              // glu at the same times
-  WT* wsm = reinterpret_cast<WT*>(glt + (kDwT + kDwMaxK - 1));          // [kDwC][kDwMaxK+1]
-  typedef float RedT[kDwC][kDwMaxK + 1];
-  RedT* dwred = reinterpret_cast<RedT*>(wsm + kDwC);                    // [4][kDwC][kDwMaxK+1]
+  typedef float RedT[kDwMaxK][kDwC];
+  RedT* dwred = reinterpret_cast<RedT*>(glt + (kDwT + kDwMaxK - 1));    // [4][k][channel]: conflict-free
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i / ksz][i % ksz] = bf2f(w[(long)(c0 + i / ksz) * ksz + i % ksz]);
+  float wr[kDwMaxK];
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
   for (int r = tg; r < kDwT + ksz - 1; r += 4) {
     const int t = t0 + r - half;
     float dv = 0.f, gl = 0.f;
@@ -502,7 +542,9 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
     const int t = t0 + tt;
     if (t >= T) break;
     float acc = 0.f;
-    for (int k = 0; k < ksz; ++k) acc = fmaf(dyt[tt + 2 * half - k][cl], wsm[cl][k], acc);  // dy[t - k + half]
+#pragma unroll
+    for (int k = 0; k < kDwMaxK; ++k)
+      if (k < ksz) acc = fmaf(dyt[tt + 2 * half - k][cl], wr[k], acc);  // dy[t - k + half]
     const bf16* row = g + ((long)b * T + t) * 2 * Cn;
     const float a = bf2f(row[c0 + cl]);
     const float sg = sigmoidf_(bf2f(row[Cn + c0 + cl]));
@@ -511,19 +553,23 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
     orow[Cn + c0 + cl] = f2bf(acc * a * sg * (1.f - sg));
   }
   // weight gradient: this CTA owns dy[t0 .. t0+63]; glu halo is already staged
-  for (int k = 0; k < ksz; ++k) {
-    float acc = 0.f;
-    for (int tt = tg; tt < kDwT; tt += 4) {
-      if (t0 + tt >= T) break;
-      acc = fmaf(dyt[tt + half][cl], glt[tt + k][cl], acc);  // dy[t] * glu[t + k - half]
-    }
-    dwred[tg][cl][k] = acc;
+  float acc[kDwMaxK];
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) acc[k] = 0.f;
+  for (int tt = tg; tt < kDwT; tt += 4) {
+    if (t0 + tt >= T) break;
+    const float d = dyt[tt + half][cl];
+#pragma unroll
+    for (int k = 0; k < kDwMaxK; ++k)
+      if (k < ksz) acc[k] = fmaf(d, glt[tt + k][cl], acc[k]);  // dy[t] * glu[t + k - half]
   }
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) dwred[tg][k][cl] = acc[k];
   __syncthreads();
   for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) {
-    const int c = i / ksz, k = i % ksz;
-    const float s = dwred[0][c][k] + dwred[1][c][k] + dwred[2][c][k] + dwred[3][c][k];
-    atomicAdd(&dw[(long)(c0 + c) * ksz + k], s);
+    const int k = i / kDwC, c = i % kDwC;
+    const float sacc = dwred[0][k][c] + dwred[1][k][c] + dwred[2][k][c] + dwred[3][k][c];
+    atomicAdd(&dw[(long)(c0 + c) * ksz + k], sacc);
   }
 }
 
@@ -551,10 +597,53 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long R, int
   }
 }
 
-// z = silu(bn(y))
+// Activation after BatchNorm: 1 = SiLU (Conformer conv module), 2 = ReLU (conv front end).
+__device__ __forceinline__ float bn_act(float bn, int act) { return act == 1 ? siluf_(bn) : fmaxf(bn, 0.f); }
+__device__ __forceinline__ float bn_act_grad(float bn, int act) { return act == 1 ? silu_gradf_(bn) : (bn > 0.f ? 1.f : 0.f); }
+
+// Thread mapping for per-channel reductions over x [R, C] (C/8 divides 256): a thread walks 16-byte vectors
+// with a stride that is a multiple of C/8, so it always sees the same 8 channels and accumulates in
+// registers; one shared-memory pass + one double atomic per channel per CTA finishes the job.
+// stats[c] += sum_r x[r,c] ; stats[C + c] += sum_r x[r,c]^2
 __global__ void __launch_bounds__(256)
-bn_silu_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __restrict__ mr,
-                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ z) {
+bn_stats_kernel(const bf16* __restrict__ x, long R, int Cn, double* __restrict__ stats) {
+  __shared__ float red[2][256][8];
+  const int cv = Cn >> 3;
+  const long nvec = R * cv;
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a1[j] += v[j];
+      a2[j] += v[j] * v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = a1[j];
+    red[1][threadIdx.x][j] = a2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < cv) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = threadIdx.x; k < 256; k += cv) {
+        s1 += red[0][k][j];
+        s2 += red[1][k][j];
+      }
+      atomicAdd(&stats[threadIdx.x * 8 + j], (double)s1);
+      atomicAdd(&stats[Cn + threadIdx.x * 8 + j], (double)s2);
+    }
+  }
+}
+
+// z = act(bn(y))
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __restrict__ mr,
+                  const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ z) {
   const long nvec = R * (Cn >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (Cn >> 3)) * 8;
@@ -565,65 +654,69 @@ bn_silu_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float bn = bf2f(f2bf((v[j] - mr[c + j]) * mr[Cn + c + j] * gm[j] + bt[j]));  // BN output is bf16
-      v[j] = siluf_(bn);
+      v[j] = bn_act(bn, act);
     }
     store8(z + i * 8, v);
   }
 }
 
-// pass 1 of BN+SiLU backward: s1[c] = sum dbn, s2[c] = sum dbn * xhat   (dbn = dz * silu'(bn))
+// pass 1 of BN+act backward: s1[c] = sum dbn, s2[c] = sum dbn * xhat   (dbn = dz * act'(bn))
 __global__ void __launch_bounds__(256)
-bn_silu_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
-                          const float* __restrict__ mr, const bf16* __restrict__ gamma,
-                          const bf16* __restrict__ beta, double* __restrict__ sums) {
-  const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int rl = threadIdx.x >> 5;
-  __shared__ float red[2][8][32][8];
+bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+                         const float* __restrict__ mr, const bf16* __restrict__ gamma,
+                         const bf16* __restrict__ beta, int act, double* __restrict__ sums) {
+  __shared__ float red[2][256][8];
+  const int cv = Cn >> 3;
+  const long nvec = R * cv;
   float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cv * 8 < Cn) {
-    const int c = cv * 8;
-    float gm[8], bt[8];
-    load8(gamma + c, gm);
-    load8(beta + c, bt);
-    for (long r = (long)blockIdx.y * 8 + rl; r < R; r += (long)gridDim.y * 8) {
-      float d[8], v[8];
-      load8(dz + r * Cn + c, d);
-      load8(y + r * Cn + c, v);
+  // grid stride is a multiple of cv => the channel group of this thread is fixed
+  const int c = (int)(((long)blockIdx.x * 256 + threadIdx.x) % cv) * 8;
+  float gm[8], bt[8], mean[8], rstd[8];
+  load8(gamma + c, gm);
+  load8(beta + c, bt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (v[j] - mr[c + j]) * mr[Cn + c + j];
-        const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
-        const float dbn = d[j] * silu_gradf_(bn);
-        a1[j] += dbn;
-        a2[j] += dbn * xh;
-      }
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = mr[c + j];
+    rstd[j] = mr[Cn + c + j];
+  }
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+    float d[8], v[8];
+    load8(dz + i * 8, d);
+    load8(y + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v[j] - mean[j]) * rstd[j];
+      const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
+      const float dbn = d[j] * bn_act_grad(bn, act);
+      a1[j] += dbn;
+      a2[j] += dbn * xh;
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[0][rl][threadIdx.x & 31][j] = a1[j];
-    red[1][rl][threadIdx.x & 31][j] = a2[j];
+    red[0][threadIdx.x][j] = a1[j];
+    red[1][threadIdx.x][j] = a2[j];
   }
   __syncthreads();
-  if (rl == 0 && cv * 8 < Cn) {
+  if (threadIdx.x < cv) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float s1 = 0.f, s2 = 0.f;
-      for (int k = 0; k < 8; ++k) {
-        s1 += red[0][k][threadIdx.x & 31][j];
-        s2 += red[1][k][threadIdx.x & 31][j];
+      for (int k = threadIdx.x; k < 256; k += cv) {
+        s1 += red[0][k][j];
+        s2 += red[1][k][j];
       }
-      atomicAdd(&sums[cv * 8 + j], (double)s1);
-      atomicAdd(&sums[Cn + cv * 8 + j], (double)s2);
+      atomicAdd(&sums[threadIdx.x * 8 + j], (double)s1);
+      atomicAdd(&sums[Cn + threadIdx.x * 8 + j], (double)s2);
     }
   }
 }
 
 // pass 2: dy = gamma * rstd * (dbn - s1/n - xhat * s2/n)
 __global__ void __launch_bounds__(256)
-bn_silu_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
-                         const float* __restrict__ mr, const double* __restrict__ sums,
-                         const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ dy) {
+bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+                        const float* __restrict__ mr, const double* __restrict__ sums,
+                        const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ dy) {
   const long nvec = R * (Cn >> 3);
   const float invn = 1.f / (float)R;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
@@ -638,7 +731,7 @@ bn_silu_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
       const float rstd = mr[Cn + c + j];
       const float xh = (v[j] - mr[c + j]) * rstd;
       const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
-      const float dbn = d[j] * silu_gradf_(bn);
+      const float dbn = d[j] * bn_act_grad(bn, act);
       const float m1 = (float)sums[c + j] * invn, m2 = (float)sums[Cn + c + j] * invn;
       o[j] = gm[j] * rstd * (dbn - m1 - xh * m2);
     }
@@ -763,15 +856,22 @@ extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, in
                                     void* p, void* p_drop, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
                                     void* stream) {
   ESP_ST;
-  ESP_CHECK(T <= 32 * kSmMax, "attention length %d exceeds the register softmax limit %d", T, 32 * kSmMax);
-  ESP_CHECK(ld >= T && ld <= 32 * kSmMax, "bad score row stride");
+  ESP_CHECK(T <= kSmMaxT, "attention length %d exceeds the register softmax limit %d", T, kSmMaxT);
+  ESP_CHECK(ld >= T && ld <= kSmMaxT && ld % 8 == 0, "bad score row stride %d", ld);
   ESP_CHECK(drop_p <= 0.f || p_drop != nullptr, "dropout requested but p_drop is null");
   const long rows = (long)H * B * T;
   if (rows == 0) return 0;
-  attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)scores, H, B, T, ld, lens, (bf16*)p,
-                                                                      drop_p > 0.f ? (bf16*)p_drop : nullptr, drop_p,
-                                                                      esp_dropout_thresh(drop_p), seed,
-                                                                      (const unsigned long long*)seed_ptr);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  bf16* pd = drop_p > 0.f ? (bf16*)p_drop : nullptr;
+#define ESP_SMF(NI)                                                                                           \
+  attn_softmax_fwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)scores, H, B, T, ld, lens, (bf16*)p, pd, drop_p, \
+                                                    esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
+  if (ld <= 256) ESP_SMF(1);
+  else if (ld <= 512) ESP_SMF(2);
+  else if (ld <= 768) ESP_SMF(3);
+  else if (ld <= 1024) ESP_SMF(4);
+  else ESP_SMF(5);
+#undef ESP_SMF
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -781,14 +881,21 @@ extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t 
                                     void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
                                     void* stream) {
   ESP_ST;
-  ESP_CHECK(T <= 32 * kSmMax && ld >= T && ld <= 32 * kSmMax, "bad attention softmax-bwd shape");
+  ESP_CHECK(T <= kSmMaxT && ld >= T && ld <= kSmMaxT && ld % 8 == 0, "bad attention softmax-bwd shape");
   ESP_CHECK(dbd == nullptr || ldp >= 2 * T - 1, "dBD row stride too small");
   const long rows = (long)H * B * T;
   if (rows == 0) return 0;
-  attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, T, ld,
-                                                                      (bf16*)ds, (bf16*)dbd, ldp, drop_p,
-                                                                      esp_dropout_thresh(drop_p), seed,
-                                                                      (const unsigned long long*)seed_ptr);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+#define ESP_SMB(NI)                                                                                              \
+  attn_softmax_bwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, T, ld, (bf16*)ds, \
+                                                    (bf16*)dbd, ldp, drop_p, esp_dropout_thresh(drop_p), seed,  \
+                                                    (const unsigned long long*)seed_ptr)
+  if (ld <= 256) ESP_SMB(1);
+  else if (ld <= 512) ESP_SMB(2);
+  else if (ld <= 768) ESP_SMB(3);
+  else if (ld <= 1024) ESP_SMB(4);
+  else ESP_SMB(5);
+#undef ESP_SMB
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -813,7 +920,7 @@ extern "C" int esp_glu_dwconv_bwd(const void* dy, const void* g, const void* w, 
   ESP_CHECK(C % kDwC == 0 && (ksz & 1) && ksz <= kDwMaxK, "unsupported depthwise conv shape");
   if ((long)B * T == 0) return 0;
   dim3 grid((T + kDwT - 1) / kDwT, C / kDwC, B);
-  constexpr size_t kSmem = sizeof(float) * (2 * (kDwT + kDwMaxK - 1) * (kDwC + 1) + 5 * kDwC * (kDwMaxK + 1));
+  constexpr size_t kSmem = sizeof(float) * (2 * (kDwT + kDwMaxK - 1) * (kDwC + 1) + 4 * kDwMaxK * kDwC);
   static bool cfg = false;
   if (!cfg) {
     ESP_CUDA(cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
@@ -836,31 +943,51 @@ extern "C" int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float 
   return 0;
 }
 
-extern "C" int esp_bn_silu_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
-                               void* z, void* stream) {
+// grid whose total thread count is a multiple of C/8 (needed by the fixed-channel-group reductions)
+static inline int bn_reduce_grid(long nvec) {
+  long g = (nvec + 255) / 256;
+  long cap = (long)esp_num_sms() * 8;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+extern "C" int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, void* stream) {
   ESP_ST;
-  ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
+  ESP_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_stats: C/8 must divide 256 (got C=%d)", C);
   if (R == 0) return 0;
-  bn_silu_fwd_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)y, R, C, mr, (const bf16*)gamma,
-                                                                 (const bf16*)beta, (bf16*)z);
+  bn_stats_kernel<<<bn_reduce_grid(R * (C / 8)), 256, 0, st>>>((const bf16*)x, R, C, stats);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
-extern "C" int esp_bn_silu_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
-                               const void* beta, double* sums, void* dy, float* dgamma, float* dbeta, void* stream) {
+extern "C" int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
+                              int32_t act, void* z, void* stream) {
   ESP_ST;
   ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
+  ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
+  if (R == 0) return 0;
+  bn_act_fwd_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)y, R, C, mr, (const bf16*)gamma,
+                                                                (const bf16*)beta, act, (bf16*)z);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
+                              const void* beta, int32_t act, double* sums, void* dy, float* dgamma, float* dbeta,
+                              void* stream) {
+  ESP_ST;
+  ESP_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_act_bwd: C/8 must divide 256 (got C=%d)", C);
+  ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
   if (R == 0) return 0;
   ESP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
-  dim3 grid((C / 8 + 31) / 32, (unsigned)((R + 255) / 256 > 1024 ? 1024 : (R + 255) / 256));
-  if (grid.y < 1) grid.y = 1;
-  bn_silu_bwd_reduce_kernel<<<grid, 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, (const bf16*)gamma,
-                                                  (const bf16*)beta, sums);
+  bn_act_bwd_reduce_kernel<<<bn_reduce_grid(R * (C / 8)), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr,
+                                                                       (const bf16*)gamma, (const bf16*)beta, act, sums);
   ESP_LAUNCH_CHECK();
-  bn_silu_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, sums,
-                                                                       (const bf16*)gamma, (const bf16*)beta, (bf16*)dy);
+  bn_act_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, sums,
+                                                                      (const bf16*)gamma, (const bf16*)beta, act,
+                                                                      (bf16*)dy);
   ESP_LAUNCH_CHECK();
   int n = 2;
   if (dgamma && dbeta) {

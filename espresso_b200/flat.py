@@ -19,7 +19,7 @@ ALIGN = 64  # elements; keeps every tensor 128-byte aligned in both the bf16 and
 
 
 class FlatParams:
-    def __init__(self, module: torch.nn.Module, groups=(), device=None):
+    def __init__(self, module: torch.nn.Module, groups=(), device=None, channels_last=()):
         """Re-home every parameter of `module` into one flat bf16 buffer.
 
         groups: iterable of name lists that must be laid out back to back (e.g. q/k/v projection weights,
@@ -59,27 +59,32 @@ class FlatParams:
         self.p16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=dev)
         self.g32 = torch.zeros(self.numel + TAIL, dtype=torch.float32, device=dev)
         self.p32 = None  # allocated lazily by the optimizer
+        # 4-D conv weights listed in `channels_last` keep their logical [O, I, kh, kw] shape (state_dict unchanged)
+        # but are stored O,kh,kw,I in the flat buffers, so cuDNN runs NHWC kernels without layout transposes.
+        self.channels_last = set(channels_last)
         for n in order:
             p = named[n]
-            view = self.p16[self.offsets[n]: self.offsets[n] + p.numel()].view(p.shape)
+            view = self._view(self.p16, n)
             view.copy_(p.data.to(device=dev, dtype=torch.bfloat16))
             p.data = view
         self.module = module
 
     # ---- views --------------------------------------------------------------------------------
-    def param(self, name):
+    def _view(self, buf, name):
         o, s = self.offsets[name], self.shapes[name]
         n = 1
         for d in s:
             n *= d
-        return self.p16[o: o + n].view(s)
+        flat = buf[o: o + n]
+        if name in self.channels_last and len(s) == 4:
+            return flat.view(s[0], s[2], s[3], s[1]).permute(0, 3, 1, 2)
+        return flat.view(s)
+
+    def param(self, name):
+        return self._view(self.p16, name)
 
     def grad(self, name):
-        o, s = self.offsets[name], self.shapes[name]
-        n = 1
-        for d in s:
-            n *= d
-        return self.g32[o: o + n].view(s)
+        return self._view(self.g32, name)
 
     def span(self, buf, names, shape):
         """One view covering adjacent parameters (asserts adjacency)."""

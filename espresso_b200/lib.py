@@ -59,8 +59,9 @@ SIGNATURES = {
     "esp_glu_dwconv_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_glu_dwconv_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_bn_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _i32, _vp, _vp]),
-    "esp_bn_silu_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "esp_bn_silu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "esp_bn_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "esp_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "esp_bn_act_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "esp_sumsq_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "esp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _vp, _vp]),

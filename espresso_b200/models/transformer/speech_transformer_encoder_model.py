@@ -123,10 +123,39 @@ class _TransformerLayer(nn.Module):
         self.final_layer_norm = _Affine(d)
 
 
+class _BNReLUFn(torch.autograd.Function):
+    """BatchNorm2d (batch statistics) + ReLU on a channels-last activation, forward and backward in the native
+    kernels (esp_bn_stats / esp_bn_finalize / esp_bn_act_fwd / esp_bn_act_bwd).  x is [B, C, T, F] with
+    channels_last strides, i.e. memory [B, T, F, C]."""
+
+    @staticmethod
+    def forward(ctx, x, bn, gw, gb, training):
+        xr = x.permute(0, 2, 3, 1)  # [B, T, F, C] contiguous view
+        assert xr.is_contiguous()
+        C = xr.shape[-1]
+        R = xr.numel() // C
+        stats = _ops.bn_stats(xr, C) if training else None
+        mr = _ops.bn_finalize(stats, R, C, 1e-5, 0.1, bn.running_mean, bn.running_var, training)
+        z = _ops.bn_act_fwd(xr, mr, bn.weight.data, bn.bias.data, _ops.BN_ACT_RELU)
+        ctx.save_for_backward(xr, mr)
+        ctx.bn, ctx.gw, ctx.gb = bn, gw, gb
+        return z.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dz):
+        xr, mr = ctx.saved_tensors
+        dzr = dz.permute(0, 2, 3, 1).contiguous()
+        dx = _ops.bn_act_bwd(dzr, xr, mr, ctx.bn.weight.data, ctx.bn.bias.data, ctx.gw, ctx.gb, _ops.BN_ACT_RELU)
+        return dx.permute(0, 3, 1, 2), None, None, None, None
+
+
 class ConvBNReLU(nn.Module):
     """espresso/modules/speech_convolutions.py:20-102.  (Conv2d 3x3 -> BatchNorm2d -> ReLU) x N, then
-    [B, C, T', F'] -> [B, T', C*F'] with padded frames zeroed.  Round 1: this 3%-of-FLOPs stack still calls
-    cuDNN through torch (see DESIGN.md "not yet native"); everything after it is espresso_b200 kernels."""
+    [B, C, T', F'] -> [B, T', C*F'].  Activations and conv weights are kept channels-last; BatchNorm + ReLU
+    (forward, backward, running statistics) run in the native kernels.  The 3x3 convolutions themselves still
+    go to cuDNN through torch this round (DESIGN.md "not yet native").  The reference's zeroing of padded
+    frames at this point (:97-100) is dropped: the encoder zeroes the same rows again after fc0 /
+    layernorm_embedding (speech_transformer_encoder.py:354-357), which makes the first one a no-op."""
 
     def __init__(self, out_channels, kernel_sizes, strides, in_channels=1):
         super().__init__()
@@ -138,8 +167,10 @@ class ConvBNReLU(nn.Module):
             k = tuple(k) if isinstance(k, (list, tuple)) else (k, k)
             s = tuple(s) if isinstance(s, (list, tuple)) else (s, s)
             self.convolutions.append(nn.Conv2d(cin, c, k, stride=s, padding=((k[0] - 1) // 2, (k[1] - 1) // 2)))
-            self.batchnorms.append(nn.BatchNorm2d(c))
+            self.batchnorms.append(_BN(c))
             cin = c
+        self.flat = None
+        self.flat_prefix = ""
 
     def output_lengths(self, in_lengths):
         out = in_lengths
@@ -150,12 +181,20 @@ class ConvBNReLU(nn.Module):
 
     def forward(self, src, src_lengths):
         x = src.view(src.size(0), src.size(1), self.in_channels, src.size(2) // self.in_channels).transpose(1, 2)
-        for conv, bn in zip(self.convolutions, self.batchnorms):
-            x = F.relu(bn(conv(x)))
-        x = x.transpose(1, 2).contiguous()
+        x = x.contiguous(memory_format=torch.channels_last)
+        for i, (conv, bn) in enumerate(zip(self.convolutions, self.batchnorms)):
+            x = conv(x)
+            if not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
+            gw = self.flat.grad(self.flat_prefix + "batchnorms.%d.weight" % i)
+            gb = self.flat.grad(self.flat_prefix + "batchnorms.%d.bias" % i)
+            if self.training:
+                bn.num_batches_tracked += 1
+            x = _BNReLUFn.apply(x, bn, gw, gb, self.training)
+        # B x C x T' x F' -> B x T' x (C * F')   (channel-major inner index, as in the reference)
+        x = x.permute(0, 2, 1, 3).contiguous()
         x = x.view(x.size(0), x.size(1), x.size(2) * x.size(3))
-        x_lengths = self.output_lengths(src_lengths)
-        return x, x_lengths
+        return x, self.output_lengths(src_lengths)
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -219,11 +258,13 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         for i in range(len(self.layers)):
             groups.append(["layers.%d.self_attn.%s_proj.weight" % (i, c) for c in "qkv"])
             groups.append(["layers.%d.self_attn.%s_proj.bias" % (i, c) for c in "qkv"])
-        self.flat = FlatParams(self, groups=groups, device=device)
-        for m in self.modules():  # floating buffers of the torch conv front follow the model dtype (model.bfloat16())
-            if isinstance(m, nn.BatchNorm2d):
-                m.running_mean.data = m.running_mean.data.to(torch.bfloat16)
-                m.running_var.data = m.running_var.data.to(torch.bfloat16)
+        cl = [n for n, p in self.named_parameters() if n.startswith("pre_encoder.convolutions") and p.dim() == 4]
+        self.flat = FlatParams(self, groups=groups, device=device, channels_last=cl)
+        if self.pre_encoder is not None:
+            self.pre_encoder.flat, self.pre_encoder.flat_prefix = self.flat, "pre_encoder."
+            for bn in self.pre_encoder.batchnorms:  # running statistics stay fp32 (native BN kernels)
+                bn.running_mean.data = bn.running_mean.data.float()
+                bn.running_var.data = bn.running_var.data.float()
         e = self.cfg.encoder
         ecfg = dict(embed_dim=e.embed_dim, ffn_dim=e.ffn_embed_dim, heads=e.attention_heads, layers=e.layers,
                     layer_type=e.layer_type, dw_kernel=e.depthwise_conv_kernel_size, dropout=self.cfg.dropout,

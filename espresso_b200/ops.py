@@ -295,26 +295,47 @@ def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
     return mr
 
 
-def bn_silu_fwd(y, mr, gamma, beta):
+BN_ACT_SILU, BN_ACT_RELU = 1, 2
+
+
+def bn_stats(x, C_):
+    """Per-channel (sum, sum of squares) of channels-last x [..., C] -> double [2, C]."""
+    _need_cuda(x)
+    _bf(x)
+    assert x.is_contiguous() and x.shape[-1] == C_
+    stats = torch.zeros(2, C_, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().esp_bn_stats(_ptr(x), x.numel() // C_, C_, _ptr(stats), _stream()))
+    return stats
+
+
+def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU):
     _need_cuda(y, mr, gamma, beta)
     _bf(y, gamma, beta)
     assert y.is_contiguous()
     Cn = y.shape[-1]
     z = torch.empty_like(y)
-    _lib.check(_lib.load().esp_bn_silu_fwd(_ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(z), _stream()))
+    _lib.check(_lib.load().esp_bn_act_fwd(_ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act, _ptr(z), _stream()))
     return z
 
 
-def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU):
     _need_cuda(dz, y, mr, gamma, beta)
     _bf(dz, y, gamma, beta)
     assert dz.is_contiguous() and y.is_contiguous()
     Cn = y.shape[-1]
     sums = torch.empty(2, Cn, device=y.device, dtype=torch.float64)
     dy = torch.empty_like(y)
-    _lib.check(_lib.load().esp_bn_silu_bwd(_ptr(dz), _ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), _ptr(sums),
-                                           _ptr(dy), _ptr(dgamma_acc), _ptr(dbeta_acc), _stream()))
+    _lib.check(_lib.load().esp_bn_act_bwd(_ptr(dz), _ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act,
+                                          _ptr(sums), _ptr(dy), _ptr(dgamma_acc), _ptr(dbeta_acc), _stream()))
     return dy
+
+
+def bn_silu_fwd(y, mr, gamma, beta):
+    return bn_act_fwd(y, mr, gamma, beta, BN_ACT_SILU)
+
+
+def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+    return bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, BN_ACT_SILU)
 
 
 # ----------------------------------------------------------------------------------------------

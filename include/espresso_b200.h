@@ -146,17 +146,22 @@ int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t 
  *   y = depthwise_conv_k(GLU(g)) with 'same' zero padding over the padded length T, g [B,T,2C], w [C,k];
  *   stats (double [2,C], +=): per-channel sum and sum of squares of y for BatchNorm1d batch statistics.
  *   bn_finalize: mean / rstd (float [2,C]) from stats (training; also updates running stats with
- *   momentum, unbiased variance) or from the running stats (eval).  bn_silu: z = SiLU(BN(y)). */
+ *   momentum, unbiased variance) or from the running stats (eval). */
 int esp_glu_dwconv_fwd(const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz, void* y,
                        double* stats, void* stream);
 int esp_glu_dwconv_bwd(const void* dy, const void* g, const void* w, int32_t B, int32_t T, int32_t C, int32_t ksz,
                        void* dg, float* dw, void* stream);
 int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float eps, float momentum, float* run_mean,
                     float* run_var, int32_t training, float* mr, void* stream);
-int esp_bn_silu_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
-                    void* z, void* stream);
-int esp_bn_silu_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
-                    const void* beta, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
+/* Channels-last BatchNorm helpers shared by the Conformer conv module (act=1, SiLU; fairseq/modules/
+ * conformer_layer.py:95-96) and the conv front end (act=2, ReLU; espresso/modules/speech_convolutions.py:88-90,
+ * tensors kept NHWC so rows = B*T*F): per-channel statistics of x [R,C]; z = act(BN(y)); and the two-pass
+ * backward (sums = double[2,C] workspace; dgamma/dbeta fp32, +=). */
+int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, void* stream);
+int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
+                   int32_t act, void* z, void* stream);
+int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
+                   const void* beta, int32_t act, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
 
 /* ---- optimizer on flat buffers (fairseq/optim/fp16_optimizer.py:109-168, fairseq/optim/adam.py:150-239,
  *      fairseq/utils.py:347-397) ---------------------------------------------------------------- */

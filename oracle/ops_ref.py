@@ -207,23 +207,39 @@ def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
     return torch.stack([run_mean.float(), torch.rsqrt(run_var.float() + eps)])
 
 
-def bn_silu_fwd(y, mr, gamma, beta):
+BN_ACT_SILU, BN_ACT_RELU = 1, 2
+
+
+def bn_stats(x, C_):
+    xf = x.double().reshape(-1, C_)
+    return torch.stack([xf.sum(0), (xf * xf).sum(0)])
+
+
+def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU):
     bn = ((y.float() - mr[0]) * mr[1] * gamma.float() + beta.float()).to(BF).float()
-    return F.silu(bn).to(BF)
+    return (F.silu(bn) if act == BN_ACT_SILU else torch.relu(bn)).to(BF)
 
 
-def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU):
     Cn = y.shape[-1]
     yf = y.float().reshape(-1, Cn)
     xh = (yf - mr[0]) * mr[1]
     bn = (xh * gamma.float() + beta.float()).to(BF).float()
-    dbn = dz.float().reshape(-1, Cn) * _silu_grad(bn)
+    dbn = dz.float().reshape(-1, Cn) * (_silu_grad(bn) if act == BN_ACT_SILU else (bn > 0).float())
     s1, s2 = dbn.sum(0), (dbn * xh).sum(0)
     n = yf.shape[0]
     dy = gamma.float() * mr[1] * (dbn - s1 / n - xh * s2 / n)
     dgamma_acc += s2
     dbeta_acc += s1
     return dy.to(BF).reshape(y.shape)
+
+
+def bn_silu_fwd(y, mr, gamma, beta):
+    return bn_act_fwd(y, mr, gamma, beta, BN_ACT_SILU)
+
+
+def bn_silu_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc):
+    return bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, BN_ACT_SILU)
 
 
 def sumsq(g, out):

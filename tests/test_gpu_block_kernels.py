@@ -223,3 +223,29 @@ def test_optimizer_kernels(dev):
     z = torch.empty(1000, device=dev)
     ops.cast_bf16_f32(y, z)
     assert torch.equal(z, y.float())
+
+
+@pytest.mark.parametrize("R,C", [(5000, 64), (3333, 128), (777, 512)])
+def test_bn_relu_channels_last(dev, R, C):
+    """Conv-front BatchNorm2d + ReLU on NHWC activations (rows = B*T*F)."""
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(R)
+    x = (torch.randn(R, C) * 1.5 + 0.3).to(BF)
+    st = ops.bn_stats(x.to(dev), C)
+    _close(st, O.bn_stats(x, C), 1e-3, "bn_stats")
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    mr = ops.bn_finalize(st, R, C, 1e-5, 0.1, rm, rv, True)
+    gm, bt = (1 + 0.2 * torch.randn(C)).to(BF), (0.2 * torch.randn(C)).to(BF)
+    z = ops.bn_act_fwd(x.to(dev), mr, gm.to(dev), bt.to(dev), ops.BN_ACT_RELU)
+    zr = O.bn_act_fwd(x, mr.cpu(), gm, bt, O.BN_ACT_RELU)
+    _close(z, zr, 0.02, "bn relu")
+    dz = torch.randn(R, C).to(BF)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dx = ops.bn_act_bwd(dz.to(dev), x.to(dev), mr, gm.to(dev), bt.to(dev), dg, db, ops.BN_ACT_RELU)
+    dgr, dbr = torch.zeros(C), torch.zeros(C)
+    dxr = O.bn_act_bwd(dz, x, mr.cpu(), gm, bt, dgr, dbr, O.BN_ACT_RELU)
+    _close(dx, dxr, 0.03, "bn relu dx")
+    _close(dg, dgr, 0.02, "bn relu dgamma")
+    _close(db, dbr, 0.02, "bn relu dbeta")

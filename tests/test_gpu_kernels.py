@@ -247,10 +247,11 @@ def test_gemm_accumulate_splitk(dev, M, N, K):
     from espresso_b200 import ops
 
     torch.manual_seed(M + K)
-    dy = torch.randn(K, M, device=dev).bfloat16()  # [rows, N_out]  (A logical [M, K] = dy^T)
+    ldm = (M + 7) // 8 * 8
+    dy = torch.randn(K, ldm, device=dev).bfloat16()[:, :M]  # [rows, N_out] view with padded row stride (A = dy^T)
     x = torch.randn(K, N, device=dev).bfloat16()
     c = torch.full((M, N), 2.0, device=dev, dtype=torch.float32)
-    ops.gemm(dy, x, c, M, N, K, M if M % 8 == 0 else dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True)
+    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True)
     ref = 2.0 + dy.float().t() @ x.float()
     assert (c - ref).abs().max().item() <= 3e-3 * K ** 0.5 + 1e-2
     ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, alpha=-1.0)
