@@ -82,6 +82,22 @@ def make_batches(n_batches, world, rank, seed=7, pool=4000):
     return out
 
 
+def effective_cores():
+    """CPU cores this process may really use: affinity mask and cgroup quota, not just os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(float(q[0]) / float(q[1]))))
+    except Exception:
+        pass
+    return n
+
+
 class _Dict:
     def __len__(self):
         return V
@@ -141,7 +157,7 @@ def run_reference(args):
     from oracle import conformer as OC
     from oracle import frontend as OF
 
-    cores = os.cpu_count() or 1
+    cores = min(effective_cores(), 32)  # small per-op work: more threads only add synchronisation cost
     torch.set_num_threads(cores)
     cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=17, layer_type="conformer", dw_kernel=31, dropout=0.1,
                attention_dropout=0.1, activation_dropout=0.1, layernorm_embedding=True, final_layer_norm=False, vocab=V)
@@ -149,7 +165,7 @@ def run_reference(args):
     params = {k: v.requires_grad_(True) for k, v in sd.items() if "running_" not in k}
     sd.update(params)
     opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.98), eps=1e-8)
-    durs = [9.0, 7.0]  # bounded sample of the workload per step
+    durs = [8.0]  # bounded sample of the workload per step (one utterance)
     waves = [OF.synth_waveform(i, d) for i, d in enumerate(durs)]
     mean, std = np.zeros(80), np.ones(80) * 4.0
     audio_s = sum(len(w) for w in waves) / 16000.0
@@ -178,7 +194,7 @@ def run_reference(args):
         (loss / len(feats)).backward()
         torch.nn.utils.clip_grad_norm_(list(params.values()), 2.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for i in range(args.warmup):
         step(i)
@@ -209,7 +225,7 @@ def cpu_baseline_quick():
     from oracle import conformer as OC
     from oracle import frontend as OF
 
-    cores = os.cpu_count() or 1
+    cores = min(effective_cores(), 32)
     torch.set_num_threads(cores)
     cfg = dict(embed_dim=512, ffn_dim=2048, heads=8, layers=17, layer_type="conformer", dw_kernel=31, dropout=0.0,
                attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, final_layer_norm=False, vocab=V)
@@ -341,32 +357,39 @@ def main():
             peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        # Record every GEMM call of one eager step (arguments + operand tensors kept alive), then replay exactly
+        # those launches back to back between ONE pair of CUDA events: kernel time without launch gaps or
+        # per-launch event overhead.
         recs = []
         orig = ops.gemm
 
-        def prof_gemm(A, B, C_out, M, N, K, *a, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig(A, B, C_out, M, N, K, *a, **kw)
-            e.record()
-            recs.append((s, e, 2.0 * M * N * K * kw.get("nb1", 1) * kw.get("nb2", 1)))
-            return r
+        def rec_gemm(A, B, C_out, M, N, K, *a, **kw):
+            recs.append(((A, B, C_out, M, N, K) + a, dict(kw), 2.0 * M * N * K * kw.get("nb1", 1) * kw.get("nb2", 1)))
+            return orig(A, B, C_out, M, N, K, *a, **kw)
 
-        ops.gemm = prof_gemm
-        trainer.use_cuda_graphs = False  # the per-launch event pass runs eagerly
+        ops.gemm = rec_gemm
+        trainer.use_cuda_graphs = False
         try:
-            # plug the stream with a ~0.2 s spin kernel so the host enqueues the whole step ahead of the GPU: the
-            # per-launch events then bracket back-to-back kernels, not host launch gaps
-            torch.cuda._sleep(int(4e8))
             trainer.train_step([sample_of(resident[0], n_cpu[0])])
             torch.cuda.synchronize()
         finally:
             ops.gemm = orig
-        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        for a_, kw_, _ in recs:  # warm (tensor maps, L2 state comparable to in-step)
+            orig(*a_, **kw_)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(2e8))  # let the host run ahead so the GPU never waits for a launch
+        e0.record()
+        for a_, kw_, _ in recs:
+            orig(*a_, **kw_)
+        e1.record()
+        torch.cuda.synchronize()
+        tot_ms = e0.elapsed_time(e1)
         tot_fl = sum(f for _, _, f in recs)
+        model.flat.zero_grad()
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        roof = {"kernel": "gemm_tcgen05_kernel (all %d launches of one step)" % len(recs), "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "gemm_tcgen05_kernel (all %d launches of one step, replayed back to back)" % len(recs), "bound": "tensor", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                 "gemm_ms_per_step": tot_ms, "gemm_share_of_step": tot_ms / (ms / args.steps), "traffic": None}

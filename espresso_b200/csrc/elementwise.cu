@@ -457,6 +457,11 @@ attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ 
 // ================================================================================================
 constexpr int kDwT = 64, kDwC = 64, kDwMaxK = 31;
 
+// Thread mapping: 64 channels x 4 time groups; a thread produces kDwPerThr = 16 CONSECUTIVE outputs of one
+// channel with a register sliding window, so each staged input is read from shared memory once per thread
+// (46 loads for 16 x 31 FMAs) instead of once per tap.
+constexpr int kDwPerThr = kDwT / 4;
+
 __global__ void __launch_bounds__(256)
 glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, int B, int T, int Cn, int ksz,
                       bf16* __restrict__ y, double* __restrict__ stats) {
@@ -464,8 +469,7 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
   __shared__ float red[2][4][kDwC];
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
-  const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 time groups
-  // each thread owns one channel: its taps live in registers (no shared-memory bank conflicts)
+  const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
   float wr[kDwMaxK];
 #pragma unroll
   for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
@@ -481,19 +485,33 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
     tile[r][cl] = v;
   }
   __syncthreads();
-  float s1 = 0.f, s2 = 0.f;
-  for (int tt = tg; tt < kDwT; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float acc = 0.f;
+  const int tb = tg * kDwPerThr;  // first local output of this thread
+  float acc[kDwPerThr];
 #pragma unroll
-    for (int k = 0; k < kDwMaxK; ++k)
-      if (k < ksz) acc = fmaf(tile[tt + k][cl], wr[k], acc);
-    const bf16 ob = f2bf(acc);
-    y[((long)b * T + t) * Cn + c0 + cl] = ob;
-    const float of = bf2f(ob);
-    s1 += of;
-    s2 += of * of;
+  for (int i = 0; i < kDwPerThr; ++i) acc[i] = 0.f;
+  // input row r = tb + i + k contributes to output i with tap k
+#pragma unroll
+  for (int r = 0; r < kDwPerThr + kDwMaxK - 1; ++r) {
+    if (r < kDwPerThr + ksz - 1) {
+      const float xv = tile[tb + r][cl];
+#pragma unroll
+      for (int i = 0; i < kDwPerThr; ++i) {
+        const int k = r - i;
+        if (k >= 0 && k < kDwMaxK) acc[i] = fmaf(xv, wr[k], acc[i]);
+      }
+    }
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kDwPerThr; ++i) {
+    const int t = t0 + tb + i;
+    if (t < T) {
+      const bf16 ob = f2bf(acc[i]);
+      y[((long)b * T + t) * Cn + c0 + cl] = ob;
+      const float of = bf2f(ob);
+      s1 += of;
+      s2 += of * of;
+    }
   }
   red[0][tg][cl] = s1;
   red[1][tg][cl] = s2;
@@ -522,9 +540,6 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  float wr[kDwMaxK];
-#pragma unroll
-  for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
   for (int r = tg; r < kDwT + ksz - 1; r += 4) {
     const int t = t0 + r - half;
     float dv = 0.f, gl = 0.f;
@@ -537,34 +552,62 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
     glt[r][cl] = gl;
   }
   __syncthreads();
-  // input gradient
-  for (int tt = tg; tt < kDwT; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float acc = 0.f;
+  const int tb = tg * kDwPerThr;
+  // ---- input gradient: dglu[i] = sum_k w[k] * dy[t - k + half].  With the taps flipped (wf[k'] = w[ksz-1-k'])
+  // this is the forward correlation dglu[i] = sum_k' wf[k'] * dyt[tb + i + k'] (2*half = ksz-1): static indexing.
+  {
+    float wf[kDwMaxK];
 #pragma unroll
-    for (int k = 0; k < kDwMaxK; ++k)
-      if (k < ksz) acc = fmaf(dyt[tt + 2 * half - k][cl], wr[k], acc);  // dy[t - k + half]
-    const bf16* row = g + ((long)b * T + t) * 2 * Cn;
-    const float a = bf2f(row[c0 + cl]);
-    const float sg = sigmoidf_(bf2f(row[Cn + c0 + cl]));
-    bf16* orow = dg + ((long)b * T + t) * 2 * Cn;
-    orow[c0 + cl] = f2bf(acc * sg);
-    orow[Cn + c0 + cl] = f2bf(acc * a * sg * (1.f - sg));
+    for (int k = 0; k < kDwMaxK; ++k) wf[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + (ksz - 1 - k)]) : 0.f;
+    float acc[kDwPerThr];
+#pragma unroll
+    for (int i = 0; i < kDwPerThr; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kDwPerThr + kDwMaxK - 1; ++r) {
+      if (r < kDwPerThr + ksz - 1) {
+        const float dv = dyt[tb + r][cl];
+#pragma unroll
+        for (int i = 0; i < kDwPerThr; ++i) {
+          const int k = r - i;
+          if (k >= 0 && k < kDwMaxK) acc[i] = fmaf(dv, wf[k], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kDwPerThr; ++i) {
+      const int t = t0 + tb + i;
+      if (t < T) {
+        const bf16* row = g + ((long)b * T + t) * 2 * Cn;
+        const float a = bf2f(row[c0 + cl]);
+        const float sg = sigmoidf_(bf2f(row[Cn + c0 + cl]));
+        bf16* orow = dg + ((long)b * T + t) * 2 * Cn;
+        orow[c0 + cl] = f2bf(acc[i] * sg);
+        orow[Cn + c0 + cl] = f2bf(acc[i] * a * sg * (1.f - sg));
+      }
+    }
   }
-  // weight gradient: this CTA owns dy[t0 .. t0+63]; glu halo is already staged
-  float acc[kDwMaxK];
+  // ---- weight gradient: dw[k] += sum_i dy[tb+i] * glu[tb + i + k - half] = dyt[tb+i+half] * glt[tb+i+k]
+  {
+    float acc[kDwMaxK];
 #pragma unroll
-  for (int k = 0; k < kDwMaxK; ++k) acc[k] = 0.f;
-  for (int tt = tg; tt < kDwT; tt += 4) {
-    if (t0 + tt >= T) break;
-    const float d = dyt[tt + half][cl];
+    for (int k = 0; k < kDwMaxK; ++k) acc[k] = 0.f;
+    float dreg[kDwPerThr];
 #pragma unroll
-    for (int k = 0; k < kDwMaxK; ++k)
-      if (k < ksz) acc[k] = fmaf(d, glt[tt + k][cl], acc[k]);  // dy[t] * glu[t + k - half]
+    for (int i = 0; i < kDwPerThr; ++i) dreg[i] = (t0 + tb + i < T) ? dyt[tb + i + half][cl] : 0.f;
+#pragma unroll
+    for (int r = 0; r < kDwPerThr + kDwMaxK - 1; ++r) {
+      if (r < kDwPerThr + ksz - 1) {
+        const float gv = glt[tb + r][cl];
+#pragma unroll
+        for (int i = 0; i < kDwPerThr; ++i) {
+          const int k = r - i;
+          if (k >= 0 && k < kDwMaxK) acc[k] = fmaf(dreg[i], gv, acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kDwMaxK; ++k) dwred[tg][k][cl] = acc[k];
   }
-#pragma unroll
-  for (int k = 0; k < kDwMaxK; ++k) dwred[tg][k][cl] = acc[k];
   __syncthreads();
   for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) {
     const int k = i / kDwC, c = i % kDwC;
@@ -797,8 +840,12 @@ extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float
   ESP_ST;
   ESP_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum needs N and ld multiples of 8");
   if (R == 0 || N == 0) return 0;
-  dim3 grid((N / 8 + 31) / 32, (unsigned)((R + 8 * 32 - 1) / (8 * 32) > 2048 ? 2048 : (R + 8 * 32 - 1) / (8 * 32)));
-  if (grid.y < 1) grid.y = 1;
+  const unsigned gx = (N / 8 + 31) / 32;
+  long gy = (4L * esp_num_sms() + gx - 1) / gx;  // ~4 CTAs per SM in total
+  const long max_gy = (R + 7) / 8;
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, (unsigned)gy);
   colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, R, N, ld, scale, out);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
@@ -946,7 +993,7 @@ extern "C" int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float 
 // grid whose total thread count is a multiple of C/8 (needed by the fixed-channel-group reductions)
 static inline int bn_reduce_grid(long nvec) {
   long g = (nvec + 255) / 256;
-  long cap = (long)esp_num_sms() * 8;
+  long cap = (long)esp_num_sms() * 2;  // every CTA ends with one double atomic per channel: keep CTAs few
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
