@@ -335,16 +335,18 @@ __device__ __forceinline__ void keep8(unsigned long long seed, unsigned long lon
 // (ld % 8 == 0, so every group is hash-aligned).
 template <int NI>
 __global__ void __launch_bounds__(256)
-attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int ld, const int* __restrict__ lens,
-                        bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
+attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int Tq, int T, int ld, const int* __restrict__ lens,
+                        int causal, bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
                         unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
+  // rows = H*B*Tq queries, T keys per row; causal: key j is visible to query i iff j <= i (future_mask, -inf)
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long rows = (long)H * B * T;
+  const long rows = (long)H * B * Tq;
   if (row >= rows) return;
-  const int b = (int)((row / T) % B);
-  const int klen = lens ? min(lens[b], T) : T;
+  const int b = (int)((row / Tq) % B);
+  int klen = lens ? min(lens[b], T) : T;
+  if (causal) klen = min(klen, (int)(row % Tq) + 1);
   const bf16* sr = s_in + row * ld;
   float v[NI][8];
   float mx = -INFINITY;
@@ -394,15 +396,15 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int T, int 
 // relative-position layout dBD[row, (T-1) - i + j]  (zeros elsewhere).
 template <int NI>
 __global__ void __launch_bounds__(256)
-attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int T, int ld,
+attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int Tq, int T, int ld,
                         bf16* __restrict__ ds_out, bf16* __restrict__ dbd_out, int ldp, float drop_p,
                         uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long rows = (long)H * B * T;
+  const long rows = (long)H * B * Tq;
   if (row >= rows) return;
-  const int qi = (int)(row % T);
+  const int qi = (int)(row % Tq);
   const float dscale = drop_p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
   float pv[NI][8], dv[NI][8];
   float dot = 0.f;
@@ -899,19 +901,20 @@ extern "C" int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int6
   return 0;
 }
 
-extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
-                                    void* p, void* p_drop, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
-                                    void* stream) {
+extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t Tq, int32_t T, int32_t ld,
+                                    const int32_t* lens, int32_t causal, void* p, void* p_drop, float drop_p, uint64_t seed,
+                                    const uint64_t* seed_ptr, void* stream) {
   ESP_ST;
+  ESP_CHECK(!causal || Tq == T, "causal attention needs Tq == Tk");
   ESP_CHECK(T <= kSmMaxT, "attention length %d exceeds the register softmax limit %d", T, kSmMaxT);
   ESP_CHECK(ld >= T && ld <= kSmMaxT && ld % 8 == 0, "bad score row stride %d", ld);
   ESP_CHECK(drop_p <= 0.f || p_drop != nullptr, "dropout requested but p_drop is null");
-  const long rows = (long)H * B * T;
+  const long rows = (long)H * B * Tq;
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   bf16* pd = drop_p > 0.f ? (bf16*)p_drop : nullptr;
 #define ESP_SMF(NI)                                                                                           \
-  attn_softmax_fwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)scores, H, B, T, ld, lens, (bf16*)p, pd, drop_p, \
+  attn_softmax_fwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)scores, H, B, Tq, T, ld, lens, causal, (bf16*)p, pd, drop_p, \
                                                     esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
   if (ld <= 256) ESP_SMF(1);
   else if (ld <= 512) ESP_SMF(2);
@@ -924,17 +927,17 @@ extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, in
   return 0;
 }
 
-extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
-                                    void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
-                                    void* stream) {
+extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t Tq, int32_t T,
+                                    int32_t ld, void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed,
+                                    const uint64_t* seed_ptr, void* stream) {
   ESP_ST;
   ESP_CHECK(T <= kSmMaxT && ld >= T && ld <= kSmMaxT && ld % 8 == 0, "bad attention softmax-bwd shape");
-  ESP_CHECK(dbd == nullptr || ldp >= 2 * T - 1, "dBD row stride too small");
-  const long rows = (long)H * B * T;
+  ESP_CHECK(dbd == nullptr || (ldp >= 2 * T - 1 && Tq == T), "dBD needs Tq == Tk and ldp >= 2T-1");
+  const long rows = (long)H * B * Tq;
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define ESP_SMB(NI)                                                                                              \
-  attn_softmax_bwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, T, ld, (bf16*)ds, \
+  attn_softmax_bwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, Tq, T, ld, (bf16*)ds, \
                                                     (bf16*)dbd, ldp, drop_p, esp_dropout_thresh(drop_p), seed,  \
                                                     (const unsigned long long*)seed_ptr)
   if (ld <= 256) ESP_SMB(1);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "esp_last_error": (C.c_char_p, []),
     "esp_version": (C.c_int, []),
     "esp_launch_count": (_i64, []),
+    "esp_note_graph_replay": (None, [_i64]),
     "esp_gemm_bf16": (C.c_int, [C.POINTER(EspGemm), _vp]),
     "esp_frontend_fbank": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32,
                                      _vp, _vp, _vp]),
@@ -54,14 +55,18 @@ SIGNATURES = {
     "esp_mask_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "esp_qprep_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp]),
     "esp_qprep_bwd": (C.c_int, [_vp, _vp, _f32, _i64, _i32, _vp, _i64, _vp]),
-    "esp_attn_softmax_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _u64, _vp, _vp]),
-    "esp_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
+    "esp_attn_softmax_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _f32, _u64, _vp, _vp]),
+    "esp_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
     "esp_glu_dwconv_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_glu_dwconv_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esp_bn_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _i32, _vp, _vp]),
     "esp_bn_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "esp_bn_act_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "esp_bn_act_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "esp_lsce_loss": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "esp_embed_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _i64, _i32, _vp, _f32, _u64, _vp, _vp]),
+    "esp_embed_bwd": (C.c_int, [_vp, _vp, _i32, _f32, _i64, _i32, _vp, _f32, _u64, _vp, _vp]),
+    "esp_argmax_rows": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "esp_sumsq_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "esp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _vp, _vp]),

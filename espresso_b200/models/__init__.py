@@ -1,5 +1,8 @@
 from .transformer import (  # noqa: F401
     SpeechTransformerConfig,
+    SpeechTransformerDecoderBase,
     SpeechTransformerEncoderForPrediction,
     SpeechTransformerEncoderModel,
+    SpeechTransformerModel,
+    SpeechTransformerModelBase,
 )

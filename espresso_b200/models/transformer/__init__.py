@@ -3,3 +3,4 @@ from .speech_transformer_encoder_model import (  # noqa: F401
     SpeechTransformerEncoderForPrediction,
     SpeechTransformerEncoderModel,
 )
+from .speech_transformer_base import SpeechTransformerDecoderBase, SpeechTransformerModel, SpeechTransformerModelBase  # noqa: F401

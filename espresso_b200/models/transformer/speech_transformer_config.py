@@ -32,12 +32,21 @@ class SpeechEncoderConfig(SpeechEncDecBaseConfig):
 
 
 @dataclass
+class SpeechDecoderConfig(SpeechEncDecBaseConfig):
+    input_dim: int = 512
+    output_dim: int = 512
+
+
+@dataclass
 class SpeechTransformerConfig:
     activation_fn: str = "relu"
     dropout: float = 0.2
     attention_dropout: float = 0.2
     activation_dropout: float = 0.2
     encoder: SpeechEncoderConfig = field(default_factory=SpeechEncoderConfig)
+    decoder: SpeechDecoderConfig = field(default_factory=SpeechDecoderConfig)
+    share_decoder_input_output_embed: bool = False
+    no_cross_attention: bool = False
     max_source_positions: Optional[int] = DEFAULT_MAX_SOURCE_POSITIONS
     max_target_positions: Optional[int] = 1024
     layernorm_embedding: bool = False
@@ -49,10 +58,11 @@ class SpeechTransformerConfig:
         """Build from a (possibly nested) mapping such as the `model:` section of a recipe YAML."""
         cfg = cls()
         for k, v in d.items():
-            if k == "encoder":
+            if k in ("encoder", "decoder"):
+                sub = getattr(cfg, k)
                 for ek, ev in v.items():
-                    if hasattr(cfg.encoder, ek):
-                        setattr(cfg.encoder, ek, ev)
+                    if hasattr(sub, ek):
+                        setattr(sub, ek, ev)
             elif hasattr(cfg, k):
                 setattr(cfg, k, v)
         return cfg

@@ -244,24 +244,34 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         self.fc_out = _Linear(d, vocab_size, xavier=1.0) if vocab_size is not None else None
         self.num_updates = 0
         self.flat = None
+        self.flat_prefix = ""
         self.engine = None
         self._anchor = None
         self.dropout_seed = 1
 
     # ---- B200 wiring ----------------------------------------------------------------------------
-    def finalize_(self, device):
-        """Cast to bf16 on `device`, re-home all parameters into the flat buffers and build the engine.
-        Call once after construction / load_state_dict (fairseq does the equivalent cast in
-        fairseq/trainer.py:105-107)."""
-        self.to(device)
+    def flat_groups(self, prefix=""):
+        """Parameters that must be adjacent in the flat buffer (fused QKV views)."""
         groups = []
         for i in range(len(self.layers)):
-            groups.append(["layers.%d.self_attn.%s_proj.weight" % (i, c) for c in "qkv"])
-            groups.append(["layers.%d.self_attn.%s_proj.bias" % (i, c) for c in "qkv"])
-        cl = [n for n, p in self.named_parameters() if n.startswith("pre_encoder.convolutions") and p.dim() == 4]
-        self.flat = FlatParams(self, groups=groups, device=device, channels_last=cl)
+            groups.append([prefix + "layers.%d.self_attn.%s_proj.weight" % (i, c) for c in "qkv"])
+            groups.append([prefix + "layers.%d.self_attn.%s_proj.bias" % (i, c) for c in "qkv"])
+        return groups
+
+    def channels_last_params(self, prefix=""):
+        return [prefix + n for n, p in self.named_parameters() if n.startswith("pre_encoder.convolutions") and p.dim() == 4]
+
+    def finalize_(self, device, flat=None, prefix=""):
+        """Cast to bf16 on `device`, re-home all parameters into the flat buffers and build the engine.
+        Call once after construction / load_state_dict (fairseq does the equivalent cast in
+        fairseq/trainer.py:105-107).  `flat`/`prefix`: a FlatParams built by the owning model over
+        encoder + decoder (the parameters of this module are then named prefix + local name)."""
+        self.to(device)
+        if flat is None:
+            flat = FlatParams(self, groups=self.flat_groups(), device=device, channels_last=self.channels_last_params())
+        self.flat, self.flat_prefix = flat, prefix
         if self.pre_encoder is not None:
-            self.pre_encoder.flat, self.pre_encoder.flat_prefix = self.flat, "pre_encoder."
+            self.pre_encoder.flat, self.pre_encoder.flat_prefix = self.flat, prefix + "pre_encoder."
             for bn in self.pre_encoder.batchnorms:  # running statistics stay fp32 (native BN kernels)
                 bn.running_mean.data = bn.running_mean.data.float()
                 bn.running_var.data = bn.running_var.data.float()
@@ -271,7 +281,7 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
                     attention_dropout=self.cfg.attention_dropout, activation_dropout=self.cfg.activation_dropout,
                     layernorm_embedding=self.cfg.layernorm_embedding, final_layer_norm=self.layer_norm is not None,
                     vocab=self.vocab_size)
-        self.engine = EncoderEngine(self.flat, "", ecfg)
+        self.engine = EncoderEngine(self.flat, prefix, ecfg)
         if e.layer_type == "conformer":
             self.engine.bn_state = {i: (l.conv_module.batch_norm.running_mean, l.conv_module.batch_norm.running_var)
                                     for i, l in enumerate(self.layers)}
@@ -288,7 +298,7 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
             return
         for n, p in self.pre_encoder.named_parameters():
             if p.grad is not None:
-                self.flat.grad("pre_encoder." + n).add_(p.grad.float())
+                self.flat.grad(self.flat_prefix + "pre_encoder." + n).add_(p.grad.float())
                 p.grad = None
 
     def set_num_updates(self, num_updates):
@@ -377,7 +387,10 @@ class SpeechTransformerEncoderModel(nn.Module):
         return cls(cfg, encoder)
 
     def finalize_(self, device):
-        self.encoder.finalize_(device)
+        self.to(device)
+        flat = FlatParams(self, groups=self.encoder.flat_groups("encoder."), device=device,
+                          channels_last=self.encoder.channels_last_params("encoder."))
+        self.encoder.finalize_(device, flat=flat, prefix="encoder.")
         return self
 
     @property

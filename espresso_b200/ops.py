@@ -236,26 +236,29 @@ def qprep_bwd(dqu, dqv, scale, dq_out):
     _lib.check(_lib.load().esp_qprep_bwd(_ptr(dqu), _ptr(dqv), scale, R, d, _ptr(dq_out), dq_out.stride(0), _stream()))
 
 
-def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
-    """scores [H, B, T, ld] bf16 -> (p, p_drop) same shape; p_drop is p when drop_p == 0."""
+def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
+    """scores [H, B, Tq, ld] bf16 over T keys -> (p, p_drop) same shape; p_drop is p when drop_p == 0.
+    lens: int32 [B] valid keys per batch entry or None; causal: key j visible to query i iff j <= i."""
     _need_cuda(scores, lens)
     _bf(scores)
-    H, B, T_, ld = scores.shape
-    assert T_ == T and scores.is_contiguous()
+    H, B, Tq, ld = scores.shape
+    assert scores.is_contiguous()
     p = torch.empty_like(scores)
     pd = torch.empty_like(scores) if drop_p > 0 else None
-    _lib.check(_lib.load().esp_attn_softmax_fwd(_ptr(scores), H, B, T, ld, _ptr(lens), _ptr(p), _ptr(pd), drop_p, seed, _seed_ptr(), _stream()))
+    _lib.check(_lib.load().esp_attn_softmax_fwd(_ptr(scores), H, B, Tq, T, ld, _ptr(lens), int(causal), _ptr(p), _ptr(pd), drop_p,
+                                                seed, _seed_ptr(), _stream()))
     return p, (pd if pd is not None else p)
 
 
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
-    """Returns (dS [H,B,T,ld], dBD [H,B,T,ldp] in skewed relative-position layout or None)."""
+    """Returns (dS [H,B,Tq,ld], dBD [H,B,T,ldp] in skewed relative-position layout or None)."""
     _need_cuda(p, dp_drop)
     _bf(p, dp_drop)
-    H, B, T_, ld = p.shape
+    H, B, Tq, ld = p.shape
     ds = torch.empty_like(p)
     dbd = torch.empty(H, B, T, ldp, device=p.device, dtype=torch.bfloat16) if want_dbd else None
-    _lib.check(_lib.load().esp_attn_softmax_bwd(_ptr(p), _ptr(dp_drop), H, B, T, ld, _ptr(ds), _ptr(dbd), ldp, drop_p, seed, _seed_ptr(), _stream()))
+    _lib.check(_lib.load().esp_attn_softmax_bwd(_ptr(p), _ptr(dp_drop), H, B, Tq, T, ld, _ptr(ds), _ptr(dbd), ldp, drop_p, seed,
+                                                _seed_ptr(), _stream()))
     return ds, dbd
 
 
@@ -367,3 +370,51 @@ def cast_f32_bf16(x, y):
 def cast_bf16_f32(x, y):
     _need_cuda(x, y)
     _lib.check(_lib.load().esp_cast_bf16_f32(_ptr(x), x.numel(), _ptr(y), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder-side kernels
+# ----------------------------------------------------------------------------------------------
+def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True):
+    """logits bf16 [R, ld]; targets int32 [R] -> (loss fp32 [R], nll fp32 [R], grad bf16 [R, ld] or None)."""
+    _need_cuda(logits, targets)
+    _bf(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and targets.dtype == torch.int32
+    R, ld = logits.shape[0], logits.stride(0)
+    loss = torch.empty(R, device=logits.device, dtype=torch.float32)
+    nll = torch.empty(R, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits) if want_grad else None
+    _lib.check(_lib.load().esp_lsce_loss(_ptr(logits), ld, V, R, _ptr(targets), pad_idx, eps, grad_scale, _ptr(loss), _ptr(nll),
+                                         _ptr(grad), _stream()))
+    return loss, nll, grad
+
+
+def embed_fwd(tokens, E, pos, U, scale, pad_idx, drop_p=0.0, seed=0):
+    """tokens int32 [R] (R = B*U), E bf16 [V, d], pos bf16 [>=U, d] or None -> x bf16 [R, d]."""
+    _need_cuda(tokens, E, pos)
+    _bf(E, pos)
+    assert tokens.dtype == torch.int32
+    R, d = tokens.numel(), E.shape[1]
+    x = torch.empty(R, d, device=E.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_embed_fwd(_ptr(tokens), _ptr(E), _ptr(pos), U, d, scale, R, pad_idx, _ptr(x), drop_p, seed,
+                                         _seed_ptr(), _stream()))
+    return x
+
+
+def embed_bwd(tokens, dx, dE_acc, scale, pad_idx, drop_p=0.0, seed=0):
+    _need_cuda(tokens, dx, dE_acc)
+    _bf(dx)
+    assert dE_acc.dtype == torch.float32 and dx.is_contiguous()
+    R, d = dx.shape
+    _lib.check(_lib.load().esp_embed_bwd(_ptr(tokens), _ptr(dx), d, scale, R, pad_idx, _ptr(dE_acc), drop_p, seed, _seed_ptr(),
+                                         _stream()))
+
+
+def argmax_rows(x, V):
+    """x bf16 [R, ld] -> int32 [R] argmax over the first V columns."""
+    _need_cuda(x)
+    _bf(x)
+    R = x.shape[0]
+    out = torch.empty(R, device=x.device, dtype=torch.int32)
+    _lib.check(_lib.load().esp_argmax_rows(_ptr(x), x.stride(0), V, R, _ptr(out), _stream()))
+    return out

@@ -13,6 +13,7 @@ One process per GPU (torchrun / torch.distributed, backend nccl).  Per update:
 import torch
 import torch.distributed as dist
 
+from . import lib as _lib
 from . import ops as _ops
 
 
@@ -102,18 +103,22 @@ class Trainer:
                       "target": sample["target"].clone()}
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(graph, pool=self._pool):
                 self._step_body([static])
+            n_kernels = _lib.launch_count() - n0  # native kernels recorded in this graph
+            _lib.load().esp_note_graph_replay(-n_kernels)  # capture itself executed nothing
             if self._pool is None:
                 self._pool = graph.pool()
-            entry = (graph, static)
+            entry = (graph, static, n_kernels)
             self._graphs[key] = entry
-        graph, static = entry
+        graph, static, n_kernels = entry
         for k, v in sample["net_input"].items():
             if torch.is_tensor(v) and v.is_cuda:
                 static["net_input"][k].copy_(v, non_blocking=True)
         static["target"].copy_(sample["target"], non_blocking=True)
         graph.replay()
+        _lib.load().esp_note_graph_replay(n_kernels)
 
     def train_step(self, samples):
         """samples: list of micro-batches (update_freq entries); an empty dict is a dummy batch whose

@@ -26,6 +26,8 @@ const char* esp_last_error(void);
 int esp_version(void);
 /* number of kernel launches issued through this library since load (for bench gpu_launches) */
 int64_t esp_launch_count(void);
+/* a CUDA graph captured from this library's launches was replayed: credit the kernels it contains */
+void esp_note_graph_replay(int64_t launches);
 
 /* ---- dense contraction: C = epi(op(A) * op(B)^T), bf16 in, fp32 accumulate (tcgen05 + TMA) -----
  * replaces torch.nn.functional.linear / torch.bmm call sites:
@@ -135,11 +137,13 @@ int esp_qprep_fwd(const void* q, int64_t ldq, const void* u, const void* v, floa
 int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int64_t R, int32_t d, void* dq, int64_t ld_out,
                   void* stream);
 /* attention softmax over keys (scores [H,B,T,ld] bf16): key-padding -> -inf, fp32 softmax, optional dropout
- * copy (fairseq/modules/multihead_attention.py:841-876); backward also scatters dS into the skewed
- * relative-position layout dBD[., i, (T-1)-i+j] (inverse of :824-830). */
-int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t T, int32_t ld, const int32_t* lens,
-                         void* p, void* p_drop, float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
-int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t T, int32_t ld,
+ * copy (fairseq/modules/multihead_attention.py:841-876); Tq x Tk scores (self- or cross-attention), optional
+ * causal mask (decoder future mask, fairseq/models/transformer/transformer_decoder.py:404-419); backward also
+ * scatters dS into the skewed relative-position layout dBD[., i, (T-1)-i+j] (inverse of :824-830). */
+int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, int32_t Tq, int32_t Tk, int32_t ld,
+                         const int32_t* lens, int32_t causal, void* p, void* p_drop, float drop_p, uint64_t seed,
+                         const uint64_t* seed_ptr, void* stream);
+int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t B, int32_t Tq, int32_t Tk, int32_t ld,
                          void* ds, void* dbd, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
                          void* stream);
 /* Conformer convolution module body (fairseq/modules/conformer_layer.py:88-96):
@@ -176,6 +180,22 @@ int esp_adam_step(float* p32, float* m, float* v, const float* g, void* p16, int
                   const float* hyper_dev, void* stream);
 int esp_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream);
 int esp_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream);
+
+/* ---- decoder-side kernels --------------------------------------------------------------------
+ * Label-smoothed cross-entropy fused with the fp32 log-softmax, forward + backward
+ * (espresso/criterions/label_smoothed_cross_entropy_v2.py:82-120,216-240, uniform smoothing):
+ *   loss[r] = (1-eps-eps_i)*nll + eps_i*smooth, eps_i = eps/(V-1); rows with target == pad_idx give 0;
+ *   grad = grad_scale * (softmax - (1-eps-eps_i)*onehot - eps_i)  (bf16, same row stride; NULL = loss only). */
+int esp_lsce_loss(const void* logits, int64_t ld, int32_t V, int64_t R, const int32_t* targets, int32_t pad_idx,
+                  float eps, float grad_scale, float* loss, float* nll, void* grad, void* stream);
+/* x[r] = dropout(bf16(E[tok[r]]*scale) + pos[r % U]) (pos optional; pad tokens get no position), and the
+ * scatter-add backward into the fp32 embedding gradient (fairseq/models/transformer/transformer_decoder.py:254-300). */
+int esp_embed_fwd(const int32_t* tokens, const void* E, const void* pos, int32_t U, int32_t d, float scale, int64_t R,
+                  int32_t pad_idx, void* x, float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+int esp_embed_bwd(const int32_t* tokens, const void* dx, int32_t d, float scale, int64_t R, int32_t pad_idx, float* dE,
+                  float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+/* out[r] = argmax_v x[r, v<V]  (greedy CTC decoding, espresso/tools/ctc_decoder.py:163-188) */
+int esp_argmax_rows(const void* x, int64_t ld, int32_t V, int64_t R, int32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

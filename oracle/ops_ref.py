@@ -132,14 +132,17 @@ def qprep_bwd(dqu, dqv, scale, dq_out):
     dq_out.copy_((scale * (dqu.float() + dqv.float())).to(BF))
 
 
-def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
+def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
     assert drop_p == 0.0
-    H, B, _, ld = scores.shape
+    H, B, Tq, ld = scores.shape
     s = scores.float()[..., :T].clone()
     if lens is not None:
         km = torch.arange(T)[None, :] >= lens[:, None]  # [B, T] keys to mask
         s = s.masked_fill(km[None, :, None, :], float("-inf"))
-    p = torch.zeros(H, B, T, ld)
+    if causal:
+        fut = torch.arange(T)[None, :] > torch.arange(Tq)[:, None]
+        s = s.masked_fill(fut[None, None], float("-inf"))
+    p = torch.zeros(H, B, Tq, ld)
     p[..., :T] = torch.softmax(s, dim=-1)
     p = p.to(BF)
     return p, p
@@ -147,11 +150,11 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0):
 
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     assert drop_p == 0.0
-    H, B, _, ld = p.shape
+    H, B, Tq, ld = p.shape
     pf = p.float()[..., :T]
     dp = dp_drop.float()[..., :T]
     ds_ = pf * (dp - (dp * pf).sum(-1, keepdim=True))
-    ds = torch.zeros(H, B, T, ld)
+    ds = torch.zeros(H, B, Tq, ld)
     ds[..., :T] = ds_
     ds = ds.to(BF)
     dbd = None
@@ -327,3 +330,43 @@ def ctc_loss(logits, V, in_lens, targets, tgt_lens, blank, zero_infinity=True, g
         loss[b] = float(nll)
         grad[b, :, :V] = torch.from_numpy(g).float() * grad_scale
     return loss, (grad.to(BF) if want_grad else None)
+
+
+def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True):
+    x = logits.float()[:, :V]
+    lp = torch.log_softmax(x, dim=-1)
+    t = targets.long()
+    nll = -lp.gather(1, t[:, None]).squeeze(1)
+    smooth = -lp.sum(-1)
+    eps_i = eps / (V - 1)
+    keep = (t != pad_idx).float()
+    loss = ((1 - eps - eps_i) * nll + eps_i * smooth) * keep
+    grad = None
+    if want_grad:
+        g = torch.softmax(x, dim=-1) - eps_i
+        g[torch.arange(x.shape[0]), t] -= (1 - eps - eps_i)
+        grad = torch.zeros_like(logits, dtype=torch.float32)
+        grad[:, :V] = g * keep[:, None] * grad_scale
+        grad = grad.to(BF)
+    return loss, nll * keep, grad
+
+
+def embed_fwd(tokens, E, pos, U, scale, pad_idx, drop_p=0.0, seed=0):
+    assert drop_p == 0.0
+    t = tokens.long()
+    x = (E[t].float() * scale).to(BF).float()
+    if pos is not None:
+        pidx = torch.arange(t.numel()) % U
+        x = x + pos[pidx].float() * (t != pad_idx).float()[:, None]
+    return x.to(BF)
+
+
+def embed_bwd(tokens, dx, dE_acc, scale, pad_idx, drop_p=0.0, seed=0):
+    assert drop_p == 0.0
+    t = tokens.long()
+    keep = (t != pad_idx)
+    dE_acc.index_add_(0, t[keep], dx.float()[keep] * scale)
+
+
+def argmax_rows(x, V):
+    return x[:, :V].float().argmax(-1).to(torch.int32)

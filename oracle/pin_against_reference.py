@@ -211,7 +211,103 @@ def pin_conformer():
         print("%s encoder pinned -> tests/golden/encoder_%s.npz" % (layer_type, layer_type))
 
 
-SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer}
+def pin_encdec():
+    """Reference SpeechTransformerModelBase (Transformer encoder + Transformer decoder) with the reference's
+    label_smoothed_nll_loss vs oracle/conformer.py + oracle/decoder.py; fixture for the enc-dec path (cfg 2/5)."""
+    from espresso.criterions.label_smoothed_cross_entropy_v2 import label_smoothed_nll_loss
+    from espresso.models.transformer.speech_transformer_base import SpeechTransformerModelBase
+    from espresso.models.transformer.speech_transformer_config import SpeechTransformerConfig
+
+    from oracle import conformer as OC
+    from oracle import decoder as OD
+
+    V, pad_idx, eos_idx = 50, 1, 2
+    cfg = SpeechTransformerConfig()
+    cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
+    e = cfg.encoder
+    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
+    e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
+    e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = 64, 128, 2, 4
+    e.normalize_before, e.learned_pos, e.relative_positional_embeddings, e.layer_type = True, False, True, "transformer"
+    d = cfg.decoder
+    d.embed_dim, d.ffn_embed_dim, d.layers, d.attention_heads = 64, 128, 2, 4
+    d.normalize_before, d.learned_pos, d.relative_positional_embeddings = True, False, False
+    d.input_dim, d.output_dim = 64, 64
+    cfg.dropout = cfg.attention_dropout = cfg.activation_dropout = 0.0
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return pad_idx
+
+        def eos(self):
+            return eos_idx
+
+    class _Task:
+        feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+
+    torch.manual_seed(2)
+    m = SpeechTransformerModelBase.build_model(cfg, _Task())
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    rs = np.random.RandomState(12)
+    B, T = 3, 61
+    lens = torch.tensor([61, 50, 37])
+    feats = torch.from_numpy(rs.randn(B, T, 80).astype(np.float32))
+    for b in range(B):
+        feats[b, lens[b]:] = 0.0
+    U = 8
+    tgt = torch.full((B, U), pad_idx, dtype=torch.long)
+    prev = torch.full((B, U), pad_idx, dtype=torch.long)
+    for b, u in enumerate((7, 5, 3)):
+        toks = torch.from_numpy(rs.randint(4, V, size=u))
+        tgt[b, :u] = toks
+        tgt[b, u] = eos_idx
+        prev[b, 0] = eos_idx          # fairseq feeds </s> first (move_eos_to_beginning)
+        prev[b, 1:u + 1] = toks
+    ecfg = dict(embed_dim=64, ffn_dim=128, heads=4, layers=2, layer_type="transformer", dropout=0.0, attention_dropout=0.0,
+                activation_dropout=0.0, layernorm_embedding=False, final_layer_norm=True, vocab=None)
+    dcfg = dict(dec_embed_dim=64, dec_heads=4, dec_layers=2, pad=pad_idx, dropout=0.0, attention_dropout=0.0,
+                activation_dropout=0.0)
+    eps = 0.1
+    m.train()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m.zero_grad()
+    logits, extra = m(feats, lens, prev)
+    lprobs = m.get_normalized_probs((logits, extra), log_probs=True)
+    loss, nll = label_smoothed_nll_loss(lprobs.view(-1, lprobs.size(-1)), tgt.view(-1), eps, ignore_index=pad_idx, reduce=True,
+                                        smoothing_type="uniform")
+    loss.backward()
+    pnames = dict(m.named_parameters())
+    sd = {k: v.clone().requires_grad_(k in pnames) for k, v in sd0.items()}
+    enc, ol, pad = OC.encoder_forward(sd, ecfg, feats, lens, training=True)
+    o_logits = OD.decoder_forward(sd, dcfg, prev, enc, pad if bool(pad.any()) else None, training=True)
+    o_loss, o_nll = OD.label_smoothed_ce(o_logits, tgt, eps, pad_idx)
+    o_loss.backward()
+    dl = (o_logits - logits).abs().max().item()
+    print("encdec: |logits diff|=%.3g loss ref=%.6f oracle=%.6f nll ref=%.6f oracle=%.6f" % (dl, loss.item(), o_loss.item(), nll.item(), o_nll.item()))
+    assert dl < 2e-4 and abs(loss.item() - o_loss.item()) < 1e-3 * abs(loss.item())
+    worst = 0.0
+    for n, p_ in m.named_parameters():
+        dg = (sd[n].grad - p_.grad).abs().max().item() / max(p_.grad.abs().max().item(), 1e-3)
+        worst = max(worst, dg)
+    print("   worst relative grad diff %.3g" % worst)
+    assert worst < 2e-3
+    out = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    out.update({"grad." + n: p_.grad.numpy() for n, p_ in m.named_parameters()})
+    out.update(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), prev_output_tokens=prev.numpy(),
+               logits=logits.detach().numpy(), loss=np.float64(loss.item()), nll=np.float64(nll.item()), eps=np.float64(eps))
+    np.savez_compressed(os.path.join(GOLDEN, "encdec_transformer.npz"), **out)
+    print("encdec pinned -> tests/golden/encdec_transformer.npz")
+
+
+SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec}
 
 
 def main(argv):

@@ -76,15 +76,15 @@ def test_encoder_vs_reference_fixture(layer_type, golden_dir):
     for k in g.files:
         if not k.startswith("grad.encoder."):
             continue
-        name = k[len("grad.encoder."):]
-        if (name.startswith("pre_encoder.convolutions") and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
             continue  # analytically zero gradients
         ours = m.flat.grad(name).cpu().numpy()
         refg = g[k]
-        worst.append((np.abs(ours - refg).max() / max(np.abs(refg).max(), 1e-2), name))
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
     worst.sort(reverse=True)
-    assert worst[0][0] < 0.3, worst[:5]
-    assert max(w[0] for w in worst if not w[1].startswith("pre_encoder")) < 0.12, worst[:8]
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.1, worst[:8]
     assert np.median([w[0] for w in worst]) < 0.03
     m.eval()
     with torch.no_grad():
@@ -149,3 +149,89 @@ def test_full_size_layer_shapes():
     assert torch.isfinite(loss).item()
     assert torch.isfinite(m.flat.grads).all().item()
     assert m.flat.grads.abs().max().item() > 0
+
+
+def test_encdec_vs_reference_fixture(golden_dir):
+    """speech_transformer_base (Transformer encoder + decoder) + label-smoothed CE on the GPU vs the fixture recorded
+    from the real reference model."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_orchestration import _build_encdec
+    from espresso_b200.criterions import LabelSmoothedCrossEntropyV2Criterion
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g).finalize_(dev)
+    crit = LabelSmoothedCrossEntropyV2Criterion(_Task(50), label_smoothing=float(g["eps"]))
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]).to(dev), "src_lengths": torch.from_numpy(g["lens"]).to(dev),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"]).to(dev)},
+              "target": torch.from_numpy(g["target"]).to(dev)}
+    m.train()
+    m.flat.zero_grad()
+    loss, sample_size, log = crit(m, sample)
+    loss.backward()
+    m.encoder.sync_torch_grads_()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) < 0.03 * float(g["loss"])
+    assert abs(log["nll_loss"].item() - float(g["nll"])) < 0.03 * float(g["nll"])
+    worst = []
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+            continue
+        ours, refg = m.flat.grad(name).cpu().numpy(), g[k]
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.1, worst[:8]
+
+
+def test_lsce_embed_argmax_kernels():
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    for V in (50, 5004, 9000):
+        ld = (V + 7) // 8 * 8
+        R = 37
+        x = (torch.randn(R, ld) * 2).bfloat16()
+        t = torch.randint(0, V, (R,), dtype=torch.int32)
+        t[::5] = 1  # pad rows
+        loss, nll, grad = ops.lsce_loss(x.to(dev), V, t.to(dev), 1, 0.1, grad_scale=0.5)
+        lr, nr, gr = O.lsce_loss(x, V, t, 1, 0.1, grad_scale=0.5)
+        assert torch.allclose(loss.cpu(), lr, rtol=1e-4, atol=1e-3) and torch.allclose(nll.cpu(), nr, rtol=1e-4, atol=1e-3)
+        assert (grad.float().cpu() - gr.float()).abs().max().item() < 4e-3
+        assert not grad[:, V:].any()
+        am = ops.argmax_rows(x.to(dev), V)
+        assert torch.equal(am.cpu(), O.argmax_rows(x, V))
+    E = torch.randn(50, 64).bfloat16()
+    pos = torch.randn(9, 64).bfloat16()
+    tok = torch.randint(0, 50, (4 * 9,), dtype=torch.int32)
+    tok[3] = 1
+    y = ops.embed_fwd(tok.to(dev), E.to(dev), pos.to(dev), 9, 8.0, 1)
+    assert (y.float().cpu() - O.embed_fwd(tok, E, pos, 9, 8.0, 1).float()).abs().max().item() < 0.07
+    dx = torch.randn(36, 64).bfloat16()
+    dE, dEr = torch.zeros(50, 64, device=dev), torch.zeros(50, 64)
+    ops.embed_bwd(tok.to(dev), dx.to(dev), dE, 8.0, 1)
+    O.embed_bwd(tok, dx, dEr, 8.0, 1)
+    assert (dE.cpu() - dEr).abs().max().item() < 1e-3
+    # rectangular + causal softmax
+    H, B, Tq, Tk = 2, 3, 9, 21
+    ld = 24
+    s = (torch.randn(H, B, Tq, ld) * 2).bfloat16()
+    lens = torch.tensor([21, 13, 5], dtype=torch.int32)
+    p, _ = ops.attn_softmax_fwd(s.to(dev), Tk, lens.to(dev))
+    pr, _ = O.attn_softmax_fwd(s, Tk, lens)
+    assert (p.float().cpu() - pr.float()).abs().max().item() < 0.01
+    sq = (torch.randn(H, B, 16, 16) * 2).bfloat16()
+    l2 = torch.tensor([16, 9, 3], dtype=torch.int32)
+    p, _ = ops.attn_softmax_fwd(sq.to(dev), 16, l2.to(dev), causal=True)
+    pr, _ = O.attn_softmax_fwd(sq, 16, l2, causal=True)
+    assert (p.float().cpu() - pr.float()).abs().max().item() < 0.01
+    dp = torch.randn(H, B, Tq, ld).bfloat16()
+    ds, _ = ops.attn_softmax_bwd(ops.attn_softmax_fwd(s.to(dev), Tk, lens.to(dev))[0], dp.to(dev), Tk, 0, want_dbd=False)
+    dsr, _ = O.attn_softmax_bwd(O.attn_softmax_fwd(s, Tk, lens)[0], dp, Tk, 0, want_dbd=False)
+    assert (ds.float().cpu()[..., :Tk] - dsr.float()[..., :Tk]).abs().max().item() < 0.03

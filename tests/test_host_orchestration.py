@@ -88,18 +88,17 @@ def test_encoder_forward_backward_vs_reference_fixture(layer_type, golden_dir, c
     for k in g.files:
         if not k.startswith("grad.encoder."):
             continue
-        name = k[len("grad.encoder."):]
-        if (name.startswith("pre_encoder.convolutions") and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
             continue  # analytically zero gradients (bias feeding BatchNorm; key bias under softmax): rounding noise only
         ours = m.flat.grad(name).numpy()
         refg = g[k]
-        scale = max(np.abs(refg).max(), 1e-2)
-        err = np.abs(ours - refg).max() / scale
-        worst.append((err, name))
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
     worst.sort(reverse=True)
     print(worst[:8])
-    assert worst[0][0] < 0.3, worst[:5]  # bf16 end-to-end (incl. the bf16 torch conv front) vs fp32 reference gradients
-    assert max(w[0] for w in worst if not w[1].startswith("pre_encoder")) < 0.12, worst[:8]
+    # relative Frobenius error per tensor, bf16 end to end vs the fp32 reference gradients
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.1, worst[:8]
     med = np.median([w[0] for w in worst])
     assert med < 0.03, med
     # BatchNorm running statistics follow the reference (momentum update incl. padded frames)
@@ -169,3 +168,65 @@ def test_flat_params_layout():
     lin["c"].weight.data.fill_(3.0)
     assert float(w[16:].float().mean()) == 3.0  # parameters are views of the flat buffer
     assert fp.g32.numel() == fp.numel + 8
+
+
+# ---------------------------------------------------------------------------------------------------
+# encoder-decoder (speech_transformer_base) + label-smoothed CE vs the reference fixture
+# ---------------------------------------------------------------------------------------------------
+def _build_encdec(g, dropout=0.0):
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerModelBase
+
+    cfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=dropout, attention_dropout=dropout, activation_dropout=dropout, layernorm_embedding=False,
+        max_target_positions=200,
+        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True, learned_pos=False,
+                     relative_positional_embeddings=True, layer_type="transformer"),
+        decoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True, learned_pos=False,
+                     relative_positional_embeddings=False, input_dim=64, output_dim=64)))
+    m = SpeechTransformerModelBase.build_model(cfg, _Task(50))
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    return m
+
+
+def test_encdec_state_dict_keys_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g)
+    assert sorted(m.state_dict().keys()) == sorted(k[3:] for k in g.files if k.startswith("sd."))
+
+
+def test_encdec_forward_backward_vs_reference_fixture(golden_dir, cpu_ops):
+    from espresso_b200.criterions import LabelSmoothedCrossEntropyV2Criterion
+
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g).finalize_(torch.device("cpu"))
+    crit = LabelSmoothedCrossEntropyV2Criterion(_Task(50), label_smoothing=float(g["eps"]))
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"]),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"])},
+              "target": torch.from_numpy(g["target"])}
+    m.train()
+    m.flat.zero_grad()
+    loss, sample_size, log = crit(m, sample)
+    assert int(sample_size) == int((g["target"] != 1).sum())
+    assert abs(loss.item() - float(g["loss"])) < 0.03 * float(g["loss"])
+    assert abs(log["nll_loss"].item() - float(g["nll"])) < 0.03 * float(g["nll"])
+    loss.backward()
+    m.encoder.sync_torch_grads_()
+    worst = []
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+            continue
+        ours, refg = m.flat.grad(name).numpy(), g[k]
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
+    worst.sort(reverse=True)
+    print(worst[:6])
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.1, worst[:8]
+    assert np.median([w[0] for w in worst]) < 0.03
+    with torch.no_grad():  # still in train mode: the fixture's logits come from the training forward (batch-stat BN)
+        logits, _ = m(**sample["net_input"])
+    ref = g["logits"]
+    assert logits.shape == ref.shape
+    assert np.abs(logits.float().numpy() - ref).max() < 0.06 * np.abs(ref).max()
