@@ -418,3 +418,53 @@ def argmax_rows(x, V):
     out = torch.empty(R, device=x.device, dtype=torch.int32)
     _lib.check(_lib.load().esp_argmax_rows(_ptr(x), x.stride(0), V, R, _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# beam search step
+# ----------------------------------------------------------------------------------------------
+def beam_merge(x, V, x_is_logits, out, prev_scores=None, temperature=1.0, lm=None, lm_is_logits=True, lm_weight=0.0,
+               pad=1, unk=3, unk_penalty=0.0, eos=2, force_eos=False, eos_factor=None, ban_eos=False):
+    """x [N, ld] (bf16 logits or fp32 log-probs) -> out fp32 [N, V] masked candidate scores (+ prev_scores[n])."""
+    _need_cuda(x, out, prev_scores, lm)
+    assert x.stride(1) == 1 and out.is_contiguous() and out.dtype == torch.float32
+    N = x.shape[0]
+    _lib.check(_lib.load().esp_beam_merge(
+        _ptr(x), int(x.dtype == torch.float32), x.stride(0), int(x_is_logits), temperature, _ptr(lm),
+        int(lm is not None and lm.dtype == torch.float32), 0 if lm is None else lm.stride(0), int(lm_is_logits), lm_weight, N, V,
+        _ptr(prev_scores), pad, unk, unk_penalty, eos, int(force_eos), int(eos_factor is not None),
+        0.0 if eos_factor is None else float(eos_factor), int(ban_eos), _ptr(out), _stream()))
+    return out
+
+
+def beam_topk(cand, bsz, sent_stride, n_cand, K, V):
+    """cand fp32; per sentence top-K of n_cand candidates -> (scores [bsz,K], tokens int32, beams int32)."""
+    _need_cuda(cand)
+    s = torch.empty(bsz, K, device=cand.device, dtype=torch.float32)
+    t = torch.empty(bsz, K, device=cand.device, dtype=torch.int32)
+    b = torch.empty(bsz, K, device=cand.device, dtype=torch.int32)
+    _lib.check(_lib.load().esp_beam_topk(_ptr(cand), sent_stride, bsz, n_cand, K, V, _ptr(s), _ptr(t), _ptr(b), _stream()))
+    return s, t, b
+
+
+def beam_bookkeep(step, max_len, bsz, beam, K, eos, pad, normalize, len_penalty, cs, ct, cb, st):
+    """st: SearchState-like object with tokens/scores ping-pong buffers and finalisation slots (see
+    espresso_b200/sequence_generator.py).  Swaps the ping-pong halves."""
+    _lib.check(_lib.load().esp_beam_bookkeep(
+        step, max_len, bsz, beam, K, eos, pad, int(normalize), len_penalty, _ptr(cs), _ptr(ct), _ptr(cb), _ptr(st.tokens),
+        _ptr(st.tokens_alt), _ptr(st.scores), _ptr(st.scores_alt), _ptr(st.ignore), _ptr(st.finished), _ptr(st.nfin),
+        _ptr(st.fin_tokens), _ptr(st.fin_len), _ptr(st.fin_score), _ptr(st.fin_pos), _ptr(st.new_order), _ptr(st.n_unfinished),
+        _stream()))
+    st.tokens, st.tokens_alt = st.tokens_alt, st.tokens
+    st.scores, st.scores_alt = st.scores_alt, st.scores
+
+
+def gather_rows(src, idx, out=None):
+    """out[i] = src[idx[i]] along dim 0 (rows must be multiples of 16 bytes)."""
+    _need_cuda(src, idx)
+    assert src.is_contiguous() and idx.dtype == torch.int32
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    row_bytes = src[0].numel() * src.element_size()
+    _lib.check(_lib.load().esp_gather_rows(_ptr(src), _ptr(idx), row_bytes, idx.numel(), _ptr(out), _stream()))
+    return out

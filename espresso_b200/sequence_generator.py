@@ -1,0 +1,156 @@
+"""Batched beam search with LM shallow fusion, B200-native mirror of `SequenceGenerator`
+(fairseq/sequence_generator.py:27-621 with the Espresso patches: lm_model / lm_weight :385-393, eos_factor
+:404-410) and `BeamSearch.step` (fairseq/search.py:103-144).
+
+generate(models, sample) -> List[bsz] of List[<= beam] of {"tokens" (ends with eos), "score", "attention",
+"alignment", "positional_scores"}, sorted by score -- the reference's contract (:744-752).
+
+The per-step tensor work is three native kernels (esp_beam_merge, esp_beam_topk, esp_beam_bookkeep) plus
+esp_gather_rows for the incremental state; hypothesis bookkeeping and finalisation live in device buffers, and the
+only host<->device traffic per step is one 4-byte "how many sentences are unfinished" read.  Finished sentences are
+kept in the batch (static shapes) instead of being compacted away (:507-541): results are identical.
+
+Model protocol (implemented by espresso_b200 models and by test doubles):
+    enc = model.forward_encoder(net_input)                       # any object
+    model.max_decoder_positions() -> int
+    state = model.init_incremental_state(enc, bsz, beam)          # encoder state replicated per beam if needed
+    values, is_logits = model.decode_step(step, tokens, state, new_order)
+        tokens: int32 [bsz*beam, max_len+2] device buffer (columns 0..step are valid);
+        new_order: int32 [bsz*beam] source row of each hypothesis since the previous step (None at step 0);
+        values: [bsz*beam, >= V] bf16/fp32 logits (is_logits) or fp32 log-probabilities.
+"""
+import math
+
+import torch
+
+from . import ops as _ops
+
+
+class _SearchState:
+    pass
+
+
+class SequenceGenerator:
+    def __init__(self, models, tgt_dict, beam_size=1, max_len_a=0, max_len_b=200, max_len=0, min_len=1,
+                 normalize_scores=True, len_penalty=1.0, unk_penalty=0.0, temperature=1.0, lm_model=None, lm_weight=1.0,
+                 eos_factor=None, eos=None, **unused):
+        self.models = models if isinstance(models, (list, tuple)) else [models]
+        if len(self.models) != 1:
+            raise NotImplementedError("ensembles are not on the B200 path yet")
+        self.tgt_dict = tgt_dict
+        self.pad, self.unk = tgt_dict.pad(), tgt_dict.unk()
+        self.eos = tgt_dict.eos() if eos is None else eos
+        self.vocab_size = len(tgt_dict)
+        self.beam_size = min(beam_size, self.vocab_size - 1)
+        self.max_len_a, self.max_len_b, self.min_len = max_len_a, max_len_b, min_len
+        self.max_len = max_len or self.models[0].max_decoder_positions()
+        self.normalize_scores, self.len_penalty, self.unk_penalty = normalize_scores, len_penalty, unk_penalty
+        self.temperature = temperature
+        assert temperature > 0, "--temperature must be greater than 0"
+        self.lm_model, self.lm_weight = lm_model, lm_weight
+        self.eos_factor = eos_factor
+        assert eos_factor is None or eos_factor >= 1.0, "--eos-factor must be >= 1.0 if set"
+
+    @torch.no_grad()
+    def generate(self, models, sample, **kwargs):
+        return self._generate(sample, **kwargs)
+
+    def forward(self, sample, **kwargs):
+        return self._generate(sample, **kwargs)
+
+    @torch.no_grad()
+    def _generate(self, sample, bos_token=None, **unused):
+        model = self.models[0]
+        net_input = sample["net_input"]
+        src_tokens = net_input["src_tokens"]
+        dev = src_tokens.device
+        bsz, src_len = src_tokens.shape[:2]
+        beam, V = self.beam_size, self.vocab_size
+        max_len = min(int(self.max_len_a * src_len + self.max_len_b), self.max_len - 1)  # :285-288
+        assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"
+        N, L = bsz * beam, max_len + 2
+
+        enc = model.forward_encoder(net_input)
+        state = model.init_incremental_state(enc, bsz, beam)
+        lm_state = self.lm_model.init_incremental_state(None, bsz, beam) if self.lm_model is not None else None
+
+        st = _SearchState()
+        st.tokens = torch.full((N, L), self.pad, dtype=torch.int32, device=dev)
+        st.tokens[:, 0] = self.eos if bos_token is None else bos_token
+        st.tokens_alt = torch.empty_like(st.tokens)
+        st.scores = torch.zeros(N, L - 1, dtype=torch.float32, device=dev)
+        st.scores_alt = torch.zeros_like(st.scores)
+        st.ignore = torch.zeros(N, dtype=torch.uint8, device=dev)
+        st.finished = torch.zeros(bsz, dtype=torch.uint8, device=dev)
+        st.nfin = torch.zeros(bsz, dtype=torch.int32, device=dev)
+        st.fin_tokens = torch.full((bsz, beam, L - 1), self.pad, dtype=torch.int32, device=dev)
+        st.fin_len = torch.zeros(bsz, beam, dtype=torch.int32, device=dev)
+        st.fin_score = torch.zeros(bsz, beam, dtype=torch.float32, device=dev)
+        st.fin_pos = torch.zeros(bsz, beam, L - 1, dtype=torch.float32, device=dev)
+        st.new_order = torch.arange(N, dtype=torch.int32, device=dev)
+        st.n_unfinished = torch.full((1,), bsz, dtype=torch.int32, device=dev)
+        cand = torch.empty(N, V, dtype=torch.float32, device=dev)
+        prev = torch.empty(N, dtype=torch.float32, device=dev)
+
+        new_order = None
+        for step in range(max_len + 1):  # one extra step for the eos marker
+            values, is_logits = model.decode_step(step, st.tokens, state, new_order)
+            lm_vals, lm_logits = (None, True)
+            if self.lm_model is not None:
+                lm_vals, lm_logits = self.lm_model.decode_step(step, st.tokens, lm_state, new_order)
+            if step > 0:
+                prev.copy_(st.scores[:, step - 1])
+            _ops.beam_merge(values, V, is_logits, cand, prev_scores=prev if step > 0 else None, temperature=self.temperature,
+                            lm=lm_vals, lm_is_logits=lm_logits, lm_weight=self.lm_weight, pad=self.pad, unk=self.unk,
+                            unk_penalty=self.unk_penalty, eos=self.eos, force_eos=step >= max_len,
+                            eos_factor=self.eos_factor, ban_eos=step < self.min_len)
+            n_cand = V if step == 0 else beam * V  # step 0: all beams are identical, use the first (search.py:119-122)
+            K = min(2 * beam, n_cand - 1)
+            cs, ct, cb = _ops.beam_topk(cand, bsz, beam * V, n_cand, K, V)
+            _ops.beam_bookkeep(step, max_len, bsz, beam, K, self.eos, self.pad, self.normalize_scores, self.len_penalty,
+                               cs, ct, cb, st)
+            new_order = st.new_order
+            if int(st.n_unfinished.item()) == 0:  # the step's single host sync
+                break
+
+        # ---- collect (:611-620): sort each sentence's hypotheses by score, descending
+        nfin = st.nfin.cpu().tolist()
+        fl, fs = st.fin_len.cpu(), st.fin_score.cpu()
+        ft, fp = st.fin_tokens.cpu(), st.fin_pos.cpu()
+        finalized = []
+        for s in range(bsz):
+            hyps = []
+            for k in range(nfin[s]):
+                n = int(fl[s, k])
+                hyps.append({"tokens": ft[s, k, :n].long(), "score": fs[s, k].clone(), "attention": None, "alignment": None,
+                             "positional_scores": fp[s, k, :n].clone()})
+            order = sorted(range(len(hyps)), key=lambda i: -float(hyps[i]["score"]))
+            finalized.append([hyps[i] for i in order])
+        return finalized
+
+
+class TableDecoderModel:
+    """Decoder double driven by per-step probability tables (the reference's TestIncrementalDecoder,
+    tests/utils.py:546-603): used to run the reference's known-answer beam-search tests against this generator."""
+
+    def __init__(self, beam_probs, vocab_size, eos, max_positions=100):
+        self.beam_probs, self.V, self.eos, self.max_pos = beam_probs, vocab_size, eos, max_positions
+
+    def max_decoder_positions(self):
+        return self.max_pos
+
+    def forward_encoder(self, net_input):
+        return None
+
+    def init_incremental_state(self, enc, bsz, beam):
+        return {"order": None}
+
+    def decode_step(self, step, tokens, state, new_order):
+        N = tokens.shape[0]
+        probs = torch.zeros(N, self.V, dtype=torch.float32)
+        if step < len(self.beam_probs):
+            t = self.beam_probs[step]
+            probs[:, self.eos:] = t if t.shape[0] == N else t[: N]
+        else:
+            probs[:, self.eos] = 1.0
+        return probs.log().to(tokens.device), False

@@ -197,6 +197,30 @@ int esp_embed_bwd(const int32_t* tokens, const void* dx, int32_t d, float scale,
 /* out[r] = argmax_v x[r, v<V]  (greedy CTC decoding, espresso/tools/ctc_decoder.py:163-188) */
 int esp_argmax_rows(const void* x, int64_t ld, int32_t V, int64_t R, int32_t* out, void* stream);
 
+/* ---- batched beam search step (fairseq/sequence_generator.py:355-609, fairseq/search.py:103-144) -------------
+ * merge: out[n, v] = masked fused log-prob + prev_scores[n]: fp32 log-softmax of x/temperature (x_is_logits) or x as
+ *   given, + lm_weight * (LM log-probs) (:385-393), NaN -> -inf, pad -> -inf, unk -= penalty, force_eos (step >=
+ *   max_len, :401-403), eos_factor gate (:404-410), ban_eos (step < min_len, :422-424).  x / lm: bf16 or fp32 rows.
+ * topk: per sentence, the best K of n_cand = nb*V candidates (row stride sent_stride), ordered by (score desc, flat
+ *   index asc); token = idx % V, beam = idx / V.
+ * bookkeep: finalise eos candidates, pick the next `beam` hypotheses, re-gather tokens [N, max_len+2] / cumulative
+ *   scores [N, max_len+1] into the *_out buffers, emit new_order (source row of every new hypothesis) and keep a
+ *   device count of unfinished sentences.  fin_tokens / fin_pos: [bsz, beam, max_len+1]; fin_len / fin_score: [bsz, beam].
+ * gather_rows: dst[i, :] = src[idx[i], :] for incremental-state reordering (multihead_attention.py:964-989). */
+int esp_beam_merge(const void* x, int32_t x_f32, int64_t ld_x, int32_t x_is_logits, float temperature, const void* lm,
+                   int32_t lm_f32, int64_t ld_lm, int32_t lm_is_logits, float lm_weight, int32_t N, int32_t V,
+                   const float* prev_scores, int32_t pad, int32_t unk, float unk_penalty, int32_t eos, int32_t force_eos,
+                   int32_t use_eos_factor, float eos_factor, int32_t ban_eos, float* out, void* stream);
+int esp_beam_topk(const float* cand, int64_t sent_stride, int32_t bsz, int32_t n_cand, int32_t K, int32_t V,
+                  float* out_scores, int32_t* out_tokens, int32_t* out_beams, void* stream);
+int esp_beam_bookkeep(int32_t step, int32_t max_len, int32_t bsz, int32_t beam, int32_t K, int32_t eos, int32_t pad,
+                      int32_t normalize, float len_penalty, const float* cand_scores, const int32_t* cand_tokens,
+                      const int32_t* cand_beams, const int32_t* tokens_in, int32_t* tokens_out, const float* scores_in,
+                      float* scores_out, uint8_t* ignore, uint8_t* finished, int32_t* nfin, int32_t* fin_tokens,
+                      int32_t* fin_len, float* fin_score, float* fin_pos, int32_t* new_order, int32_t* n_unfinished,
+                      void* stream);
+int esp_gather_rows(const void* src, const int32_t* idx, int64_t row_bytes, int64_t n_rows, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

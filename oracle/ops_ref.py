@@ -370,3 +370,111 @@ def embed_bwd(tokens, dx, dE_acc, scale, pad_idx, drop_p=0.0, seed=0):
 
 def argmax_rows(x, V):
     return x[:, :V].float().argmax(-1).to(torch.int32)
+
+
+def beam_merge(x, V, x_is_logits, out, prev_scores=None, temperature=1.0, lm=None, lm_is_logits=True, lm_weight=0.0,
+               pad=1, unk=3, unk_penalty=0.0, eos=2, force_eos=False, eos_factor=None, ban_eos=False):
+    lp = x.float()[:, :V]
+    if x_is_logits:
+        lp = torch.log_softmax(lp / temperature, dim=-1)
+    lp = lp.clone()
+    if lm is not None:
+        l = lm.float()[:, :V]
+        lp += lm_weight * (torch.log_softmax(l, dim=-1) if lm_is_logits else l)
+    lp[lp != lp] = float("-inf")
+    lp[:, pad] = float("-inf")
+    lp[:, unk] -= unk_penalty
+    if force_eos:
+        lp[:, :eos] = float("-inf")
+        lp[:, eos + 1:] = float("-inf")
+    elif eos_factor is not None:
+        dis = lp[:, eos] < eos_factor * lp.max(dim=1)[0]
+        lp[dis, eos] = float("-inf")
+    if ban_eos:
+        lp[:, eos] = float("-inf")
+    if prev_scores is not None:
+        lp = lp + prev_scores[:, None]
+    out.copy_(lp)
+    return out
+
+
+def beam_topk(cand, bsz, sent_stride, n_cand, K, V):
+    flat = cand.reshape(-1)
+    s = torch.empty(bsz, K)
+    t = torch.empty(bsz, K, dtype=torch.int32)
+    b = torch.empty(bsz, K, dtype=torch.int32)
+    for i in range(bsz):
+        c = flat[i * sent_stride: i * sent_stride + n_cand]
+        order = sorted(range(n_cand), key=lambda j: (-float(c[j]) if c[j] == c[j] else float("inf"), j))[:K]
+        for r, j in enumerate(order):
+            s[i, r], t[i, r], b[i, r] = c[j], j % V, j // V
+    return s, t, b
+
+
+def beam_bookkeep(step, max_len, bsz, beam, K, eos, pad, normalize, len_penalty, cs, ct, cb, st):
+    NEG = float("-inf")
+    L = max_len + 2
+    tin, sin = st.tokens, st.scores
+    tout, sout = st.tokens_alt, st.scores_alt
+    for s in range(bsz):
+        rb = s * beam
+        if st.finished[s]:
+            tout[rb:rb + beam] = tin[rb:rb + beam]
+            sout[rb:rb + beam] = sin[rb:rb + beam]
+            st.new_order[rb:rb + beam] = torch.arange(rb, rb + beam, dtype=torch.int32)
+            continue
+        had_eos = False
+        for c in range(min(beam, K)):
+            if int(ct[s, c]) == eos and float(cs[s, c]) != NEG and not st.ignore[rb + c]:
+                had_eos = True
+                slot = int(st.nfin[s])
+                if slot < beam:
+                    row = rb + int(cb[s, c])
+                    st.fin_tokens[s, slot, :step] = tin[row, 1:step + 1]
+                    st.fin_tokens[s, slot, step] = eos
+                    cum = torch.cat([sin[row, :step], cs[s, c].reshape(1)])
+                    pos = cum.clone()
+                    pos[1:] = cum[1:] - cum[:-1]
+                    st.fin_pos[s, slot, :step + 1] = pos
+                    st.fin_len[s, slot] = step + 1
+                    st.fin_score[s, slot] = cs[s, c] / (step + 1) ** len_penalty if normalize else cs[s, c]
+                    st.nfin[s] = slot + 1
+        done = False
+        if had_eos and (int(st.nfin[s]) == beam or step == max_len):
+            st.finished[s] = 1
+            st.n_unfinished -= 1
+            done = True
+        if done or step >= max_len:
+            tout[rb:rb + beam] = tin[rb:rb + beam]
+            sout[rb:rb + beam] = sin[rb:rb + beam]
+            st.new_order[rb:rb + beam] = torch.arange(rb, rb + beam, dtype=torch.int32)
+            continue
+        chosen = []
+        for want_masked in (False, True):
+            for c in range(K):
+                raw = int(ct[s, c]) == eos and float(cs[s, c]) != NEG
+                masked = (raw or bool(st.ignore[rb + c])) if c < beam else raw
+                if masked == want_masked and len(chosen) < beam:
+                    chosen.append((c, masked))
+        while len(chosen) < beam:
+            chosen.append((0, True))
+        for k, (c, masked) in enumerate(chosen):
+            old = rb + int(cb[s, c])
+            tout[rb + k, :step + 1] = tin[old, :step + 1]
+            tout[rb + k, step + 1] = ct[s, c]
+            tout[rb + k, step + 2:] = pad
+            sout[rb + k, :step] = sin[old, :step]
+            sout[rb + k, step] = cs[s, c]
+            st.new_order[rb + k] = old
+        for k, (c, masked) in enumerate(chosen):
+            st.ignore[rb + k] = 1 if masked else 0
+    st.tokens, st.tokens_alt = tout, tin
+    st.scores, st.scores_alt = sout, sin
+
+
+def gather_rows(src, idx, out=None):
+    r = src[idx.long()]
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
