@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...flat import FlatParams
-from ...modules.decoder_engine import DecoderEngine
+from ...modules.decoder_engine import DecoderEngine, IncrementalDecoder
 from ...registry import register_model
 from .speech_transformer_config import DEFAULT_MAX_SOURCE_POSITIONS, SpeechTransformerConfig, eval_str_nested_list_or_tuple
 from .speech_transformer_encoder_model import (ConvBNReLU, SpeechTransformerEncoderForPrediction, _Affine, _Linear,
@@ -140,6 +140,7 @@ class SpeechTransformerModelBase(nn.Module):
         self.decoder = decoder
         self.num_updates = 0
         self.frontend = None
+        self.t_max_hint = 1 << 30  # generators may lower this to bound the KV caches (max decode length)
 
     @classmethod
     def build_embedding(cls, cfg, dictionary, embed_dim):
@@ -215,6 +216,27 @@ class SpeechTransformerModelBase(nn.Module):
     def get_normalized_probs(self, net_output, log_probs, sample=None):
         logits = net_output[0].float()
         return F.log_softmax(logits, dim=-1) if log_probs else F.softmax(logits, dim=-1)
+
+    # ---- generator protocol (espresso_b200/sequence_generator.py) --------------------------------
+    def max_decoder_positions(self):
+        return self.decoder.max_positions()
+
+    def forward_encoder(self, net_input):
+        src_tokens, src_lengths = net_input["src_tokens"], net_input["src_lengths"]
+        if src_tokens.dim() == 2:
+            src_tokens, src_lengths = self.frontend(src_tokens, src_lengths, None, None)
+        return self.encoder(src_tokens, src_lengths, src_lengths_cpu=net_input.get("src_lengths_cpu"))
+
+    def init_incremental_state(self, encoder_out, bsz, beam):
+        enc = encoder_out["b200_out"]
+        has_pad = len(encoder_out["encoder_padding_mask"]) > 0
+        lens = encoder_out["src_lengths"][0].to(torch.int32) if has_pad else None
+        self.decoder.engine.training = False
+        inc = IncrementalDecoder(self.decoder.engine)
+        return {"inc": inc, "st": inc.init_state(enc, lens, bsz, beam, min(self.decoder.max_positions(), self.t_max_hint) + 2)}
+
+    def decode_step(self, step, tokens, state, new_order):
+        return state["inc"].step(step, tokens, state["st"], new_order), True
 
 
 # legacy class name kept by the reference (espresso/models/transformer/speech_transformer_legacy.py:23-24)

@@ -226,3 +226,77 @@ class DecoderEngine(EncoderEngine):
         _ops.embed_bwd(s["tok"], dx, self.G("embed_tokens.weight"), s["scale"], cfg["pad"], pdrop, self._seed(998, 0))
         self.saved = None
         return denc.view(B, Tk, d)
+
+
+class IncrementalDecoder:
+    """One-token-per-hypothesis decoder step for beam search (eval only), over the same flat parameters as
+    DecoderEngine.  Mirrors the incremental branch of the reference decoder
+    (fairseq/models/transformer/transformer_decoder.py:300-305 `prev_output_tokens[:, -1:]`,
+    fairseq/modules/transformer_layer.py:384-533 with incremental_state, multihead_attention.py:639-760).
+
+    State: per layer a K/V cache [T_max, N, 2d] written in place by the K/V projection GEMM, an ancestry table
+    [T_max, N] (see csrc/decode_attn.cu) and the encoder-attention K/V [bsz, Tk, 2d] computed once per sentence
+    (the reference's beamable encoder attention, multihead_attention.py:661-669)."""
+
+    def __init__(self, engine: DecoderEngine):
+        self.e = engine
+
+    def init_state(self, enc, enc_lens, bsz, beam, t_max):
+        """enc bf16 [bsz, Tk, d] or None (language model: no encoder attention)."""
+        e = self.e
+        d, Lr = e.d, e.cfg["layers"]
+        N = bsz * beam
+        dev = e.flat.p16.device
+        st = dict(N=N, beam=beam, bsz=bsz, enc_lens=enc_lens, t_max=t_max)
+        st["kv"] = [torch.empty(t_max, N, 2 * d, device=dev, dtype=torch.bfloat16) for _ in range(Lr)]
+        st["anc"] = torch.zeros(t_max, N, device=dev, dtype=torch.int32)
+        st["anc_alt"] = torch.zeros_like(st["anc"])
+        st["cross"] = None
+        if enc is not None:
+            Tk = enc.shape[1]
+            enc2 = enc.reshape(bsz * Tk, d)
+            cross = []
+            for li in range(Lr):
+                Wkv, bkv, _, _ = e._proj("layers.%d." % li, "encoder_attn", "kv")
+                cross.append(_ops.linear(enc2, Wkv, bkv).view(bsz, Tk, 2 * d))
+            st["cross"] = cross
+        return st
+
+    def step(self, step, tokens, st, new_order):
+        """tokens int32 [N, L] (column `step` is the newest token) -> logits bf16 [N, ldV]."""
+        e = self.e
+        cfg = e.cfg
+        d, H, V = e.d, e.H, cfg["vocab"]
+        N = st["N"]
+        _ops.decode_update_ancestry(st["anc"], st["anc_alt"], new_order if step > 0 else None, step)
+        st["anc"], st["anc_alt"] = st["anc_alt"], st["anc"]
+        scale = 1.0 if cfg.get("no_scale_embedding", False) else math.sqrt(d)
+        tok = tokens[:, step].contiguous()
+        pos = e.positions(st["t_max"], tokens.device)[step: step + 1]
+        x = _ops.embed_fwd(tok, e.P("embed_tokens.weight"), pos, 1, scale, cfg["pad"])
+        if cfg.get("layernorm_embedding", False):
+            x, _, _ = _ops.layer_norm_fwd(x, e.P("layernorm_embedding.weight"), e.P("layernorm_embedding.bias"), LN_EPS)
+        for li in range(cfg["layers"]):
+            lp = "layers.%d." % li
+            ln, _, _ = _ops.layer_norm_fwd(x, e.P(lp + "self_attn_layer_norm.weight"), e.P(lp + "self_attn_layer_norm.bias"), LN_EPS)
+            W, b, _, _ = e._proj(lp, "self_attn", "qkv")
+            q = _ops.linear(ln, W[:d], b[:d])
+            _ops.linear(ln, W[d:], b[d:], out=st["kv"][li][step])  # K | V of this step, written into the cache
+            ctx = _ops.decode_self_attn(q, st["kv"][li], st["anc"], step + 1, H, e.scaling)
+            x = _ops.linear(ctx, e.P(lp + "self_attn.out_proj.weight"), e.P(lp + "self_attn.out_proj.bias"), R=x, ldr=d, beta=1.0)
+            if st["cross"] is not None:
+                ln, _, _ = _ops.layer_norm_fwd(x, e.P(lp + "encoder_attn_layer_norm.weight"), e.P(lp + "encoder_attn_layer_norm.bias"),
+                                               LN_EPS)
+                q = _ops.linear(ln, e.P(lp + "encoder_attn.q_proj.weight"), e.P(lp + "encoder_attn.q_proj.bias"))
+                ctx = _ops.decode_cross_attn(q, st["cross"][li], st["enc_lens"], st["beam"], H, e.scaling)
+                x = _ops.linear(ctx, e.P(lp + "encoder_attn.out_proj.weight"), e.P(lp + "encoder_attn.out_proj.bias"), R=x, ldr=d,
+                                beta=1.0)
+            ln, _, _ = _ops.layer_norm_fwd(x, e.P(lp + "final_layer_norm.weight"), e.P(lp + "final_layer_norm.bias"), LN_EPS)
+            hh = _ops.linear(ln, e.P(lp + "fc1.weight"), e.P(lp + "fc1.bias"), act=ACT_RELU)
+            x = _ops.linear(hh, e.P(lp + "fc2.weight"), e.P(lp + "fc2.bias"), R=x, ldr=d, beta=1.0)
+        x, _, _ = _ops.layer_norm_fwd(x, e.P("layer_norm.weight"), e.P("layer_norm.bias"), LN_EPS)
+        ldV = _r8(V)
+        logits = torch.empty(N, ldV, device=x.device, dtype=torch.bfloat16)
+        Wo = e.out_weight()
+        _ops.gemm(x, Wo, logits, N, V, d, d, Wo.stride(0), ldV)
+        return logits

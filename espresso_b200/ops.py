@@ -468,3 +468,33 @@ def gather_rows(src, idx, out=None):
     row_bytes = src[0].numel() * src.element_size()
     _lib.check(_lib.load().esp_gather_rows(_ptr(src), _ptr(idx), row_bytes, idx.numel(), _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# incremental decoding
+# ----------------------------------------------------------------------------------------------
+def decode_self_attn(q, kv_cache, anc, T, H, scale):
+    """q bf16 [N, d]; kv_cache bf16 [T_max, N, 2d]; anc int32 [T_max, N]; attends over times 0..T-1 -> [N, d]."""
+    _need_cuda(q, kv_cache, anc)
+    _bf(q, kv_cache)
+    N, d = q.shape
+    out = torch.empty_like(q)
+    _lib.check(_lib.load().esp_decode_self_attn(_ptr(q), _ptr(kv_cache), _ptr(anc), N, H, d // H, T, scale, _ptr(out), _stream()))
+    return out
+
+
+def decode_cross_attn(q, kv, lens, beam, H, scale):
+    """q bf16 [N, d]; kv bf16 [bsz, Tk, 2d]; lens int32 [bsz] or None -> [N, d]."""
+    _need_cuda(q, kv, lens)
+    _bf(q, kv)
+    N, d = q.shape
+    out = torch.empty_like(q)
+    _lib.check(_lib.load().esp_decode_cross_attn(_ptr(q), _ptr(kv), _ptr(lens), N, beam, H, d // H, kv.shape[1], scale, _ptr(out),
+                                                 _stream()))
+    return out
+
+
+def decode_update_ancestry(anc_in, anc_out, new_order, step):
+    _need_cuda(anc_in, anc_out, new_order)
+    N = anc_in.shape[1]
+    _lib.check(_lib.load().esp_decode_update_ancestry(_ptr(anc_in), _ptr(anc_out), _ptr(new_order), N, step, _stream()))

@@ -70,9 +70,15 @@ class SequenceGenerator:
         assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"
         N, L = bsz * beam, max_len + 2
 
+        for m_ in (model, self.lm_model):
+            if m_ is not None and hasattr(m_, "t_max_hint"):
+                m_.t_max_hint = max_len + 1
         enc = model.forward_encoder(net_input)
         state = model.init_incremental_state(enc, bsz, beam)
         lm_state = self.lm_model.init_incremental_state(None, bsz, beam) if self.lm_model is not None else None
+        for s_ in (state, lm_state):  # models may size their caches from this
+            if isinstance(s_, dict):
+                s_["max_len"] = max_len
 
         st = _SearchState()
         st.tokens = torch.full((N, L), self.pad, dtype=torch.int32, device=dev)

@@ -221,6 +221,18 @@ int esp_beam_bookkeep(int32_t step, int32_t max_len, int32_t bsz, int32_t beam, 
                       void* stream);
 int esp_gather_rows(const void* src, const int32_t* idx, int64_t row_bytes, int64_t n_rows, void* dst, void* stream);
 
+/* ---- incremental decoding (fairseq/modules/multihead_attention.py:639-760,878-897,964-989) --------------
+ * One query per hypothesis.  Self-attention: kv_cache [T_max, N, 2d] (k | v) is written in place by the K/V
+ * projection GEMM of each step; anc [T_max, N] maps (time, hypothesis) -> cache row, so beam reordering never
+ * moves K/V (update_ancestry re-gathers only the int table).  Cross-attention: kv [bsz, Tk, 2d] per SENTENCE
+ * (hypothesis n reads sentence n / beam), lens = valid encoder frames or NULL. */
+int esp_decode_self_attn(const void* q, const void* kv_cache, const int32_t* anc, int32_t N, int32_t H, int32_t hd, int32_t T,
+                         float scale, void* out, void* stream);
+int esp_decode_cross_attn(const void* q, const void* kv, const int32_t* lens, int32_t N, int32_t beam, int32_t H, int32_t hd,
+                          int32_t Tk, float scale, void* out, void* stream);
+int esp_decode_update_ancestry(const int32_t* anc_in, int32_t* anc_out, const int32_t* new_order, int32_t N, int32_t step,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -478,3 +478,39 @@ def gather_rows(src, idx, out=None):
         out.copy_(r)
         return out
     return r
+
+
+def decode_self_attn(q, kv_cache, anc, T, H, scale):
+    N, d = q.shape
+    hd = d // H
+    rows = anc[:T].long()                                   # [T, N]
+    kvs = kv_cache[:T].float()[torch.arange(T)[:, None], rows]  # [T, N, 2d]
+    k = kvs[..., :d].reshape(T, N, H, hd)
+    v = kvs[..., d:].reshape(T, N, H, hd)
+    qh = q.float().reshape(N, H, hd)
+    s = torch.einsum("nhc,tnhc->nht", qh, k) * scale
+    p = torch.softmax(s, dim=-1).to(BF).float()
+    return torch.einsum("nht,tnhc->nhc", p, v).reshape(N, d).to(BF)
+
+
+def decode_cross_attn(q, kv, lens, beam, H, scale):
+    N, d = q.shape
+    hd = d // H
+    bsz, Tk, _ = kv.shape
+    sent = torch.arange(N) // beam
+    k = kv.float()[sent][..., :d].reshape(N, Tk, H, hd)
+    v = kv.float()[sent][..., d:].reshape(N, Tk, H, hd)
+    s = torch.einsum("nhc,nthc->nht", q.float().reshape(N, H, hd), k) * scale
+    if lens is not None:
+        mask = torch.arange(Tk)[None, :] >= lens[sent][:, None]
+        s = s.masked_fill(mask[:, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1).to(BF).float()
+    return torch.einsum("nht,nthc->nhc", p, v).reshape(N, d).to(BF)
+
+
+def decode_update_ancestry(anc_in, anc_out, new_order, step):
+    N = anc_in.shape[1]
+    if step > 0:
+        src = anc_in[:step]
+        anc_out[:step] = src[:, new_order.long()] if new_order is not None else src
+    anc_out[step] = torch.arange(N, dtype=anc_out.dtype)

@@ -230,3 +230,33 @@ def test_encdec_forward_backward_vs_reference_fixture(golden_dir, cpu_ops):
     ref = g["logits"]
     assert logits.shape == ref.shape
     assert np.abs(logits.float().numpy() - ref).max() < 0.06 * np.abs(ref).max()
+
+
+def test_incremental_decoding_matches_teacher_forcing(golden_dir, cpu_ops):
+    """Each incremental step (KV cache + ancestry table + per-sentence encoder K/V, beam-replicated rows with a
+    shuffled beam order) must reproduce the teacher-forced decoder logits of the same prefix."""
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g).finalize_(torch.device("cpu"))
+    m.eval()
+    feats, lens = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"])
+    prev = torch.from_numpy(g["prev_output_tokens"])
+    B, U = prev.shape
+    with torch.no_grad():
+        full, _ = m(feats, lens, prev)                      # [B, U, V] teacher forced (eval mode)
+        enc = m.forward_encoder({"src_tokens": feats, "src_lengths": lens})
+        beam = 2
+        state = m.init_incremental_state(enc, B, beam)
+        N = B * beam
+        tokens = torch.full((N, U + 2), 1, dtype=torch.int32)
+        rows = torch.arange(N)
+        perm = None
+        for step in range(U):
+            # hypothesis n carries sentence n // beam's prefix; swap the two beams of every sentence each step
+            tokens[:, : step + 1] = prev[rows // beam, : step + 1].to(torch.int32)
+            logits, is_logits = m.decode_step(step, tokens, state, perm)
+            assert is_logits
+            ref = full[rows // beam, step].float()
+            got = logits[:, :50].float()
+            ok = prev[rows // beam, step] != 1               # positions fed with <pad> are not comparable
+            assert (got[ok] - ref[ok]).abs().max() < 0.08 * ref.abs().max(), step
+            perm = (rows ^ 1).to(torch.int32)                # new_order: take the sibling beam's state
