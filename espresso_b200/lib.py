@@ -75,6 +75,10 @@ SIGNATURES = {
     "esp_decode_self_attn": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "esp_decode_cross_attn": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "esp_decode_update_ancestry": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "esp_joint_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esp_joint_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esp_rnnt_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "esp_rnnt_loss": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "esp_sumsq_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
     "esp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _f32, _f32,
                                 _vp, _vp, _vp]),

@@ -5,4 +5,5 @@ from .transformer import (  # noqa: F401
     SpeechTransformerEncoderModel,
     SpeechTransformerModel,
     SpeechTransformerModelBase,
+    SpeechTransformerTransducerModelBase,
 )

@@ -4,3 +4,4 @@ from .speech_transformer_encoder_model import (  # noqa: F401
     SpeechTransformerEncoderModel,
 )
 from .speech_transformer_base import SpeechTransformerDecoderBase, SpeechTransformerModel, SpeechTransformerModelBase  # noqa: F401
+from .speech_transformer_transducer_base import SpeechTransformerTransducerModelBase  # noqa: F401

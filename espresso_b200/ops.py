@@ -498,3 +498,46 @@ def decode_update_ancestry(anc_in, anc_out, new_order, step):
     _need_cuda(anc_in, anc_out, new_order)
     N = anc_in.shape[1]
     _lib.check(_lib.load().esp_decode_update_ancestry(_ptr(anc_in), _ptr(anc_out), _ptr(new_order), N, step, _stream()))
+
+
+# ----------------------------------------------------------------------------------------------
+# transducer
+# ----------------------------------------------------------------------------------------------
+def joint_fwd(enc, dec):
+    """enc bf16 [B, T, J], dec bf16 [B, U1, J] -> relu(enc[:, :, None] + dec[:, None]) [B, T, U1, J]."""
+    _need_cuda(enc, dec)
+    _bf(enc, dec)
+    assert enc.is_contiguous() and dec.is_contiguous()
+    B, T, J = enc.shape
+    U1 = dec.shape[1]
+    out = torch.empty(B, T, U1, J, device=enc.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_joint_fwd(_ptr(enc), _ptr(dec), B, T, U1, J, _ptr(out), _stream()))
+    return out
+
+
+def joint_bwd(df, f):
+    """-> (denc bf16 [B, T, J], ddec fp32 [B, U1, J])."""
+    _need_cuda(df, f)
+    _bf(df, f)
+    assert df.is_contiguous() and f.is_contiguous()
+    B, T, U1, J = f.shape
+    denc = torch.empty(B, T, J, device=f.device, dtype=torch.bfloat16)
+    ddec = torch.zeros(B, U1, J, device=f.device, dtype=torch.float32)
+    _lib.check(_lib.load().esp_joint_bwd(_ptr(df), _ptr(f), B, T, U1, J, _ptr(denc), _ptr(ddec), _stream()))
+    return denc, ddec
+
+
+def rnnt_loss(logits, V, t_lens, u_lens, targets, blank, grad_scale=1.0, want_grad=True):
+    """logits bf16 [B, T, U1, ld]; targets int32 [B, u_max]; -> (loss fp32 [B], grad bf16 like logits or None)."""
+    _need_cuda(logits, t_lens, u_lens, targets)
+    _bf(logits)
+    assert logits.is_contiguous() and targets.dtype == torch.int32 and t_lens.dtype == torch.int32 and u_lens.dtype == torch.int32
+    B, T, U1, ld = logits.shape
+    L = _lib.load()
+    ws = torch.empty(int(L.esp_rnnt_workspace_bytes(B, T, U1)), device=logits.device, dtype=torch.uint8)
+    loss = torch.empty(B, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits) if want_grad else None
+    tg = targets.contiguous()
+    _lib.check(L.esp_rnnt_loss(_ptr(logits), ld, V, B, T, U1, _ptr(t_lens), _ptr(u_lens), _ptr(tg), tg.shape[1], blank, grad_scale,
+                               _ptr(loss), _ptr(grad), _ptr(ws), _stream()))
+    return loss, grad

@@ -65,7 +65,7 @@ class Trainer:
                 continue
             loss, sample_size, log = self.criterion(model, sample)
             loss.backward()
-            model.encoder.sync_torch_grads_()
+            (model.sync_torch_grads_ if hasattr(model, "sync_torch_grads_") else model.encoder.sync_torch_grads_)()
             # logging scalars ride in the gradient buffer's tail
             tail[0] += sample_size
             tail[1] += log["ntokens"]

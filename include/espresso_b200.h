@@ -233,6 +233,21 @@ int esp_decode_cross_attn(const void* q, const void* kv, const int32_t* lens, in
 int esp_decode_update_ancestry(const int32_t* anc_in, int32_t* anc_out, const int32_t* new_order, int32_t N, int32_t step,
                                void* stream);
 
+/* ---- transducer (RNN-T) ---------------------------------------------------------------------------------
+ * joint: F[b,t,u,:] = relu(enc[b,t,:] + dec[b,u,:]) (espresso/models/transformer/speech_transformer_transducer_base.py:
+ *   279-299, after the two projection+LayerNorm stages); backward: denc = sum_u dF*(F>0) (bf16, written),
+ *   ddec += sum_t dF*(F>0) (fp32, accumulated).
+ * rnnt_loss: torchaudio.functional.rnnt_loss(logits [B,T,U1,V] (row stride ld), targets int32 [B,u_max], t_lens, u_lens,
+ *   blank, clamp=-1, fused_log_softmax=True) as called by espresso/criterions/transducer_loss.py:130-140: loss fp32 [B]
+ *   (negative log-likelihood per utterance) and grad = grad_scale * d(sum loss)/d(logits) (bf16, same layout; cells
+ *   outside the utterance's lattice and padded columns are zero).  workspace: esp_rnnt_workspace_bytes(B, T, U1). */
+int esp_joint_fwd(const void* enc, const void* dec, int32_t B, int32_t T, int32_t U1, int32_t J, void* out, void* stream);
+int esp_joint_bwd(const void* df, const void* f, int32_t B, int32_t T, int32_t U1, int32_t J, void* denc, float* ddec, void* stream);
+int64_t esp_rnnt_workspace_bytes(int32_t B, int32_t T, int32_t U1);
+int esp_rnnt_loss(const void* logits, int64_t ld, int32_t V, int32_t B, int32_t T, int32_t U1, const int32_t* t_lens,
+                  const int32_t* u_lens, const int32_t* targets, int32_t u_max, int32_t blank, float grad_scale, float* loss,
+                  void* grad, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -514,3 +514,29 @@ def decode_update_ancestry(anc_in, anc_out, new_order, step):
         src = anc_in[:step]
         anc_out[:step] = src[:, new_order.long()] if new_order is not None else src
     anc_out[step] = torch.arange(N, dtype=anc_out.dtype)
+
+
+def joint_fwd(enc, dec):
+    return torch.relu(enc.float()[:, :, None, :] + dec.float()[:, None, :, :]).to(BF)
+
+
+def joint_bwd(df, f):
+    g = df.float() * (f.float() > 0).float()
+    return g.sum(2).to(BF), g.sum(1)
+
+
+def rnnt_loss(logits, V, t_lens, u_lens, targets, blank, grad_scale=1.0, want_grad=True):
+    """Oracle: the reference's own call -- torchaudio.functional.rnnt_loss with fused log-softmax, clamp=-1
+    (espresso/criterions/transducer_loss.py:130-140), differentiated by autograd, on fp32 copies of the bf16 logits."""
+    import torchaudio
+
+    with torch.enable_grad():
+        x = logits.detach().float()[..., :V].clone().requires_grad_(True)
+        loss = torchaudio.functional.rnnt_loss(x, targets.int(), t_lens.int(), u_lens.int(), blank=blank, clamp=-1.0, reduction="none")
+        grad = None
+        if want_grad:
+            loss.sum().backward()
+            grad = torch.zeros_like(logits, dtype=torch.float32)
+            grad[..., :V] = x.grad * grad_scale
+            grad = grad.to(BF)
+    return loss.detach(), grad

@@ -307,7 +307,104 @@ def pin_encdec():
     print("encdec pinned -> tests/golden/encdec_transformer.npz")
 
 
-SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec}
+def pin_transducer():
+    """Reference SpeechTransformerTransducerModelBase (Conformer encoder + LSTM predictor + joint) with the criterion's
+    torchaudio rnnt_loss call vs oracle/conformer.py + oracle/transducer.py; fixture for the RNN-T path (cfg 4)."""
+    import torchaudio
+
+    from espresso.models.transformer.speech_transformer_transducer_base import SpeechTransformerTransducerModelBase
+    from espresso.models.transformer.speech_transformer_transducer_config import SpeechTransformerTransducerConfig
+
+    from oracle import conformer as OC
+    from oracle import transducer as OT
+
+    V, pad_idx, eos_idx, blank = 50, 1, 2, 0
+    cfg = SpeechTransformerTransducerConfig()
+    cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
+    e = cfg.encoder
+    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
+    e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
+    e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = 64, 128, 2, 4
+    e.normalize_before, e.learned_pos, e.relative_positional_embeddings, e.layer_type = True, False, True, "conformer"
+    e.depthwise_conv_kernel_size = 31
+    d = cfg.decoder
+    d.embed_dim, d.hidden_size, d.layers, d.dropout_in, d.dropout_out, d.residual = 64, 64, 2, 0.0, 0.0, False
+    cfg.joint_dim = 64
+    cfg.layernorm_embedding = True
+    cfg.dropout = cfg.attention_dropout = cfg.activation_dropout = 0.0
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return pad_idx
+
+        def eos(self):
+            return eos_idx
+
+    class _Task:
+        feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+
+    torch.manual_seed(3)
+    m = SpeechTransformerTransducerModelBase.build_model(cfg, _Task())
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    rs = np.random.RandomState(13)
+    B, T = 3, 61
+    lens = torch.tensor([61, 50, 37])
+    feats = torch.from_numpy(rs.randn(B, T, 80).astype(np.float32))
+    for b in range(B):
+        feats[b, lens[b]:] = 0.0
+    U = 6
+    tgt = torch.full((B, U + 1), pad_idx, dtype=torch.long)
+    prev = torch.full((B, U + 1), pad_idx, dtype=torch.long)
+    for b, u in enumerate((6, 4, 2)):
+        toks = torch.from_numpy(rs.randint(4, V, size=u))
+        tgt[b, :u] = toks
+        tgt[b, u] = eos_idx
+        prev[b, 0] = eos_idx
+        prev[b, 1:u + 1] = toks
+    m.train()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m.zero_grad()
+    logits, enc_lens = m(feats, lens, prev)
+    u_lens = ((tgt != pad_idx) & (tgt != eos_idx)).sum(-1).int()
+    loss = torchaudio.functional.rnnt_loss(logits, tgt[:, :-1].int().contiguous(), enc_lens.int(), u_lens, blank=blank, clamp=-1.0,
+                                           reduction="sum")  # espresso/criterions/transducer_loss.py:130-140
+    loss.backward()
+    pnames = dict(m.named_parameters())
+    sd = {k: v.clone().requires_grad_(k in pnames) for k, v in sd0.items()}
+    ecfg = dict(embed_dim=64, ffn_dim=128, heads=4, layers=2, layer_type="conformer", dw_kernel=31, dropout=0.0,
+                attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, final_layer_norm=False, vocab=None)
+    enc, ol, _ = OC.encoder_forward(sd, ecfg, feats, lens, training=True)
+    dec = OT.predictor(sd, prev, 2, pad_idx)
+    o_logits = OT.joint_logits(sd, enc, dec)
+    o_loss = OT.transducer_loss(o_logits, ol, tgt, pad_idx, eos_idx, blank)
+    o_loss.backward()
+    dl = (o_logits - logits).abs().max().item()
+    print("transducer: |logits diff|=%.3g loss ref=%.6f oracle=%.6f" % (dl, loss.item(), o_loss.item()))
+    assert dl < 2e-4 and abs(loss.item() - o_loss.item()) < 1e-4 * abs(loss.item())
+    worst = 0.0
+    for n, p_ in m.named_parameters():
+        dg = (sd[n].grad - p_.grad).abs().max().item() / max(p_.grad.abs().max().item(), 1e-3)
+        worst = max(worst, dg)
+    print("   worst relative grad diff %.3g" % worst)
+    assert worst < 1e-2  # fp32 recurrences (LSTM, RNN-T lattice) accumulate in a different order
+    out = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    out.update({"grad." + n: p_.grad.numpy() for n, p_ in m.named_parameters()})
+    out.update(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), prev_output_tokens=prev.numpy(),
+               logits=logits.detach().numpy(), loss=np.float64(loss.item()), enc_lens=enc_lens.numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "transducer_conformer.npz"), **out)
+    print("transducer pinned -> tests/golden/transducer_conformer.npz")
+
+
+SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+            "transducer": pin_transducer}
 
 
 def main(argv):

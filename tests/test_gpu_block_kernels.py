@@ -249,3 +249,45 @@ def test_bn_relu_channels_last(dev, R, C):
     _close(dx, dxr, 0.03, "bn relu dx")
     _close(dg, dgr, 0.02, "bn relu dgamma")
     _close(db, dbr, 0.02, "bn relu dbeta")
+
+
+@pytest.mark.parametrize("B,T,U,V", [(2, 5, 3, 8), (3, 40, 12, 50), (2, 30, 9, 5004), (2, 20, 0, 16)])
+def test_rnnt_loss_vs_torchaudio(dev, B, T, U, V):
+    """RNN-T loss + gradient vs the reference's own call (torchaudio.functional.rnnt_loss, fused log-softmax)."""
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(T + V)
+    U1 = U + 1
+    ld = (V + 7) // 8 * 8
+    x = torch.zeros(B, T, U1, ld)
+    x[..., :V] = torch.randn(B, T, U1, V) * 1.5
+    x = x.to(BF)
+    t_lens = torch.tensor([T] + [max(1, T - 3 * i) for i in range(1, B)], dtype=torch.int32)
+    u_lens = torch.tensor([U] + [max(0, U - 2 * i) for i in range(1, B)], dtype=torch.int32)
+    tg = torch.randint(1, V, (B, max(U, 1)), dtype=torch.int32)
+    loss, grad = ops.rnnt_loss(x.to(dev), V, t_lens.to(dev), u_lens.to(dev), tg.to(dev), 0, grad_scale=0.5)
+    lr, gr = O.rnnt_loss(x, V, t_lens, u_lens, tg, 0, grad_scale=0.5)
+    assert torch.allclose(loss.cpu(), lr, rtol=1e-5, atol=1e-3), (loss.cpu(), lr)
+    g = grad.float().cpu()
+    assert (g[..., :V] - gr.float()[..., :V]).abs().max().item() < 4e-3
+    assert not g[..., V:].any()
+    for b in range(B):  # cells outside the utterance's lattice get zero gradient
+        assert not g[b, t_lens[b]:].any() and not g[b, :, u_lens[b] + 1:].any()
+
+
+def test_joint_kernels(dev):
+    from espresso_b200 import ops
+    from oracle import ops_ref as O
+
+    torch.manual_seed(2)
+    B, T, U1, J = 3, 17, 6, 64
+    e, d = torch.randn(B, T, J).to(BF), torch.randn(B, U1, J).to(BF)
+    f = ops.joint_fwd(e.to(dev), d.to(dev))
+    fr = O.joint_fwd(e, d)
+    _close(f, fr, 0.01, "joint fwd")
+    df = torch.randn(B, T, U1, J).to(BF)
+    de, dd = ops.joint_bwd(df.to(dev), f)
+    der, ddr = O.joint_bwd(df, fr)
+    _close(de, der, 0.02, "joint denc")
+    _close(dd, ddr, 0.01, "joint ddec")

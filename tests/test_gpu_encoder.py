@@ -235,3 +235,39 @@ def test_lsce_embed_argmax_kernels():
     ds, _ = ops.attn_softmax_bwd(ops.attn_softmax_fwd(s.to(dev), Tk, lens.to(dev))[0], dp.to(dev), Tk, 0, want_dbd=False)
     dsr, _ = O.attn_softmax_bwd(O.attn_softmax_fwd(s, Tk, lens)[0], dp, Tk, 0, want_dbd=False)
     assert (ds.float().cpu()[..., :Tk] - dsr.float()[..., :Tk]).abs().max().item() < 0.03
+
+
+def test_transducer_vs_reference_fixture(golden_dir):
+    """Conformer-Transducer (encoder engine + cuDNN LSTM predictor + native joint / fc_out GEMM / RNN-T loss) on the GPU
+    vs the fixture recorded from the real reference model + torchaudio rnnt_loss."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_orchestration import _build_transducer
+    from espresso_b200.criterions import TransducerLossCriterion
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    m = _build_transducer(g).finalize_(dev)
+    crit = TransducerLossCriterion(_Task(50))
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]).to(dev), "src_lengths": torch.from_numpy(g["lens"]).to(dev),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"]).to(dev)},
+              "target": torch.from_numpy(g["target"]).to(dev)}
+    m.train()
+    m.flat.zero_grad()
+    loss, sample_size, log = crit(m, sample)
+    loss.backward()
+    m.sync_torch_grads_()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) < 0.03 * float(g["loss"])
+    worst = []
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+            continue
+        ours, refg = m.flat.grad(name).cpu().numpy(), g[k]
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.12, worst[:8]

@@ -260,3 +260,52 @@ def test_incremental_decoding_matches_teacher_forcing(golden_dir, cpu_ops):
             ok = prev[rows // beam, step] != 1               # positions fed with <pad> are not comparable
             assert (got[ok] - ref[ok]).abs().max() < 0.08 * ref.abs().max(), step
             perm = (rows ^ 1).to(torch.int32)                # new_order: take the sibling beam's state
+
+
+# ---------------------------------------------------------------------------------------------------
+# transducer (Conformer encoder + LSTM predictor + joint) + RNN-T loss vs the reference fixture
+# ---------------------------------------------------------------------------------------------------
+def _build_transducer(g):
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerTransducerModelBase
+
+    cfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True,
+        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True, learned_pos=False,
+                     relative_positional_embeddings=True, layer_type="conformer", depthwise_conv_kernel_size=31)))
+    m = SpeechTransformerTransducerModelBase.build_model(cfg, _Task(50), decoder_hidden_size=64, decoder_layers=2,
+                                                         decoder_embed_dim=64, joint_dim=64, decoder_dropout_in=0.0,
+                                                         decoder_dropout_out=0.0)
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    return m
+
+
+def test_transducer_keys_and_forward_backward_vs_reference_fixture(golden_dir, cpu_ops):
+    from espresso_b200.criterions import TransducerLossCriterion
+
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    m = _build_transducer(g)
+    assert sorted(m.state_dict().keys()) == sorted(k[3:] for k in g.files if k.startswith("sd."))
+    m.finalize_(torch.device("cpu"))
+    crit = TransducerLossCriterion(_Task(50))
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"]),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"])},
+              "target": torch.from_numpy(g["target"])}
+    m.train()
+    m.flat.zero_grad()
+    loss, sample_size, log = crit(m, sample)
+    assert abs(loss.item() - float(g["loss"])) < 0.03 * float(g["loss"])
+    loss.backward()
+    m.sync_torch_grads_()
+    worst = []
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[len("grad."):]
+        if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+            continue
+        ours, refg = m.flat.grad(name).numpy(), g[k]
+        worst.append((np.linalg.norm(ours - refg) / max(np.linalg.norm(refg), 1e-3), name))
+    worst.sort(reverse=True)
+    print(worst[:6])
+    assert worst[0][0] < 0.25, worst[:5]
+    assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.12, worst[:8]
