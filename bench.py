@@ -334,11 +334,19 @@ def main():
             return float(mx[0]), float(t[1])
         return float(t[0]), float(t[1])
 
+    def note(msg):
+        if rank == 0:
+            print("[bench] " + msg, file=sys.stderr, flush=True)
+
+    note("model + data ready (world=%d)" % world)
     if not args.eager:  # every distinct batch shape: one eager pass + one capture pass (not timed, not warm-up)
-        for _ in range(2):
+        for p_ in range(2):
             for j in range(n_distinct):
                 trainer.train_step([sample_of(resident[j], n_cpu[j])])
+            torch.cuda.synchronize()
+            note("prepare pass %d done" % p_)
     timed(args.warmup, False)
+    note("warm-up done")
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

@@ -55,8 +55,9 @@ class Trainer:
         self._hyper.copy_(self._hyper_host, non_blocking=True)
         self._seed.copy_(self._seed_host, non_blocking=True)
 
-    def _step_body(self, samples):
-        """Everything between "inputs are on the device" and "parameters are updated" -- pure device work."""
+    def _fwd_bwd(self, samples):
+        """Forward + hand-written backward of every micro-batch into the flat gradient buffer -- pure device work;
+        this is the part captured in a CUDA graph per input shape."""
         model, flat = self.model, self.flat
         flat.zero_grad()
         tail = flat.tail
@@ -71,12 +72,21 @@ class Trainer:
             tail[1] += log["ntokens"]
             tail[2] += log["nsentences"]
             tail[3] += log["loss"].float()
+
+    def _reduce_and_update(self):
+        """ONE collective (gradients + stats tail), then grad-norm + fused Adam reading lr/step/sample_size from device
+        memory.  Kept outside the CUDA graph: the NCCL call stays an ordinary stream operation."""
+        flat = self.flat
         if self.world > 1:
             dist.all_reduce(flat.g32, op=dist.ReduceOp.SUM, group=self.pg)
         _ops.sumsq(flat.grads, self._sumsq)
         _ops.adam_step(flat.p32, flat.m, flat.v, flat.grads, flat.p16, 0.0, self.betas[0], self.betas[1], self.eps,
-                       self.weight_decay, 1, self._sumsq, denom_dev=tail[0:1], clip_norm=self.clip_norm,
+                       self.weight_decay, 1, self._sumsq, denom_dev=flat.tail[0:1], clip_norm=self.clip_norm,
                        gnorm_out=self._gnorm, hyper_dev=self._hyper)
+
+    def _step_body(self, samples):
+        self._fwd_bwd(samples)
+        self._reduce_and_update()
 
     @staticmethod
     def _signature(sample):
@@ -105,7 +115,7 @@ class Trainer:
             torch.cuda.synchronize()
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph, pool=self._pool):
-                self._step_body([static])
+                self._fwd_bwd([static])
             n_kernels = _lib.launch_count() - n0  # native kernels recorded in this graph
             _lib.load().esp_note_graph_replay(-n_kernels)  # capture itself executed nothing
             if self._pool is None:
@@ -119,6 +129,7 @@ class Trainer:
         static["target"].copy_(sample["target"], non_blocking=True)
         graph.replay()
         _lib.load().esp_note_graph_replay(n_kernels)
+        self._reduce_and_update()
 
     def train_step(self, samples):
         """samples: list of micro-batches (update_freq entries); an empty dict is a dummy batch whose
