@@ -377,6 +377,7 @@ def main():
 
         ops.gemm = rec_gemm
         trainer.use_cuda_graphs = False
+        trainer.world = 1  # rank-0-only pass: no collective (the other ranks are not in this code path)
         try:
             trainer.train_step([sample_of(resident[0], n_cpu[0])])
             torch.cuda.synchronize()
