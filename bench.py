@@ -311,14 +311,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream()
+
+    def upload(j):
+        """H2D of step inputs from pinned host memory on the copy stream (like the reference's pinned DataLoader +
+        non_blocking move_to_cuda, fairseq/trainer.py:1298-1338); returns (tensors, event)."""
+        with torch.cuda.stream(copy_stream):
+            d = to_dev(pinned[j])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
     def timed(nsteps, from_host):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         audio = 0.0
         e0.record()
+        nxt = upload(0) if from_host else None
         for i in range(nsteps):
             j = i % n_distinct
-            d = to_dev(pinned[j]) if from_host else resident[j]
+            if from_host:
+                d, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                for t in d.values():
+                    if torch.is_tensor(t):
+                        t.record_stream(torch.cuda.current_stream())
+                if i + 1 < nsteps:
+                    nxt = upload((i + 1) % n_distinct)  # overlaps with this step's compute
+            else:
+                d = resident[j]
             trainer.train_step([sample_of(d, n_cpu[j])])
             audio += pinned[j]["audio_s"]
             if from_host:

@@ -124,8 +124,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 consecutive bf16 as four 16-byte vectors (caller guarantees alignment and range)
+struct Packed32 { uint4 q[4]; };
+__device__ __forceinline__ void ldg32(const bf16* p, Packed32& o) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o.q[j] = __ldg(reinterpret_cast<const uint4*>(p) + j);
+}
+__device__ __forceinline__ void unpack32(const Packed32& o, float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unpack_bf16x2(o.q[j].x, v[8 * j + 0], v[8 * j + 1]);
+    unpack_bf16x2(o.q[j].y, v[8 * j + 2], v[8 * j + 3]);
+    unpack_bf16x2(o.q[j].z, v[8 * j + 4], v[8 * j + 5]);
+    unpack_bf16x2(o.q[j].w, v[8 * j + 6], v[8 * j + 7]);
+  }
+}
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Shared-memory matrix descriptor (SWIZZLE_128B).  Field layout: cute/arch/mma_sm100_desc.hpp
 // (SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
@@ -390,9 +406,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = nt * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
-        if (!row_ok) continue;
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);  // asynchronous
         const int valid = p.N - n0;  // >= 1; >= 32 for a full chunk
+        // Put every global operand of this chunk in flight BEFORE waiting for the TMEM load, so the latencies
+        // (TMEM, bias from L2, aux / residual from HBM) overlap instead of adding up.
+        Packed32 pk_bias, pk_aux, pk_res;
+        const bf16* bias_p = e.bias ? e.bias + n0 : nullptr;
+        const bf16* aux_p = (e.act >= ESP_ACT_RELU_BWD) ? e.aux + aux_off + n0 : nullptr;
+        const bf16* res_p = (e.R && !e.skew_r && !e.r_f32) ? (const bf16*)e.R + r_off + n0 : nullptr;
+        const bool full = row_ok && valid >= 32 && !e.atomic;
+        const bool f_bias = full && bias_p && al16(bias_p);
+        const bool f_aux = full && aux_p && al16(aux_p);
+        const bool f_res = full && res_p && al16(res_p);
+        if (f_bias) ldg32(bias_p, pk_bias);
+        if (f_aux) ldg32(aux_p, pk_aux);
+        if (f_res) ldg32(res_p, pk_res);
+        tmem_ld_wait();
+        if (!row_ok) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -409,9 +439,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           continue;
         }
-        if (e.bias) {
+        if (bias_p) {
           float bv[32];
-          load32(e.bias + n0, valid, bv);
+          if (f_bias) unpack32(pk_bias, bv);
+          else load32(bias_p, valid, bv);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += bv[j];
         }
@@ -425,7 +456,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         } else if (e.act == ESP_ACT_SILU_BWD) {
           float u[32];
-          load32(e.aux + aux_off + n0, valid, u);
+          if (f_aux) unpack32(pk_aux, u);
+          else load32(aux_p, valid, u);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float sg = fast_sigmoid(u[j]);
@@ -433,7 +465,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else if (e.act == ESP_ACT_RELU_BWD) {
           float u[32];
-          load32(e.aux + aux_off + n0, valid, u);
+          if (f_aux) unpack32(pk_aux, u);
+          else load32(aux_p, valid, u);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
         }
@@ -457,7 +490,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (j < valid) v[j] += e.beta * rr[j];
           } else {
             float rv[32];
-            load32((const bf16*)e.R + r_off + n0, valid, rv);
+            if (f_res) unpack32(pk_res, rv);
+            else load32(res_p, valid, rv);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(e.beta, rv[j], v[j]);
           }
