@@ -58,7 +58,8 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t p, float& lo, float& hi) 
   hi = __high2float(t);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// ex2.approx + rcp.approx: ~2 ulp, far below the bf16 rounding of every consumer (1 + inf -> rcp = 0 is the right limit)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x*sigmoid(x)]
 __device__ __forceinline__ float silu_gradf_(float x) {
@@ -83,6 +84,28 @@ __host__ __device__ __forceinline__ bool esp_dropout_keep(unsigned long long see
   const unsigned long long h = esp_hash_u64(seed, idx >> 2);
   return (uint32_t)((h >> (16 * (idx & 3))) & 0xFFFFull) >= thresh;
 }
+#ifdef __CUDACC__
+// keep decisions of 8 consecutive elements whose first logical index idx0 is a multiple of 8: two hashes, not eight
+__device__ __forceinline__ void esp_keep8(unsigned long long seed, unsigned long long idx0, uint32_t thresh, bool (&k)[8]) {
+  const unsigned long long h0 = esp_hash_u64(seed, idx0 >> 2), h1 = esp_hash_u64(seed, (idx0 >> 2) + 1);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    k[t] = ((uint32_t)(h0 >> (16 * t)) & 0xFFFFu) >= thresh;
+    k[4 + t] = ((uint32_t)(h1 >> (16 * t)) & 0xFFFFu) >= thresh;
+  }
+}
+// i = q * n + r for a grid-stride index: 32-bit division whenever the index fits (64-bit division is ~100 instructions)
+__device__ __forceinline__ void esp_divmod(long i, unsigned n, long& q, unsigned& r) {
+  if ((unsigned long long)i >> 32) {
+    q = i / (long)n;
+    r = (unsigned)(i - q * (long)n);
+  } else {
+    const unsigned iq = (unsigned)i / n;
+    q = iq;
+    r = (unsigned)i - iq * n;
+  }
+}
+#endif
 static inline uint32_t esp_dropout_thresh(float p) {
   double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;

@@ -23,12 +23,22 @@ constexpr float kNegInf = -INFINITY;
 __device__ __forceinline__ float lse2(float a, float b) {
   const float m = fmaxf(a, b);
   if (m == kNegInf) return kNegInf;
-  return m + logf(expf(a - m) + expf(b - m));
+  return m + logf(__expf(a - m) + __expf(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
   if (m == kNegInf) return kNegInf;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+// branch-free 3-term logsumexp for the scan's serial chain (c = -inf when the skip transition is not allowed);
+// ex2/lg2.approx: ~1e-7 relative per step, far inside the loss tolerance
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);  // the largest term contributes exactly 1
+  const float mm = (m == kNegInf) ? 0.f : m;
+  const float r = mm + __logf(1.f + __expf(mid - mm) + __expf(lo - mm));
+  return (m == kNegInf) ? kNegInf : r;
 }
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -97,21 +107,21 @@ ctc_prep_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
     const int vi = threadIdx.x + i * kPrepThreads;
     if (vi < nvec) {
       float a, c;
-      unpack_bf16x2(cache[i].x, a, c); sum += expf(a - mx) + expf(c - mx);
-      unpack_bf16x2(cache[i].y, a, c); sum += expf(a - mx) + expf(c - mx);
-      unpack_bf16x2(cache[i].z, a, c); sum += expf(a - mx) + expf(c - mx);
-      unpack_bf16x2(cache[i].w, a, c); sum += expf(a - mx) + expf(c - mx);
+      unpack_bf16x2(cache[i].x, a, c); sum += __expf(a - mx) + __expf(c - mx);
+      unpack_bf16x2(cache[i].y, a, c); sum += __expf(a - mx) + __expf(c - mx);
+      unpack_bf16x2(cache[i].z, a, c); sum += __expf(a - mx) + __expf(c - mx);
+      unpack_bf16x2(cache[i].w, a, c); sum += __expf(a - mx) + __expf(c - mx);
     }
   }
   for (int vi = threadIdx.x + kPrepCache * kPrepThreads; vi < nvec; vi += kPrepThreads) {
     const uint4 q = *reinterpret_cast<const uint4*>(row + vi * 8);
     float a, c;
-    unpack_bf16x2(q.x, a, c); sum += expf(a - mx) + expf(c - mx);
-    unpack_bf16x2(q.y, a, c); sum += expf(a - mx) + expf(c - mx);
-    unpack_bf16x2(q.z, a, c); sum += expf(a - mx) + expf(c - mx);
-    unpack_bf16x2(q.w, a, c); sum += expf(a - mx) + expf(c - mx);
+    unpack_bf16x2(q.x, a, c); sum += __expf(a - mx) + __expf(c - mx);
+    unpack_bf16x2(q.y, a, c); sum += __expf(a - mx) + __expf(c - mx);
+    unpack_bf16x2(q.z, a, c); sum += __expf(a - mx) + __expf(c - mx);
+    unpack_bf16x2(q.w, a, c); sum += __expf(a - mx) + __expf(c - mx);
   }
-  for (int v = nvec * 8 + threadIdx.x; v < V; v += kPrepThreads) sum += expf(bf2f(row[v]) - mx);
+  for (int v = nvec * 8 + threadIdx.x; v < V; v += kPrepThreads) sum += __expf(bf2f(row[v]) - mx);
   sum = block_sum(sum, red);
   const float lse = mx + logf(sum);
   if (threadIdx.x == 0) lse_out[(long)b * t_max + t] = lse;
@@ -124,14 +134,27 @@ ctc_prep_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
   }
 }
 
-// ---- scan: alpha / beta recursions, one warp each, C states per lane ----------------------------
+// ---- scan: alpha / beta recursions -----------------------------------------------------------------
+// One CTA per utterance; threads [0, G) run alpha (t ascending), threads [G, 2G) run beta (t descending), C
+// consecutive states per thread (C = 1 up to 512 extended states).  A time step of one direction is: publish the
+// current column to shared memory (double-buffered by step parity), one named barrier over the G threads of that
+// direction, read the two neighbours, one 3-term logsumexp.  The serial chain per step is therefore ~one barrier +
+// one logsumexp regardless of the target length; emission rows are prefetched kScanDepth steps ahead.
+constexpr int kScanDepth = 4;
+
+__device__ __forceinline__ void group_barrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <int C>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(1024)
 ctc_scan_kernel(const float* __restrict__ lp_ext, float* __restrict__ alpha, float* __restrict__ beta,
                 int t_max, int s_max, const int* __restrict__ in_lens, const int* __restrict__ targets,
-                int u_max, const int* __restrict__ tgt_lens, int blank, float* __restrict__ nll) {
+                int u_max, const int* __restrict__ tgt_lens, int blank, float* __restrict__ nll, int G) {
+  extern __shared__ float scan_sh[];  // [2 directions][2 parities][G*C + 4]
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dir = threadIdx.x >= G;  // 0 alpha, 1 beta
+  const int tid = threadIdx.x - dir * G;
   const int T = in_lens[b];
   const int U = tgt_lens[b];
   const int S = 2 * U + 1;
@@ -139,127 +162,96 @@ ctc_scan_kernel(const float* __restrict__ lp_ext, float* __restrict__ alpha, flo
     if (threadIdx.x == 0) nll[b] = (U == 0) ? 0.f : INFINITY;
     return;
   }
+  const int W = G * C + 4;  // column buffer: 2 pad cells (-inf) on each side
+  float* buf0 = scan_sh + dir * 2 * W;
+  float* buf1 = buf0 + W;
+  if (tid < 2) {
+    buf0[tid] = kNegInf; buf0[W - 1 - tid] = kNegInf;
+    buf1[tid] = kNegInf; buf1[W - 1 - tid] = kNegInf;
+  }
   const long base = (long)b * t_max * s_max;
-  const int s0 = lane * C;
+  const int s0 = tid * C;
+  const float* lp = lp_ext + base;
   // which states may take the s-2 (alpha) / s+2 (beta) skip transition
-  bool skip[C];
+  bool skip[C], live[C];
 #pragma unroll
   for (int i = 0; i < C; ++i) {
     const int s = s0 + i;
+    live[i] = s < S;
     skip[i] = false;
     if ((s & 1) && s < S) {
       const int u = s >> 1;
-      if (warp == 0) {
+      if (dir == 0) {
         if (u >= 1) skip[i] = targets[(long)b * u_max + u] != targets[(long)b * u_max + u - 1];
       } else {
         if (u + 1 < U) skip[i] = targets[(long)b * u_max + u] != targets[(long)b * u_max + u + 1];
       }
     }
   }
-  float cur[C], em[C], nxt[C];
-  if (warp == 0) {
-    // ---------------- alpha, t ascending ----------------
-    const float* lp = lp_ext + base;
+  float cur[C], pre[kScanDepth][C];
+  float* out = (dir == 0 ? alpha : beta) + base;
+  const int tstart = dir == 0 ? 0 : T - 1;
+  const int tstep = dir == 0 ? 1 : -1;
+  // t = tstart: initial column
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      const int s = s0 + i;
-      em[i] = (s < S) ? lp[s] : kNegInf;
-      cur[i] = (s < 2 && s < S) ? em[i] : kNegInf;
-    }
-    float* al = alpha + base;
+  for (int i = 0; i < C; ++i) {
+    const int s = s0 + i;
+    const bool init = dir == 0 ? (s < 2) : (s >= S - 2);
+    cur[i] = (live[i] && init) ? lp[(long)tstart * s_max + s] : kNegInf;
+    if (live[i]) out[(long)tstart * s_max + s] = cur[i];
+  }
 #pragma unroll
-    for (int i = 0; i < C; ++i)
-      if (s0 + i < S) al[s0 + i] = cur[i];
-    if (T > 1) {
+  for (int d = 0; d < kScanDepth; ++d) {
+    const int t = tstart + tstep * (1 + d);
 #pragma unroll
-      for (int i = 0; i < C; ++i) nxt[i] = (s0 + i < S) ? lp[s_max + s0 + i] : kNegInf;
-    }
-    for (int t = 1; t < T; ++t) {
+    for (int i = 0; i < C; ++i) pre[d][i] = (live[i] && t >= 0 && t < T) ? lp[(long)t * s_max + s0 + i] : 0.f;
+  }
+  int par = 0;
+  for (int n0 = 1; n0 < T; n0 += kScanDepth) {
 #pragma unroll
-      for (int i = 0; i < C; ++i) em[i] = nxt[i];
-      if (t + 1 < T) {
-        const float* lpn = lp + (long)(t + 1) * s_max;
+    for (int d = 0; d < kScanDepth; ++d) {
+      const int n = n0 + d;  // step count from the start; CTA-uniform
+      if (n < T) {
+        const int t = tstart + tstep * n;
+        float em[C];
 #pragma unroll
-        for (int i = 0; i < C; ++i) nxt[i] = (s0 + i < S) ? lpn[s0 + i] : kNegInf;
+        for (int i = 0; i < C; ++i) em[i] = pre[d][i];
+        const int tn = t + tstep * kScanDepth;
+        if (n + kScanDepth < T) {
+#pragma unroll
+          for (int i = 0; i < C; ++i)
+            if (live[i]) pre[d][i] = lp[(long)tn * s_max + s0 + i];
+        }
+        float* bufp = par ? buf1 : buf0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) bufp[2 + s0 + i] = cur[i];
+        group_barrier(1 + dir, G);
+        float nw[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          // alpha: neighbours s-1, s-2 ; beta: s+1, s+2 (pad cells hold -inf)
+          const int q = 2 + s0 + i;
+          const float n1 = dir == 0 ? bufp[q - 1] : bufp[q + 1];
+          const float n2 = dir == 0 ? bufp[q - 2] : bufp[q + 2];
+          const float acc = lse3_fast(cur[i], n1, skip[i] ? n2 : kNegInf);
+          nw[i] = live[i] ? acc + em[i] : kNegInf;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          cur[i] = nw[i];
+          if (live[i]) out[(long)t * s_max + s0 + i] = cur[i];
+        }
+        par ^= 1;
       }
-      // neighbours s-1, s-2 of this lane's first states live in the previous lane
-      float p1 = __shfl_up_sync(0xffffffffu, cur[C - 1], 1);
-      float p2 = __shfl_up_sync(0xffffffffu, cur[C - 2], 1);
-      if (lane == 0) { p1 = kNegInf; p2 = kNegInf; }
-      float nw[C];
-#pragma unroll
-      for (int i = 0; i < C; ++i) {
-        // i==0: s-1 -> p1, s-2 -> p2 ; i==1: s-1 -> cur[0], s-2 -> p1
-        const float b1 = (i == 0) ? p1 : cur[i >= 1 ? i - 1 : 0];
-        const float b2 = (i == 0) ? p2 : (i == 1 ? p1 : cur[i >= 2 ? i - 2 : 0]);
-        const float acc = skip[i] ? lse3(cur[i], b1, b2) : lse2(cur[i], b1);
-        nw[i] = (s0 + i < S) ? acc + em[i] : kNegInf;
-      }
-      float* alt = al + (long)t * s_max;
-#pragma unroll
-      for (int i = 0; i < C; ++i) {
-        cur[i] = nw[i];
-        if (s0 + i < S) alt[s0 + i] = cur[i];
-      }
     }
+  }
+  if (dir == 0) {
     // nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
-    float last = kNegInf, last2 = kNegInf;
+    float* bufp = par ? buf1 : buf0;
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      if (s0 + i == S - 1) last = cur[i];
-      if (s0 + i == S - 2) last2 = cur[i];
-    }
-    last = warp_max(last);
-    last2 = warp_max(last2);
-    if (lane == 0) nll[b] = -lse2(last, last2);
-  } else {
-    // ---------------- beta, t descending ----------------
-    const float* lp = lp_ext + base;
-    const float* lpl = lp + (long)(T - 1) * s_max;
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-      const int s = s0 + i;
-      em[i] = (s < S) ? lpl[s] : kNegInf;
-      cur[i] = (s < S && s >= S - 2) ? em[i] : kNegInf;
-    }
-    float* be = beta + base;
-    {
-      float* bt = be + (long)(T - 1) * s_max;
-#pragma unroll
-      for (int i = 0; i < C; ++i)
-        if (s0 + i < S) bt[s0 + i] = cur[i];
-    }
-    if (T > 1) {
-      const float* lpn = lp + (long)(T - 2) * s_max;
-#pragma unroll
-      for (int i = 0; i < C; ++i) nxt[i] = (s0 + i < S) ? lpn[s0 + i] : kNegInf;
-    }
-    for (int t = T - 2; t >= 0; --t) {
-#pragma unroll
-      for (int i = 0; i < C; ++i) em[i] = nxt[i];
-      if (t - 1 >= 0) {
-        const float* lpn = lp + (long)(t - 1) * s_max;
-#pragma unroll
-        for (int i = 0; i < C; ++i) nxt[i] = (s0 + i < S) ? lpn[s0 + i] : kNegInf;
-      }
-      float n1 = __shfl_down_sync(0xffffffffu, cur[0], 1);
-      float n2 = __shfl_down_sync(0xffffffffu, cur[1], 1);
-      if (lane == 31) { n1 = kNegInf; n2 = kNegInf; }
-      float nw[C];
-#pragma unroll
-      for (int i = 0; i < C; ++i) {
-        const float b1 = (i == C - 1) ? n1 : cur[i + 1 < C ? i + 1 : 0];
-        const float b2 = (i == C - 1) ? n2 : (i == C - 2 ? n1 : cur[i + 2 < C ? i + 2 : 0]);
-        const float acc = skip[i] ? lse3(cur[i], b1, b2) : lse2(cur[i], b1);
-        nw[i] = (s0 + i < S) ? acc + em[i] : kNegInf;
-      }
-      float* bt = be + (long)t * s_max;
-#pragma unroll
-      for (int i = 0; i < C; ++i) {
-        cur[i] = nw[i];
-        if (s0 + i < S) bt[s0 + i] = cur[i];
-      }
-    }
+    for (int i = 0; i < C; ++i) bufp[2 + s0 + i] = cur[i];
+    group_barrier(1, G);
+    if (tid == 0) nll[b] = -lse2(bufp[2 + S - 1], S >= 2 ? bufp[2 + S - 2] : kNegInf);
   }
 }
 
@@ -291,15 +283,37 @@ ctc_grad_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
     const float ab = alpha[off + s] + beta[off + s];
     if (ab != kNegInf) {
       const int lab = (s & 1) ? targets[(long)b * u_max + (s >> 1)] : blank;
-      atomicAdd(&occ[lab], expf(ab - lab_lp + loss));
+      atomicAdd(&occ[lab], __expf(ab - lab_lp + loss));
     }
   }
   __syncthreads();
   const bf16* row = logits + (long)b * stride_b + (long)t * stride_t;
   const float lse = lse_in[(long)b * t_max + t];
+  const bool vec_ok = (ld_pad % 8 == 0) && (((stride_b | stride_t) & 7) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  if (vec_ok) {
+    // 16-byte path: 8 vocabulary entries per thread and iteration
+    for (int v0 = threadIdx.x * 8; v0 < ld_pad; v0 += kGradThreads * 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(row + v0);
+      float x[8];
+      unpack_bf16x2(q.x, x[0], x[1]);
+      unpack_bf16x2(q.y, x[2], x[3]);
+      unpack_bf16x2(q.z, x[4], x[5]);
+      unpack_bf16x2(q.w, x[6], x[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (v0 + j < V) ? (__expf(x[j] - lse) - occ[v0 + j]) * grad_scale : 0.f;
+      uint4 o;
+      o.x = pack_bf16x2(x[0], x[1]);
+      o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]);
+      o.w = pack_bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(grow + v0) = o;
+    }
+    return;
+  }
   for (int v = threadIdx.x; v < ld_pad; v += kGradThreads) {
     float g = 0.f;
-    if (v < V) g = (expf(bf2f(row[v]) - lse) - occ[v]) * grad_scale;
+    if (v < V) g = (__expf(bf2f(row[v]) - lse) - occ[v]) * grad_scale;
     grow[v] = f2bf(g);
   }
 }
@@ -317,7 +331,7 @@ inline long align256(long x) { return (x + 255) / 256 * 256; }
 }  // namespace
 
 extern "C" int64_t esp_ctc_workspace_bytes(int32_t B, int32_t t_max, int32_t u_max) {
-  const long s_max = 2L * u_max + 1;
+  const long s_max = (2L * u_max + 1 + 3) / 4 * 4;  // rows padded to 16 bytes for vector access
   const long cells = (long)B * t_max * s_max;
   return align256((long)B * t_max * 4) + 3 * align256(cells * 4) + align256((long)B * 4);
 }
@@ -332,7 +346,7 @@ extern "C" int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride
   ESP_CHECK(logits && in_lens && tgt_lens && loss && workspace, "null pointer passed to esp_ctc_loss");
   ESP_CHECK(u_max == 0 || targets != nullptr, "targets is null");
   ESP_CHECK(blank >= 0 && blank < V, "blank index out of range");
-  const int s_max = 2 * u_max + 1;
+  const int s_max = (2 * u_max + 1 + 3) / 4 * 4;  // rows padded to 16 bytes for vector access
   ESP_CHECK(s_max <= 32 * 32, "CTC target too long for the register scan (u_max=%d > 511)", u_max);
   char* ws = (char*)workspace;
   float* lse = (float*)ws; ws += align256((long)B * t_max * 4);
@@ -346,15 +360,18 @@ extern "C" int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride
                                                             targets, u_max, tgt_lens, blank, lse, lp_ext, s_max);
     ESP_LAUNCH_CHECK();
   }
-#define ESP_SCAN(C)                                                                                          \
-  ctc_scan_kernel<C><<<B, 64, 0, st>>>(lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens, \
-                                       blank, nll)
-  if (s_max <= 64) ESP_SCAN(2);
-  else if (s_max <= 128) ESP_SCAN(4);
-  else if (s_max <= 256) ESP_SCAN(8);
-  else if (s_max <= 512) ESP_SCAN(16);
-  else ESP_SCAN(32);
-#undef ESP_SCAN
+  {
+    const int C = s_max > 512 ? 2 : 1;
+    int G = ((s_max + C - 1) / C + 31) / 32 * 32;
+    if (G > 512) G = 512;
+    const size_t smem = (size_t)4 * (G * C + 4) * sizeof(float);
+    if (C == 1)
+      ctc_scan_kernel<1><<<B, 2 * G, smem, st>>>(lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
+                                                 blank, nll, G);
+    else
+      ctc_scan_kernel<2><<<B, 2 * G, smem, st>>>(lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
+                                                 blank, nll, G);
+  }
   ESP_LAUNCH_CHECK();
   ctc_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(nll, B, zero_infinity, loss);
   ESP_LAUNCH_CHECK();

@@ -26,6 +26,18 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   unpack_bf16x2(q.z, v[4], v[5]);
   unpack_bf16x2(q.w, v[6], v[7]);
 }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  unpack_bf16x2(q.x, v[0], v[1]);
+  unpack_bf16x2(q.y, v[2], v[3]);
+  unpack_bf16x2(q.z, v[4], v[5]);
+  unpack_bf16x2(q.w, v[6], v[7]);
+}
+// 8 consecutive floats (32-byte aligned offsets: channel groups of 8)
+__device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   uint4 q;
   q.x = pack_bf16x2(v[0], v[1]);
@@ -34,6 +46,16 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   q.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = q;
 }
+
+// Column reductions (bias / LayerNorm parameter gradients) finish in two levels so that neither same-sector atomic
+// contention nor a long serial tail is on the critical path: every CTA adds its per-column partial sums to one of
+// kRedSlots scratch rows (fire-and-forget RED, contention / kRedSlots), the LAST CTA to finish (ticket counter) sums
+// the kRedSlots rows, accumulates into the destination and re-zeroes the scratch.  Scratch is module-static device
+// memory: kernels of one stream serialise, and the library is driven from one stream per device.
+constexpr int kRedSlots = 8;
+constexpr int kRedMaxCols = 4096;
+__device__ float g_red_slots[2][kRedSlots][kRedMaxCols];
+__device__ unsigned int g_red_ticket[1 + kRedMaxCols / 256];
 
 inline int grid_for(long work_items, int per_block, int max_waves = 8) {
   long g = (work_items + per_block - 1) / per_block;
@@ -105,11 +127,12 @@ ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const 
         float g[8], bb[8], o[8];
         load8(gamma + vi * 8, g);
         load8(beta + vi * 8, bb);
+        bool keep[8];
+        if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)r * d + vi * 8, drop_thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float t = (v[i][j] - mean) * rstd * g[j] + bb[j];
-          if (drop_p > 0.f)
-            t = esp_dropout_keep(seed, (unsigned long long)r * d + vi * 8 + j, drop_thresh) ? t * drop_scale : 0.f;
+          if (drop_p > 0.f) t = keep[j] ? t * drop_scale : 0.f;
           o[j] = zero_row ? 0.f : t;
         }
         store8(yr + vi * 8, o);
@@ -141,11 +164,26 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm_red[i] = 0.f;
   __syncthreads();
+  uint4 gq[NV];  // gamma stays in registers (packed) for every row of this warp
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    gq[i] = vi < nvec ? *reinterpret_cast<const uint4*>(gamma + vi * 8) : make_uint4(0, 0, 0, 0);
+  }
   for (long r = warp0; r < R; r += nwarps) {
     bool zero_row = false;
     if (lens) {
       const int b = (int)(r / T), t = (int)(r % T);
       zero_row = t >= lens[b];
+    }
+    // all global loads of the row are issued before the first reduction (dres included)
+    uint4 rq[NV];
+    if (dres) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) rq[i] = *reinterpret_cast<const uint4*>(dres + r * d + vi * 8);
+      }
     }
     const float mean = mean_in[r], rstd = rstd_in[r];
     float gdy[NV][8], xh[NV][8];
@@ -157,13 +195,14 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
         float a[8], xv[8], g[8];
         load8(dy + r * d + vi * 8, a);
         load8(x + r * d + vi * 8, xv);
-        load8(gamma + vi * 8, g);
+        unpack8(gq[i], g);
+        bool keep[8];
+        if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)r * d + vi * 8, drop_thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float dyv = a[j];
           if (zero_row) dyv = 0.f;
-          else if (drop_p > 0.f)
-            dyv = esp_dropout_keep(seed, (unsigned long long)r * d + vi * 8 + j, drop_thresh) ? dyv * drop_scale : 0.f;
+          else if (drop_p > 0.f) dyv = keep[j] ? dyv * drop_scale : 0.f;
           const float h = (xv[j] - mean) * rstd;
           xh[i][j] = h;
           gdy[i][j] = dyv * g[j];
@@ -182,7 +221,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       if (vi < nvec) {
         float o[8];
         float rr[8];
-        if (dres) load8(dres + r * d + vi * 8, rr);
+        if (dres) unpack8(rq[i], rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           o[j] = rstd * (gdy[i][j] - s1 - xh[i][j] * s2);
@@ -192,7 +231,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       }
     }
   }
-  // block reduce of the per-column partial sums, then one atomic per column per CTA
+  // block reduce of the per-column partial sums in shared memory, then the contention-free cross-CTA reduction
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
@@ -205,25 +244,62 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     }
   }
   __syncthreads();
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  const int slot = blockIdx.x % kRedSlots;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    if (dgamma) atomicAdd(&dgamma[i], sm_red[i]);
-    if (dbeta) atomicAdd(&dbeta[i], sm_red[d + i]);
+    atomicAdd(&g_red_slots[0][slot][i], sm_red[i]);
+    atomicAdd(&g_red_slots[1][slot][i], sm_red[d + i]);
   }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_red_ticket[0], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) {
+      a0 += __ldcg(&g_red_slots[0][k][c]);
+      a1 += __ldcg(&g_red_slots[1][k][c]);
+    }
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) {
+      __stcg(&g_red_slots[0][k][c], 0.f);
+      __stcg(&g_red_slots[1][k][c], 0.f);
+    }
+    if (dgamma) dgamma[c] += a0;
+    if (dbeta) dbeta[c] += a1;
+  }
+  if (threadIdx.x == 0) g_red_ticket[0] = 0u;
 }
 
 // ================================================================================================
 // generic elementwise / reductions over [R, N] bf16 (N % 8 == 0, row stride ld)
 // ================================================================================================
-// out[n] += scale * sum_r x[r, n]     (fp32 accumulate, atomics across CTAs)
+// out[n] += scale * sum_r x[r, n]     (fp32; per-CTA partials, last CTA of each column block finishes)
+// grid (column blocks of 256 columns, row splits); block = 32 column-vectors x 8 row lanes
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long R, int N, long ld, float scale, float* __restrict__ out) {
-  // block = 32 column-vectors x 8 row lanes
   const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
   __shared__ float red[8][32][8];
+  __shared__ int s_last;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cv * 8 < N) {
-    for (long r = (long)blockIdx.y * 8 + rl; r < R; r += (long)gridDim.y * 8) {
+    const long stride = (long)gridDim.y * 8;
+    long r = (long)blockIdx.y * 8 + rl;
+    for (; r + 3 * stride < R; r += 4 * stride) {  // 4 independent loads in flight per thread
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(x + r * ld + cv * 8, v0);
+      load8(x + (r + stride) * ld + cv * 8, v1);
+      load8(x + (r + 2 * stride) * ld + cv * 8, v2);
+      load8(x + (r + 3 * stride) * ld + cv * 8, v3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; r < R; r += stride) {
       float v[8];
       load8(x + r * ld + cv * 8, v);
 #pragma unroll
@@ -233,14 +309,34 @@ colsum_kernel(const bf16* __restrict__ x, long R, int N, long ld, float scale, f
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[rl][threadIdx.x & 31][j] = acc[j];
   __syncthreads();
-  if (rl == 0 && cv * 8 < N) {
+  if (rl == 0) {
+    const int slot = blockIdx.y % kRedSlots;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x & 31][j];
-      atomicAdd(&out[cv * 8 + j], s * scale);
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sacc += red[k][threadIdx.x & 31][j];
+      const int col = cv * 8 + j;
+      if (col < N) atomicAdd(&g_red_slots[0][slot][col], sacc);
     }
   }
+  // one ticket per column block: its last row-split CTA finishes the block's 256 columns
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_red_ticket[1 + blockIdx.x], 1u) == gridDim.y - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float a0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) a0 += __ldcg(&g_red_slots[0][k][c]);
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) __stcg(&g_red_slots[0][k][c], 0.f);
+    out[c] += a0 * scale;
+  }
+  if (threadIdx.x == 0) g_red_ticket[1 + blockIdx.x] = 0u;
 }
 
 // y = dropout(x) * scale  (same counter RNG as the GEMM epilogue: index = r*N + n)
@@ -252,15 +348,16 @@ dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, fl
   const long nvec = R * (N >> 3);
   const float ds = drop_p > 0.f ? scale * 65536.f / (65536.f - (float)thresh) : scale;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / (N >> 3);
-    const int c = (int)(i % (N >> 3)) * 8;
+    long r;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(N >> 3), r, cvi);
+    const int c = (int)cvi * 8;
     float v[8];
     load8(x + r * ldx + c, v);
+    bool keep[8];
+    if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)r * N + c, thresh, keep);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool keep = drop_p > 0.f ? esp_dropout_keep(seed, (unsigned long long)r * N + c + j, thresh) : true;
-      v[j] = keep ? v[j] * ds : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = (drop_p > 0.f && !keep[j]) ? 0.f : v[j] * ds;
     store8(y + r * ldy + c, v);
   }
 }
@@ -270,8 +367,10 @@ __global__ void __launch_bounds__(256)
 mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ lens, int B, int T, int N) {
   const long nvec = (long)B * T * (N >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / (N >> 3);
-    const int b = (int)(r / T), t = (int)(r % T);
+    long r;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(N >> 3), r, cvi);
+    const int b = (int)((unsigned)r / (unsigned)T), t = (int)((unsigned)r % (unsigned)T);  // B*T < 2^31
     if (t >= lens[b]) *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(0, 0, 0, 0);
   }
 }
@@ -282,8 +381,10 @@ qprep_fwd_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ 
                  long R, int d, bf16* __restrict__ qu, bf16* __restrict__ qv) {
   const long nvec = R * (d >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / (d >> 3);
-    const int c = (int)(i % (d >> 3)) * 8;
+    long r;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(d >> 3), r, cvi);
+    const int c = (int)cvi * 8;
     float a[8], bu[8], bv[8], o1[8], o2[8];
     load8(q + r * ldq + c, a);
     load8(u + c, bu);
@@ -304,8 +405,10 @@ qprep_bwd_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, flo
                  bf16* __restrict__ dq, long ld_out) {
   const long nvec = R * (d >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / (d >> 3);
-    const int c = (int)(i % (d >> 3)) * 8;
+    long r;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(d >> 3), r, cvi);
+    const int c = (int)cvi * 8;
     float a[8], b[8], o[8];
     load8(dqu + r * d + c, a);
     load8(dqv + r * d + c, b);
@@ -320,16 +423,6 @@ qprep_bwd_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, flo
 // scores layout [H, B, T, ld] bf16.  T <= 32*kSmMax.
 // ================================================================================================
 constexpr int kSmMaxT = 1280;  // keys per row (36 s of audio after 4x subsampling = 900)
-
-// keep decisions of 8 consecutive elements whose first logical index idx0 is a multiple of 4
-__device__ __forceinline__ void keep8(unsigned long long seed, unsigned long long idx0, uint32_t thresh, bool (&k)[8]) {
-  const unsigned long long h0 = esp_hash_u64(seed, idx0 >> 2), h1 = esp_hash_u64(seed, (idx0 >> 2) + 1);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    k[t] = ((uint32_t)(h0 >> (16 * t)) & 0xFFFFu) >= thresh;
-    k[4 + t] = ((uint32_t)(h1 >> (16 * t)) & 0xFFFFu) >= thresh;
-  }
-}
 
 // Each lane owns NI groups of 8 consecutive keys: j = (i*32 + lane)*8 + e.  Dropout indices are row*ld + j
 // (ld % 8 == 0, so every group is hash-aligned).
@@ -383,7 +476,7 @@ attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int Tq, int
       store8(p_out + row * ld + j, o);
       if (pd_out) {
         bool k[8];
-        keep8(seed, (unsigned long long)row * ld + j, thresh, k);
+        esp_keep8(seed, (unsigned long long)row * ld + j, thresh, k);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = k[e] ? o[e] * ds : 0.f;
         store8(pd_out + row * ld + j, o);
@@ -417,7 +510,7 @@ attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ 
       load8(p_in + row * ld + j, pv[i]);
       load8(dpd + row * ld + j, dv[i]);
       bool k[8];
-      if (drop_p > 0.f) keep8(seed, (unsigned long long)row * ld + j, thresh, k);
+      if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)row * ld + j, thresh, k);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         if (j + e >= T) { pv[i][e] = 0.f; dv[i][e] = 0.f; }
@@ -475,16 +568,21 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
   float wr[kDwMaxK];
 #pragma unroll
   for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
-  for (int r = tg; r < kDwT + ksz - 1; r += 4) {
+  // staging with 16-byte loads: one task = 8 channels of one row
+  for (int i = threadIdx.x; i < (kDwT + ksz - 1) * (kDwC / 8); i += blockDim.x) {
+    const int r = i >> 3, cv = (i & 7) * 8;
     const int t = t0 + r - half;
-    float v = 0.f;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (t >= 0 && t < T) {
-      const bf16* row = g + ((long)b * T + t) * 2 * Cn;
-      const float a = bf2f(row[c0 + cl]);
-      const float gate = bf2f(row[Cn + c0 + cl]);
-      v = bf2f(f2bf(a * sigmoidf_(gate)));  // GLU output is a bf16 tensor in the reference
+      const bf16* row = g + ((long)b * T + t) * 2 * Cn + c0 + cv;
+      float a[8], gate[8];
+      load8(row, a);
+      load8(row + Cn, gate);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf2f(f2bf(a[j] * sigmoidf_(gate[j])));  // GLU output is bf16 in the reference
     }
-    tile[r][cl] = v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[r][cv + j] = v[j];
   }
   __syncthreads();
   const int tb = tg * kDwPerThr;  // first local output of this thread
@@ -542,16 +640,24 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  for (int r = tg; r < kDwT + ksz - 1; r += 4) {
+  for (int i = threadIdx.x; i < (kDwT + ksz - 1) * (kDwC / 8); i += blockDim.x) {
+    const int r = i >> 3, cv = (i & 7) * 8;
     const int t = t0 + r - half;
-    float dv = 0.f, gl = 0.f;
+    float dv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (t >= 0 && t < T) {
-      dv = bf2f(dy[((long)b * T + t) * Cn + c0 + cl]);
-      const bf16* row = g + ((long)b * T + t) * 2 * Cn;
-      gl = bf2f(f2bf(bf2f(row[c0 + cl]) * sigmoidf_(bf2f(row[Cn + c0 + cl]))));
+      load8(dy + ((long)b * T + t) * Cn + c0 + cv, dv);
+      const bf16* row = g + ((long)b * T + t) * 2 * Cn + c0 + cv;
+      float a[8], gate[8];
+      load8(row, a);
+      load8(row + Cn, gate);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gl[j] = bf2f(f2bf(a[j] * sigmoidf_(gate[j])));
     }
-    dyt[r][cl] = dv;
-    glt[r][cl] = gl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dyt[r][cv + j] = dv[j];
+      glt[r][cv + j] = gl[j];
+    }
   }
   __syncthreads();
   const int tb = tg * kDwPerThr;
@@ -691,14 +797,19 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __res
                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ z) {
   const long nvec = R * (Cn >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (Cn >> 3)) * 8;
-    float v[8], gm[8], bt[8];
+    long rq_;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(Cn >> 3), rq_, cvi);
+    const int c = (int)cvi * 8;
+    float v[8], gm[8], bt[8], mu[8], rs[8];
     load8(y + i * 8, v);
     load8(gamma + c, gm);
     load8(beta + c, bt);
+    loadf8(mr + c, mu);
+    loadf8(mr + Cn + c, rs);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float bn = bf2f(f2bf((v[j] - mr[c + j]) * mr[Cn + c + j] * gm[j] + bt[j]));  // BN output is bf16
+      const float bn = bf2f(f2bf((v[j] - mu[j]) * rs[j] * gm[j] + bt[j]));  // BN output is bf16
       v[j] = bn_act(bn, act);
     }
     store8(z + i * 8, v);
@@ -719,15 +830,14 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
   float gm[8], bt[8], mean[8], rstd[8];
   load8(gamma + c, gm);
   load8(beta + c, bt);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    mean[j] = mr[c + j];
-    rstd[j] = mr[Cn + c + j];
-  }
-  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+  loadf8(mr + c, mean);
+  loadf8(mr + Cn + c, rstd);
+  const long stride = (long)gridDim.x * 256;
+  long i = (long)blockIdx.x * 256 + threadIdx.x;
+  auto accumulate = [&](const uint4& dq, const uint4& vq) {
     float d[8], v[8];
-    load8(dz + i * 8, d);
-    load8(y + i * 8, v);
+    unpack8(dq, d);
+    unpack8(vq, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (v[j] - mean[j]) * rstd[j];
@@ -736,7 +846,19 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
       a1[j] += dbn;
       a2[j] += dbn * xh;
     }
+  };
+  for (; i + 3 * stride < nvec; i += 4 * stride) {  // 8 independent 16-byte loads in flight per thread
+    uint4 dq[4], vq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dq[u] = *reinterpret_cast<const uint4*>(dz + (i + u * stride) * 8);
+      vq[u] = *reinterpret_cast<const uint4*>(y + (i + u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) accumulate(dq[u], vq[u]);
   }
+  for (; i < nvec; i += stride)
+    accumulate(*reinterpret_cast<const uint4*>(dz + i * 8), *reinterpret_cast<const uint4*>(y + i * 8));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     red[0][threadIdx.x][j] = a1[j];
@@ -760,36 +882,44 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
 // pass 2: dy = gamma * rstd * (dbn - s1/n - xhat * s2/n)
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
-                        const float* __restrict__ mr, const double* __restrict__ sums,
+                        const float* __restrict__ mr, const float* __restrict__ coef,
                         const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ dy) {
   const long nvec = R * (Cn >> 3);
-  const float invn = 1.f / (float)R;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (Cn >> 3)) * 8;
-    float d[8], v[8], gm[8], bt[8], o[8];
+    long rq_;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)(Cn >> 3), rq_, cvi);
+    const int c = (int)cvi * 8;
+    float d[8], v[8], gm[8], bt[8], o[8], mu[8], rs[8], m1[8], m2[8];
     load8(dz + i * 8, d);
     load8(y + i * 8, v);
     load8(gamma + c, gm);
     load8(beta + c, bt);
+    loadf8(mr + c, mu);
+    loadf8(mr + Cn + c, rs);
+    loadf8(coef + c, m1);
+    loadf8(coef + Cn + c, m2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float rstd = mr[Cn + c + j];
-      const float xh = (v[j] - mr[c + j]) * rstd;
+      const float xh = (v[j] - mu[j]) * rs[j];
       const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
       const float dbn = d[j] * bn_act_grad(bn, act);
-      const float m1 = (float)sums[c + j] * invn, m2 = (float)sums[Cn + c + j] * invn;
-      o[j] = gm[j] * rstd * (dbn - m1 - xh * m2);
+      o[j] = gm[j] * rs[j] * (dbn - m1[j] - xh * m2[j]);
     }
     store8(dy + i * 8, o);
   }
 }
-// dgamma += s2 ; dbeta += s1
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int Cn, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
+// dgamma += s2 ; dbeta += s1 ; and the float means m1 = s1/n, m2 = s2/n used by the apply pass (written over the
+// double sums' storage reinterpreted as floats: sums[0..2C) doubles -> coef[0..2C) floats at the same base)
+__global__ void bn_param_grad_kernel(double* __restrict__ sums, long R, int Cn, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
-  atomicAdd(&dgamma[c], (float)sums[Cn + c]);
-  atomicAdd(&dbeta[c], (float)sums[c]);
+  const double s1 = sums[c], s2 = sums[Cn + c];
+  if (dgamma) atomicAdd(&dgamma[c], (float)s2);
+  if (dbeta) atomicAdd(&dbeta[c], (float)s1);
+  coef[c] = (float)(s1 / (double)R);
+  coef[Cn + c] = (float)(s2 / (double)R);
 }
 
 }  // namespace
@@ -825,6 +955,7 @@ extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* me
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported", d);
   if (R == 0) return 0;
+  ESP_CHECK(d <= kRedMaxCols, "LayerNorm backward: at most %d columns", kRedMaxCols);
 #define ESP_LN_BWD(NV)                                                                                             \
   ln_bwd_kernel<NV><<<grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st>>>(                                          \
       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
@@ -842,15 +973,20 @@ extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float
   ESP_ST;
   ESP_CHECK(N % 8 == 0 && ld % 8 == 0, "colsum needs N and ld multiples of 8");
   if (R == 0 || N == 0) return 0;
-  const unsigned gx = (N / 8 + 31) / 32;
-  long gy = (4L * esp_num_sms() + gx - 1) / gx;  // ~4 CTAs per SM in total
-  const long max_gy = (R + 7) / 8;
-  if (gy > max_gy) gy = max_gy;
-  if (gy < 1) gy = 1;
-  dim3 grid(gx, (unsigned)gy);
-  colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, R, N, ld, scale, out);
-  ESP_LAUNCH_CHECK();
-  esp_count_launch(1);
+  int launches = 0;
+  for (int c0 = 0; c0 < N; c0 += kRedMaxCols) {  // wide matrices (vocabulary-sized) go in column panels
+    const int n = (N - c0 < kRedMaxCols) ? (N - c0) : kRedMaxCols;
+    const unsigned gx = (n / 8 + 31) / 32;
+    long gy = (2L * esp_num_sms() + gx - 1) / gx;  // ~2 CTAs per SM in total
+    const long max_gy = (R + 31) / 32;              // at least 4 rows per row lane
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    dim3 grid(gx, (unsigned)gy);
+    colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x + c0, R, n, ld, scale, out + c0);
+    ESP_LAUNCH_CHECK();
+    ++launches;
+  }
+  esp_count_launch(launches);
   return 0;
 }
 
@@ -1035,16 +1171,15 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t 
   bn_act_bwd_reduce_kernel<<<bn_reduce_grid(R * (C / 8)), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr,
                                                                        (const bf16*)gamma, (const bf16*)beta, act, sums);
   ESP_LAUNCH_CHECK();
-  bn_act_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, sums,
+  // the float coefficient table reuses the tail of the caller's `sums` workspace: 2C doubles = room for 2C extra floats
+  // after the doubles were consumed -- keep it separate instead: coefficients go to the second half of a 4C-float view
+  float* coef = reinterpret_cast<float*>(sums + 2 * C);
+  bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, R, C, dgamma, dbeta, coef);
+  ESP_LAUNCH_CHECK();
+  bn_act_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, coef,
                                                                       (const bf16*)gamma, (const bf16*)beta, act,
                                                                       (bf16*)dy);
   ESP_LAUNCH_CHECK();
-  int n = 2;
-  if (dgamma && dbeta) {
-    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
-    ESP_LAUNCH_CHECK();
-    ++n;
-  }
-  esp_count_launch(n);
+  esp_count_launch(3);
   return 0;
 }

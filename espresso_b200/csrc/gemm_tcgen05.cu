@@ -421,6 +421,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (f_bias) ldg32(bias_p, pk_bias);
         if (f_aux) ldg32(aux_p, pk_aux);
         if (f_res) ldg32(res_p, pk_res);
+        // skewed residual (relative-position scores): 32 consecutive but arbitrarily aligned bf16 -> 17 aligned words,
+        // re-aligned with a funnel shift when the first element sits in the upper half of its word
+        uint32_t sk[17];
+        const bool f_skew = full && e.R && e.skew_r;
+        bool sk_odd = false;
+        if (f_skew) {
+          const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
+          sk_odd = (reinterpret_cast<uintptr_t>(rr) & 2) != 0;
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(rr - (sk_odd ? 1 : 0));
+#pragma unroll
+          for (int j = 0; j < 17; ++j) sk[j] = __ldg(wp + j);
+        }
         tmem_ld_wait();
         if (!row_ok) continue;
         float v[32];
@@ -479,10 +491,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (e.skew_r) {
             // Transformer-XL skew fused into the score GEMM: R is BD_full[row m, (skew_r-1)-m+n]
             // (fairseq/modules/multihead_attention.py:824-830 as_strided trick).
-            const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
+            if (f_skew) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < valid) v[j] += e.beta * bf2f(rr[j]);
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t w = sk_odd ? __funnelshift_r(sk[j], sk[j + 1], 16) : sk[j];
+                float lo, hi;
+                unpack_bf16x2(w, lo, hi);
+                v[2 * j] += e.beta * lo;
+                v[2 * j + 1] += e.beta * hi;
+              }
+            } else {
+              const bf16* rr = (const bf16*)e.R + r_off + (e.skew_r - 1 - m) + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) v[j] += e.beta * bf2f(rr[j]);
+            }
           } else if (e.r_f32) {
             const float* rr = (const float*)e.R + r_off + n0;
 #pragma unroll

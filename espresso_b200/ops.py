@@ -326,7 +326,7 @@ def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU):
     _bf(dz, y, gamma, beta)
     assert dz.is_contiguous() and y.is_contiguous()
     Cn = y.shape[-1]
-    sums = torch.empty(2, Cn, device=y.device, dtype=torch.float64)
+    sums = torch.empty(3, Cn, device=y.device, dtype=torch.float64)  # 2C double sums + 2C float coefficients
     dy = torch.empty_like(y)
     _lib.check(_lib.load().esp_bn_act_bwd(_ptr(dz), _ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act,
                                           _ptr(sums), _ptr(dy), _ptr(dgamma_acc), _ptr(dbeta_acc), _stream()))

@@ -160,7 +160,7 @@ int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float eps, float 
 /* Channels-last BatchNorm helpers shared by the Conformer conv module (act=1, SiLU; fairseq/modules/
  * conformer_layer.py:95-96) and the conv front end (act=2, ReLU; espresso/modules/speech_convolutions.py:88-90,
  * tensors kept NHWC so rows = B*T*F): per-channel statistics of x [R,C]; z = act(BN(y)); and the two-pass
- * backward (sums = double[2,C] workspace; dgamma/dbeta fp32, +=). */
+ * backward (sums = double[3,C] workspace: 2C sums + 2C float coefficients; dgamma/dbeta fp32, +=). */
 int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, void* stream);
 int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
                    int32_t act, void* z, void* stream);
