@@ -108,6 +108,9 @@ class _Dict:
     def eos(self):
         return 2
 
+    def unk(self):
+        return 3
+
     def index(self, s):
         return 0
 
@@ -213,6 +216,65 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def decode_rtf(dev, n_utts=1000, per_batch=50, seconds=10.0):
+    """Second half of the headline metric (BASELINE.json configs[4]): batched beam-5 decoding with Transformer-LM
+    shallow fusion, 1000 synthetic 10 s utterances from raw waveforms, through espresso_b200.SequenceGenerator
+    (the reference's speech_recognize.py path: fairseq/sequence_generator.py:212-621).  RTF = decode seconds / audio
+    seconds, timed with CUDA events around generate() calls (host bookkeeping and the final D2H included); decode
+    settings of examples/asr_librispeech/run_torchaudio.sh:180-198 (lm-weight 0.47, eos-factor 1.5, max-len-a 0.08)."""
+    from espresso_b200.data.frontend import OnTheFlyFbank
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerModelBase
+    from espresso_b200.models.transformer_lm import TransformerLanguageModel
+    from espresso_b200.sequence_generator import SequenceGenerator
+
+    torch.manual_seed(5)
+    cfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=False, max_target_positions=1024,
+        encoder=dict(embed_dim=256, ffn_embed_dim=1024, layers=12, attention_heads=4, normalize_before=True,
+                     learned_pos=False, relative_positional_embeddings=True, layer_type="transformer"),
+        decoder=dict(embed_dim=256, ffn_embed_dim=1024, layers=6, attention_heads=4, normalize_before=True,
+                     learned_pos=False, relative_positional_embeddings=False, input_dim=256, output_dim=256)))
+    model = SpeechTransformerModelBase.build_model(cfg, _Task()).finalize_(dev)
+    model.frontend = OnTheFlyFbank(np.full(80, 15.0), np.full(80, 4.0))
+    model.eval()
+    lm = TransformerLanguageModel(_Dict(), embed_dim=512, ffn_embed_dim=2048, layers=6, attention_heads=8,
+                                  max_target_positions=1024).finalize_(dev)
+    gen = SequenceGenerator([model], _Dict(), beam_size=5, max_len_a=0.08, max_len_b=0, lm_model=lm, lm_weight=0.47,
+                            eos_factor=1.5)
+    n = int(seconds * 16000)
+    rs = np.random.RandomState(3)
+    waves = [torch.from_numpy(np.stack([synth_wave(rs, n) for _ in range(per_batch)]).astype(np.float32)).pin_memory()
+             for _ in range(2)]
+    lens_h = torch.full((per_batch,), n, dtype=torch.int32)
+
+    def one(i):
+        w = waves[i % 2].to(dev, non_blocking=True)
+        sample = {"net_input": {"src_tokens": w, "src_lengths": lens_h.to(dev, non_blocking=True),
+                                "src_lengths_cpu": lens_h.long()}}
+        return gen.generate([model], sample)
+
+    for i in range(2):  # warm-up
+        hyp = one(i)
+    torch.cuda.synchronize()
+    n_batches = max(1, n_utts // per_batch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ntok = 0
+    e0.record()
+    for i in range(n_batches):
+        hyp = one(i)
+        ntok += sum(len(h[0]["tokens"]) for h in hyp)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    audio = n_batches * per_batch * seconds
+    return {"metric": "beam-5 decode real-time factor (decode seconds / audio second)", "rtf": sec / audio,
+            "audio_s_per_s": audio / sec, "utterances": n_batches * per_batch, "utterance_s": seconds, "batch": per_batch,
+            "beam": 5, "lm_weight": 0.47, "eos_factor": 1.5, "max_len_a": 0.08, "ms_per_batch": 1e3 * sec / n_batches,
+            "best_hyp_tokens_per_utt": ntok / (n_batches * per_batch),
+            "model": "SpeechTransformerModel 12-enc/6-dec d=256 (rel-pos encoder) + Transformer LM 6x512 shallow fusion, "
+                     "V=%d, random init, raw 16 kHz waveforms in pinned host memory" % V}
+
+
 def workload_config(n):
     return {"workload": "Conformer encoder 17x512 (ffn 2048, 8 heads, conv-k31, sinusoidal rel-pos) + CTC, V=5004, on-the-fly "
                         "fbank80+CMVN+adaptive SpecAugment from raw 16 kHz waveforms, Adam + clip 2.0, dropout 0.1",
@@ -256,6 +318,8 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug only: override layer count (invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="disable CUDA-graph capture of the step")
+    ap.add_argument("--no-decode", action="store_true", help="skip the beam-5 decode RTF leg")
+    ap.add_argument("--decode-only", action="store_true", help="run only the beam-5 decode RTF leg (debugging)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -279,6 +343,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
 
+    if args.decode_only:
+        print(json.dumps({"decode": decode_rtf(dev)}))
+        return
     torch.manual_seed(1)
     enc = dict(MODEL)
     if args.layers is not None:
@@ -439,6 +506,10 @@ def main():
             out["INVALID"] = "layer count overridden for debugging"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_quick()
+        if world == 1 and not args.no_decode:  # configs[4] is a 1xB200 measurement
+            del trainer
+            torch.cuda.empty_cache()
+            out["decode"] = decode_rtf(dev)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -3,6 +3,7 @@
 #include "espresso_b200.h"
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -27,6 +28,15 @@ int esp_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+bool esp_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ESP_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 extern "C" const char* esp_last_error(void) { return g_err; }

@@ -1,5 +1,6 @@
 // espresso_b200 -- shared device/host helpers for the sm_100a kernels.
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -66,6 +67,65 @@ __device__ __forceinline__ float silu_gradf_(float x) {
   float s = sigmoidf_(x);
   return s * (1.f + x * (1.f - s));
 }
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every hot-path kernel starts with esp_pdl(): it lets the NEXT kernel of the stream be scheduled as soon as this
+// grid's CTAs have all started (its CTAs then sit in griddepcontrol.wait), and blocks this kernel until every
+// kernel before it has completed and flushed.  With esp_launch() (below) setting the programmatic-serialisation
+// attribute, launch latency and kernel prologues overlap the tail of the previous kernel -- in eager streams and in
+// captured CUDA graphs alike.  Without the attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void esp_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void esp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void esp_pdl() {
+  esp_pdl_trigger();
+  esp_pdl_wait();
+}
+
+bool esp_pdl_enabled();  // capi.cu: ESP_PDL=0 in the environment disables the launch attribute
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t esp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = esp_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t esp_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (esp_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---- counter-based RNG for dropout ---------------------------------------------------------------
 // Stateless: the backward pass regenerates the identical mask from (seed, logical element index), so

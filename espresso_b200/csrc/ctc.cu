@@ -71,6 +71,7 @@ ctc_prep_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
                 const int* __restrict__ in_lens, const int* __restrict__ targets, int u_max,
                 const int* __restrict__ tgt_lens, int blank, float* __restrict__ lse_out,
                 float* __restrict__ lp_ext, int s_max) {
+  esp_pdl();
   __shared__ float red[32];
   const int b = blockIdx.y, t = blockIdx.x;
   if (t >= in_lens[b]) return;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(1024)
 ctc_scan_kernel(const float* __restrict__ lp_ext, float* __restrict__ alpha, float* __restrict__ beta,
                 int t_max, int s_max, const int* __restrict__ in_lens, const int* __restrict__ targets,
                 int u_max, const int* __restrict__ tgt_lens, int blank, float* __restrict__ nll, int G) {
+  esp_pdl();
   extern __shared__ float scan_sh[];  // [2 directions][2 parities][G*C + 4]
   const int b = blockIdx.x;
   const int dir = threadIdx.x >= G;  // 0 alpha, 1 beta
@@ -265,6 +267,7 @@ ctc_grad_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
                 const float* __restrict__ lse_in, const float* __restrict__ lp_ext,
                 const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
                 int s_max, bf16* __restrict__ grad) {
+  esp_pdl();
   extern __shared__ float occ[];
   const int b = blockIdx.y, t = blockIdx.x;
   bf16* grow = grad + (long)b * stride_b + (long)t * stride_t;
@@ -319,6 +322,7 @@ ctc_grad_kernel(const bf16* __restrict__ logits, long stride_b, long stride_t, i
 }
 
 __global__ void ctc_finalize_kernel(const float* __restrict__ nll, int B, int zero_infinity, float* __restrict__ loss) {
+  esp_pdl();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float l = nll[b];
@@ -356,7 +360,7 @@ extern "C" int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride
   float* beta = (float*)ws; ws += align256(cells * 4);
   float* nll = (float*)ws;
   if (t_max > 0) {
-    ctc_prep_kernel<<<dim3(t_max, B), kPrepThreads, 0, st>>>((const bf16*)logits, stride_b, stride_t, V, t_max, in_lens,
+    esp_launch(ctc_prep_kernel, dim3(t_max, B), kPrepThreads, 0, st, (const bf16*)logits, stride_b, stride_t, V, t_max, in_lens,
                                                             targets, u_max, tgt_lens, blank, lse, lp_ext, s_max);
     ESP_LAUNCH_CHECK();
   }
@@ -366,14 +370,14 @@ extern "C" int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride
     if (G > 512) G = 512;
     const size_t smem = (size_t)4 * (G * C + 4) * sizeof(float);
     if (C == 1)
-      ctc_scan_kernel<1><<<B, 2 * G, smem, st>>>(lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
+      esp_launch(ctc_scan_kernel<1>, B, 2 * G, smem, st, lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
                                                  blank, nll, G);
     else
-      ctc_scan_kernel<2><<<B, 2 * G, smem, st>>>(lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
+      esp_launch(ctc_scan_kernel<2>, B, 2 * G, smem, st, lp_ext, alpha, beta, t_max, s_max, in_lens, targets, u_max, tgt_lens,
                                                  blank, nll, G);
   }
   ESP_LAUNCH_CHECK();
-  ctc_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(nll, B, zero_infinity, loss);
+  esp_launch(ctc_finalize_kernel, (B + 127) / 128, 128, 0, st, nll, B, zero_infinity, loss);
   ESP_LAUNCH_CHECK();
   int launches = 3;
   if (grad && t_max > 0) {
@@ -390,7 +394,7 @@ extern "C" int esp_ctc_loss(const void* logits, int64_t stride_b, int64_t stride
       ESP_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V * 4));
       cfg_bytes = V * 4;
     }
-    ctc_grad_kernel<<<dim3(t_max, B), kGradThreads, V * 4, st>>>(
+    esp_launch(ctc_grad_kernel, dim3(t_max, B), kGradThreads, V * 4, st, 
         (const bf16*)logits, stride_b, stride_t, V, ld_pad, t_max, in_lens, targets, u_max, tgt_lens, blank,
         zero_infinity, grad_scale, lse, lp_ext, alpha, beta, nll, s_max, (bf16*)grad);
     ESP_LAUNCH_CHECK();

@@ -76,6 +76,7 @@ ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const 
               long R, int d, bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed0,
               const unsigned long long* __restrict__ seed_ptr) {
+  esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -149,6 +150,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
               int d, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed0,
               const unsigned long long* __restrict__ seed_ptr) {
+  esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   extern __shared__ float sm_red[];  // [2][d]
   const int lane = threadIdx.x & 31;
@@ -282,6 +284,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
 // grid (column blocks of 256 columns, row splits); block = 32 column-vectors x 8 row lanes
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long R, int N, long ld, float scale, float* __restrict__ out) {
+  esp_pdl();
   const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
   __shared__ float red[8][32][8];
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(256)
 dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, float scale, float drop_p,
                uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr,
                bf16* __restrict__ y) {
+  esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const long nvec = R * (N >> 3);
   const float ds = drop_p > 0.f ? scale * 65536.f / (65536.f - (float)thresh) : scale;
@@ -365,6 +369,7 @@ dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, fl
 // zero rows t >= lens[b] of x [B, T, N]
 __global__ void __launch_bounds__(256)
 mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ lens, int B, int T, int N) {
+  esp_pdl();
   const long nvec = (long)B * T * (N >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     long r;
@@ -379,6 +384,7 @@ mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ lens, int B, int 
 __global__ void __launch_bounds__(256)
 qprep_fwd_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ u, const bf16* __restrict__ v, float s,
                  long R, int d, bf16* __restrict__ qu, bf16* __restrict__ qv) {
+  esp_pdl();
   const long nvec = R * (d >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     long r;
@@ -403,6 +409,7 @@ qprep_fwd_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ 
 __global__ void __launch_bounds__(256)
 qprep_bwd_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, float s, long R, int d,
                  bf16* __restrict__ dq, long ld_out) {
+  esp_pdl();
   const long nvec = R * (d >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     long r;
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(const bf16* __restrict__ s_in, int H, int B, int Tq, int T, int ld, const int* __restrict__ lens,
                         int causal, bf16* __restrict__ p_out, bf16* __restrict__ pd_out, float drop_p, uint32_t thresh,
                         unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
+  esp_pdl();
   // rows = H*B*Tq queries, T keys per row; causal: key j is visible to query i iff j <= i (future_mask, -inf)
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
@@ -492,6 +500,7 @@ __global__ void __launch_bounds__(256)
 attn_softmax_bwd_kernel(const bf16* __restrict__ p_in, const bf16* __restrict__ dpd, int H, int B, int Tq, int T, int ld,
                         bf16* __restrict__ ds_out, bf16* __restrict__ dbd_out, int ldp, float drop_p,
                         uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr) {
+  esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -560,14 +569,15 @@ constexpr int kDwPerThr = kDwT / 4;
 __global__ void __launch_bounds__(256)
 glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, int B, int T, int Cn, int ksz,
                       bf16* __restrict__ y, double* __restrict__ stats) {
+  esp_pdl();
   __shared__ float tile[kDwT + kDwMaxK - 1][kDwC + 1];
   __shared__ float red[2][4][kDwC];
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  float wr[kDwMaxK];
-#pragma unroll
-  for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + k]) : 0.f;
+  // taps of the tile's 64 channels: one coalesced pass into shared memory, then 31 conflict-free reads per thread
+  __shared__ float wsm[kDwC * kDwMaxK];
+  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i] = bf2f(w[(long)c0 * ksz + i]);
   // staging with 16-byte loads: one task = 8 channels of one row
   for (int i = threadIdx.x; i < (kDwT + ksz - 1) * (kDwC / 8); i += blockDim.x) {
     const int r = i >> 3, cv = (i & 7) * 8;
@@ -585,6 +595,9 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
     for (int j = 0; j < 8; ++j) tile[r][cv + j] = v[j];
   }
   __syncthreads();
+  float wr[kDwMaxK];
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < ksz ? wsm[cl * ksz + k] : 0.f;
   const int tb = tg * kDwPerThr;  // first local output of this thread
   float acc[kDwPerThr];
 #pragma unroll
@@ -631,6 +644,7 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
 __global__ void __launch_bounds__(256)
 glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, const bf16* __restrict__ w, int B,
                       int T, int Cn, int ksz, bf16* __restrict__ dg, float* __restrict__ dw) {
+  esp_pdl();
   extern __shared__ __align__(16) uint8_t dw_smem[];
   typedef float TileT[kDwC + 1];
   TileT* dyt = reinterpret_cast<TileT*>(dw_smem);                       // dy at t0-half .. t0+63+half
@@ -640,6 +654,8 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
   const int b = blockIdx.z, t0 = blockIdx.x * kDwT, c0 = blockIdx.y * kDwC;
   const int half = ksz >> 1;
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  __shared__ float wsm[kDwC * kDwMaxK];
+  for (int i = threadIdx.x; i < kDwC * ksz; i += blockDim.x) wsm[i] = bf2f(w[(long)c0 * ksz + i]);
   for (int i = threadIdx.x; i < (kDwT + ksz - 1) * (kDwC / 8); i += blockDim.x) {
     const int r = i >> 3, cv = (i & 7) * 8;
     const int t = t0 + r - half;
@@ -666,7 +682,7 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
   {
     float wf[kDwMaxK];
 #pragma unroll
-    for (int k = 0; k < kDwMaxK; ++k) wf[k] = k < ksz ? bf2f(w[(long)(c0 + cl) * ksz + (ksz - 1 - k)]) : 0.f;
+    for (int k = 0; k < kDwMaxK; ++k) wf[k] = k < ksz ? wsm[cl * ksz + (ksz - 1 - k)] : 0.f;
     float acc[kDwPerThr];
 #pragma unroll
     for (int i = 0; i < kDwPerThr; ++i) acc[i] = 0.f;
@@ -729,6 +745,7 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, long R, int Cn, float eps, float momentum,
                                    float* __restrict__ run_mean, float* __restrict__ run_var, int training,
                                    float* __restrict__ mr) {
+  esp_pdl();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   if (training) {
@@ -758,6 +775,7 @@ __device__ __forceinline__ float bn_act_grad(float bn, int act) { return act == 
 // stats[c] += sum_r x[r,c] ; stats[C + c] += sum_r x[r,c]^2
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const bf16* __restrict__ x, long R, int Cn, double* __restrict__ stats) {
+  esp_pdl();
   __shared__ float red[2][256][8];
   const int cv = Cn >> 3;
   const long nvec = R * cv;
@@ -795,6 +813,7 @@ bn_stats_kernel(const bf16* __restrict__ x, long R, int Cn, double* __restrict__
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __restrict__ mr,
                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ z) {
+  esp_pdl();
   const long nvec = R * (Cn >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     long rq_;
@@ -821,6 +840,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
                          const float* __restrict__ mr, const bf16* __restrict__ gamma,
                          const bf16* __restrict__ beta, int act, double* __restrict__ sums) {
+  esp_pdl();
   __shared__ float red[2][256][8];
   const int cv = Cn >> 3;
   const long nvec = R * cv;
@@ -884,6 +904,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
                         const float* __restrict__ mr, const float* __restrict__ coef,
                         const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ dy) {
+  esp_pdl();
   const long nvec = R * (Cn >> 3);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     long rq_;
@@ -913,6 +934,7 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
 // double sums' storage reinterpreted as floats: sums[0..2C) doubles -> coef[0..2C) floats at the same base)
 __global__ void bn_param_grad_kernel(double* __restrict__ sums, long R, int Cn, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, float* __restrict__ coef) {
+  esp_pdl();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   const double s1 = sums[c], s2 = sums[Cn + c];
@@ -936,7 +958,7 @@ extern "C" int esp_layer_norm_fwd(const void* x, const void* gamma, const void* 
   ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported (need d%%8==0, d<=2048)", d);
   if (R == 0) return 0;
 #define ESP_LN_FWD(NV)                                                                                              \
-  ln_fwd_kernel<NV><<<grid_for(R, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, eps, R, d, \
+  esp_launch(ln_fwd_kernel<NV>, grid_for(R, 8), 256, 0, st, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, eps, R, d, \
                                                      (bf16*)y, mean, rstd, lens, T, drop_p, esp_dropout_thresh(drop_p), seed,       \
                                                      (const unsigned long long*)seed_ptr)
   if (d <= 512) ESP_LN_FWD(2);
@@ -957,7 +979,7 @@ extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* me
   if (R == 0) return 0;
   ESP_CHECK(d <= kRedMaxCols, "LayerNorm backward: at most %d columns", kRedMaxCols);
 #define ESP_LN_BWD(NV)                                                                                             \
-  ln_bwd_kernel<NV><<<grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st>>>(                                          \
+  esp_launch(ln_bwd_kernel<NV>, grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st,                                           \
       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
       dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
   if (d <= 512) ESP_LN_BWD(2);
@@ -982,7 +1004,7 @@ extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
     dim3 grid(gx, (unsigned)gy);
-    colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x + c0, R, n, ld, scale, out + c0);
+    esp_launch(colsum_kernel, grid, 256, 0, st, (const bf16*)x + c0, R, n, ld, scale, out + c0);
     ESP_LAUNCH_CHECK();
     ++launches;
   }
@@ -995,7 +1017,7 @@ extern "C" int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int
   ESP_ST;
   ESP_CHECK(N % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dropout needs N/ld multiples of 8");
   if (R == 0 || N == 0) return 0;
-  dropout_kernel<<<grid_for(R * (N / 8), 256), 256, 0, st>>>((const bf16*)x, R, N, ldx, ldy, scale, drop_p,
+  esp_launch(dropout_kernel, grid_for(R * (N / 8), 256), 256, 0, st, (const bf16*)x, R, N, ldx, ldy, scale, drop_p,
                                                              esp_dropout_thresh(drop_p), seed,
                                                              (const unsigned long long*)seed_ptr, (bf16*)y);
   ESP_LAUNCH_CHECK();
@@ -1007,7 +1029,7 @@ extern "C" int esp_mask_rows(void* x, const int32_t* lens, int32_t B, int32_t T,
   ESP_ST;
   ESP_CHECK(N % 8 == 0, "mask_rows needs N %% 8 == 0");
   if ((long)B * T * N == 0) return 0;
-  mask_rows_kernel<<<grid_for((long)B * T * (N / 8), 256), 256, 0, st>>>((bf16*)x, lens, B, T, N);
+  esp_launch(mask_rows_kernel, grid_for((long)B * T * (N / 8), 256), 256, 0, st, (bf16*)x, lens, B, T, N);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -1018,7 +1040,7 @@ extern "C" int esp_qprep_fwd(const void* q, int64_t ldq, const void* u, const vo
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && ldq % 8 == 0, "qprep needs d/ld multiples of 8");
   if (R == 0) return 0;
-  qprep_fwd_kernel<<<grid_for(R * (d / 8), 256), 256, 0, st>>>((const bf16*)q, ldq, (const bf16*)u, (const bf16*)v,
+  esp_launch(qprep_fwd_kernel, grid_for(R * (d / 8), 256), 256, 0, st, (const bf16*)q, ldq, (const bf16*)u, (const bf16*)v,
                                                                scale, R, d, (bf16*)qu, (bf16*)qv);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
@@ -1030,7 +1052,7 @@ extern "C" int esp_qprep_bwd(const void* dqu, const void* dqv, float scale, int6
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && ld_out % 8 == 0, "qprep needs d/ld multiples of 8");
   if (R == 0) return 0;
-  qprep_bwd_kernel<<<grid_for(R * (d / 8), 256), 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, scale, R, d,
+  esp_launch(qprep_bwd_kernel, grid_for(R * (d / 8), 256), 256, 0, st, (const bf16*)dqu, (const bf16*)dqv, scale, R, d,
                                                                (bf16*)dq, ld_out);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
@@ -1050,7 +1072,7 @@ extern "C" int esp_attn_softmax_fwd(const void* scores, int32_t H, int32_t B, in
   const unsigned grid = (unsigned)((rows + 7) / 8);
   bf16* pd = drop_p > 0.f ? (bf16*)p_drop : nullptr;
 #define ESP_SMF(NI)                                                                                           \
-  attn_softmax_fwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)scores, H, B, Tq, T, ld, lens, causal, (bf16*)p, pd, drop_p, \
+  esp_launch(attn_softmax_fwd_kernel<NI>, grid, 256, 0, st, (const bf16*)scores, H, B, Tq, T, ld, lens, causal, (bf16*)p, pd, drop_p, \
                                                     esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
   if (ld <= 256) ESP_SMF(1);
   else if (ld <= 512) ESP_SMF(2);
@@ -1073,7 +1095,7 @@ extern "C" int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t 
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define ESP_SMB(NI)                                                                                              \
-  attn_softmax_bwd_kernel<NI><<<grid, 256, 0, st>>>((const bf16*)p, (const bf16*)dp_drop, H, B, Tq, T, ld, (bf16*)ds, \
+  esp_launch(attn_softmax_bwd_kernel<NI>, grid, 256, 0, st, (const bf16*)p, (const bf16*)dp_drop, H, B, Tq, T, ld, (bf16*)ds, \
                                                     (bf16*)dbd, ldp, drop_p, esp_dropout_thresh(drop_p), seed,  \
                                                     (const unsigned long long*)seed_ptr)
   if (ld <= 256) ESP_SMB(1);
@@ -1094,7 +1116,7 @@ extern "C" int esp_glu_dwconv_fwd(const void* g, const void* w, int32_t B, int32
   ESP_CHECK((ksz & 1) && ksz <= kDwMaxK, "depthwise kernel size must be odd and <= %d", kDwMaxK);
   if ((long)B * T == 0) return 0;
   dim3 grid((T + kDwT - 1) / kDwT, C / kDwC, B);
-  glu_dwconv_fwd_kernel<<<grid, 256, 0, st>>>((const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)y, stats);
+  esp_launch(glu_dwconv_fwd_kernel, grid, 256, 0, st, (const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)y, stats);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -1112,7 +1134,7 @@ extern "C" int esp_glu_dwconv_bwd(const void* dy, const void* g, const void* w, 
     ESP_CUDA(cudaFuncSetAttribute(glu_dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     cfg = true;
   }
-  glu_dwconv_bwd_kernel<<<grid, 256, kSmem, st>>>((const bf16*)dy, (const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)dg, dw);
+  esp_launch(glu_dwconv_bwd_kernel, grid, 256, kSmem, st, (const bf16*)dy, (const bf16*)g, (const bf16*)w, B, T, C, ksz, (bf16*)dg, dw);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -1123,7 +1145,7 @@ extern "C" int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float 
   ESP_ST;
   ESP_CHECK(mr != nullptr, "bn_finalize: null output");
   ESP_CHECK(training ? stats != nullptr : (run_mean && run_var), "bn_finalize: missing statistics");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, R, C, eps, momentum, run_mean, run_var, training, mr);
+  esp_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, st, stats, R, C, eps, momentum, run_mean, run_var, training, mr);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -1141,7 +1163,7 @@ extern "C" int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, 
   ESP_ST;
   ESP_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_stats: C/8 must divide 256 (got C=%d)", C);
   if (R == 0) return 0;
-  bn_stats_kernel<<<bn_reduce_grid(R * (C / 8)), 256, 0, st>>>((const bf16*)x, R, C, stats);
+  esp_launch(bn_stats_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)x, R, C, stats);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -1153,7 +1175,7 @@ extern "C" int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* 
   ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
   ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
   if (R == 0) return 0;
-  bn_act_fwd_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)y, R, C, mr, (const bf16*)gamma,
+  esp_launch(bn_act_fwd_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)y, R, C, mr, (const bf16*)gamma,
                                                                 (const bf16*)beta, act, (bf16*)z);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
@@ -1168,15 +1190,15 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t 
   ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
   if (R == 0) return 0;
   ESP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
-  bn_act_bwd_reduce_kernel<<<bn_reduce_grid(R * (C / 8)), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr,
+  esp_launch(bn_act_bwd_reduce_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)dz, (const bf16*)y, R, C, mr,
                                                                        (const bf16*)gamma, (const bf16*)beta, act, sums);
   ESP_LAUNCH_CHECK();
   // the float coefficient table reuses the tail of the caller's `sums` workspace: 2C doubles = room for 2C extra floats
   // after the doubles were consumed -- keep it separate instead: coefficients go to the second half of a 4C-float view
   float* coef = reinterpret_cast<float*>(sums + 2 * C);
-  bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, R, C, dgamma, dbeta, coef);
+  esp_launch(bn_param_grad_kernel, (C + 127) / 128, 128, 0, st, sums, R, C, dgamma, dbeta, coef);
   ESP_LAUNCH_CHECK();
-  bn_act_bwd_apply_kernel<<<grid_for(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dz, (const bf16*)y, R, C, mr, coef,
+  esp_launch(bn_act_bwd_apply_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)dz, (const bf16*)y, R, C, mr, coef,
                                                                       (const bf16*)gamma, (const bf16*)beta, act,
                                                                       (bf16*)dy);
   ESP_LAUNCH_CHECK();

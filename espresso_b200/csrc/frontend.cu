@@ -112,6 +112,7 @@ frontend_kernel(const WaveT* __restrict__ wave, long wave_ld, const int* __restr
                 const int* __restrict__ freq_masks, int n_freq_masks, const int* __restrict__ time_masks,
                 int max_time_masks, void* __restrict__ out, int out_f32, int t_max, int* __restrict__ out_lens,
                 double* __restrict__ ws_sum, unsigned int* __restrict__ ws_cnt) {
+  esp_pdl();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int b = blockIdx.y;
@@ -310,7 +311,7 @@ extern "C" int esp_frontend_fbank(const void* wave, int32_t wave_i16, int64_t wa
       ESP_CUDA(cudaFuncSetAttribute(frontend_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg = true;
     }
-    frontend_kernel<int16_t><<<grid, kWarps * 32, smem, st>>>(
+    esp_launch(frontend_kernel<int16_t>, grid, kWarps * 32, smem, st, 
         (const int16_t*)wave, wave_ld, n_samples, cmvn_mean, cmvn_std, freq_masks, n_freq_masks, time_masks,
         max_time_masks, out, out_f32, t_max, out_lens, ws_sum, ws_cnt);
   } else {
@@ -319,7 +320,7 @@ extern "C" int esp_frontend_fbank(const void* wave, int32_t wave_i16, int64_t wa
       ESP_CUDA(cudaFuncSetAttribute(frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg = true;
     }
-    frontend_kernel<float><<<grid, kWarps * 32, smem, st>>>(
+    esp_launch(frontend_kernel<float>, grid, kWarps * 32, smem, st, 
         (const float*)wave, wave_ld, n_samples, cmvn_mean, cmvn_std, freq_masks, n_freq_masks, time_masks,
         max_time_masks, out, out_f32, t_max, out_lens, ws_sum, ws_cnt);
   }

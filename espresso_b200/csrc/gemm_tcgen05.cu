@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "espresso_b200.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 void esp_count_launch(int n);
 
@@ -92,6 +93,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       :
       : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// multicast variants for a 2-CTA cluster: data and the mbarrier signal land at the same CTA-relative offsets in every
+// CTA of `mask`
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                               int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      :
+      : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -228,7 +255,10 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_K, bool B_K>
+// MC = 2: the kernel runs as 2-CTA clusters along M.  The two CTAs of a cluster work on M-adjacent tiles of the same
+// (N tile, batch, K split), so they need the SAME B tile: each loads half of it and multicasts it to both, which cuts
+// the L2->SM operand traffic per CTA from (128 + BN) to (128 + BN/2) rows per k-block -- the bound of these tiles.
+template <int BN, bool A_K, bool B_K, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const KParams p) {
@@ -249,13 +279,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (p.M + BM - 1) / BM;
+  // With MC = 2 a work item is a PAIR of M tiles: "tiles_m" counts pairs and this CTA owns tile 2*pair + rank
+  // (a missing odd tile is all out-of-bounds rows: TMA zero-fills, the epilogue's row guard drops it).
+  const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
+  const int tiles_m = ((p.M + BM - 1) / BM + MC - 1) / MC;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int nbatch = p.nb1 * p.nb2;
   const int num_kb_all = (p.K + BK - 1) / BK;
   const int kb_per = (num_kb_all + p.ksplit - 1) / p.ksplit;
-  const int total_tiles = tiles_m * tiles_n * nbatch * p.ksplit;  // work items = output tiles x K splits
+  const int total_tiles = tiles_m * tiles_n * nbatch * p.ksplit;  // work items = output tiles (pairs) x K splits
+  const int work0 = blockIdx.x / MC, work_stride = gridDim.x / MC;
 
+  esp_pdl_trigger();  // the next kernel may be scheduled behind this grid's CTAs (it waits for our completion itself)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -263,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC);  // MC > 1: the peer's producer also writes this slot, so both consumers free it
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -280,20 +315,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail; nothing before
+  // this point touches global memory written by earlier kernels
+  esp_pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer =====================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      for (int work = work0; work < total_tiles; work += work_stride) {
         const int ks = work % p.ksplit;
         const int tile = work / p.ksplit;
         const int kb0 = ks * kb_per;
         const int kb1 = min(num_kb_all, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K split (all three roles skip it identically)
-        const int mt = tile % tiles_m;
+        const int mt = (tile % tiles_m) * MC + crank;
         const int rest = tile / tiles_m;
         const int nt = rest % tiles_n;
         const int bt = rest / tiles_n;
@@ -313,13 +352,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(s), mt * BM + 64 * j, kb * BK,
                           b1 * p.a_b1, b2 * p.a_b2);
           }
-          if (B_K) {
-            tma_load_4d(sb, &tmB, full_bar(s), kb * BK, nt * BN, b1 * p.b_b1, b2 * p.b_b2);
-          } else {
+          if (MC == 1) {
+            if (B_K) {
+              tma_load_4d(sb, &tmB, full_bar(s), kb * BK, nt * BN, b1 * p.b_b1, b2 * p.b_b2);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), nt * BN + 64 * j, kb * BK,
-                          b1 * p.b_b1, b2 * p.b_b2);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), nt * BN + 64 * j, kb * BK,
+                            b1 * p.b_b1, b2 * p.b_b2);
+            }
+          } else {
+            // this CTA fetches half `crank` of the B tile for both CTAs (the tensor map's box is BN/2 rows when
+            // B is K-major; MN-major tiles are made of 64-wide chunks, half of them each)
+            if (B_K) {
+              tma_load_4d_mc(sb + crank * (BN / 2) * 128, &tmB, full_bar(s), kb * BK, nt * BN + crank * (BN / 2),
+                             b1 * p.b_b1, b2 * p.b_b2, (uint16_t)0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                tma_load_4d_mc(sb + jj * (BK * 128), &tmB, full_bar(s), nt * BN + 64 * jj, kb * BK, b1 * p.b_b1,
+                               b2 * p.b_b2, (uint16_t)0x3);
+              }
+            }
           }
         }
       }
@@ -332,7 +387,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              ((B_K ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, ti = 0;
-      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      for (int work = work0; work < total_tiles; work += work_stride) {
         const int ks = work % p.ksplit;
         const int kb0 = ks * kb_per;
         const int kb1 = min(num_kb_all, kb0 + kb_per);
@@ -361,7 +416,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     : make_sdesc(sb + k * 2048, BK * 128, 1024);
             umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (in both CTAs of a multicast pair)
+          if (MC > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)0x3);
+          else tcgen05_commit(empty_bar(s));
         }
         tcgen05_commit(tfull_bar(as));  // accumulator complete -> epilogue
       }
@@ -376,13 +433,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const EpiParams& e = p.ep;
     const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
     uint32_t ti = 0;
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    for (int work = work0; work < total_tiles; work += work_stride) {
       const int ks = work % p.ksplit;
       const int tile = work / p.ksplit;
       const int kb0 = ks * kb_per;
       const int kb1 = min(num_kb_all, kb0 + kb_per);
       if (kb0 >= kb1) continue;
-      const int mt = tile % tiles_m;
+      const int mt = (tile % tiles_m) * MC + crank;
       const int rest = tile / tiles_m;
       const int nt = rest % tiles_n;
       const int bt = rest / tiles_n;
@@ -541,6 +598,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();  // no CTA exits while its peer may still signal or write into its shared memory
   if (warp == 2) {
     tcgen05_fence_after();
     constexpr int kCols = kAccStages * BN;
@@ -551,6 +609,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+bool esp_gemm_multicast_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ESP_GEMM_MULTICAST");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -601,31 +668,54 @@ int make_tmap(CUtensorMap* tm, const void* base, long inner, long rows, long ld,
   return 0;
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, int MC>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t st) {
   using L = SmemLayout<BN, A_K, B_K>;
   static bool configured = false;
-  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K>;
+  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC>;
   if (!configured) {
     ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int tiles = ((kp.M + BM - 1) / BM) * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2 * kp.ksplit;
-  int grid = tiles < esp_num_sms() ? tiles : esp_num_sms();
+  const int tiles_m = (((kp.M + BM - 1) / BM) + MC - 1) / MC;
+  const int work = tiles_m * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2 * kp.ksplit;
+  // persistent grid = what is co-resident.  Clusters must sit inside one GPC, so with odd SM counts per GPC fewer
+  // than SMs/2 pairs fit at once: ask the runtime instead of assuming.
+  static int slots = 0;
+  if (slots == 0) {
+    slots = esp_num_sms() / MC;
+    if (MC > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(esp_num_sms() / MC * MC);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = L::kTotal;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = MC;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) == cudaSuccess && n > 0 && n < slots) slots = n;
+      (void)cudaGetLastError();
+    }
+  }
+  int grid = (work < slots ? work : slots) * MC;
   if (grid < 1) return 0;
-  kfn<<<grid, kThreads, L::kTotal, st>>>(ta, tb, kp);
+  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, MC, ta, tb, kp);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
-template <int BN>
+template <int BN, int MC>
 int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp,
                    cudaStream_t st) {
-  if (ak && bk) return launch<BN, true, true>(ta, tb, kp, st);
-  if (ak && !bk) return launch<BN, true, false>(ta, tb, kp, st);
-  if (!ak && bk) return launch<BN, false, true>(ta, tb, kp, st);
-  return launch<BN, false, false>(ta, tb, kp, st);
+  if (ak && bk) return launch<BN, true, true, MC>(ta, tb, kp, st);
+  if (ak && !bk) return launch<BN, true, false, MC>(ta, tb, kp, st);
+  if (!ak && bk) return launch<BN, false, true, MC>(ta, tb, kp, st);
+  return launch<BN, false, false, MC>(ta, tb, kp, st);
 }
 
 }  // namespace
@@ -665,11 +755,14 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
     else bn = g->N > 128 ? 128 : (g->N > 64 && tiles_for(64) < sms ? 64 : 128);
   }
   if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) bn = g->tile_n;
+  // 2-CTA multicast pairs along M: worth it when the pairing wastes (almost) no tile
+  int mc = 1;
+  if (bn >= 128 && esp_gemm_multicast_enabled() && (tm % 2 == 0 || tm >= 16)) mc = 2;
   int rc;
   if (ak) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, nb1, g->sA1, nb2, g->sA2, BM);
   else    rc = make_tmap(&ta, g->A, g->M, g->K, g->lda, nb1, g->sA1, nb2, g->sA2, BK);
   if (rc) return rc;
-  if (bk) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, nb1, g->sB1, nb2, g->sB2, bn);
+  if (bk) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, nb1, g->sB1, nb2, g->sB2, bn / mc);
   else    rc = make_tmap(&tb, g->B, g->N, g->K, g->ldb, nb1, g->sB1, nb2, g->sB2, BK);
   if (rc) return rc;
 
@@ -693,7 +786,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
   ESP_CHECK(!g->accumulate || g->c_f32, "accumulate (atomic) output must be fp32");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
-  if (bn == 64) return dispatch_major<64>(ak, bk, ta, tb, kp, st);
-  if (bn == 256) return dispatch_major<256>(ak, bk, ta, tb, kp, st);
-  return dispatch_major<128>(ak, bk, ta, tb, kp, st);
+  if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, kp, st);
+  if (bn == 256) return mc == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, kp, st);
+  return mc == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, kp, st);
 }

@@ -18,6 +18,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, long n, float* __restrict__ out) {
+  esp_pdl();
   float s = 0.f;
   const long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -44,6 +45,7 @@ adam_kernel(float* __restrict__ p32, float* __restrict__ m, float* __restrict__ 
             bf16* __restrict__ p16, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
             float step, const float* __restrict__ sumsq, const float* __restrict__ denom_ptr,
             float denom_const, float clip_norm, float* __restrict__ gnorm_out, const float* __restrict__ hyper) {
+  esp_pdl();
   if (hyper) {  // schedule values live in device memory so a captured graph replays with fresh ones
     lr = hyper[0];
     step = hyper[1];
@@ -75,10 +77,12 @@ adam_kernel(float* __restrict__ p32, float* __restrict__ m, float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 cast_f32_to_bf16_kernel(const float* __restrict__ x, long n, bf16* __restrict__ y) {
+  esp_pdl();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = f2bf(x[i]);
 }
 __global__ void __launch_bounds__(256)
 cast_bf16_to_f32_kernel(const bf16* __restrict__ x, long n, float* __restrict__ y) {
+  esp_pdl();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = bf2f(x[i]);
 }
 
@@ -96,7 +100,7 @@ extern "C" int esp_sumsq_f32(const float* g, int64_t n, float* out, void* stream
   ESP_CHECK(((uintptr_t)g & 15) == 0, "sumsq input must be 16-byte aligned");
   ESP_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (n > 0) {
-    sumsq_kernel<<<grid_n(n / 4 + 1), 256, 0, st>>>(g, n, out);
+    esp_launch(sumsq_kernel, grid_n(n / 4 + 1), 256, 0, st, g, n, out);
     ESP_LAUNCH_CHECK();
     esp_count_launch(1);
   }
@@ -111,7 +115,7 @@ extern "C" int esp_adam_step(float* p32, float* m, float* v, const float* g, voi
   ESP_CHECK(step >= 1 || hyper_dev != nullptr, "Adam step count must start at 1");
   ESP_CHECK(sumsq != nullptr, "Adam needs the squared gradient norm (esp_sumsq_f32)");
   if (n == 0) return 0;
-  adam_kernel<<<grid_n(n), 256, 0, st>>>(p32, m, v, g, (bf16*)p16, n, lr, beta1, beta2, eps, weight_decay, (float)step,
+  esp_launch(adam_kernel, grid_n(n), 256, 0, st, p32, m, v, g, (bf16*)p16, n, lr, beta1, beta2, eps, weight_decay, (float)step,
                                         sumsq, denom_dev, denom_const, clip_norm, gnorm_out, hyper_dev);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
@@ -121,7 +125,7 @@ extern "C" int esp_adam_step(float* p32, float* m, float* v, const float* g, voi
 extern "C" int esp_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return 0;
-  cast_f32_to_bf16_kernel<<<grid_n(n), 256, 0, st>>>(x, n, (bf16*)y);
+  esp_launch(cast_f32_to_bf16_kernel, grid_n(n), 256, 0, st, x, n, (bf16*)y);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -129,7 +133,7 @@ extern "C" int esp_cast_f32_bf16(const float* x, int64_t n, void* y, void* strea
 extern "C" int esp_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return 0;
-  cast_bf16_to_f32_kernel<<<grid_n(n), 256, 0, st>>>((const bf16*)x, n, y);
+  esp_launch(cast_bf16_to_f32_kernel, grid_n(n), 256, 0, st, (const bf16*)x, n, y);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
