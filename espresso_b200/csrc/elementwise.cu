@@ -55,7 +55,8 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 constexpr int kRedSlots = 8;
 constexpr int kRedMaxCols = 4096;
 __device__ float g_red_slots[2][kRedSlots][kRedMaxCols];
-__device__ unsigned int g_red_ticket[1 + kRedMaxCols / 256];
+__device__ unsigned int g_red_ticket[2 + kRedMaxCols / 256];
+constexpr int kTicketDropout = 1 + kRedMaxCols / 256;
 
 inline int grid_for(long work_items, int per_block, int max_waves = 8) {
   long g = (work_items + per_block - 1) / per_block;
@@ -144,7 +145,7 @@ ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const 
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat*mean(g*dy*xhat)) [+ dres];  dgamma += dy*xhat; dbeta += dy
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 2 ? 2 : 1)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, const bf16* __restrict__ dres, long R,
               int d, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -178,40 +179,50 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       const int b = (int)(r / T), t = (int)(r % T);
       zero_row = t >= lens[b];
     }
-    // all global loads of the row are issued before the first reduction (dres included)
-    uint4 rq[NV];
-    if (dres) {
+    // All global loads of the row are issued up front and stay PACKED in registers (bf16 pairs); both passes unpack
+    // them again, which is cheaper than keeping 2 x NV x 8 floats alive (register pressure decides the occupancy of
+    // this latency-bound kernel).
+    uint4 dq[NV], xq[NV], rq[NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < nvec) rq[i] = *reinterpret_cast<const uint4*>(dres + r * d + vi * 8);
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        dq[i] = *reinterpret_cast<const uint4*>(dy + r * d + vi * 8);
+        xq[i] = *reinterpret_cast<const uint4*>(x + r * d + vi * 8);
+        if (dres) rq[i] = *reinterpret_cast<const uint4*>(dres + r * d + vi * 8);
       }
     }
     const float mean = mean_in[r], rstd = rstd_in[r];
-    float gdy[NV][8], xh[NV][8];
+    const float dsc = (drop_p > 0.f) ? drop_scale : 1.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
+        if (zero_row) {
+          dq[i] = make_uint4(0, 0, 0, 0);
+        } else if (drop_p > 0.f) {
+          // dropped elements are zeroed in the packed copy; the 1/(1-p) scale is applied on unpack
+          bool keep[8];
+          esp_keep8(seed, (unsigned long long)r * d + vi * 8, drop_thresh, keep);
+          dq[i].x &= (keep[0] ? 0x0000FFFFu : 0u) | (keep[1] ? 0xFFFF0000u : 0u);
+          dq[i].y &= (keep[2] ? 0x0000FFFFu : 0u) | (keep[3] ? 0xFFFF0000u : 0u);
+          dq[i].z &= (keep[4] ? 0x0000FFFFu : 0u) | (keep[5] ? 0xFFFF0000u : 0u);
+          dq[i].w &= (keep[6] ? 0x0000FFFFu : 0u) | (keep[7] ? 0xFFFF0000u : 0u);
+        }
         float a[8], xv[8], g[8];
-        load8(dy + r * d + vi * 8, a);
-        load8(x + r * d + vi * 8, xv);
+        unpack8(dq[i], a);
+        unpack8(xq[i], xv);
         unpack8(gq[i], g);
-        bool keep[8];
-        if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)r * d + vi * 8, drop_thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float dyv = a[j];
-          if (zero_row) dyv = 0.f;
-          else if (drop_p > 0.f) dyv = keep[j] ? dyv * drop_scale : 0.f;
+          const float dyv = a[j] * dsc;
           const float h = (xv[j] - mean) * rstd;
-          xh[i][j] = h;
-          gdy[i][j] = dyv * g[j];
+          const float gd = dyv * g[j];
           ag[i][j] += dyv * h;
           ab[i][j] += dyv;
-          s1 += gdy[i][j];
-          s2 += gdy[i][j] * h;
+          s1 += gd;
+          s2 += gd * h;
         }
       }
     }
@@ -221,12 +232,15 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        float o[8];
-        float rr[8];
+        float a[8], xv[8], g[8], o[8], rr[8];
+        unpack8(dq[i], a);
+        unpack8(xq[i], xv);
+        unpack8(gq[i], g);
         if (dres) unpack8(rq[i], rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = rstd * (gdy[i][j] - s1 - xh[i][j] * s2);
+          const float h = (xv[j] - mean) * rstd;
+          o[j] = rstd * (a[j] * dsc * g[j] - s1 - h * s2);
           if (dres) o[j] += rr[j];
         }
         store8(dx + r * d + vi * 8, o);
@@ -364,6 +378,65 @@ dropout_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, fl
     for (int j = 0; j < 8; ++j) v[j] = (drop_p > 0.f && !keep[j]) ? 0.f : v[j] * ds;
     store8(y + r * ldy + c, v);
   }
+}
+
+// y = dropout(x) * scale AND colsum[n] += sum_r y[r, n] in the same pass (the bias gradient of the Linear whose output
+// gradient this is).  Needs 256 % (N/8) == 0, so a thread always sees the same 8 columns.
+__global__ void __launch_bounds__(256)
+dropout_colsum_kernel(const bf16* __restrict__ x, long R, int N, long ldx, long ldy, float scale, float drop_p,
+                      uint32_t thresh, unsigned long long seed0, const unsigned long long* __restrict__ seed_ptr,
+                      bf16* __restrict__ y, float* __restrict__ colsum) {
+  esp_pdl();
+  __shared__ float red[256][9];
+  __shared__ int s_last;
+  const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
+  const int cv = N >> 3;
+  const long nvec = R * cv;
+  const float ds = drop_p > 0.f ? scale * 65536.f / (65536.f - (float)thresh) : scale;
+  const int c = (int)(((long)blockIdx.x * 256 + threadIdx.x) % cv) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+    long r;
+    unsigned cvi;
+    esp_divmod(i, (unsigned)cv, r, cvi);
+    float v[8];
+    load8(x + r * ldx + c, v);
+    bool keep[8];
+    if (drop_p > 0.f) esp_keep8(seed, (unsigned long long)r * N + c, thresh, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (drop_p > 0.f && !keep[j]) ? 0.f : bf2f(f2bf(v[j] * ds));
+      acc[j] += v[j];  // the sum of what is stored (bf16), like a separate pass over y would see
+    }
+    store8(y + r * ldy + c, v);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < cv) {
+    const int slot = blockIdx.x % kRedSlots;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sacc = 0.f;
+      for (int k = threadIdx.x; k < 256; k += cv) sacc += red[k][j];
+      atomicAdd(&g_red_slots[0][slot][threadIdx.x * 8 + j], sacc);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_red_ticket[kTicketDropout], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float a0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) a0 += __ldcg(&g_red_slots[0][k][n]);
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) __stcg(&g_red_slots[0][k][n], 0.f);
+    colsum[n] += a0;
+  }
+  if (threadIdx.x == 0) g_red_ticket[kTicketDropout] = 0u;
 }
 
 // zero rows t >= lens[b] of x [B, T, N]
@@ -774,17 +847,22 @@ __device__ __forceinline__ float bn_act_grad(float bn, int act) { return act == 
 // registers; one shared-memory pass + one double atomic per channel per CTA finishes the job.
 // stats[c] += sum_r x[r,c] ; stats[C + c] += sum_r x[r,c]^2
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const bf16* __restrict__ x, long R, int Cn, double* __restrict__ stats) {
+bn_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ pre_bias, long R, int Cn,
+                double* __restrict__ stats) {
   esp_pdl();
   __shared__ float red[2][256][8];
   const int cv = Cn >> 3;
   const long nvec = R * cv;
   float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float pb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // grid stride is a multiple of cv => the channel group of this thread is fixed
+  if (pre_bias) load8(pre_bias + (int)(((long)blockIdx.x * 256 + threadIdx.x) % cv) * 8, pb);
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
     float v[8];
     load8(x + i * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (pre_bias) v[j] = bf2f(f2bf(v[j] + pb[j]));  // the tensor being normalised is bf16(x + bias)
       a1[j] += v[j];
       a2[j] += v[j] * v[j];
     }
@@ -811,7 +889,7 @@ bn_stats_kernel(const bf16* __restrict__ x, long R, int Cn, double* __restrict__
 
 // z = act(bn(y))
 __global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __restrict__ mr,
+bn_act_fwd_kernel(const bf16* __restrict__ y, const bf16* __restrict__ pre_bias, long R, int Cn, const float* __restrict__ mr,
                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ z) {
   esp_pdl();
   const long nvec = R * (Cn >> 3);
@@ -826,6 +904,12 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __res
     load8(beta + c, bt);
     loadf8(mr + c, mu);
     loadf8(mr + Cn + c, rs);
+    if (pre_bias) {
+      float pb[8];
+      load8(pre_bias + c, pb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf2f(f2bf(v[j] + pb[j]));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float bn = bf2f(f2bf((v[j] - mu[j]) * rs[j] * gm[j] + bt[j]));  // BN output is bf16
@@ -837,7 +921,7 @@ bn_act_fwd_kernel(const bf16* __restrict__ y, long R, int Cn, const float* __res
 
 // pass 1 of BN+act backward: s1[c] = sum dbn, s2[c] = sum dbn * xhat   (dbn = dz * act'(bn))
 __global__ void __launch_bounds__(256)
-bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, const bf16* __restrict__ pre_bias, long R, int Cn,
                          const float* __restrict__ mr, const bf16* __restrict__ gamma,
                          const bf16* __restrict__ beta, int act, double* __restrict__ sums) {
   esp_pdl();
@@ -852,6 +936,8 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
   load8(beta + c, bt);
   loadf8(mr + c, mean);
   loadf8(mr + Cn + c, rstd);
+  float pb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pre_bias) load8(pre_bias + c, pb);
   const long stride = (long)gridDim.x * 256;
   long i = (long)blockIdx.x * 256 + threadIdx.x;
   auto accumulate = [&](const uint4& dq, const uint4& vq) {
@@ -860,6 +946,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
     unpack8(vq, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (pre_bias) v[j] = bf2f(f2bf(v[j] + pb[j]));
       const float xh = (v[j] - mean[j]) * rstd[j];
       const float bn = bf2f(f2bf(xh * gm[j] + bt[j]));
       const float dbn = d[j] * bn_act_grad(bn, act);
@@ -901,7 +988,7 @@ bn_act_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y
 
 // pass 2: dy = gamma * rstd * (dbn - s1/n - xhat * s2/n)
 __global__ void __launch_bounds__(256)
-bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, long R, int Cn,
+bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, const bf16* __restrict__ pre_bias, long R, int Cn,
                         const float* __restrict__ mr, const float* __restrict__ coef,
                         const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int act, bf16* __restrict__ dy) {
   esp_pdl();
@@ -920,6 +1007,12 @@ bn_act_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
     loadf8(mr + Cn + c, rs);
     loadf8(coef + c, m1);
     loadf8(coef + Cn + c, m2);
+    if (pre_bias) {
+      float pb[8];
+      load8(pre_bias + c, pb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf2f(f2bf(v[j] + pb[j]));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (v[j] - mu[j]) * rs[j];
@@ -1013,15 +1106,27 @@ extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float
 }
 
 extern "C" int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
-                           uint64_t seed, const uint64_t* seed_ptr, void* y, void* stream) {
+                           uint64_t seed, const uint64_t* seed_ptr, void* y, float* colsum, void* stream) {
   ESP_ST;
   ESP_CHECK(N % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dropout needs N/ld multiples of 8");
   if (R == 0 || N == 0) return 0;
+  if (colsum && N <= 2048 && 256 % (N / 8) == 0) {
+    // bias gradient in the same pass; one wave of CTAs (the tail is a cross-CTA reduction)
+    long g = (R * (N / 8) + 255) / 256;
+    const long cap = 4L * esp_num_sms();
+    if (g > cap) g = cap;
+    esp_launch(dropout_colsum_kernel, (unsigned)g, 256, 0, st, (const bf16*)x, R, N, ldx, ldy, scale, drop_p,
+               esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr, (bf16*)y, colsum);
+    ESP_LAUNCH_CHECK();
+    esp_count_launch(1);
+    return 0;
+  }
   esp_launch(dropout_kernel, grid_for(R * (N / 8), 256), 256, 0, st, (const bf16*)x, R, N, ldx, ldy, scale, drop_p,
                                                              esp_dropout_thresh(drop_p), seed,
                                                              (const unsigned long long*)seed_ptr, (bf16*)y);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
+  if (colsum) return esp_colsum(y, R, N, ldy, 1.f, colsum, stream);
   return 0;
 }
 
@@ -1159,38 +1264,38 @@ static inline int bn_reduce_grid(long nvec) {
   return (int)(g < 1 ? 1 : g);
 }
 
-extern "C" int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, void* stream) {
+extern "C" int esp_bn_stats(const void* x, const void* pre_bias, int64_t R, int32_t C, double* stats, void* stream) {
   ESP_ST;
   ESP_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_stats: C/8 must divide 256 (got C=%d)", C);
   if (R == 0) return 0;
-  esp_launch(bn_stats_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)x, R, C, stats);
+  esp_launch(bn_stats_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)x, (const bf16*)pre_bias, R, C, stats);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
-extern "C" int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
-                              int32_t act, void* z, void* stream) {
+extern "C" int esp_bn_act_fwd(const void* y, const void* pre_bias, int64_t R, int32_t C, const float* mr, const void* gamma,
+                              const void* beta, int32_t act, void* z, void* stream) {
   ESP_ST;
   ESP_CHECK(C % 8 == 0, "BatchNorm channels must be a multiple of 8");
   ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
   if (R == 0) return 0;
-  esp_launch(bn_act_fwd_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)y, R, C, mr, (const bf16*)gamma,
+  esp_launch(bn_act_fwd_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)y, (const bf16*)pre_bias, R, C, mr, (const bf16*)gamma,
                                                                 (const bf16*)beta, act, (bf16*)z);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
-extern "C" int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
-                              const void* beta, int32_t act, double* sums, void* dy, float* dgamma, float* dbeta,
-                              void* stream) {
+extern "C" int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bias, int64_t R, int32_t C, const float* mr,
+                              const void* gamma, const void* beta, int32_t act, double* sums, void* dy, float* dgamma,
+                              float* dbeta, void* stream) {
   ESP_ST;
   ESP_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_act_bwd: C/8 must divide 256 (got C=%d)", C);
   ESP_CHECK(act == 1 || act == 2, "bn_act: act must be 1 (SiLU) or 2 (ReLU)");
   if (R == 0) return 0;
   ESP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
-  esp_launch(bn_act_bwd_reduce_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)dz, (const bf16*)y, R, C, mr,
+  esp_launch(bn_act_bwd_reduce_kernel, bn_reduce_grid(R * (C / 8)), 256, 0, st, (const bf16*)dz, (const bf16*)y, (const bf16*)pre_bias, R, C, mr,
                                                                        (const bf16*)gamma, (const bf16*)beta, act, sums);
   ESP_LAUNCH_CHECK();
   // the float coefficient table reuses the tail of the caller's `sums` workspace: 2C doubles = room for 2C extra floats
@@ -1198,7 +1303,7 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t 
   float* coef = reinterpret_cast<float*>(sums + 2 * C);
   esp_launch(bn_param_grad_kernel, (C + 127) / 128, 128, 0, st, sums, R, C, dgamma, dbeta, coef);
   ESP_LAUNCH_CHECK();
-  esp_launch(bn_act_bwd_apply_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)dz, (const bf16*)y, R, C, mr, coef,
+  esp_launch(bn_act_bwd_apply_kernel, grid_for(R * (C / 8), 256), 256, 0, st, (const bf16*)dz, (const bf16*)y, (const bf16*)pre_bias, R, C, mr, coef,
                                                                       (const bf16*)gamma, (const bf16*)beta, act,
                                                                       (bf16*)dy);
   ESP_LAUNCH_CHECK();

@@ -129,24 +129,25 @@ class _BNReLUFn(torch.autograd.Function):
     channels_last strides, i.e. memory [B, T, F, C]."""
 
     @staticmethod
-    def forward(ctx, x, bn, gw, gb, training):
+    def forward(ctx, x, bn, gw, gb, training, conv_bias):
         xr = x.permute(0, 2, 3, 1)  # [B, T, F, C] contiguous view
         assert xr.is_contiguous()
         C = xr.shape[-1]
         R = xr.numel() // C
-        stats = _ops.bn_stats(xr, C) if training else None
+        stats = _ops.bn_stats(xr, C, pre_bias=conv_bias) if training else None
         mr = _ops.bn_finalize(stats, R, C, 1e-5, 0.1, bn.running_mean, bn.running_var, training)
-        z = _ops.bn_act_fwd(xr, mr, bn.weight.data, bn.bias.data, _ops.BN_ACT_RELU)
+        z = _ops.bn_act_fwd(xr, mr, bn.weight.data, bn.bias.data, _ops.BN_ACT_RELU, pre_bias=conv_bias)
         ctx.save_for_backward(xr, mr)
-        ctx.bn, ctx.gw, ctx.gb = bn, gw, gb
+        ctx.bn, ctx.gw, ctx.gb, ctx.conv_bias = bn, gw, gb, conv_bias
         return z.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dz):
         xr, mr = ctx.saved_tensors
         dzr = dz.permute(0, 2, 3, 1).contiguous()
-        dx = _ops.bn_act_bwd(dzr, xr, mr, ctx.bn.weight.data, ctx.bn.bias.data, ctx.gw, ctx.gb, _ops.BN_ACT_RELU)
-        return dx.permute(0, 3, 1, 2), None, None, None, None
+        dx = _ops.bn_act_bwd(dzr, xr, mr, ctx.bn.weight.data, ctx.bn.bias.data, ctx.gw, ctx.gb, _ops.BN_ACT_RELU,
+                             pre_bias=ctx.conv_bias)
+        return dx.permute(0, 3, 1, 2), None, None, None, None, None
 
 
 class ConvBNReLU(nn.Module):
@@ -183,14 +184,18 @@ class ConvBNReLU(nn.Module):
         x = src.view(src.size(0), src.size(1), self.in_channels, src.size(2) // self.in_channels).transpose(1, 2)
         x = x.contiguous(memory_format=torch.channels_last)
         for i, (conv, bn) in enumerate(zip(self.convolutions, self.batchnorms)):
-            x = conv(x)
+            # The convolution runs WITHOUT its bias: the bias is added inside the BatchNorm kernels (pre_bias), which
+            # removes one full pass over the activation in forward (bias add) and one in backward (bias-gradient
+            # reduction).  The gradient of a bias in front of a batch-statistics BatchNorm is identically zero
+            # (the reference computes rounding noise there), so conv.bias receives no gradient.
+            x = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
             if not x.is_contiguous(memory_format=torch.channels_last):
                 x = x.contiguous(memory_format=torch.channels_last)
             gw = self.flat.grad(self.flat_prefix + "batchnorms.%d.weight" % i)
             gb = self.flat.grad(self.flat_prefix + "batchnorms.%d.bias" % i)
             if self.training:
                 bn.num_batches_tracked += 1
-            x = _BNReLUFn.apply(x, bn, gw, gb, self.training)
+            x = _BNReLUFn.apply(x, bn, gw, gb, self.training, conv.bias.data if conv.bias is not None else None)
         # B x C x T' x F' -> B x T' x (C * F')   (channel-major inner index, as in the reference)
         x = x.permute(0, 2, 1, 3).contiguous()
         x = x.view(x.size(0), x.size(1), x.size(2) * x.size(3))

@@ -123,9 +123,9 @@ class EncoderEngine:
         ln_n, w1_n, w2_n = names
         x, mean, rstd, ln, U, Hh = saved
         W1, W2 = self.P(lp + w1_n + ".weight"), self.P(lp + w2_n + ".weight")
-        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha)
+        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha,
+                          colsum_acc=self.G(lp + w2_n + ".bias"))  # bias gradient in the same pass
         self._wgrad(dZ, Hh, self.G(lp + w2_n + ".weight"))
-        _ops.colsum(dZ, self.G(lp + w2_n + ".bias"))
         dU = self._dgrad(dZ, W2, act=act_bwd, aux=U, ld_aux=U.stride(0), drop_p=self._drop("activation_dropout"),
                          drop_mode=2, seed=self._seed(li, opbase))
         self._wgrad(dU, ln, self.G(lp + w1_n + ".weight"))
@@ -168,9 +168,8 @@ class EncoderEngine:
         k, v = qkv[:, d:2 * d], qkv[:, 2 * d:]
         ldt, ldp = _r8(T), _r8(2 * T - 1)
         dev = dy.device
-        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
+        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11), colsum_acc=self.G(lp + "self_attn.out_proj.bias"))
         self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"))
-        _ops.colsum(dO, self.G(lp + "self_attn.out_proj.bias"))
         dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
         dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
         _ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),

@@ -195,15 +195,16 @@ def colsum(x, out_acc, scale=1.0):
     _lib.check(_lib.load().esp_colsum(_ptr(x), R, N, x.stride(0), scale, _ptr(out_acc), _stream()))
 
 
-def dropout(x, p, seed, scale=1.0, out=None):
-    """y = dropout_p(x) * scale with the GEMM-epilogue RNG (index r*N+n)."""
-    _need_cuda(x)
+def dropout(x, p, seed, scale=1.0, out=None, colsum_acc=None):
+    """y = dropout_p(x) * scale with the GEMM-epilogue RNG (index r*N+n); colsum_acc (fp32 [N]) += column sums of y."""
+    _need_cuda(x, colsum_acc)
+    assert colsum_acc is None or colsum_acc.dtype == torch.float32
     _bf(x)
     assert x.stride(1) == 1
     R, N = x.shape
     if out is None:
         out = torch.empty(R, N, device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.load().esp_dropout(_ptr(x), R, N, x.stride(0), out.stride(0), scale, p, seed, _seed_ptr(), _ptr(out), _stream()))
+    _lib.check(_lib.load().esp_dropout(_ptr(x), R, N, x.stride(0), out.stride(0), scale, p, seed, _seed_ptr(), _ptr(out), _ptr(colsum_acc), _stream()))
     return out
 
 
@@ -301,34 +302,35 @@ def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
 BN_ACT_SILU, BN_ACT_RELU = 1, 2
 
 
-def bn_stats(x, C_):
-    """Per-channel (sum, sum of squares) of channels-last x [..., C] -> double [2, C]."""
-    _need_cuda(x)
-    _bf(x)
+def bn_stats(x, C_, pre_bias=None):
+    """Per-channel (sum, sum of squares) of channels-last x [..., C] (+ pre_bias[c], rounded to bf16) -> double [2, C]."""
+    _need_cuda(x, pre_bias)
+    _bf(x, pre_bias)
     assert x.is_contiguous() and x.shape[-1] == C_
     stats = torch.zeros(2, C_, device=x.device, dtype=torch.float64)
-    _lib.check(_lib.load().esp_bn_stats(_ptr(x), x.numel() // C_, C_, _ptr(stats), _stream()))
+    _lib.check(_lib.load().esp_bn_stats(_ptr(x), _ptr(pre_bias), x.numel() // C_, C_, _ptr(stats), _stream()))
     return stats
 
 
-def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU):
-    _need_cuda(y, mr, gamma, beta)
-    _bf(y, gamma, beta)
+def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU, pre_bias=None):
+    _need_cuda(y, mr, gamma, beta, pre_bias)
+    _bf(y, gamma, beta, pre_bias)
     assert y.is_contiguous()
     Cn = y.shape[-1]
     z = torch.empty_like(y)
-    _lib.check(_lib.load().esp_bn_act_fwd(_ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act, _ptr(z), _stream()))
+    _lib.check(_lib.load().esp_bn_act_fwd(_ptr(y), _ptr(pre_bias), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act,
+                                          _ptr(z), _stream()))
     return z
 
 
-def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU):
-    _need_cuda(dz, y, mr, gamma, beta)
-    _bf(dz, y, gamma, beta)
+def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU, pre_bias=None):
+    _need_cuda(dz, y, mr, gamma, beta, pre_bias)
+    _bf(dz, y, gamma, beta, pre_bias)
     assert dz.is_contiguous() and y.is_contiguous()
     Cn = y.shape[-1]
     sums = torch.empty(3, Cn, device=y.device, dtype=torch.float64)  # 2C double sums + 2C float coefficients
     dy = torch.empty_like(y)
-    _lib.check(_lib.load().esp_bn_act_bwd(_ptr(dz), _ptr(y), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act,
+    _lib.check(_lib.load().esp_bn_act_bwd(_ptr(dz), _ptr(y), _ptr(pre_bias), y.numel() // Cn, Cn, _ptr(mr), _ptr(gamma), _ptr(beta), act,
                                           _ptr(sums), _ptr(dy), _ptr(dgamma_acc), _ptr(dbeta_acc), _stream()))
     return dy
 

@@ -65,6 +65,10 @@ class SequenceGenerator:
         src_tokens = net_input["src_tokens"]
         dev = src_tokens.device
         bsz, src_len = src_tokens.shape[:2]
+        if src_tokens.dim() == 2 and src_tokens.is_floating_point():
+            # raw waveform batch [B, samples] (on-device front end): the reference's T_src is the padded number of
+            # feature FRAMES (src_tokens.size(1) of [B, T, F], sequence_generator.py:270,285-288)
+            src_len = 1 + (src_len - 400) // 160 if src_len >= 400 else 0
         beam, V = self.beam_size, self.vocab_size
         max_len = min(int(self.max_len_a * src_len + self.max_len_b), self.max_len - 1)  # :285-288
         assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"

@@ -126,9 +126,10 @@ int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const f
                        void* stream);
 /* out[n] += scale * sum_r x[r,n]   (bias / pos_bias gradients) */
 int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream);
-/* y = dropout(x) * scale, same counter RNG / indexing (r*N+n) as the GEMM epilogue */
+/* y = dropout(x) * scale, same counter RNG / indexing (r*N+n) as the GEMM epilogue; colsum (fp32 [N] or NULL):
+ * colsum[n] += sum_r y[r,n] in the same pass (the bias gradient when y is a Linear's output gradient) */
 int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int64_t ldy, float scale, float drop_p,
-                uint64_t seed, const uint64_t* seed_ptr, void* y, void* stream);
+                uint64_t seed, const uint64_t* seed_ptr, void* y, float* colsum, void* stream);
 /* zero rows t >= lens[b] of x [B,T,N] */
 int esp_mask_rows(void* x, const int32_t* lens, int32_t B, int32_t T, int32_t N, void* stream);
 /* q_u = (q+u)*s, q_v = (q+v)*s  (fairseq/modules/multihead_attention.py:679-688) and the backward sum */
@@ -161,11 +162,16 @@ int esp_bn_finalize(const double* stats, int64_t R, int32_t C, float eps, float 
  * conformer_layer.py:95-96) and the conv front end (act=2, ReLU; espresso/modules/speech_convolutions.py:88-90,
  * tensors kept NHWC so rows = B*T*F): per-channel statistics of x [R,C]; z = act(BN(y)); and the two-pass
  * backward (sums = double[3,C] workspace: 2C sums + 2C float coefficients; dgamma/dbeta fp32, +=). */
-int esp_bn_stats(const void* x, int64_t R, int32_t C, double* stats, void* stream);
-int esp_bn_act_fwd(const void* y, int64_t R, int32_t C, const float* mr, const void* gamma, const void* beta,
-                   int32_t act, void* z, void* stream);
-int esp_bn_act_bwd(const void* dz, const void* y, int64_t R, int32_t C, const float* mr, const void* gamma,
-                   const void* beta, int32_t act, double* sums, void* dy, float* dgamma, float* dbeta, void* stream);
+/* pre_bias (bf16 [C] or NULL): the normalised tensor is bf16(x + pre_bias[c]) without materialising it -- the bias of
+ * the convolution in front of the BatchNorm (espresso/modules/speech_convolutions.py:88-90: Conv2d has bias=True),
+ * so the convolution itself runs bias-free and no separate bias-add / bias-gradient pass over the activation exists
+ * (the bias gradient through a batch-statistics BatchNorm is identically zero). */
+int esp_bn_stats(const void* x, const void* pre_bias, int64_t R, int32_t C, double* stats, void* stream);
+int esp_bn_act_fwd(const void* y, const void* pre_bias, int64_t R, int32_t C, const float* mr, const void* gamma,
+                   const void* beta, int32_t act, void* z, void* stream);
+int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bias, int64_t R, int32_t C, const float* mr,
+                   const void* gamma, const void* beta, int32_t act, double* sums, void* dy, float* dgamma,
+                   float* dbeta, void* stream);
 
 /* ---- optimizer on flat buffers (fairseq/optim/fp16_optimizer.py:109-168, fairseq/optim/adam.py:150-239,
  *      fairseq/utils.py:347-397) ---------------------------------------------------------------- */

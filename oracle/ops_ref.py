@@ -106,9 +106,11 @@ def colsum(x, out_acc, scale=1.0):
     out_acc += scale * x.float().sum(0)
 
 
-def dropout(x, p, seed, scale=1.0, out=None):
+def dropout(x, p, seed, scale=1.0, out=None, colsum_acc=None):
     assert p == 0.0
     y = (x.float() * scale).to(BF)
+    if colsum_acc is not None:
+        colsum_acc += y.float().sum(0)
     if out is not None:
         out.copy_(y)
         return out
@@ -213,17 +215,25 @@ def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
 BN_ACT_SILU, BN_ACT_RELU = 1, 2
 
 
-def bn_stats(x, C_):
+def _pre(y, pre_bias):
+    """bf16(y + pre_bias[c]): the conv bias folded into the BatchNorm kernels."""
+    return y if pre_bias is None else (y.float() + pre_bias.float()).to(BF)
+
+
+def bn_stats(x, C_, pre_bias=None):
+    x = _pre(x, pre_bias)
     xf = x.double().reshape(-1, C_)
     return torch.stack([xf.sum(0), (xf * xf).sum(0)])
 
 
-def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU):
+def bn_act_fwd(y, mr, gamma, beta, act=BN_ACT_SILU, pre_bias=None):
+    y = _pre(y, pre_bias)
     bn = ((y.float() - mr[0]) * mr[1] * gamma.float() + beta.float()).to(BF).float()
     return (F.silu(bn) if act == BN_ACT_SILU else torch.relu(bn)).to(BF)
 
 
-def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU):
+def bn_act_bwd(dz, y, mr, gamma, beta, dgamma_acc, dbeta_acc, act=BN_ACT_SILU, pre_bias=None):
+    y = _pre(y, pre_bias)
     Cn = y.shape[-1]
     yf = y.float().reshape(-1, Cn)
     xh = (yf - mr[0]) * mr[1]
