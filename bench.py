@@ -489,7 +489,17 @@ def main():
         roof = {"kernel": "gemm_tcgen05_kernel (all %d launches of one step, replayed back to back)" % len(recs), "bound": "tensor", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
-                "gemm_ms_per_step": tot_ms, "gemm_share_of_step": tot_ms / (ms / args.steps), "traffic": None}
+                "gemm_ms_per_step": tot_ms, "gemm_share_of_step": tot_ms / (ms / args.steps), "traffic": None,
+                "launches": len(recs), "achieved_is": "sum of 2*M*N*K over the step's GEMM launches / their summed device time"}
+        try:  # DRAM bytes per launch from the committed ncu capture of the same command (profiles/)
+            tr = _json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_unit"] = "bytes per launch (dram read+write, mean over %d launches, ncu)" % tr["launches"]
+            roof["algorithmic_bytes_per_launch"] = sum(
+                2.0 * (a_[3] * a_[5] + a_[4] * a_[5] + a_[3] * a_[4]) * kw_.get("nb1", 1) * kw_.get("nb2", 1)
+                for a_, kw_, _ in recs) / max(len(recs), 1)
+        except Exception:
+            pass
 
     if rank == 0:
         val = audio / (ms * 1e-3)

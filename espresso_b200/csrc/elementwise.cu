@@ -1113,7 +1113,7 @@ extern "C" int esp_dropout(const void* x, int64_t R, int32_t N, int64_t ldx, int
   if (colsum && N <= 2048 && 256 % (N / 8) == 0) {
     // bias gradient in the same pass; one wave of CTAs (the tail is a cross-CTA reduction)
     long g = (R * (N / 8) + 255) / 256;
-    const long cap = 4L * esp_num_sms();
+    const long cap = 2L * esp_num_sms();  // few CTAs: the tail is a cross-CTA reduction (atomics per CTA)
     if (g > cap) g = cap;
     esp_launch(dropout_colsum_kernel, (unsigned)g, 256, 0, st, (const bf16*)x, R, N, ldx, ldy, scale, drop_p,
                esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr, (bf16*)y, colsum);

@@ -38,13 +38,12 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
     trainer.train_step([sample])
     torch.cuda.synchronize()
-agg = collections.defaultdict(lambda: [0, 0.0])
-for ev in prof.events():
-    if ev.device_time_total <= 0 or not ev.name.startswith("aten::") or ev.cpu_children:
+rows = []
+for ev in prof.key_averages(group_by_stack_n=12):
+    t = getattr(ev, "self_device_time_total", 0) or 0
+    if t <= 0 or not ev.key.startswith("aten::"):
         continue
-    frame = next((s for s in ev.stack if "/espresso_b200/" in s or "/bench.py" in s), "?")
-    key = (ev.name, frame.split("/root/repo/")[-1] if "/root/repo/" in frame else frame[-90:])
-    agg[key][0] += 1
-    agg[key][1] += ev.device_time_total
-for (name, frame), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-    print("%5d x %9.1f us  %-28s %s" % (n, t, name, frame))
+    frame = next((f for f in ev.stack if "/espresso_b200/" in f or "bench.py" in f), "?")
+    rows.append((t, ev.count, ev.key, frame.split("/root/repo/")[-1][:110]))
+for t, n, name, frame in sorted(rows, reverse=True)[:40]:
+    print("%5d x %9.1f us  %-26s %s" % (n, t, name, frame))
