@@ -389,15 +389,21 @@ def main():
             ev.record(copy_stream)
         return d, ev
 
-    def timed(nsteps, from_host):
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def timed(nsteps, from_host, do_upload=True, read_loss=True, sync_each=False):
+        losses = []
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         audio = 0.0
         e0.record()
-        nxt = upload(0) if from_host else None
+        nxt = upload(0) if (from_host and do_upload) else None
         for i in range(nsteps):
             j = i % n_distinct
-            if from_host:
+            if from_host and not do_upload:
+                d = resident[j]
+            elif from_host:
                 d, ev = nxt
                 torch.cuda.current_stream().wait_event(ev)
                 for t in d.values():
@@ -409,8 +415,22 @@ def main():
                 d = resident[j]
             trainer.train_step([sample_of(d, n_cpu[j])])
             audio += pinned[j]["audio_s"]
-            if from_host:
-                _ = trainer.last_stats[3].item()  # D2H read of the step's loss
+            if from_host and sync_each:
+                _ = trainer.last_stats[3].item()
+            elif from_host and read_loss:
+                # D2H read of EVERY step's loss into pinned memory; the host consumes it one step late (after the next
+                # step has been queued), as a training loop that logs asynchronously does, so the GPU never idles
+                # waiting for Python between steps.
+                slot = i % 2
+                loss_host[slot].copy_(trainer.last_stats[3:4], non_blocking=True)
+                loss_ev[slot].record()
+                if i > 0:
+                    loss_ev[1 - slot].synchronize()
+                    losses.append(float(loss_host[1 - slot][0]))
+        if from_host and read_loss and not sync_each and nsteps > 0:
+            loss_ev[(nsteps - 1) % 2].synchronize()
+            losses.append(float(loss_host[(nsteps - 1) % 2][0]))
+            assert len(losses) == nsteps and all(np.isfinite(losses))
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -441,8 +461,14 @@ def main():
     l0 = lib.launch_count()
     ms, audio = timed(args.steps, False)
     launches = lib.launch_count() - l0
+    timed(max(3, args.warmup), True)  # warm the host-buffer path too (copy-stream allocator pool, pinned staging)
     ms_e2e, audio_e2e = timed(args.steps, True)
     clk = clocks.stop() if rank == 0 else None
+    if os.environ.get("ESP_BENCH_E2E_DEBUG"):
+        for name, kw in (("upload+lagged read", {}), ("upload only", dict(read_loss=False)), ("lagged read only", dict(do_upload=False)),
+                         ("upload+item()", dict(sync_each=True)), ("item() only", dict(do_upload=False, sync_each=True))):
+            m_, _a = timed(args.steps, True, **kw)
+            note("e2e variant %-20s %.2f ms/step" % (name, m_ / args.steps))
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): one extra step with per-launch CUDA events ---------
     roof = None
