@@ -17,6 +17,8 @@ class SpeechEncDecBaseConfig:
     normalize_before: bool = True
     learned_pos: bool = False
     relative_positional_embeddings: bool = False
+    share_learned_relative_positional_embeddings_across_layers: bool = False
+    share_learned_relative_positional_embeddings_across_heads: bool = False
     layerdrop: float = 0.0
 
 

@@ -58,20 +58,36 @@ class _PosEmbStub(nn.Module):
         self.register_buffer("_float_tensor", torch.zeros(1))
 
 
+class _LearnedRelPos(nn.Module):
+    """espresso/modules/learned_relative_positional_embedding.py:13-45: table of 2*max_size-1 relative positions
+    (padding_idx None), N(0, dim^-0.5) init; state_dict key `weight` like the reference's nn.Embedding."""
+    def __init__(self, dim, max_size):
+        super().__init__()
+        self.max_size = max_size
+        self.weight = nn.Parameter(torch.empty(2 * max_size - 1, dim))
+        nn.init.normal_(self.weight, mean=0.0, std=dim ** -0.5)
+
+
 class _SelfAttn(nn.Module):
-    def __init__(self, d, H):
+    def __init__(self, d, H, positional_embedding=None):
+        """positional_embedding: None -> sinusoidal relative positions (pos_bias_u/v + pos_proj, Transformer-XL);
+        a _LearnedRelPos -> learned table, no biases / projection (fairseq/modules/multihead_attention.py:150-167)."""
         super().__init__()
         g = 1 / math.sqrt(2)
-        self.pos_bias_u = nn.Parameter(torch.empty(d))
-        self.pos_bias_v = nn.Parameter(torch.empty(d))
-        nn.init.xavier_uniform_(self.pos_bias_u.data.view(H, -1))
-        nn.init.xavier_uniform_(self.pos_bias_v.data.view(H, -1))
+        if positional_embedding is None:
+            self.pos_bias_u = nn.Parameter(torch.empty(d))
+            self.pos_bias_v = nn.Parameter(torch.empty(d))
+            nn.init.xavier_uniform_(self.pos_bias_u.data.view(H, -1))
+            nn.init.xavier_uniform_(self.pos_bias_v.data.view(H, -1))
         self.k_proj = _Linear(d, d, xavier=g)
         self.v_proj = _Linear(d, d, xavier=g)
         self.q_proj = _Linear(d, d, xavier=g)
         self.out_proj = _Linear(d, d, xavier=1.0)
-        self.positional_embedding = _PosEmbStub()
-        self.pos_proj = _Linear(d, d, bias=False, xavier=g)
+        if positional_embedding is None:
+            self.positional_embedding = _PosEmbStub()
+            self.pos_proj = _Linear(d, d, bias=False, xavier=g)
+        else:
+            self.positional_embedding = positional_embedding
 
 
 class _FFN(nn.Module):
@@ -103,10 +119,10 @@ class _ConvModule(nn.Module):
 
 
 class _ConformerLayer(nn.Module):
-    def __init__(self, d, ffn, H, k):
+    def __init__(self, d, ffn, H, k, positional_embedding=None):
         super().__init__()
         self.ffn1 = _FFN(d, ffn)
-        self.self_attn = _SelfAttn(d, H)
+        self.self_attn = _SelfAttn(d, H, positional_embedding)
         self.self_attn_layer_norm = _Affine(d)
         self.conv_module = _ConvModule(d, k)
         self.ffn2 = _FFN(d, ffn)
@@ -114,9 +130,9 @@ class _ConformerLayer(nn.Module):
 
 
 class _TransformerLayer(nn.Module):
-    def __init__(self, d, ffn, H):
+    def __init__(self, d, ffn, H, positional_embedding=None):
         super().__init__()
-        self.self_attn = _SelfAttn(d, H)
+        self.self_attn = _SelfAttn(d, H, positional_embedding)
         self.self_attn_layer_norm = _Affine(d)
         self.fc1 = _Linear(d, ffn, xavier=1.0)
         self.fc2 = _Linear(ffn, d, xavier=1.0)
@@ -225,9 +241,9 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         super().__init__()
         self.cfg = cfg
         e = cfg.encoder
-        if not e.relative_positional_embeddings or e.learned_pos:
-            raise NotImplementedError("B200 encoder: sinusoidal relative positions only (recipes transformer_ctc / "
-                                      "conformer_transducer); learned tables are a next-round item")
+        if not e.relative_positional_embeddings:
+            raise NotImplementedError("B200 encoder: relative positional embeddings only (all shipped recipes); absolute "
+                                      "positions in the encoder are not on the path")
         if not e.normalize_before:
             raise NotImplementedError("post-LN encoder layers are not on the recipes' path")
         self.register_buffer("version", torch.Tensor([3]))
@@ -236,12 +252,24 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         self.max_source_positions = cfg.max_source_positions
         self.fc0 = _Linear(input_size, d, xavier=1.0)
         self.layernorm_embedding = _Affine(d) if cfg.layernorm_embedding else None
+        # relative position source per layer (speech_transformer_encoder.py:121-158): sinusoidal (None here), or
+        # learned tables -- per layer or one shared instance, of width d or head_dim (shared across heads)
+        if e.learned_pos:
+            max_size = int(self.output_lengths(cfg.max_source_positions)) if pre_encoder is not None else cfg.max_source_positions
+            dim = d // e.attention_heads if e.share_learned_relative_positional_embeddings_across_heads else d
+            if e.share_learned_relative_positional_embeddings_across_layers:
+                pos = [_LearnedRelPos(dim, max_size)] * e.layers
+            else:
+                pos = [_LearnedRelPos(dim, max_size) for _ in range(e.layers)]
+        else:
+            pos = [None] * e.layers
         if e.layer_type == "conformer":
-            self.layers = nn.ModuleList([_ConformerLayer(d, e.ffn_embed_dim, e.attention_heads, e.depthwise_conv_kernel_size)
-                                         for _ in range(e.layers)])
+            self.layers = nn.ModuleList([_ConformerLayer(d, e.ffn_embed_dim, e.attention_heads, e.depthwise_conv_kernel_size,
+                                                         pos[i]) for i in range(e.layers)])
             self.layer_norm = None
         elif e.layer_type == "transformer":
-            self.layers = nn.ModuleList([_TransformerLayer(d, e.ffn_embed_dim, e.attention_heads) for _ in range(e.layers)])
+            self.layers = nn.ModuleList([_TransformerLayer(d, e.ffn_embed_dim, e.attention_heads, pos[i])
+                                         for i in range(e.layers)])
             self.layer_norm = _Affine(d)
         else:
             raise NotImplementedError(e.layer_type)
@@ -286,6 +314,12 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
                     attention_dropout=self.cfg.attention_dropout, activation_dropout=self.cfg.activation_dropout,
                     layernorm_embedding=self.cfg.layernorm_embedding, final_layer_norm=self.layer_norm is not None,
                     vocab=self.vocab_size)
+        if e.learned_pos:  # layer -> flat name of its table (a table shared across layers is registered once)
+            seen = {}
+            ecfg["learned_pos_tables"] = {
+                i: seen.setdefault(id(l.self_attn.positional_embedding.weight),
+                                   prefix + "layers.%d.self_attn.positional_embedding.weight" % i)
+                for i, l in enumerate(self.layers)}
         self.engine = EncoderEngine(self.flat, prefix, ecfg)
         if e.layer_type == "conformer":
             self.engine.bn_state = {i: (l.conv_module.batch_norm.running_mean, l.conv_module.batch_norm.running_var)

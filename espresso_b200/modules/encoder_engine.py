@@ -48,7 +48,8 @@ class EncoderEngine:
     def __init__(self, flat, prefix, cfg):
         """cfg keys: embed_dim, ffn_dim, heads, layers, layer_type ('conformer'|'transformer'), dw_kernel,
         dropout, attention_dropout, activation_dropout, layernorm_embedding, final_layer_norm, vocab (or None),
-        learned_rel_pos (False only for now)."""
+        learned_pos_tables (None, or {layer index: flat parameter name of that layer's learned relative-position
+        table} -- shared tables map several layers to one name)."""
         self.flat = flat
         self.pre = prefix
         self.cfg = dict(cfg)
@@ -57,6 +58,8 @@ class EncoderEngine:
         self.hd = self.d // self.H
         self.scaling = self.hd ** -0.5
         self._pe = {}
+        self._zeros_d = None
+        self.pos_tables = cfg.get("learned_pos_tables")  # espresso/modules/learned_relative_positional_embedding.py
         self.bn_state = None  # {layer: (running_mean fp32, running_var fp32)} provided by the module
         self.training = True
         self.seed = 0
@@ -80,6 +83,18 @@ class EncoderEngine:
         if key not in self._pe:
             self._pe[key] = sinusoidal_relative_table(T, self.d, device)
         return self._pe[key]
+
+    def _learned_positions(self, li, T, device):
+        """Rows of layer li's learned table for relative positions -(T-1)..T-1 (learned_relative_positional_embedding.py
+        :71-78: start = n/2 - T + 1, clamped when T > max_size).  Returns (pe [2T-1, E] bf16, index tensor)."""
+        name = self.pos_tables[li]
+        tab = self.flat.param(name)
+        n = tab.shape[0]
+        key = ("pos", T, n, str(device))
+        if key not in self._pe:
+            self._pe[key] = torch.arange(n // 2 - T + 1, n // 2 + T, device=device).clamp_(0, n - 1)
+        idx = self._pe[key]
+        return tab.index_select(0, idx), idx
 
     def _drop(self, kind):
         if not self.training:
@@ -143,12 +158,24 @@ class EncoderEngine:
         Wqkv, bqkv, _, _ = self._qkv(lp)
         qkv = _ops.linear(ln, Wqkv, bqkv)
         q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
-        qu, qv = _ops.qprep_fwd(q, self.P(lp + "self_attn.pos_bias_u"), self.P(lp + "self_attn.pos_bias_v"), self.scaling)
-        pe = self.pe(T, x.device)
-        Pp = _ops.linear(pe, self.P(lp + "self_attn.pos_proj.weight"))  # [2T-1, d], batch independent
+        learned = self.pos_tables is not None
+        if learned:
+            # learned relative positions: q is only scaled (no pos_bias_u / pos_bias_v), the table rows are used as they
+            # are (no pos_proj); a table of width head_dim is shared by all heads (head stride 0 in the GEMM)
+            if self._zeros_d is None or self._zeros_d.device != x.device:
+                self._zeros_d = torch.zeros(d, device=x.device, dtype=torch.bfloat16)
+            qu, _unused = _ops.qprep_fwd(q, self._zeros_d, self._zeros_d, self.scaling)
+            qv = qu
+            Pp, _ = self._learned_positions(li, T, x.device)
+        else:
+            qu, qv = _ops.qprep_fwd(q, self.P(lp + "self_attn.pos_bias_u"), self.P(lp + "self_attn.pos_bias_v"), self.scaling)
+            pe = self.pe(T, x.device)
+            Pp = _ops.linear(pe, self.P(lp + "self_attn.pos_proj.weight"))  # [2T-1, d], batch independent
+        E = Pp.shape[1]
+        ph = hd if E == d else 0  # head stride of the position operand
         ldt, ldp = _r8(T), _r8(2 * T - 1)
         BD = torch.empty(H, B, T, ldp, device=x.device, dtype=torch.bfloat16)
-        _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, d, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, 0),
+        _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, E, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(ph, 0),
                   sC=(B * T * ldp, T * ldp))
         S = torch.empty(H, B, T, ldt, device=x.device, dtype=torch.bfloat16)
         _ops.gemm(qu, k, S, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
@@ -186,16 +213,25 @@ class EncoderEngine:
         _ops.gemm(dS, qu, dqkv[:, d:2 * d], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
                   sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
         # dq_v = dBD P ; dP = sum_b dBD^T q_v
+        learned = self.pos_tables is not None
+        E = Pp.shape[1]
+        ph = hd if E == d else 0
         dqv = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        _ops.gemm(dBD, Pp, dqv, T, hd, 2 * T - 1, ldp, d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldp, T * ldp),
-                  sB=(hd, 0), sC=(hd, T * d))
+        _ops.gemm(dBD, Pp, dqv, T, hd, 2 * T - 1, ldp, E, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldp, T * ldp),
+                  sB=(ph, 0), sC=(hd, T * d))
         dPp = torch.empty(2 * T - 1, d, device=dev, dtype=torch.bfloat16)
         _ops.gemm(dBD, qv, dPp, 2 * T - 1, hd, B * T, ldp, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=1,
                   sA=(B * T * ldp, 0), sB=(hd, 0), sC=(hd, 0))
-        self._wgrad(dPp, self.pe(T, dev), self.G(lp + "self_attn.pos_proj.weight"))
         _ops.qprep_bwd(dqu, dqv, self.scaling, dqkv[:, :d])
-        _ops.colsum(dqu, self.G(lp + "self_attn.pos_bias_u"), scale=self.scaling)
-        _ops.colsum(dqv, self.G(lp + "self_attn.pos_bias_v"), scale=self.scaling)
+        if learned:
+            # scatter-add into the table rows that were read (a width-head_dim table sums its heads first)
+            _, idx = self._learned_positions(li, T, dev)
+            dpe = dPp.float() if E == d else dPp.float().view(2 * T - 1, H, hd).sum(1)
+            self.flat.grad(self.pos_tables[li]).index_add_(0, idx, dpe)
+        else:
+            self._wgrad(dPp, self.pe(T, dev), self.G(lp + "self_attn.pos_proj.weight"))
+            _ops.colsum(dqu, self.G(lp + "self_attn.pos_bias_u"), scale=self.scaling)
+            _ops.colsum(dqv, self.G(lp + "self_attn.pos_bias_v"), scale=self.scaling)
         Wqkv, _, gW, gb = self._qkv(lp)
         self._wgrad(dqkv, ln, gW)
         _ops.colsum(dqkv, gb)

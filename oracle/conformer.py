@@ -69,13 +69,24 @@ def relpos_mha(sd, p, x, pad_mask, H, attn_drop, training):
     q = F.linear(x, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
     k = F.linear(x, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
     v = F.linear(x, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
-    qv = ((q + sd[p + "pos_bias_v"]) * s).view(B, T, H, hd).transpose(1, 2)   # [B,H,T,hd]
-    qu = ((q + sd[p + "pos_bias_u"]) * s).view(B, T, H, hd).transpose(1, 2)
     kh = k.view(B, T, H, hd).transpose(1, 2)
     vh = v.view(B, T, H, hd).transpose(1, 2)
+    if p + "positional_embedding.weight" in sd:
+        # learned relative positions (espresso/modules/learned_relative_positional_embedding.py:47-88 +
+        # multihead_attention.py:799-823 with `learnable`): no pos_bias_u/v, no pos_proj; the table has
+        # 2*max_size-1 rows of width d or head_dim (shared across heads), rows max_size-T .. max_size+T-2 are used
+        tab = sd[p + "positional_embedding.weight"]
+        n_emb, E = tab.shape
+        pos = torch.arange(n_emb // 2 - T + 1, n_emb // 2 + T, device=x.device).clamp(0, n_emb - 1)
+        pe = tab[pos]                                                           # [2T-1, E]
+        qu = qv = (q * s).view(B, T, H, hd).transpose(1, 2)
+        ph = (pe[:, None, :].expand(-1, H, -1) if E == hd else pe.view(2 * T - 1, H, hd)).permute(1, 2, 0)
+    else:
+        qv = ((q + sd[p + "pos_bias_v"]) * s).view(B, T, H, hd).transpose(1, 2)   # [B,H,T,hd]
+        qu = ((q + sd[p + "pos_bias_u"]) * s).view(B, T, H, hd).transpose(1, 2)
+        pe = F.linear(rel_pos_table(T, d, x.dtype).to(x.device), sd[p + "pos_proj.weight"])  # [2T-1, d]
+        ph = pe.view(2 * T - 1, H, hd).permute(1, 2, 0)                             # [H, hd, 2T-1]
     ac = qu @ kh.transpose(-1, -2)                                             # [B,H,T,T]
-    pe = F.linear(rel_pos_table(T, d, x.dtype).to(x.device), sd[p + "pos_proj.weight"])  # [2T-1, d]
-    ph = pe.view(2 * T - 1, H, hd).permute(1, 2, 0)                             # [H, hd, 2T-1]
     bd_full = qv @ ph[None]                                                     # [B,H,T,2T-1]
     i = torch.arange(T, device=x.device)[:, None]
     j = torch.arange(T, device=x.device)[None, :]

@@ -100,7 +100,7 @@ def pin_ctc():
     print("ctc pinned -> tests/golden/ctc.npz")
 
 
-def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50):
+def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50, learned_pos=False, share_heads=False):
     from espresso.models.transformer.speech_transformer_config import SpeechTransformerConfig
     from espresso.models.transformer.speech_transformer_encoder_model import SpeechTransformerEncoderModel
 
@@ -111,7 +111,8 @@ def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50):
     e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
     e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
     e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = d, ffn, layers, heads
-    e.normalize_before, e.learned_pos, e.relative_positional_embeddings = True, False, True
+    e.normalize_before, e.learned_pos, e.relative_positional_embeddings = True, learned_pos, True
+    e.share_learned_relative_positional_embeddings_across_heads = share_heads
     e.layer_type, e.depthwise_conv_kernel_size = layer_type, 31
     cfg.layernorm_embedding = True
     cfg.dropout = cfg.attention_dropout = cfg.activation_dropout = 0.0
@@ -137,8 +138,12 @@ def pin_conformer():
 
     from oracle import conformer as O
 
-    for layer_type in ("conformer", "transformer"):
-        m = _ref_model(layer_type)
+    for variant in ("conformer", "transformer", "transformer_learned", "conformer_learned_sh"):
+        layer_type = variant.split("_")[0]
+        learned = "learned" in variant
+        m = _ref_model(layer_type, learned_pos=learned, share_heads=variant.endswith("_sh"))
+        if learned:  # max_source_positions 3600 -> tables of 2*900-1 rows; keep the fixture small
+            assert any("positional_embedding.weight" in k for k in m.state_dict())
         # make LayerNorm/BatchNorm affine params and biases non-trivial so every gradient path is exercised
         g = torch.Generator().manual_seed(5)
         with torch.no_grad():
@@ -207,8 +212,8 @@ def pin_conformer():
             out["logits_" + mode] = logits.detach().transpose(0, 1).numpy()   # B x T' x V
             out["loss_" + mode] = np.float64(loss.item())
         out.update(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), out_lens=olens.numpy())
-        np.savez_compressed(os.path.join(GOLDEN, "encoder_%s.npz" % layer_type), **out)
-        print("%s encoder pinned -> tests/golden/encoder_%s.npz" % (layer_type, layer_type))
+        np.savez_compressed(os.path.join(GOLDEN, "encoder_%s.npz" % variant), **out)
+        print("%s encoder pinned -> tests/golden/encoder_%s.npz" % (variant, variant))
 
 
 def pin_encdec():

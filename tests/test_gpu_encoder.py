@@ -41,8 +41,12 @@ def _build(layer_type, g, dropout=0.0, dev="cuda:0"):
 
     cfg = SpeechTransformerConfig.from_dict(dict(
         dropout=dropout, attention_dropout=dropout, activation_dropout=dropout, layernorm_embedding=True,
-        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True, learned_pos=False,
-                     relative_positional_embeddings=True, layer_type=layer_type, depthwise_conv_kernel_size=31)))
+        max_source_positions=3600,
+        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True,
+                     learned_pos="learned" in layer_type,
+                     share_learned_relative_positional_embeddings_across_heads=layer_type.endswith("_sh"),
+                     relative_positional_embeddings=True, layer_type=layer_type.split("_")[0],
+                     depthwise_conv_kernel_size=31)))
     m = SpeechTransformerEncoderModel.build_model(cfg, _Task(50))
     m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
     return m.finalize_(torch.device(dev))
@@ -53,7 +57,7 @@ def _sample(g, dev):
             "target": torch.from_numpy(g["target"]).to(dev), "ntokens": 13}
 
 
-@pytest.mark.parametrize("layer_type", ["conformer", "transformer"])
+@pytest.mark.parametrize("layer_type", ["conformer", "transformer", "transformer_learned", "conformer_learned_sh"])
 def test_encoder_vs_reference_fixture(layer_type, golden_dir):
     from espresso_b200 import lib
     from espresso_b200.criterions import CtcLossCriterion
