@@ -1,5 +1,5 @@
-"""`label_smoothed_cross_entropy_v2` criterion (espresso/criterions/label_smoothed_cross_entropy_v2.py:124-243,
-uniform smoothing), B200-native: fp32 log-softmax + NLL + smoothing + their gradient in one fused kernel
+"""`label_smoothed_cross_entropy_v2` criterion (espresso/criterions/label_smoothed_cross_entropy_v2.py:49-243;
+uniform, unigram and temporal smoothing), B200-native: fp32 log-softmax + NLL + smoothing + their gradient in one fused kernel
 (esp_lsce_loss); the [B*U, V] fp32 log-prob tensor of the reference is never materialised.  The model is called
 with `epoch=` like the reference does (:167)."""
 import math
@@ -12,9 +12,10 @@ from ..registry import register_criterion
 
 class _LsceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits_bu, V, targets, pad_idx, eps, unit_grad):
+    def forward(ctx, logits_bu, V, targets, pad_idx, eps, unit_grad, smoothing=0, unigram=None):
         B, U, ld = logits_bu.shape
-        loss, nll, grad = _ops.lsce_loss(logits_bu.view(B * U, ld), V, targets, pad_idx, eps, 1.0, True)
+        loss, nll, grad = _ops.lsce_loss(logits_bu.view(B * U, ld), V, targets, pad_idx, eps, 1.0, True,
+                                         smoothing=smoothing, unigram=unigram, U=U)
         ctx.grad = grad.view(B, U, ld)
         ctx.unit_grad = unit_grad
         ctx.mark_non_differentiable(nll)
@@ -26,16 +27,26 @@ class _LsceFn(torch.autograd.Function):
         ctx.grad = None
         if not ctx.unit_grad:
             g = (g.float() * dloss.view(g.shape[0], g.shape[1], 1)).to(g.dtype)
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None, None
 
 
 @register_criterion("label_smoothed_cross_entropy_v2")
 class LabelSmoothedCrossEntropyV2Criterion(torch.nn.Module):
+    _SMOOTHING = {"uniform": 0, "unigram": 1, "temporal": 2}
+
     def __init__(self, task=None, sentence_avg=False, label_smoothing=0.1, smoothing_type="uniform", pad_idx=None,
-                 unit_grad_output=True):
+                 unit_grad_output=True, unigram_pseudo_count=1.0, unigram_counts=None):
+        """unigram smoothing builds the distribution like the reference (:151-155): dictionary.count (or
+        `unigram_counts`) + pseudo count, normalised."""
         super().__init__()
-        if smoothing_type != "uniform":
-            raise NotImplementedError("unigram / temporal label smoothing are next-round items (SURVEY.md §8f)")
+        if smoothing_type not in self._SMOOTHING:
+            raise ValueError("Unsupported smoothing type: {}".format(smoothing_type))
+        self.smoothing_type = smoothing_type
+        self.unigram_tensor = None
+        if smoothing_type == "unigram":
+            counts = unigram_counts if unigram_counts is not None else task.target_dictionary.count
+            u = torch.as_tensor(counts, dtype=torch.float32).clone() + unigram_pseudo_count
+            self.unigram_tensor = u / u.sum()
         self.padding_idx = pad_idx if pad_idx is not None else task.target_dictionary.pad()
         self.eps = label_smoothing
         self.sentence_avg = sentence_avg
@@ -47,7 +58,10 @@ class LabelSmoothedCrossEntropyV2Criterion(torch.nn.Module):
         V = net_output[0].size(-1)
         target = sample["target"]
         tgt = target.reshape(-1).to(torch.int32)
-        loss_r, nll_r = _LsceFn.apply(out, V, tgt, self.padding_idx, self.eps, self.unit_grad_output)
+        if self.unigram_tensor is not None and self.unigram_tensor.device != out.device:
+            self.unigram_tensor = self.unigram_tensor.to(out.device)
+        loss_r, nll_r = _LsceFn.apply(out, V, tgt, self.padding_idx, self.eps, self.unit_grad_output,
+                                      self._SMOOTHING[self.smoothing_type], self.unigram_tensor)
         loss, nll = loss_r.sum(), nll_r.sum()
         ntokens = sample["ntokens"] if "ntokens" in sample else target.ne(self.padding_idx).sum()
         nsent = target.size(0)

@@ -1,9 +1,13 @@
 // espresso_b200 -- label-smoothed cross-entropy fused with the fp32 log-softmax, forward + backward.
 //
-// Replaces espresso/criterions/label_smoothed_cross_entropy_v2.py:82-120,216-240 (uniform smoothing):
-//   lprobs = log_softmax(logits.float());  nll = -lprobs[target];  smooth = -sum_v lprobs[v]
-//   loss = (1 - eps - eps_i) * nll + eps_i * smooth,  eps_i = eps / (V - 1);  rows with target == pad give 0
-// and its autograd:  dloss/dlogits = softmax - (1 - eps - eps_i) * onehot(target) - eps_i.
+// Replaces espresso/criterions/label_smoothed_cross_entropy_v2.py:49-120,216-240:
+//   lprobs = log_softmax(logits.float());  nll = -lprobs[target]
+//   uniform : loss = (1 - eps - eps_i) * nll + eps_i * (-sum_v lprobs[v]),  eps_i = eps / (V - 1)
+//   unigram : loss = (1 - eps) * nll + eps * (-sum_v u[v] lprobs[v])        (u = smoothed unigram distribution)
+//   temporal: loss = (1 - eps) * nll + eps * (-sum_v m[v] lprobs[v]),  m = the neighbouring targets at distance
+//             +-1 / +-2 with weights 5 : 2, normalised, <pad> neighbours dropped (arXiv 1612.02695)
+// rows with target == pad give 0.  In every case loss = a * nll + sum_v w_v * (-lprobs[v]) and the autograd is
+//   dloss/dlogits = softmax * (a + sum_v w_v) - a * onehot(target) - w.
 // One CTA per target token: the logits row is read once (cached in registers), the gradient row is written
 // once; the [B*U, V] fp32 log-prob tensor is never materialised.  Algorithmic bytes: 4*V per token.
 // Also: embedding lookup (x = E[tok]*scale + pos) and its scatter-add backward
@@ -41,9 +45,25 @@ __device__ __forceinline__ float blk_sum(float v, float* red) {
   return r;
 }
 
+// smoothing weights of one row: w_v = base (uniform) + wu * unigram[v] + the (at most 4) temporal neighbours
+struct SmoothW {
+  float base, wu;
+  const float* unigram;
+  int nb[4];
+  float nw[4];
+  __device__ __forceinline__ float at(int v) const {
+    float w = base;
+    if (unigram) w += wu * __ldg(unigram + v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w += (v == nb[k]) ? nw[k] : 0.f;
+    return w;
+  }
+};
+
 __global__ void __launch_bounds__(kThreads)
 lsce_kernel(const bf16* __restrict__ logits, long ld, int V, const int* __restrict__ targets, int pad_idx, float eps,
-            float grad_scale, float* __restrict__ loss, float* __restrict__ nll, bf16* __restrict__ grad) {
+            int smoothing, const float* __restrict__ unigram, int U, float grad_scale, float* __restrict__ loss,
+            float* __restrict__ nll, bf16* __restrict__ grad) {
   __shared__ float red[32];
   const long r = blockIdx.x;
   const bf16* row = logits + r * ld;
@@ -56,6 +76,38 @@ lsce_kernel(const bf16* __restrict__ logits, long ld, int V, const int* __restri
       for (int v = threadIdx.x; v < ld_pad; v += kThreads) g[v] = f2bf(0.f);
     }
     return;
+  }
+  // ---- smoothing weights of this row
+  SmoothW sw;
+  sw.base = 0.f; sw.wu = 0.f; sw.unigram = nullptr;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sw.nb[k] = -1; sw.nw[k] = 0.f; }
+  float a_nll;  // weight of the nll term
+  if (smoothing == 0) {
+    sw.base = eps / (float)(V - 1);
+    a_nll = 1.f - eps - sw.base;
+  } else if (smoothing == 1) {
+    sw.unigram = unigram;
+    sw.wu = eps;
+    a_nll = 1.f - eps;
+  } else {
+    // temporal: rows are [B, U]; neighbours inside the same sentence, <pad> neighbours carry no mass
+    a_nll = 1.f - eps;
+    const int t = (int)(r % U);
+    const int off[4] = {-2, -1, 1, 2};
+    const float cnt[4] = {2.f, 5.f, 5.f, 2.f};
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int tt = t + off[k];
+      if (tt >= 0 && tt < U) {
+        const int id = targets[r + off[k]];
+        if (id != pad_idx) { sw.nb[k] = id; sw.nw[k] = cnt[k]; tot += cnt[k]; }
+      }
+    }
+    const float inv = tot > 0.f ? eps / tot : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sw.nw[k] *= inv;
   }
   const int nvec = V / 8;  // rows are 16-byte aligned (ld % 8 == 0)
   float x[kCache][8];
@@ -76,51 +128,51 @@ lsce_kernel(const bf16* __restrict__ logits, long ld, int V, const int* __restri
   for (int v = kCache * kThreads * 8 + threadIdx.x; v < nvec * 8; v += kThreads) mx = fmaxf(mx, bf2f(row[v]));
   for (int v = nvec * 8 + threadIdx.x; v < V; v += kThreads) mx = fmaxf(mx, bf2f(row[v]));
   mx = blk_max(mx, red);
-  float se = 0.f, sx = 0.f;
+  // se = sum exp(x - mx); swx = sum_v w_v x_v; sws = sum_v w_v   (dense part: uniform constant or unigram vector)
+  float se = 0.f, swx = 0.f, sws = 0.f;
+  auto acc = [&](int v, float a) {
+    se += expf(a - mx);
+    const float w = sw.base + (sw.unigram ? sw.wu * __ldg(sw.unigram + v) : 0.f);
+    swx += w * a;
+    sws += w;
+  };
 #pragma unroll
   for (int i = 0; i < kCache; ++i) {
     const int vi = threadIdx.x + i * kThreads;
     if (vi < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        se += expf(x[i][j] - mx);
-        sx += x[i][j];
-      }
+      for (int j = 0; j < 8; ++j) acc(vi * 8 + j, x[i][j]);
     }
   }
-  for (int v = kCache * kThreads * 8 + threadIdx.x; v < nvec * 8; v += kThreads) {
-    const float a = bf2f(row[v]);
-    se += expf(a - mx);
-    sx += a;
-  }
-  for (int v = nvec * 8 + threadIdx.x; v < V; v += kThreads) {
-    const float a = bf2f(row[v]);
-    se += expf(a - mx);
-    sx += a;
-  }
+  for (int v = kCache * kThreads * 8 + threadIdx.x; v < nvec * 8; v += kThreads) acc(v, bf2f(row[v]));
+  for (int v = nvec * 8 + threadIdx.x; v < V; v += kThreads) acc(v, bf2f(row[v]));
   se = blk_sum(se, red);
-  sx = blk_sum(sx, red);
+  swx = blk_sum(swx, red);
+  sws = blk_sum(sws, red);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // sparse (temporal) part
+    if (sw.nb[k] >= 0) {
+      swx += sw.nw[k] * bf2f(row[sw.nb[k]]);
+      sws += sw.nw[k];
+    }
+  }
   const float lse = mx + logf(se);
-  const float eps_i = eps / (float)(V - 1);
-  const float wt = 1.f - eps - eps_i;
   if (threadIdx.x == 0) {
     const float n = lse - bf2f(row[tgt]);
-    const float smooth = (float)V * lse - sx;  // -sum_v (x_v - lse)
     nll[r] = n;
-    loss[r] = wt * n + eps_i * smooth;
+    loss[r] = a_nll * n + (sws * lse - swx);  // sum_v w_v * (lse - x_v)
   }
   if (!grad) return;
   bf16* g = grad + r * ld;
+  const float coef = a_nll + sws;  // = 1 for uniform smoothing and for normalised unigram / temporal weights
+  auto gval = [&](int v, float a) { return (coef * expf(a - lse) - (v == tgt ? a_nll : 0.f) - sw.at(v)) * grad_scale; };
 #pragma unroll
   for (int i = 0; i < kCache; ++i) {
     const int vi = threadIdx.x + i * kThreads;
     if (vi < nvec) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int v = vi * 8 + j;
-        o[j] = (expf(x[i][j] - lse) - (v == tgt ? wt : 0.f) - eps_i) * grad_scale;
-      }
+      for (int j = 0; j < 8; ++j) o[j] = gval(vi * 8 + j, x[i][j]);
       uint4 q;
       q.x = pack_bf16x2(o[0], o[1]);
       q.y = pack_bf16x2(o[2], o[3]);
@@ -129,10 +181,8 @@ lsce_kernel(const bf16* __restrict__ logits, long ld, int V, const int* __restri
       *reinterpret_cast<uint4*>(g + vi * 8) = q;
     }
   }
-  for (int v = kCache * kThreads * 8 + threadIdx.x; v < nvec * 8; v += kThreads)
-    g[v] = f2bf((expf(bf2f(row[v]) - lse) - (v == tgt ? wt : 0.f) - eps_i) * grad_scale);
-  for (int v = nvec * 8 + threadIdx.x; v < ld_pad; v += kThreads)
-    g[v] = f2bf(v < V ? (expf(bf2f(row[v]) - lse) - (v == tgt ? wt : 0.f) - eps_i) * grad_scale : 0.f);
+  for (int v = kCache * kThreads * 8 + threadIdx.x; v < nvec * 8; v += kThreads) g[v] = f2bf(gval(v, bf2f(row[v])));
+  for (int v = nvec * 8 + threadIdx.x; v < ld_pad; v += kThreads) g[v] = f2bf(v < V ? gval(v, bf2f(row[v])) : 0.f);
 }
 
 // x[r, :] = E[tok[r], :] * scale + pos[r % U, :]   (pos optional), optional dropout
@@ -234,12 +284,17 @@ inline int grid1d(long n, int per) {
 }  // namespace
 
 extern "C" int esp_lsce_loss(const void* logits, int64_t ld, int32_t V, int64_t R, const int32_t* targets, int32_t pad_idx,
-                             float eps, float grad_scale, float* loss, float* nll, void* grad, void* stream) {
+                             float eps, int32_t smoothing_type, const float* unigram, int32_t U, float grad_scale,
+                             float* loss, float* nll, void* grad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ESP_CHECK(V > 1 && ld >= V && ld % 8 == 0, "LS-CE needs V > 1 and a row stride that is a multiple of 8 (ld=%ld, V=%d)", (long)ld, V);
   ESP_CHECK(logits && targets && loss && nll, "null pointer passed to esp_lsce_loss");
+  ESP_CHECK(smoothing_type >= 0 && smoothing_type <= 2, "smoothing_type: 0 uniform, 1 unigram, 2 temporal");
+  ESP_CHECK(smoothing_type != 1 || unigram != nullptr, "unigram smoothing needs the unigram distribution (fp32 [V])");
+  ESP_CHECK(smoothing_type != 2 || (U > 0 && R % U == 0), "temporal smoothing needs rows = B * U (U=%d, R=%ld)", U, (long)R);
   if (R == 0) return 0;
-  lsce_kernel<<<(unsigned)R, kThreads, 0, st>>>((const bf16*)logits, ld, V, targets, pad_idx, eps, grad_scale, loss, nll,
+  lsce_kernel<<<(unsigned)R, kThreads, 0, st>>>((const bf16*)logits, ld, V, targets, pad_idx, eps, smoothing_type,
+                                               smoothing_type == 1 ? unigram : nullptr, U > 0 ? U : 1, grad_scale, loss, nll,
                                                (bf16*)grad);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);

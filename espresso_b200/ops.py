@@ -377,17 +377,22 @@ def cast_bf16_f32(x, y):
 # ----------------------------------------------------------------------------------------------
 # decoder-side kernels
 # ----------------------------------------------------------------------------------------------
-def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True):
-    """logits bf16 [R, ld]; targets int32 [R] -> (loss fp32 [R], nll fp32 [R], grad bf16 [R, ld] or None)."""
-    _need_cuda(logits, targets)
+SMOOTH_UNIFORM, SMOOTH_UNIGRAM, SMOOTH_TEMPORAL = 0, 1, 2
+
+
+def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True, smoothing=SMOOTH_UNIFORM, unigram=None, U=0):
+    """logits bf16 [R, ld]; targets int32 [R] -> (loss fp32 [R], nll fp32 [R], grad bf16 [R, ld] or None).
+    smoothing: uniform | unigram (unigram fp32 [V]) | temporal (rows are [B, U])."""
+    _need_cuda(logits, targets, unigram)
+    assert unigram is None or (unigram.dtype == torch.float32 and unigram.numel() >= V and unigram.is_contiguous())
     _bf(logits)
     assert logits.dim() == 2 and logits.stride(1) == 1 and targets.dtype == torch.int32
     R, ld = logits.shape[0], logits.stride(0)
     loss = torch.empty(R, device=logits.device, dtype=torch.float32)
     nll = torch.empty(R, device=logits.device, dtype=torch.float32)
     grad = torch.empty_like(logits) if want_grad else None
-    _lib.check(_lib.load().esp_lsce_loss(_ptr(logits), ld, V, R, _ptr(targets), pad_idx, eps, grad_scale, _ptr(loss), _ptr(nll),
-                                         _ptr(grad), _stream()))
+    _lib.check(_lib.load().esp_lsce_loss(_ptr(logits), ld, V, R, _ptr(targets), pad_idx, eps, smoothing, _ptr(unigram), U,
+                                         grad_scale, _ptr(loss), _ptr(nll), _ptr(grad), _stream()))
     return loss, nll, grad
 
 

@@ -189,11 +189,14 @@ int esp_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream);
 
 /* ---- decoder-side kernels --------------------------------------------------------------------
  * Label-smoothed cross-entropy fused with the fp32 log-softmax, forward + backward
- * (espresso/criterions/label_smoothed_cross_entropy_v2.py:82-120,216-240, uniform smoothing):
- *   loss[r] = (1-eps-eps_i)*nll + eps_i*smooth, eps_i = eps/(V-1); rows with target == pad_idx give 0;
- *   grad = grad_scale * (softmax - (1-eps-eps_i)*onehot - eps_i)  (bf16, same row stride; NULL = loss only). */
+ * (espresso/criterions/label_smoothed_cross_entropy_v2.py:49-120,216-240).  smoothing_type 0 = uniform:
+ *   loss[r] = (1-eps-eps_i)*nll + eps_i*smooth, eps_i = eps/(V-1); 1 = unigram (`unigram` fp32 [V], the smoothed
+ *   unigram distribution): (1-eps)*nll - eps*sum_v u[v]*lprobs[v]; 2 = temporal (rows are [B, U]; neighbouring
+ *   targets at distance 1 / 2 weighted 5 : 2, normalised, <pad> neighbours dropped).  Rows with target == pad_idx
+ *   give 0.  grad = grad_scale * dloss/dlogits (bf16, same row stride; NULL = loss only). */
 int esp_lsce_loss(const void* logits, int64_t ld, int32_t V, int64_t R, const int32_t* targets, int32_t pad_idx,
-                  float eps, float grad_scale, float* loss, float* nll, void* grad, void* stream);
+                  float eps, int32_t smoothing_type, const float* unigram, int32_t U, float grad_scale, float* loss,
+                  float* nll, void* grad, void* stream);
 /* x[r] = dropout(bf16(E[tok[r]]*scale) + pos[r % U]) (pos optional; pad tokens get no position), and the
  * scatter-add backward into the fp32 embedding gradient (fairseq/models/transformer/transformer_decoder.py:254-300). */
 int esp_embed_fwd(const int32_t* tokens, const void* E, const void* pos, int32_t U, int32_t d, float scale, int64_t R,

@@ -342,19 +342,46 @@ def ctc_loss(logits, V, in_lens, targets, tgt_lens, blank, zero_infinity=True, g
     return loss, (grad.to(BF) if want_grad else None)
 
 
-def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True):
+SMOOTH_UNIFORM, SMOOTH_UNIGRAM, SMOOTH_TEMPORAL = 0, 1, 2
+
+
+def smoothing_weights(V, targets, pad_idx, eps, smoothing=SMOOTH_UNIFORM, unigram=None, U=0):
+    """(a, w [R, V]) with loss = a * nll + sum_v w_v * (-lprobs_v)
+    (espresso/criterions/label_smoothed_cross_entropy_v2.py:49-79 temporal mask, :95-119 combination)."""
+    t = targets.long()
+    R = t.numel()
+    if smoothing == SMOOTH_UNIFORM:
+        eps_i = eps / (V - 1)
+        return 1 - eps - eps_i, torch.full((R, V), eps_i)
+    if smoothing == SMOOTH_UNIGRAM:
+        return 1 - eps, (eps * unigram.float()[:V])[None, :].expand(R, V)
+    tt = t.view(-1, U)
+    m = torch.zeros(tt.shape[0], U, V)
+    for off, c in ((-2, 2.0), (-1, 5.0), (1, 5.0), (2, 2.0)):
+        src = torch.full_like(tt, pad_idx)
+        if off < 0:
+            src[:, -off:] = tt[:, :off]
+        else:
+            src[:, :-off] = tt[:, off:]
+        m.scatter_add_(-1, src[:, :, None], torch.full((tt.shape[0], U, 1), c))
+    m[:, :, pad_idx] = 0
+    tot = m.sum(-1, keepdim=True)
+    tot[tot == 0] = 1.0
+    return 1 - eps, eps * (m / tot).view(R, V)
+
+
+def lsce_loss(logits, V, targets, pad_idx, eps, grad_scale=1.0, want_grad=True, smoothing=SMOOTH_UNIFORM, unigram=None, U=0):
     x = logits.float()[:, :V]
     lp = torch.log_softmax(x, dim=-1)
     t = targets.long()
     nll = -lp.gather(1, t[:, None]).squeeze(1)
-    smooth = -lp.sum(-1)
-    eps_i = eps / (V - 1)
+    a, w = smoothing_weights(V, targets, pad_idx, eps, smoothing, unigram, U)
     keep = (t != pad_idx).float()
-    loss = ((1 - eps - eps_i) * nll + eps_i * smooth) * keep
+    loss = (a * nll - (w * lp).sum(-1)) * keep
     grad = None
     if want_grad:
-        g = torch.softmax(x, dim=-1) - eps_i
-        g[torch.arange(x.shape[0]), t] -= (1 - eps - eps_i)
+        g = torch.softmax(x, dim=-1) * (a + w.sum(-1, keepdim=True)) - w
+        g[torch.arange(x.shape[0]), t] -= a
         grad = torch.zeros_like(logits, dtype=torch.float32)
         grad[:, :V] = g * keep[:, None] * grad_scale
         grad = grad.to(BF)

@@ -408,7 +408,42 @@ def pin_transducer():
     print("transducer pinned -> tests/golden/transducer_conformer.npz")
 
 
-SECTIONS = {"frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_label_smoothing():
+    """label_smoothed_nll_loss + temporal_label_smoothing_prob_mask of the reference on seeded logits, for the three
+    smoothing types (espresso/criterions/label_smoothed_cross_entropy_v2.py:49-120) vs oracle/ops_ref.lsce_loss."""
+    from espresso.criterions.label_smoothed_cross_entropy_v2 import label_smoothed_nll_loss, temporal_label_smoothing_prob_mask
+
+    from oracle import ops_ref as O
+
+    rs = np.random.RandomState(4)
+    B, U, V, pad, eps = 3, 7, 40, 1, 0.1
+    logits = torch.from_numpy((2.0 * rs.randn(B, U, V)).astype(np.float32)).to(torch.bfloat16).float()
+    target = torch.from_numpy(rs.randint(2, V, size=(B, U)))
+    target[1, 5:] = pad
+    target[2, 2:] = pad
+    target[0, 3] = target[0, 2]  # a repeated neighbour
+    counts = torch.from_numpy(rs.randint(0, 50, size=V).astype(np.float32))
+    uni = (counts + 1.0) / (counts + 1.0).sum()
+    out = dict(logits=logits.numpy(), target=target.numpy(), unigram=uni.numpy(), eps=np.float32(eps), pad=np.int64(pad))
+    for name, mode in (("uniform", 0), ("unigram", 1), ("temporal", 2)):
+        x = logits.clone().requires_grad_(True)
+        lp = torch.log_softmax(x, dim=-1)
+        pm = temporal_label_smoothing_prob_mask(lp, target, padding_index=pad) if name == "temporal" else None
+        loss, nll = label_smoothed_nll_loss(lp.view(-1, V), target.view(-1, 1), eps, ignore_index=pad, reduce=True,
+                                            smoothing_type=name, prob_mask=pm, unigram_tensor=uni[:, None])
+        loss.backward()
+        ol, on, og = O.lsce_loss(logits.view(-1, V).to(torch.bfloat16), V, target.view(-1).int(), pad, eps, smoothing=mode,
+                                 unigram=uni, U=U)
+        assert abs(ol.sum().item() - loss.item()) < 1e-4 * abs(loss.item()), (name, ol.sum().item(), loss.item())
+        assert abs(on.sum().item() - nll.item()) < 1e-4 * abs(nll.item())
+        assert (og.float().view(B, U, V) - x.grad).abs().max().item() < 4e-3  # bf16 gradient storage
+        out["loss_" + name], out["nll_" + name], out["grad_" + name] = np.float64(loss.item()), np.float64(nll.item()), x.grad.numpy()
+        print("label smoothing %-8s loss ref=%.6f oracle=%.6f" % (name, loss.item(), ol.sum().item()))
+    np.savez_compressed(os.path.join(GOLDEN, "label_smoothing.npz"), **out)
+    print("label smoothing pinned -> tests/golden/label_smoothing.npz")
+
+
+SECTIONS = {"label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

@@ -211,6 +211,30 @@ def test_lsce_embed_argmax_kernels():
         assert not grad[:, V:].any()
         am = ops.argmax_rows(x.to(dev), V)
         assert torch.equal(am.cpu(), O.argmax_rows(x, V))
+        # unigram and temporal smoothing (rows viewed as [B, U] for the temporal neighbours)
+        uni = torch.rand(V) + 0.01
+        uni = uni / uni.sum()
+        for mode, Uu in ((ops.SMOOTH_UNIGRAM, 0), (ops.SMOOTH_TEMPORAL, 37), (ops.SMOOTH_TEMPORAL, 1)):
+            kw = dict(smoothing=mode, unigram=uni.to(dev) if mode == ops.SMOOTH_UNIGRAM else None, U=Uu)
+            kwr = dict(smoothing=mode, unigram=uni, U=Uu)
+            loss, nll, grad = ops.lsce_loss(x.to(dev), V, t.to(dev), 1, 0.1, grad_scale=0.5, **kw)
+            lr, nr, gr = O.lsce_loss(x, V, t, 1, 0.1, grad_scale=0.5, **kwr)
+            assert torch.allclose(loss.cpu(), lr, rtol=1e-4, atol=2e-3), (V, mode)
+            assert torch.allclose(nll.cpu(), nr, rtol=1e-4, atol=1e-3)
+            assert (grad.float().cpu() - gr.float()).abs().max().item() < 4e-3, (V, mode)
+    # the reference's own outputs for the three smoothing types (tests/golden/label_smoothing.npz)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "label_smoothing.npz"))
+    lg = torch.from_numpy(g["logits"])
+    Bq, Uq, Vq = lg.shape
+    xq = torch.zeros(Bq * Uq, (Vq + 7) // 8 * 8, dtype=torch.bfloat16)
+    xq[:, :Vq] = lg.view(-1, Vq).bfloat16()
+    tq = torch.from_numpy(g["target"]).view(-1).int()
+    for name, mode in (("uniform", 0), ("unigram", 1), ("temporal", 2)):
+        loss, nll, grad = ops.lsce_loss(xq.to(dev), Vq, tq.to(dev), int(g["pad"]), float(g["eps"]), smoothing=mode,
+                                        unigram=torch.from_numpy(g["unigram"]).to(dev), U=Uq)
+        assert abs(loss.sum().item() - float(g["loss_" + name])) < 2e-4 * abs(float(g["loss_" + name])), name
+        assert abs(nll.sum().item() - float(g["nll_" + name])) < 2e-4 * abs(float(g["nll_" + name])), name
+        assert np.abs(grad[:, :Vq].float().cpu().view(Bq, Uq, Vq).numpy() - g["grad_" + name]).max() < 4e-3, name
     E = torch.randn(50, 64).bfloat16()
     pos = torch.randn(9, 64).bfloat16()
     tok = torch.randint(0, 50, (4 * 9,), dtype=torch.int32)

@@ -66,3 +66,23 @@ def test_ctc_oracle_edge_cases():
     assert abs(nll - 4 * np.log(3.0)) < 1e-9
     nll, grad = octc.ctc_loss_and_grad(x, 1, [1, 2], 0)  # infeasible -> zero_infinity
     assert nll == 0.0 and not grad.any()
+
+
+def test_label_smoothing_variants_match_reference_fixture(golden_dir):
+    """oracle/ops_ref.lsce_loss (uniform / unigram / temporal) vs the reference's label_smoothed_nll_loss +
+    temporal_label_smoothing_prob_mask outputs recorded by oracle/pin_against_reference.py."""
+    import torch
+
+    from oracle import ops_ref as O
+
+    g = np.load(os.path.join(golden_dir, "label_smoothing.npz"))
+    logits = torch.from_numpy(g["logits"])
+    B, U, V = logits.shape
+    tgt = torch.from_numpy(g["target"]).view(-1).int()
+    uni = torch.from_numpy(g["unigram"])
+    for name, mode in (("uniform", 0), ("unigram", 1), ("temporal", 2)):
+        loss, nll, grad = O.lsce_loss(logits.view(-1, V).to(torch.bfloat16), V, tgt, int(g["pad"]), float(g["eps"]),
+                                      smoothing=mode, unigram=uni, U=U)
+        assert abs(loss.sum().item() - float(g["loss_" + name])) < 1e-4 * abs(float(g["loss_" + name])), name
+        assert abs(nll.sum().item() - float(g["nll_" + name])) < 1e-4 * abs(float(g["nll_" + name])), name
+        assert np.abs(grad.float().view(B, U, V).numpy() - g["grad_" + name]).max() < 4e-3, name
