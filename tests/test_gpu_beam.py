@@ -199,3 +199,32 @@ def test_ctc_greedy_decoder(golden_dir):
         seq = torch.unique_consecutive(seq)
         seq = seq[seq != 0]
         assert toks[b][toks[b] != 1].tolist() == seq.tolist()
+
+
+def test_simple_greedy_decoder_on_gpu(golden_dir):
+    """Greedy validation decoder through the CUDA incremental path: consistent with the teacher-forced decoder."""
+    from test_host_orchestration import _build_encdec, _Dict
+    from espresso_b200.tools.simple_greedy_decoder import SimpleGreedyDecoder
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g).finalize_(dev)
+    m.eval()
+    feats, lens = torch.from_numpy(g["feats"]).to(dev), torch.from_numpy(g["lens"]).to(dev)
+    target = torch.from_numpy(g["target"]).to(dev)
+    sample = {"net_input": {"src_tokens": feats, "src_lengths": lens}, "target": target}
+    tokens, lprobs, _ = SimpleGreedyDecoder([m], _Dict(50), for_validation=True).decode([m], sample)
+    B, L = tokens.shape
+    prev = torch.cat([torch.full((B, 1), 2, dtype=torch.long, device=dev), tokens[:, :-1]], dim=1)
+    with torch.no_grad():
+        full, _ = m(feats, lens, prev)
+    ref_lp = torch.log_softmax(full[:, :, :50].float(), dim=-1)
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    for step in range(L):
+        top2 = ref_lp[:, step].topk(2, dim=-1).values
+        ok = (~finished) & ((top2[:, 0] - top2[:, 1]) > 0.05)
+        assert torch.equal(tokens[ok, step], ref_lp[ok, step].argmax(-1)), step
+        if step < target.size(1) and (~finished).any():
+            live = ~finished
+            assert (lprobs[live, step] - ref_lp[live, step]).abs().max() < 0.08 * ref_lp[live, step].abs().max()
+        finished |= tokens[:, step] == 2

@@ -313,3 +313,39 @@ def test_transducer_keys_and_forward_backward_vs_reference_fixture(golden_dir, c
     print(worst[:6])
     assert worst[0][0] < 0.25, worst[:5]
     assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.12, worst[:8]
+
+
+def test_simple_greedy_decoder_consistent_with_teacher_forcing(golden_dir, cpu_ops):
+    """SimpleGreedyDecoder (espresso/tools/simple_greedy_decoder.py:89-166 semantics) through the incremental engine:
+    feeding its own output back through the teacher-forced decoder must reproduce the same arg-max tokens (where the
+    top-2 margin is clear of bf16 noise) and the returned validation log-probs."""
+    from espresso_b200.tools.simple_greedy_decoder import SimpleGreedyDecoder
+
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    m = _build_encdec(g).finalize_(torch.device("cpu"))
+    m.eval()
+    feats, lens = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"])
+    target = torch.from_numpy(g["target"])
+    sample = {"net_input": {"src_tokens": feats, "src_lengths": lens}, "target": target}
+    dec = SimpleGreedyDecoder([m], _Dict(50), for_validation=True)
+    tokens, lprobs, _ = dec.decode([m], sample)
+    B, L = tokens.shape
+    assert lprobs.shape == (B, target.size(1), 50) and L >= 1
+    prev = torch.cat([torch.full((B, 1), 2, dtype=torch.long), tokens[:, :-1]], dim=1)
+    with torch.no_grad():
+        full, _ = m(feats, lens, prev)                       # [B, L, ldV]
+    ref_lp = torch.log_softmax(full[:, :, :50].float(), dim=-1)
+    finished = torch.zeros(B, dtype=torch.bool)
+    for step in range(L):
+        top2 = ref_lp[:, step].topk(2, dim=-1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 0.05
+        live = ~finished
+        assert torch.equal(tokens[live & clear, step], ref_lp[live & clear, step].argmax(-1)), step
+        assert (tokens[finished, step] == 2).all()           # finished hypotheses keep emitting eos
+        if step < target.size(1):
+            assert (lprobs[live, step] - ref_lp[live, step]).abs().max() < 0.08 * ref_lp[live, step].abs().max()
+            if finished.any():
+                assert torch.allclose(lprobs[finished, step], torch.full((1,), -np.log(50.0), dtype=torch.float32))
+        finished |= tokens[:, step] == 2
+    hyp = dec.generate([m], sample)
+    assert len(hyp) == B and all(len(h) == 1 for h in hyp)
