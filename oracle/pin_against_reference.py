@@ -407,6 +407,31 @@ def pin_transducer():
     np.savez_compressed(os.path.join(GOLDEN, "transducer_conformer.npz"), **out)
     print("transducer pinned -> tests/golden/transducer_conformer.npz")
 
+    # ---- greedy decoding (validation decoder): the reference's TransducerGreedyDecoder vs oracle/transducer.greedy_decode
+    from espresso.tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+    class _DDict(_Dict):
+        def bos(self):
+            return blank
+
+    torch.nn.Module.load_state_dict(m, sd0)  # (plain nn.Module load: fairseq's override trips on Conformer layers) fixture weights + running stats
+    m.eval()
+    gout = {}
+    for name, kw in (("e2", dict(max_num_expansions_per_step=2)), ("e1_eos", dict(max_num_expansions_per_step=1, model_predicts_eos=True))):
+        dec = TransducerGreedyDecoder([m], _DDict(), blank=blank, **kw)
+        r_tok, r_sc, _ = dec.decode([m], {"net_input": {"src_tokens": feats, "src_lengths": lens}})
+        with torch.no_grad():
+            sde = {k: v.clone() for k, v in sd0.items()}
+            enc_e, ol_e, _ = OC.encoder_forward(sde, ecfg, feats, lens, training=False)
+            o_tok, o_sc, o_mar = OT.greedy_decode(sde, enc_e, ol_e, 2, pad_idx, blank, eos_idx, eos_idx, **kw)
+        assert torch.equal(o_tok, r_tok), (name, o_tok, r_tok)
+        assert (o_sc - r_sc).abs().max().item() < 1e-3, (o_sc, r_sc)
+        print("transducer greedy %-7s: tokens identical (%d non-blank), |score diff| %.3g"
+              % (name, int((r_tok != blank).sum()), (o_sc - r_sc).abs().max().item()))
+        gout["tokens_" + name], gout["scores_" + name], gout["margins_" + name] = r_tok.numpy(), r_sc.numpy(), o_mar.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "transducer_greedy.npz"), **gout)
+    print("transducer greedy decoder pinned -> tests/golden/transducer_greedy.npz")
+
 
 def pin_label_smoothing():
     """label_smoothed_nll_loss + temporal_label_smoothing_prob_mask of the reference on seeded logits, for the three

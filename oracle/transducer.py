@@ -43,3 +43,60 @@ def transducer_loss(logits, enc_lens, target, pad, eos, blank):
     u_lens = ((target != pad) & (target != eos)).sum(-1).int()
     return torchaudio.functional.rnnt_loss(logits.float(), target[:, :-1].int().contiguous(), enc_lens.int(), u_lens, blank=blank,
                                            clamp=-1.0, reduction="sum")
+
+
+def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_expansions_per_step=2, temperature=1.0,
+                  model_predicts_eos=False, max_len=0):
+    """Restates espresso/tools/transducer_greedy_decoder.py:91-251 (no LM): frame-synchronous greedy search, at most
+    `max_num_expansions_per_step` non-blank tokens per encoder frame, predictor state rolled back on blank.
+    enc [B, T, d] (eval-mode encoder output), enc_lens [B].
+    Returns (tokens int64 [B, T*(E+1)], scores [B], margins [B, T, E+1] = top-1 minus top-2 log-prob of every decision,
+    +inf where no decision was taken)."""
+    B, T, _ = enc.shape
+    T = min(int(enc_lens.max()), max_len) if max_len > 0 else int(enc_lens.max())
+    E = max_num_expansions_per_step
+    tokens = torch.full((B, T, E + 1), blank, dtype=torch.long)
+    scores = torch.zeros(B, T, E + 1)
+    margins = torch.full((B, T, E + 1), float("inf"))
+    prev = torch.full((B,), bos, dtype=torch.long)
+    hid = [sd["decoder.layers.%d.weight_hh" % i].shape[1] for i in range(n_layers)]
+    hs = [torch.zeros(B, h) for h in hid]
+    cs = [torch.zeros(B, h) for h in hid]
+    for t in range(T):
+        blank_mask = t >= enc_lens
+        k = 0
+        while not bool(blank_mask.all()) and k < E + 1:
+            # one predictor step from the cached state
+            x = F.embedding(prev, sd["decoder.embed_tokens.weight"], padding_idx=pad)
+            nh, nc = [], []
+            for i in range(n_layers):
+                p = "decoder.layers.%d." % i
+                gates = F.linear(x, sd[p + "weight_ih"], sd[p + "bias_ih"]) + F.linear(hs[i], sd[p + "weight_hh"], sd[p + "bias_hh"])
+                i_, f_, g_, o_ = gates.chunk(4, dim=1)
+                c = torch.sigmoid(f_) * cs[i] + torch.sigmoid(i_) * torch.tanh(g_)
+                h = torch.sigmoid(o_) * torch.tanh(c)
+                nh.append(h)
+                nc.append(c)
+                x = h
+            logits = joint_logits(sd, enc[:, t:t + 1], x[:, None, :])[:, 0, 0]  # [B, V]
+            lp = torch.log_softmax(logits / temperature, dim=-1)
+            if model_predicts_eos:
+                lp[:, blank] = torch.logaddexp(lp[:, blank], lp[:, eos])
+                lp[:, eos] = float("-inf")
+            if k < E:
+                top2 = lp.topk(2, dim=-1)
+                sc, tok = top2.values[:, 0], top2.indices[:, 0]
+                margins[~blank_mask, t, k] = (top2.values[:, 0] - top2.values[:, 1])[~blank_mask]
+                scores[:, t, k] = torch.where(blank_mask, torch.zeros_like(sc), sc)
+                blank_mask = blank_mask | (tok == blank)
+                tokens[:, t, k] = torch.where(blank_mask, torch.full_like(tok, blank), tok)
+                prev = torch.where(blank_mask, prev, tok)
+            else:
+                scores[:, t, k] = torch.where(blank_mask, scores[:, t, k], lp[:, blank])
+                blank_mask = torch.ones_like(blank_mask)
+            # rows that emitted blank (or are done with this frame) keep the old predictor state
+            keep_old = blank_mask[:, None]
+            hs = [torch.where(keep_old, o, n) for o, n in zip(hs, nh)]
+            cs = [torch.where(keep_old, o, n) for o, n in zip(cs, nc)]
+            k += 1
+    return tokens.view(B, -1), scores.view(B, -1).sum(-1), margins

@@ -228,3 +228,27 @@ def test_simple_greedy_decoder_on_gpu(golden_dir):
             live = ~finished
             assert (lprobs[live, step] - ref_lp[live, step]).abs().max() < 0.08 * ref_lp[live, step].abs().max()
         finished |= tokens[:, step] == 2
+
+
+@pytest.mark.parametrize("variant,kw", [("e2", dict(max_num_expansions_per_step=2)),
+                                        ("e1_eos", dict(max_num_expansions_per_step=1, model_predicts_eos=True))])
+def test_transducer_greedy_decoder_on_gpu(variant, kw, golden_dir):
+    """CUDA path of the transducer greedy decoder: token sequences identical to the REAL reference decoder's
+    (tests/golden/transducer_greedy.npz; all decisions have top-2 margins >= 0.8)."""
+    from test_host_orchestration import _build_transducer, _Dict
+    from espresso_b200.tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    m = _build_transducer(g).finalize_(dev)
+
+    class D(_Dict):
+        def bos(self):
+            return 0
+
+    dec = TransducerGreedyDecoder([m], D(50), blank=0, **kw)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]).to(dev), "src_lengths": torch.from_numpy(g["lens"]).to(dev)}}
+    tokens, scores, _ = dec.decode([m], sample)
+    assert np.array_equal(tokens.cpu().numpy(), gg["tokens_" + variant])
+    assert np.abs(scores.cpu().numpy() - gg["scores_" + variant]).max() < 0.03 * np.abs(gg["scores_" + variant]).max()

@@ -349,3 +349,31 @@ def test_simple_greedy_decoder_consistent_with_teacher_forcing(golden_dir, cpu_o
         finished |= tokens[:, step] == 2
     hyp = dec.generate([m], sample)
     assert len(hyp) == B and all(len(h) == 1 for h in hyp)
+
+
+@pytest.mark.parametrize("variant,kw", [("e2", dict(max_num_expansions_per_step=2)),
+                                        ("e1_eos", dict(max_num_expansions_per_step=1, model_predicts_eos=True))])
+def test_transducer_greedy_decoder_matches_reference_tokens(variant, kw, golden_dir, cpu_ops):
+    """TransducerGreedyDecoder through the host orchestration vs the REAL reference decoder's output recorded in
+    tests/golden/transducer_greedy.npz (every recorded decision has a top-2 margin >= 0.8, far above bf16 noise, so
+    the token sequences must be identical; the summed log-prob score within bf16 tolerance)."""
+    from espresso_b200.tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    assert np.isfinite(gg["margins_" + variant]).sum() > 30 and gg["margins_" + variant][np.isfinite(gg["margins_" + variant])].min() > 0.5
+    m = _build_transducer(g).finalize_(torch.device("cpu"))
+
+    class D(_Dict):
+        def bos(self):
+            return 0
+
+    dec = TransducerGreedyDecoder([m], D(50), blank=0, **kw)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"])}}
+    tokens, scores, _ = dec.decode([m], sample)
+    assert np.array_equal(tokens.numpy(), gg["tokens_" + variant])
+    assert np.abs(scores.numpy() - gg["scores_" + variant]).max() < 0.03 * np.abs(gg["scores_" + variant]).max()
+    hyp = dec.generate([m], sample)
+    for b in range(tokens.size(0)):
+        ref = [t for t in gg["tokens_" + variant][b].tolist() if t not in (0, 2)]
+        assert hyp[b][0]["tokens"].tolist() == ref
