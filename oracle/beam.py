@@ -2,8 +2,10 @@
 TEST INFRASTRUCTURE ONLY.  Follows fairseq/sequence_generator.py:212-621 (incl. finalize_hypos :657-766 and the
 batch compaction :507-541 that the product omits) and fairseq/search.py:103-144, with a step function
 `lprobs_fn(step, tokens[:, :step+1], reorder_state) -> lprobs [rows, V]` standing in for EnsembleModel.forward_decoder
-(+ LM fusion).  Pinned by the reference's own known-answer tests (tests/test_sequence_generator.py:202-283), which
-tests/test_beam_search.py replays against this function and against the product generator.
+(+ LM fusion).  Pinned twice: by the reference's own known-answer tests (tests/test_sequence_generator.py:202-283), which
+tests/test_beam_search.py replays against this function and against the product generator, and by the REAL reference
+SequenceGenerator run with LM shallow fusion / eos_factor on table models (oracle/pin_against_reference.py::pin_beam ->
+tests/golden/beam_reference.npz).
 """
 import math
 

@@ -468,7 +468,102 @@ def pin_label_smoothing():
     print("label smoothing pinned -> tests/golden/label_smoothing.npz")
 
 
-SECTIONS = {"label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def _table_lprobs(seed, V, step, tokens):
+    """Deterministic pseudo-random log-prob rows that depend on the hypothesis prefix (same function as
+    tests/test_beam_search.py::_RandomModel.lprobs)."""
+    rows = tokens.shape[0]
+    out = torch.empty(rows, V)
+    for r in range(rows):
+        h = hash((seed, step) + tuple(int(t) for t in tokens[r, : step + 1].tolist())) % (2 ** 31)
+        g = torch.Generator().manual_seed(h)
+        out[r] = torch.log_softmax(torch.randn(V, generator=g) * 2.0, dim=-1)
+    return out
+
+
+def pin_beam():
+    """The REAL reference SequenceGenerator (fairseq/sequence_generator.py, Espresso's version with lm_model /
+    lm_weight / eos_factor) on table-driven fake models, incl. LM shallow fusion, eos_factor, unk penalty, min_len and
+    length penalty -- paths the reference's own known-answer tests do not exercise -- vs oracle/beam.generate."""
+    import argparse
+
+    from fairseq.sequence_generator import SequenceGenerator
+    from tests import utils as ref_test_utils
+
+    from oracle import beam as OB
+
+    PAD, EOS, UNK = 1, 2, 3
+    out = {}
+    cases = [dict(seed=1, beam=2, bsz=3, V=9, eos_factor=None, lenpen=1.0, lm=None),
+             dict(seed=2, beam=5, bsz=4, V=17, eos_factor=1.5, lenpen=1.0, lm=0.47),
+             dict(seed=3, beam=3, bsz=2, V=8, eos_factor=None, lenpen=0.5, lm=0.3),
+             dict(seed=4, beam=4, bsz=3, V=6, eos_factor=2.0, lenpen=1.0, lm=None),
+             dict(seed=5, beam=5, bsz=5, V=40, eos_factor=1.5, lenpen=1.0, lm=1.0)]
+    for ci, c in enumerate(cases):
+        V, seed = c["V"], c["seed"]
+        d = ref_test_utils.dummy_dictionary(vocab_size=V - 4)
+        assert len(d) == V and d.pad() == PAD and d.eos() == EOS and d.unk() == UNK
+
+        class Dec(ref_test_utils.TestIncrementalDecoder):
+            def forward(self, prev_output_tokens, encoder_out=None, incremental_state=None):
+                step = prev_output_tokens.size(1) - 1
+                lp = _table_lprobs(seed, V, step, prev_output_tokens)
+                return lp[:, None, :], {"attn": [None]}
+
+            def get_normalized_probs(self, net_output, log_probs, _):
+                return net_output[0]
+
+        class LM:
+            """FairseqLanguageModel stand-in (plain object): log-probs from a second table keyed by the prefix."""
+            def __init__(self):
+                self.decoder = self
+
+            def eval(self):
+                return self
+
+            def reorder_incremental_state_scripting(self, state, order):
+                pass
+
+            def __call__(self, tokens, incremental_state=None):
+                return (_table_lprobs(seed + 1000, V, tokens.size(1) - 1, tokens)[:, None, :], None)
+
+            def get_normalized_probs(self, net_output, log_probs, sample=None):
+                return net_output[0]
+
+        args = argparse.Namespace(beam_probs=[], max_decoder_positions=40)
+        model = ref_test_utils.TestModel(ref_test_utils.TestEncoder(args, d), Dec(args, d))
+        kw = dict(beam_size=c["beam"], max_len_a=0.0, max_len_b=12, min_len=2, len_penalty=c["lenpen"], unk_penalty=0.3)
+        gen = SequenceGenerator([model], d, lm_model=LM() if c["lm"] is not None else None,
+                                lm_weight=c["lm"] if c["lm"] is not None else 1.0, eos_factor=c["eos_factor"], **kw)
+        src = torch.full((c["bsz"], 7), 5, dtype=torch.long)
+        src[:, -1] = EOS
+        sample = {"net_input": {"src_tokens": src, "src_lengths": torch.full((c["bsz"],), 7)}}
+        ref = gen.forward(sample)
+
+        def fn(step, tokens, ro):
+            lp = _table_lprobs(seed, V, step, tokens)
+            if c["lm"] is not None:
+                lp = lp + c["lm"] * _table_lprobs(seed + 1000, V, step, tokens)
+            return lp
+
+        ours = OB.generate(fn, c["bsz"], 7, V, PAD, UNK, EOS, model_max_len=40, eos_factor=c["eos_factor"], **kw)
+        n_h = 0
+        for b, (rh, oh) in enumerate(zip(ref, ours)):
+            assert len(rh) == len(oh), (ci, b, len(rh), len(oh))
+            for k, (r_, o_) in enumerate(zip(rh, oh)):
+                assert r_["tokens"].tolist() == o_["tokens"].tolist(), (ci, b, k)
+                assert abs(float(r_["score"]) - float(o_["score"])) < 1e-5
+                out["c%d_b%d_k%d_tokens" % (ci, b, k)] = r_["tokens"].numpy()
+                out["c%d_b%d_k%d_score" % (ci, b, k)] = np.float32(float(r_["score"]))
+                n_h += 1
+            out["c%d_b%d_n" % (ci, b)] = np.int64(len(rh))
+        print("beam case %d (beam %d, V %d, lm %s, eos_factor %s): %d hypotheses identical" % (ci, c["beam"], V, c["lm"], c["eos_factor"], n_h))
+    out["cases"] = np.array([[c["seed"], c["beam"], c["bsz"], c["V"], -1.0 if c["eos_factor"] is None else c["eos_factor"], c["lenpen"],
+                              -1.0 if c["lm"] is None else c["lm"]] for c in cases], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "beam_reference.npz"), **out)
+    print("beam search pinned -> tests/golden/beam_reference.npz")
+
+
+SECTIONS = {"beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

@@ -2,6 +2,7 @@
 tables from tests/utils.py:67-166) replayed against (1) the oracle restatement of the reference algorithm and
 (2) the product SequenceGenerator with the oracle's per-op kernels monkeypatched in; plus randomised equivalence
 of the two (tokens bit-exact).  The CUDA kernels are checked against the same per-op reference in test_gpu_beam.py."""
+import os
 import math
 
 import numpy as np
@@ -164,3 +165,62 @@ def test_product_matches_oracle_on_random_models(seed, beam, bsz, Vn, eos_factor
             assert h["tokens"].tolist() == r["tokens"].tolist()
             assert abs(float(h["score"]) - float(r["score"])) < 1e-5
             assert (h["positional_scores"] - r["positional_scores"]).abs().max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# hypotheses of the REAL reference SequenceGenerator (LM shallow fusion, eos_factor, unk penalty, min_len, length
+# penalty) recorded by oracle/pin_against_reference.py::pin_beam -> tests/golden/beam_reference.npz
+# ---------------------------------------------------------------------------------------------------
+def _reference_cases(golden_dir):
+    import numpy as np
+
+    g = np.load(os.path.join(golden_dir, "beam_reference.npz"))
+    for ci, (seed, beam, bsz, Vn, eos_factor, lenpen, lm) in enumerate(g["cases"].tolist()):
+        ref = [[(g["c%d_b%d_k%d_tokens" % (ci, b, k)].tolist(), float(g["c%d_b%d_k%d_score" % (ci, b, k)]))
+                for k in range(int(g["c%d_b%d_n" % (ci, b)]))] for b in range(int(bsz))]
+        yield dict(seed=int(seed), beam=int(beam), bsz=int(bsz), V=int(Vn), eos_factor=None if eos_factor < 0 else eos_factor,
+                   lenpen=lenpen, lm=None if lm < 0 else lm), ref
+
+
+def test_oracle_beam_search_matches_reference_generator(golden_dir):
+    n = 0
+    for c, ref in _reference_cases(golden_dir):
+        m, lm = _RandomModel(c["V"], c["seed"]), _RandomModel(c["V"], c["seed"] + 1000)
+
+        def fn(step, tokens, ro):
+            lp = m.lprobs(step, tokens)
+            return lp if c["lm"] is None else lp + c["lm"] * lm.lprobs(step, tokens)
+
+        got = OB.generate(fn, c["bsz"], 7, c["V"], PAD, UNK, EOS, model_max_len=40, beam_size=c["beam"], max_len_a=0.0,
+                          max_len_b=12, min_len=2, len_penalty=c["lenpen"], unk_penalty=0.3, eos_factor=c["eos_factor"])
+        for hs, rs in zip(got, ref):
+            assert len(hs) == len(rs)
+            for h, (toks, score) in zip(hs, rs):
+                assert h["tokens"].tolist() == toks and abs(float(h["score"]) - score) < 1e-5
+                n += 1
+    assert n > 50
+
+
+def test_product_generator_matches_reference_generator(golden_dir, cpu_ops):
+    """espresso_b200.SequenceGenerator (host orchestration over the reference ops) reproduces the real reference
+    generator's hypotheses, token for token, incl. LM shallow fusion and eos_factor."""
+    from espresso_b200.sequence_generator import SequenceGenerator
+
+    for c, ref in _reference_cases(golden_dir):
+        Vn = c["V"]
+
+        class D(_Dict):
+            def __len__(self):
+                return Vn
+
+        m = _RandomModel(Vn, c["seed"])
+        lm = _RandomModel(Vn, c["seed"] + 1000) if c["lm"] is not None else None
+        gen = SequenceGenerator([m], D(), beam_size=c["beam"], max_len_a=0.0, max_len_b=12, min_len=2, len_penalty=c["lenpen"],
+                                unk_penalty=0.3, eos_factor=c["eos_factor"], lm_model=lm, lm_weight=c["lm"] or 1.0)
+        sample = {"net_input": {"src_tokens": torch.zeros(c["bsz"], 7, dtype=torch.long), "src_lengths": torch.full((c["bsz"],), 7)}}
+        got = gen.generate([m], sample)
+        for hs, rs in zip(got, ref):
+            assert len(hs) == len(rs)
+            for h, (toks, score) in zip(hs, rs):
+                assert h["tokens"].tolist() == toks, (c, toks, h["tokens"].tolist())
+                assert abs(float(h["score"]) - score) < 1e-4

@@ -252,3 +252,39 @@ def test_transducer_greedy_decoder_on_gpu(variant, kw, golden_dir):
     tokens, scores, _ = dec.decode([m], sample)
     assert np.array_equal(tokens.cpu().numpy(), gg["tokens_" + variant])
     assert np.abs(scores.cpu().numpy() - gg["scores_" + variant]).max() < 0.03 * np.abs(gg["scores_" + variant]).max()
+
+
+def test_cuda_generator_matches_reference_generator(golden_dir):
+    """CUDA beam search (esp_beam_merge / _topk / _bookkeep) vs the hypotheses of the REAL reference SequenceGenerator
+    recorded in tests/golden/beam_reference.npz: LM shallow fusion, eos_factor, unk penalty, min_len, length penalty.
+    Token indices must be bit-exact."""
+    from test_beam_search import _Dict, _RandomModel, _reference_cases
+    from espresso_b200.sequence_generator import SequenceGenerator
+
+    dev = torch.device("cuda:0")
+    n = 0
+    for c, ref in _reference_cases(golden_dir):
+        Vn = c["V"]
+
+        class D(_Dict):
+            def __len__(self):
+                return Vn
+
+        class GpuModel(_RandomModel):
+            def decode_step(self, step, tokens, state, new_order):
+                return self.lprobs(step, tokens.cpu()).to(dev), False
+
+        m = GpuModel(Vn, c["seed"])
+        lm = GpuModel(Vn, c["seed"] + 1000) if c["lm"] is not None else None
+        gen = SequenceGenerator([m], D(), beam_size=c["beam"], max_len_a=0.0, max_len_b=12, min_len=2, len_penalty=c["lenpen"],
+                                unk_penalty=0.3, eos_factor=c["eos_factor"], lm_model=lm, lm_weight=c["lm"] or 1.0)
+        sample = {"net_input": {"src_tokens": torch.zeros(c["bsz"], 7, dtype=torch.long, device=dev),
+                                "src_lengths": torch.full((c["bsz"],), 7, device=dev)}}
+        got = gen.generate([m], sample)
+        for hs, rs in zip(got, ref):
+            assert len(hs) == len(rs)
+            for h, (toks, score) in zip(hs, rs):
+                assert h["tokens"].tolist() == toks
+                assert abs(float(h["score"]) - score) < 1e-4
+                n += 1
+    assert n > 50
