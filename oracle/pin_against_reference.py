@@ -563,7 +563,90 @@ def pin_beam():
     print("beam search pinned -> tests/golden/beam_reference.npz")
 
 
-SECTIONS = {"beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_optimizer():
+    """fairseq's Adam (fairseq/optim/adam.py:110-239, decoupled weight decay, bias-corrected step) after
+    fairseq.utils.clip_grad_norm_ (fairseq/utils.py:347-397) and the division by sample_size that
+    Trainer.train_step applies (fairseq/trainer.py:950-975), over several updates, vs oracle/ops_ref.adam_step on flat
+    buffers; plus the noam / tri_stage learning-rate schedules of the reference at a spread of update counts."""
+    from argparse import Namespace
+
+    from fairseq.optim.adam import Adam
+    from fairseq.utils import clip_grad_norm_
+
+    from oracle import ops_ref as O
+
+    g = torch.Generator().manual_seed(9)
+    shapes = [(7, 5), (13,), (4, 3, 2)]
+    params = [torch.nn.Parameter(torch.randn(*s_, generator=g)) for s_ in shapes]
+    n = sum(p_.numel() for p_ in params)
+    lr, betas, eps, wd, clip = 3e-3, (0.9, 0.98), 1e-8, 0.01, 0.5
+    opt = Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=wd)
+    p32 = torch.cat([p_.detach().reshape(-1) for p_ in params]).clone()
+    m, v = torch.zeros(n), torch.zeros(n)
+    p16 = p32.to(torch.bfloat16)
+    out = {"p0": p32.numpy().copy()}
+    for step in range(1, 5):
+        grads = [torch.randn(*s_, generator=g) * (3.0 if step == 2 else 0.2) for s_ in shapes]
+        sample_size = float(2 + step)
+        flat_g = torch.cat([x.reshape(-1) for x in grads]).clone()
+        for p_, gr in zip(params, grads):
+            p_.grad = gr / sample_size                      # multiply_grads(1 / sample_size)
+        gnorm = clip_grad_norm_(params, clip)
+        opt.step()
+        sumsq = (flat_g * flat_g).sum().reshape(1)
+        gn_out = torch.zeros(1)
+        O.adam_step(p32, m, v, flat_g, p16, lr, betas[0], betas[1], eps, wd, step, sumsq, denom_const=sample_size,
+                    clip_norm=clip, gnorm_out=gn_out)
+        ref_flat = torch.cat([p_.detach().reshape(-1) for p_ in params])
+        assert abs(gn_out.item() - gnorm.item()) < 1e-5 * gnorm.item(), (gn_out.item(), gnorm.item())
+        assert (ref_flat - p32).abs().max().item() < 1e-6, (step, (ref_flat - p32).abs().max().item())
+        out["g%d" % step], out["ss%d" % step], out["p%d" % step], out["gnorm%d" % step] = (
+            flat_g.numpy(), np.float64(sample_size), ref_flat.numpy().copy(), np.float64(gnorm.item()))
+    out["hyper"] = np.array([lr, betas[0], betas[1], eps, wd, clip])
+    print("optimizer: 4 clipped AdamW-style updates identical to fairseq's Adam (max diff < 1e-6)")
+
+    # ---- learning-rate schedules
+    from espresso.optim.lr_scheduler.noam_lr_scheduler import NoamLRScheduler
+    from fairseq.optim.lr_scheduler.tri_stage_lr_scheduler import TriStageLRSchedule
+
+    from espresso_b200.optim import NoamLRScheduler as OurNoam
+    from espresso_b200.optim import TriStageLRScheduler as OurTri
+
+    steps = [0, 1, 10, 99, 100, 101, 5000, 24999, 25000, 25001, 100000]
+    ref = NoamLRScheduler.__new__(NoamLRScheduler)
+    ref.cfg, ref.optimizer, ref.best = None, Namespace(set_lr=lambda x: None, get_lr=lambda: 0.0), None
+    ref.factor, ref.warmup_steps, ref.model_size, ref.final_lr = 5.0, 25000, 512, 1e-6
+    ours = OurNoam(5.0, 25000, 512, 1e-6)
+    noam = []
+    for s_ in steps:
+        a, b = ref.step_update(s_), ours.step_update(s_)
+        assert abs(a - b) <= 1e-12 * max(abs(a), 1e-12), (s_, a, b)
+        noam.append(a)
+    tcfg = Namespace(lr=[5e-4], init_lr_scale=0.01, final_lr_scale=0.05, phase_ratio=None, warmup_steps=100, hold_steps=200,
+                     decay_steps=300, max_update=0)
+    # run the reference constructor body without its FairseqOptimizer type check
+    import fairseq.optim.lr_scheduler.fairseq_lr_scheduler as _fl
+    _orig = _fl.FairseqLRScheduler.__init__
+    _fl.FairseqLRScheduler.__init__ = lambda self, cfg, optimizer: (setattr(self, "cfg", cfg), setattr(self, "optimizer", optimizer),
+                                                                    setattr(self, "best", None)) and None
+    try:
+        tref = TriStageLRSchedule(tcfg, Namespace(set_lr=lambda x: None, get_lr=lambda: 0.0))
+    finally:
+        _fl.FairseqLRScheduler.__init__ = _orig
+    tours = OurTri(5e-4, 100, 200, 300, init_lr_scale=0.01, final_lr_scale=0.05)
+    tsteps = [0, 1, 50, 99, 100, 150, 299, 300, 301, 450, 599, 600, 601, 5000]
+    tri = []
+    for s_ in tsteps:
+        a, b = tref.step_update(s_), tours.step_update(s_)
+        assert abs(a - b) <= 1e-12 * max(abs(a), 1e-12), (s_, a, b)
+        tri.append(a)
+    out.update(noam_steps=np.array(steps), noam_lr=np.array(noam), tri_steps=np.array(tsteps), tri_lr=np.array(tri))
+    print("lr schedules: noam and tri_stage identical to the reference at %d + %d update counts" % (len(steps), len(tsteps)))
+    np.savez_compressed(os.path.join(GOLDEN, "optimizer.npz"), **out)
+    print("optimizer + schedules pinned -> tests/golden/optimizer.npz")
+
+
+SECTIONS = {"optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 
