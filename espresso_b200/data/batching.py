@@ -20,29 +20,26 @@ def ordered_indices(src_sizes, tgt_sizes=None, shuffle_seed=None):
 
 
 def batch_by_size(indices, num_tokens, max_tokens=None, max_sentences=None, required_batch_size_multiple=1):
-    """Greedy packing identical to fairseq's batch_by_size_vec: a batch closes when adding the next sample
-    would exceed max_tokens (= longest sample * batch size) or max_sentences."""
-    max_tokens = int(max_tokens) if max_tokens else -1
-    max_sentences = int(max_sentences) if max_sentences else -1
-    mult = required_batch_size_multiple
-    batches, cur, cur_max = [], [], 0
-    for i in indices:
-        nt = int(num_tokens[i])
-        assert max_tokens <= 0 or nt <= max_tokens, "sentence at index %d exceeds max_tokens limit" % i
-        new_max = max(cur_max, nt)
-        n_after = len(cur) + 1
-        overflow = (max_sentences > 0 and len(cur) == max_sentences) or (max_tokens > 0 and n_after * new_max > max_tokens)
-        if overflow and cur:
-            keep = max(mult * (len(cur) // mult), len(cur) % mult)
-            batches.append(np.array(cur[:keep], dtype=np.int64))
-            cur = cur[keep:]
-            cur_max = max([int(num_tokens[j]) for j in cur], default=0)
-            new_max = max(cur_max, nt)
-        cur.append(int(i))
-        cur_max = new_max
-    if cur:
-        batches.append(np.array(cur, dtype=np.int64))
-    return batches
+    """fairseq.data.data_utils.batch_by_size (fairseq/data/data_utils.py:282-365): pack the samples `indices` (in that
+    order) into batches under max_tokens (= longest sample * batch size), max_sentences and a batch-size multiple.
+    `num_tokens[i]` is the size of sample i.  The packing itself is native (esp_batch_by_size in the C ABI, the
+    counterpart of the reference's Cython batch_by_size_vec); returns a list of int64 index arrays."""
+    import ctypes
+
+    from .. import lib as _lib
+
+    indices = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
+    n = int(indices.shape[0])
+    if n == 0:
+        return []
+    sizes = np.ascontiguousarray(np.asarray(num_tokens, dtype=np.int64)[indices])
+    ends = np.zeros(n, dtype=np.int32)
+    k = _lib.load().esp_batch_by_size(sizes.ctypes.data_as(ctypes.c_void_p), n, int(max_tokens) if max_tokens else -1,
+                                      int(max_sentences) if max_sentences else -1, int(required_batch_size_multiple),
+                                      ends.ctypes.data_as(ctypes.c_void_p))
+    if k < 0:
+        raise AssertionError(_lib.load().esp_last_error().decode())
+    return np.split(indices, ends[:k])
 
 
 def shard_batches(batches, world_size, rank, fill_value=None):

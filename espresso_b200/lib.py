@@ -40,6 +40,7 @@ SIGNATURES = {
     "esp_last_error": (C.c_char_p, []),
     "esp_version": (C.c_int, []),
     "esp_launch_count": (_i64, []),
+    "esp_batch_by_size": (_i64, [_vp, _i64, _i64, _i64, _i32, _vp]),
     "esp_note_graph_replay": (None, [_i64]),
     "esp_gemm_bf16": (C.c_int, [C.POINTER(EspGemm), _vp]),
     "esp_frontend_fbank": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32,

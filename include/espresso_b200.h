@@ -257,6 +257,13 @@ int esp_rnnt_loss(const void* logits, int64_t ld, int32_t V, int32_t B, int32_t 
                   const int32_t* u_lens, const int32_t* targets, int32_t u_max, int32_t blank, float grad_scale, float* loss,
                   void* grad, void* workspace, void* stream);
 
+/* ---- host-side batch packing (no GPU work) -------------------------------------------------------
+ * The native packer behind fairseq.data.data_utils.batch_by_size (fairseq/data/data_utils_fast.pyx:20-105,
+ * batch_by_size_vec): num_tokens[i] = size of the i-th sample in packing order; writes the split points into
+ * ends[0..n) and returns how many there are (use them like numpy.split), -1 on error. */
+int64_t esp_batch_by_size(const int64_t* num_tokens, int64_t n, int64_t max_tokens, int64_t max_sentences,
+                          int32_t bsz_mult, int32_t* ends);
+
 #ifdef __cplusplus
 }
 #endif

@@ -646,7 +646,45 @@ def pin_optimizer():
     print("optimizer + schedules pinned -> tests/golden/optimizer.npz")
 
 
-SECTIONS = {"optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_batching():
+    """The reference's native batch packer (fairseq/data/data_utils_fast.pyx, compiled from /root/reference into
+    oracle/_ref/ by oracle/build_ref.sh) vs espresso_b200.data.batching.batch_by_size (esp_batch_by_size in the C ABI)
+    on random size lists, max_tokens / max_sentences / batch-size multiples incl. the tail-overflow corner."""
+    import subprocess
+    import sys as _sys
+
+    ref_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    subprocess.check_call(["bash", os.path.join(os.path.dirname(os.path.abspath(__file__)), "build_ref.sh")])
+    _sys.path.insert(0, ref_dir)
+    import data_utils_fast as R
+
+    from espresso_b200.data import batching as Bt
+
+    rs = np.random.RandomState(21)
+    out, n_cases = {}, 0
+    for trial in range(400):
+        n = int(rs.randint(1, 120))
+        sizes = rs.randint(1, 400, size=n).astype(np.int64)
+        order = np.argsort(sizes, kind="mergesort").astype(np.int64) if rs.rand() < 0.7 else rs.permutation(n).astype(np.int64)
+        mt = int(rs.choice([0, 400, 1000, 4000]))
+        ms = int(rs.choice([0, 1, 5, 24]))
+        mult = int(rs.choice([1, 1, 8, 4, 3]))
+        if mt and sizes.max() > mt:
+            mt = int(sizes.max())
+        ref = R.batch_by_size_vec(order, sizes[order], mt if mt else -1, ms if ms else -1, mult)
+        got = Bt.batch_by_size(order, sizes, mt or None, ms or None, mult)
+        assert len(ref) == len(got) and all(np.array_equal(a, b) for a, b in zip(ref, got)), (trial, mt, ms, mult)
+        if trial < 60:  # a committed subset for hosts without /root/reference
+            out["c%d_sizes" % n_cases], out["c%d_order" % n_cases] = sizes, order
+            out["c%d_cfg" % n_cases] = np.array([mt, ms, mult], dtype=np.int64)
+            out["c%d_ends" % n_cases] = np.cumsum([len(b) for b in ref]).astype(np.int64)
+            n_cases += 1
+    out["n_cases"] = np.int64(n_cases)
+    np.savez_compressed(os.path.join(GOLDEN, "batching.npz"), **out)
+    print("batching: 400 random cases identical to the reference's compiled Cython packer; %d cases -> tests/golden/batching.npz" % n_cases)
+
+
+SECTIONS = {"batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

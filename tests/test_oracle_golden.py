@@ -116,3 +116,39 @@ def test_adam_clip_and_lr_schedules_match_fairseq_fixture(golden_dir):
     tri = TriStageLRScheduler(5e-4, 100, 200, 300, init_lr_scale=0.01, final_lr_scale=0.05)
     for s_, ref in zip(g["tri_steps"].tolist(), g["tri_lr"].tolist()):
         assert abs(tri.step_update(int(s_)) - ref) <= 1e-12 * max(abs(ref), 1e-12)
+
+
+def test_batch_packer_matches_reference_cython_fixture(golden_dir):
+    """esp_batch_by_size (C ABI, host code) vs the batches produced by the reference's compiled Cython packer
+    (fairseq/data/data_utils_fast.pyx) recorded in tests/golden/batching.npz; and live against oracle/_ref when the
+    compiled reference is present."""
+    from espresso_b200.data import batching as Bt
+
+    g = np.load(os.path.join(golden_dir, "batching.npz"))
+    for c in range(int(g["n_cases"])):
+        sizes, order = g["c%d_sizes" % c], g["c%d_order" % c]
+        mt, ms, mult = (int(x) for x in g["c%d_cfg" % c])
+        got = Bt.batch_by_size(order, sizes, mt or None, ms or None, mult)
+        assert np.array_equal(np.cumsum([len(b) for b in got]), g["c%d_ends" % c]), c
+        assert np.array_equal(np.concatenate(got), order)
+    assert Bt.batch_by_size(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 100, None, 1) == []
+    try:
+        Bt.batch_by_size(np.arange(3), np.array([5, 500, 7]), 100, None, 1)
+        raise RuntimeError("oversized sample must be rejected")
+    except AssertionError:
+        pass
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    import glob
+    import sys
+    if glob.glob(os.path.join(ref_dir, "data_utils_fast*.so")):
+        sys.path.insert(0, ref_dir)
+        import data_utils_fast as R
+        rs = np.random.RandomState(3)
+        for _ in range(100):
+            n = int(rs.randint(1, 200))
+            sizes = rs.randint(1, 300, size=n).astype(np.int64)
+            order = rs.permutation(n).astype(np.int64)
+            mult = int(rs.choice([1, 8]))
+            ref = R.batch_by_size_vec(order, sizes[order], 3000, 24, mult)
+            got = Bt.batch_by_size(order, sizes, 3000, 24, mult)
+            assert len(ref) == len(got) and all(np.array_equal(a, b) for a, b in zip(ref, got))
