@@ -684,7 +684,51 @@ def pin_batching():
     print("batching: 400 random cases identical to the reference's compiled Cython packer; %d cases -> tests/golden/batching.npz" % n_cases)
 
 
-SECTIONS = {"batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_collate():
+    """espresso.data.asr_dataset.collate (the reference's batch assembly) vs espresso_b200.data.collate.collate on random
+    samples with distinct source lengths (torch.sort is not stable, so ties are outside the contract)."""
+    from espresso.data.asr_dataset import collate as ref_collate
+
+    from espresso_b200.data.collate import collate as our_collate
+
+    rs = np.random.RandomState(17)
+    n_checked = 0
+    gold = {}
+    for trial in range(20):
+        B = int(rs.randint(1, 9))
+        lens = rs.choice(np.arange(5, 60), size=B, replace=False)
+        samples = []
+        for i in range(B):
+            u = int(rs.randint(1, 8))
+            tgt = torch.cat([torch.from_numpy(rs.randint(4, 50, size=u)), torch.tensor([2])]).long()
+            samples.append({"id": int(rs.randint(0, 1000)), "utt_id": "utt%d" % i, "source": torch.from_numpy(rs.randn(int(lens[i]), 80).astype(np.float32)),
+                            "target": tgt, "text": "t%d" % i})
+        for bos in (None, 0):
+            for mult in (1, 8):
+                a = ref_collate(samples, pad_idx=1, eos_idx=2, left_pad_source=False, left_pad_target=False, input_feeding=True,
+                                maybe_bos_idx=bos, pad_to_multiple=mult)
+                b = our_collate(samples, pad_idx=1, eos_idx=2, maybe_bos_idx=bos, pad_to_multiple=mult)
+                assert torch.equal(a["id"], b["id"]) and a["utt_id"] == b["utt_id"] and a["text"] == b["text"]
+                assert a["nsentences"] == b["nsentences"] and a["ntokens"] == b["ntokens"]
+                for k in ("src_tokens", "src_lengths", "prev_output_tokens"):
+                    assert torch.equal(a["net_input"][k], b["net_input"][k]), (k, trial)
+                    assert a["net_input"][k].dtype == b["net_input"][k].dtype, k
+                assert torch.equal(a["target"], b["target"])
+                n_checked += 1
+                if trial < 3 and mult == 1:  # small committed cases (feature width cut to 4 to keep the file tiny)
+                    key = "c%d_bos%d_" % (trial, -1 if bos is None else bos)
+                    gold[key + "lens"] = np.array([s_["source"].size(0) for s_ in samples])
+                    gold[key + "ids"] = np.array([s_["id"] for s_ in samples])
+                    for j, s_ in enumerate(samples):
+                        gold[key + "tgt%d" % j] = s_["target"].numpy()
+                    gold[key + "out_id"], gold[key + "out_src_lengths"] = a["id"].numpy(), a["net_input"]["src_lengths"].numpy()
+                    gold[key + "out_target"], gold[key + "out_prev"] = a["target"].numpy(), a["net_input"]["prev_output_tokens"].numpy()
+                    gold[key + "ntokens"] = np.int64(a["ntokens"])
+    np.savez_compressed(os.path.join(GOLDEN, "collate.npz"), **gold)
+    print("collate: %d batches identical to espresso.data.asr_dataset.collate -> tests/golden/collate.npz" % n_checked)
+
+
+SECTIONS = {"collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

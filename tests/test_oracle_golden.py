@@ -152,3 +152,32 @@ def test_batch_packer_matches_reference_cython_fixture(golden_dir):
             ref = R.batch_by_size_vec(order, sizes[order], 3000, 24, mult)
             got = Bt.batch_by_size(order, sizes, 3000, 24, mult)
             assert len(ref) == len(got) and all(np.array_equal(a, b) for a, b in zip(ref, got))
+
+
+def test_collate_matches_reference_fixture(golden_dir):
+    """espresso_b200.data.collate vs batches assembled by the reference's espresso.data.asr_dataset.collate
+    (tests/golden/collate.npz): ordering by length, padding, target / prev_output_tokens layout, ntokens."""
+    import torch
+
+    from espresso_b200.data.collate import collate
+
+    g = np.load(os.path.join(golden_dir, "collate.npz"))
+    keys = sorted({k[: k.index("_", k.index("bos")) + 1] for k in g.files})
+    assert keys
+    for key in keys:
+        bos = int(key.split("bos")[1].rstrip("_"))
+        lens, ids = g[key + "lens"], g[key + "ids"]
+        samples = [{"id": int(ids[j]), "utt_id": "u%d" % j, "source": torch.full((int(lens[j]), 4), float(j + 1)),
+                    "target": torch.from_numpy(g[key + "tgt%d" % j]), "text": "t%d" % j} for j in range(len(lens))]
+        b = collate(samples, pad_idx=1, eos_idx=2, maybe_bos_idx=None if bos < 0 else bos)
+        assert np.array_equal(b["id"].numpy(), g[key + "out_id"])
+        assert np.array_equal(b["net_input"]["src_lengths"].numpy(), g[key + "out_src_lengths"])
+        assert b["net_input"]["src_lengths"].dtype == torch.int32
+        assert np.array_equal(b["target"].numpy(), g[key + "out_target"])
+        assert np.array_equal(b["net_input"]["prev_output_tokens"].numpy(), g[key + "out_prev"])
+        assert b["ntokens"] == int(g[key + "ntokens"]) and b["nsentences"] == len(lens)
+        src = b["net_input"]["src_tokens"]
+        for r in range(len(lens)):  # rows carry their own sample, zero padded on the right
+            n = int(b["net_input"]["src_lengths"][r])
+            assert (src[r, :n] == src[r, 0, 0]).all() and (src[r, n:] == 0).all()
+    assert collate([], 1, 2) == {}
