@@ -728,7 +728,35 @@ def pin_collate():
     print("collate: %d batches identical to espresso.data.asr_dataset.collate -> tests/golden/collate.npz" % n_checked)
 
 
-SECTIONS = {"collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_sharding():
+    """fairseq.data.iterators.ShardedIterator (rank r takes batches r, r+W, ...; the tail is filled so every rank gets
+    the same count) vs espresso_b200.data.batching.shard_batches; AsrDataset.ordered_indices' double stable sort
+    (espresso/data/asr_dataset.py:392-408) vs batching.ordered_indices."""
+    from fairseq.data.iterators import ShardedIterator
+
+    from espresso_b200.data import batching as Bt
+
+    rs = np.random.RandomState(5)
+    for n in (0, 1, 7, 8, 9, 31):
+        batches = [rs.randint(0, 100, size=rs.randint(1, 5)).tolist() for _ in range(n)]
+        for W in (1, 2, 4, 8):
+            for r in range(W):
+                ref = list(ShardedIterator(batches, W, r, fill_value=[]))
+                ours = Bt.shard_batches(batches, W, r, fill_value=[])
+                assert ref == ours, (n, W, r)
+    for _ in range(20):
+        n = int(rs.randint(1, 200))
+        src, tgt = rs.randint(1, 50, size=n), rs.randint(1, 10, size=n)
+        seed = int(rs.randint(0, 10000))
+        np.random.seed(seed)
+        idx = np.random.permutation(n)
+        idx = idx[np.argsort(tgt[idx], kind="mergesort")]
+        ref = idx[np.argsort(src[idx], kind="mergesort")]           # asr_dataset.py:392-408 with shuffle=True
+        assert np.array_equal(ref, Bt.ordered_indices(src, tgt, shuffle_seed=seed))
+    print("sharding: ShardedIterator and ordered_indices semantics reproduced")
+
+
+SECTIONS = {"sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 
