@@ -756,7 +756,39 @@ def pin_sharding():
     print("sharding: ShardedIterator and ordered_indices semantics reproduced")
 
 
-SECTIONS = {"sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_dictionary():
+    """espresso.data.asr_dictionary.AsrDictionary (load with / without <s>, index order, counts, string(), encode_line)
+    vs espresso_b200.data.asr_dictionary.AsrDictionary on a temporary vocabulary file."""
+    import tempfile
+
+    from espresso.data.asr_dictionary import AsrDictionary as Ref
+
+    from espresso_b200.data.asr_dictionary import AsrDictionary as Ours
+
+    words = ["\u2581the", "\u2581a", "s", "ing", "<space>", "\u2581speech", "@@x", "q|", "'"]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "dict.txt")
+        with open(path, "w", encoding="utf-8") as f:
+            for i, w in enumerate(words):
+                f.write("%s %d\n" % (w, 100 - 7 * i))
+        for enable_bos in (False, True):
+            a, b = Ref.load(path, enable_bos=enable_bos), Ours.load(path, enable_bos=enable_bos)
+            assert len(a) == len(b) and a.symbols == b.symbols and a.count == b.count and a.indices == b.indices
+            assert (a.pad(), a.eos(), a.unk(), a.space(), a.nspecial) == (b.pad(), b.eos(), b.unk(), b.space(), b.nspecial)
+            if enable_bos:
+                assert a.bos() == b.bos() == 0
+            ids = torch.tensor([a.index(w) for w in ["\u2581the", "s", "zzz", "\u2581speech", "ing"]] + [a.eos()])
+            for kw in (dict(), dict(bpe_symbol="sentencepiece"), dict(escape_unk=True), dict(include_eos=True),
+                       dict(extra_symbols_to_ignore={a.pad()}), dict(bpe_symbol="@@ ")):
+                assert a.string(ids, **kw) == b.string(ids, **kw), kw
+            assert a.string(torch.stack([ids, ids])) == b.string(torch.stack([ids, ids]))
+            line = "\u2581the s zzz ing"
+            assert a.encode_line(line, add_if_not_exist=False).tolist() == b.encode_line(line, add_if_not_exist=False).tolist()
+            assert a.encode_line(line, add_if_not_exist=False, append_eos=False).tolist() == b.encode_line(line, append_eos=False).tolist()
+    print("dictionary: AsrDictionary layout, string() and encode_line identical to the reference")
+
+
+SECTIONS = {"dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

@@ -181,3 +181,30 @@ def test_collate_matches_reference_fixture(golden_dir):
             n = int(b["net_input"]["src_lengths"][r])
             assert (src[r, :n] == src[r, 0, 0]).all() and (src[r, n:] == 0).all()
     assert collate([], 1, 2) == {}
+
+
+def test_asr_dictionary_layout(tmp_path):
+    """Index order and text round trip of the dictionary mirror (pinned against the reference class by
+    oracle/pin_against_reference.py::pin_dictionary): specials first ([<s>] <pad> </s> <unk>), file order after."""
+    import torch
+
+    from espresso_b200.data.asr_dictionary import AsrDictionary
+
+    p = tmp_path / "dict.txt"
+    p.write_text("▁the 50\n▁a 40\ns 30\n<space> 3\n", encoding="utf-8")
+    d = AsrDictionary.load(str(p))
+    assert (d.pad(), d.eos(), d.unk(), len(d), d.nspecial, d.space()) == (0, 1, 2, 7, 3, 6)
+    db = AsrDictionary.load(str(p), enable_bos=True)
+    assert (db.bos(), db.pad(), db.eos(), db.unk(), len(db)) == (0, 1, 2, 3, 8) and db.index("s") == 6 and db.index("nope") == 3
+    ids = db.encode_line("▁the s zz ▁a")
+    assert ids.tolist() == [4, 6, 3, 5, 2]
+    assert db.string(ids) == "▁the s <unk> ▁a" and db.string(ids, bpe_symbol="sentencepiece") == "thes<unk> a"
+    assert db.count[4] == 50 and db.count[:4] == [1, 0, 0, 0]
+    try:
+        d.bos()
+        raise RuntimeError("bos must not exist without enable_bos")
+    except NotImplementedError:
+        pass
+    out = tmp_path / "saved.txt"
+    db.save(str(out))
+    assert AsrDictionary.load(str(out), enable_bos=True).symbols == db.symbols
