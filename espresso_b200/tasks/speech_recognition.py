@@ -1,0 +1,174 @@
+"""`speech_recognition_espresso` task: the object the reference hands to models, criterions and generators
+(espresso/tasks/speech_recognition.py:272-687).  Host logic only: dictionary set-up (the optional <s> symbol doubles as
+the CTC / transducer blank, :324-357), `feat_dim` / `feat_in_channels`, model / criterion construction through the
+registries, the generator choice per criterion (:526-596) and validation with word / character error counts
+(:598-607, 662-687; error counting restates espresso/tools/wer.py + espresso/tools/utils.py:265-330 as a plain
+Levenshtein distance).  Data loading from Kaldi/JSON manifests is out of scope: the task is built from a
+dictionary and a feature dimension, batches come from espresso_b200.data.collate."""
+from dataclasses import dataclass
+from typing import Optional
+
+from ..data.asr_dictionary import AsrDictionary
+from ..registry import CRITERION_REGISTRY, MODEL_REGISTRY, register_task
+
+
+@dataclass
+class SpeechRecognitionEspressoConfig:
+    criterion_name: str = "label_smoothed_cross_entropy_v2"  # | "ctc_loss" | "transducer_loss"
+    dict: Optional[str] = None
+    non_lang_syms: Optional[str] = None
+    feat_in_channels: int = 1
+    max_source_positions: int = 3600
+    max_target_positions: int = 1024
+    include_eos_in_transducer_loss: bool = False
+    max_num_expansions_per_step: int = 2
+    bpe: Optional[str] = None  # how token sequences become words for WER: None (tokens are words) | "sentencepiece" | ...
+    seed: int = 1
+
+
+def edit_counts(ref, hyp):
+    """(errors, len(ref)) with errors = substitutions + insertions + deletions of the best alignment."""
+    prev = list(range(len(hyp) + 1))
+    for i in range(1, len(ref) + 1):
+        cur = [i] + [0] * len(hyp)
+        for j in range(1, len(hyp) + 1):
+            cur[j] = prev[j - 1] if ref[i - 1] == hyp[j - 1] else 1 + min(prev[j - 1], cur[j - 1], prev[j])
+        prev = cur
+    return prev[len(hyp)], len(ref)
+
+
+@register_task("speech_recognition_espresso", dataclass=SpeechRecognitionEspressoConfig)
+class SpeechRecognitionEspressoTask:
+    def __init__(self, cfg, tgt_dict, feat_dim, word_dict=None):
+        self.cfg = cfg
+        self.tgt_dict, self.word_dict = tgt_dict, word_dict
+        self.feat_dim = feat_dim
+        self.feat_in_channels = cfg.feat_in_channels
+        self.extra_symbols_to_ignore = {tgt_dict.pad()}  # for validation with WER
+        self.blank_symbol = None
+        if cfg.criterion_name in ("transducer_loss", "ctc_loss"):
+            self.blank_symbol = tgt_dict[tgt_dict.bos()]  # the bos symbol is reserved for blank
+            self.extra_symbols_to_ignore.add(tgt_dict.bos())
+        self.decoder_for_validation = None
+
+    @classmethod
+    def load_dictionary(cls, filename, enable_bos=False, non_lang_syms=None):
+        return AsrDictionary.load(filename, enable_bos=enable_bos, f_non_lang_syms=non_lang_syms)
+
+    @classmethod
+    def setup_task(cls, cfg, feat_dim=80, **unused):
+        enable_blank = cfg.criterion_name in ("transducer_loss", "ctc_loss")
+        tgt_dict = cls.load_dictionary(cfg.dict, enable_bos=enable_blank, non_lang_syms=cfg.non_lang_syms)
+        return cls(cfg, tgt_dict, feat_dim)
+
+    @property
+    def target_dictionary(self):
+        return self.tgt_dict
+
+    @property
+    def word_dictionary(self):
+        return self.word_dict
+
+    def max_positions(self):
+        return (self.cfg.max_source_positions, self.cfg.max_target_positions)
+
+    # ---- construction through the registries ----------------------------------------------------------------
+    def build_model(self, model_cfg, arch="speech_transformer_encoder_model", **kw):
+        from .. import models  # noqa: F401  (importing the package registers its architectures)
+
+        return MODEL_REGISTRY[arch].build_model(model_cfg, self, **kw)
+
+    def build_criterion(self, **kw):
+        from .. import criterions  # noqa: F401  (registers ctc_loss / label_smoothed_cross_entropy_v2 / transducer_loss)
+
+        return CRITERION_REGISTRY[self.cfg.criterion_name](self, **kw)
+
+    def build_generator(self, models, args=None, seq_gen_cls=None, extra_gen_cls_kwargs=None):
+        """The decoder the reference picks per criterion (speech_recognition.py:526-596); `args` is any object with the
+        generation attributes (beam, max_len_a, max_len_b, min_len, unnormalized, lenpen, unkpen, temperature,
+        lm_weight, eos_factor, print_alignment, transducer_max_num_expansions_per_step)."""
+        g = lambda k, d=None: getattr(args, k, d) if args is not None else d  # noqa: E731
+        extra = dict(extra_gen_cls_kwargs or {})
+        if g("print_alignment", False):
+            extra["print_alignment"] = True
+        if self.cfg.criterion_name == "transducer_loss":
+            from ..tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+            if seq_gen_cls is None:
+                if g("beam", 1) != 1:
+                    raise NotImplementedError("transducer beam search is not on the B200 path yet (greedy: --beam 1)")
+                seq_gen_cls = TransducerGreedyDecoder
+            return seq_gen_cls(
+                models, self.target_dictionary, temperature=g("temperature", 1.0),
+                max_num_expansions_per_step=g("transducer_max_num_expansions_per_step", 20),
+                bos=self.target_dictionary.bos() if self.cfg.include_eos_in_transducer_loss else self.target_dictionary.eos(),
+                blank=self.target_dictionary.index(self.blank_symbol),
+                model_predicts_eos=self.cfg.include_eos_in_transducer_loss, **extra)
+        if self.cfg.criterion_name == "ctc_loss":
+            from ..tools.ctc_decoder import CTCDecoder
+
+            return (seq_gen_cls or CTCDecoder)(self.target_dictionary, blank_idx=self.target_dictionary.index(self.blank_symbol), **extra)
+        from ..sequence_generator import SequenceGenerator
+
+        return (seq_gen_cls or SequenceGenerator)(
+            models, self.target_dictionary, beam_size=g("beam", 5), max_len_a=g("max_len_a", 0), max_len_b=g("max_len_b", 200),
+            min_len=g("min_len", 1), normalize_scores=not g("unnormalized", False), len_penalty=g("lenpen", 1.0),
+            unk_penalty=g("unkpen", 0.0), temperature=g("temperature", 1.0), lm_model=extra.pop("lm_model", None),
+            lm_weight=g("lm_weight", 0.0) or 1.0, eos_factor=g("eos_factor", None), **extra)
+
+    def build_decoder_for_validation(self, model):
+        """Greedy decoders used for validation WER (speech_recognition.py:451-489)."""
+        if self.cfg.criterion_name == "transducer_loss":
+            from ..tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+            self.decoder_for_validation = TransducerGreedyDecoder(
+                [model], self.target_dictionary, max_num_expansions_per_step=self.cfg.max_num_expansions_per_step,
+                bos=self.target_dictionary.bos() if self.cfg.include_eos_in_transducer_loss else self.target_dictionary.eos(),
+                blank=self.target_dictionary.index(self.blank_symbol), model_predicts_eos=self.cfg.include_eos_in_transducer_loss)
+        elif self.cfg.criterion_name == "ctc_loss":
+            from ..tools.ctc_decoder import CTCDecoder
+
+            self.decoder_for_validation = CTCDecoder(self.target_dictionary, blank_idx=self.target_dictionary.index(self.blank_symbol))
+        else:
+            from ..tools.simple_greedy_decoder import SimpleGreedyDecoder
+
+            self.decoder_for_validation = SimpleGreedyDecoder([model], self.target_dictionary, for_validation=True)
+        return self.decoder_for_validation
+
+    # ---- steps ---------------------------------------------------------------------------------------------------
+    def train_step(self, sample, trainer):
+        """One update through espresso_b200.trainer.Trainer (fairseq/tasks/fairseq_task.py:490-522 + trainer.py:780-1097)."""
+        return trainer.train_step([sample])
+
+    def valid_step(self, sample, model, criterion):
+        import torch
+
+        model.eval()
+        with torch.no_grad():
+            loss, sample_size, logging_output = criterion(model, sample)
+        if self.decoder_for_validation is not None:
+            we, wc, ce, cc = self._inference_with_wer(self.decoder_for_validation, sample, model)
+            logging_output.update(word_error=we, word_count=wc, char_error=ce, char_count=cc)
+        return loss, sample_size, logging_output
+
+    def _inference_with_wer(self, decoder, sample, model):
+        tokens, _, _ = decoder.decode([model], sample)
+        pred = tokens.cpu()
+        target = sample["target"]
+        assert pred.size(0) == target.size(0)
+        d = self.target_dictionary
+        ignore = set(self.extra_symbols_to_ignore)
+        we = wc = ce = cc = 0
+        for i in range(target.size(0)):
+            if sample.get("text") is not None:
+                ref_tokens = sample["text"][i]
+            else:
+                ref_tokens = d.string(target[i].cpu(), extra_symbols_to_ignore=ignore)
+            hyp_tokens = d.string(pred[i], extra_symbols_to_ignore=ignore)
+            ref_words = d.string(d.encode_line(ref_tokens, append_eos=False), bpe_symbol=self.cfg.bpe).split()
+            hyp_words = d.string(d.encode_line(hyp_tokens, append_eos=False), bpe_symbol=self.cfg.bpe).split()
+            e, n = edit_counts(ref_words, hyp_words)
+            we, wc = we + e, wc + n
+            e, n = edit_counts(list(" ".join(ref_words)), list(" ".join(hyp_words)))
+            ce, cc = ce + e, cc + n
+        return we, wc, ce, cc

@@ -377,3 +377,56 @@ def test_transducer_greedy_decoder_matches_reference_tokens(variant, kw, golden_
     for b in range(tokens.size(0)):
         ref = [t for t in gg["tokens_" + variant][b].tolist() if t not in (0, 2)]
         assert hyp[b][0]["tokens"].tolist() == ref
+
+
+def test_task_mirror_builds_models_criterions_and_decoders(tmp_path, golden_dir, cpu_ops):
+    """SpeechRecognitionEspressoTask: dictionary with <s> as blank for CTC / transducer, model + criterion construction
+    through the registries, decoder choice per criterion (speech_recognition.py:526-596) and a validation step with
+    error counts."""
+    from espresso_b200.models import SpeechTransformerConfig
+    from espresso_b200.sequence_generator import SequenceGenerator
+    from espresso_b200.tasks import SpeechRecognitionEspressoConfig, SpeechRecognitionEspressoTask
+    from espresso_b200.tasks.speech_recognition import edit_counts
+    from espresso_b200.tools.ctc_decoder import CTCDecoder
+    from espresso_b200.tools.simple_greedy_decoder import SimpleGreedyDecoder
+    from espresso_b200.tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+    assert edit_counts("a b c d".split(), "a x c".split()) == (2, 4)
+    dpath = tmp_path / "dict.txt"
+    dpath.write_text("".join("w%d %d\n" % (i, 100 - i) for i in range(46)), encoding="utf-8")
+    g = np.load(os.path.join(golden_dir, "encoder_conformer.npz"))
+    # ---- CTC
+    task = SpeechRecognitionEspressoTask.setup_task(SpeechRecognitionEspressoConfig(criterion_name="ctc_loss", dict=str(dpath)))
+    d = task.target_dictionary
+    assert len(d) == 50 and d.bos() == 0 and task.blank_symbol == "<s>" and task.feat_dim == 80
+    cfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, max_source_positions=3600,
+        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=2, attention_heads=4, normalize_before=True,
+                     relative_positional_embeddings=True, layer_type="conformer", depthwise_conv_kernel_size=31)))
+    m = task.build_model(cfg)
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    m.finalize_(torch.device("cpu"))
+    crit = task.build_criterion()
+    assert isinstance(task.build_generator([m]), CTCDecoder)
+    assert isinstance(task.build_decoder_for_validation(m), CTCDecoder)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"])},
+              "target": torch.from_numpy(g["target"]), "ntokens": 13, "utt_id": ["a", "b", "c"], "text": None}
+    loss, sample_size, log = task.valid_step(sample, m, crit)
+    assert abs(loss.item() - float(g["loss_eval"])) < 0.03 * float(g["loss_eval"])
+    assert log["word_count"] == 13 and 0 <= log["word_error"] and log["char_count"] > 13
+    # ---- attention model / transducer: the decoder classes the reference would pick
+    t2 = SpeechRecognitionEspressoTask.setup_task(SpeechRecognitionEspressoConfig(dict=str(dpath)))
+    assert len(t2.target_dictionary) == 49 and t2.blank_symbol is None
+    class _M:
+        def max_decoder_positions(self):
+            return 100
+    gen = t2.build_generator([_M()], type("A", (), dict(beam=7, lm_weight=0.0, eos_factor=1.5, lenpen=0.8))())
+    assert isinstance(gen, SequenceGenerator) and gen.beam_size == 7 and gen.eos_factor == 1.5 and gen.len_penalty == 0.8
+    assert isinstance(t2.build_decoder_for_validation(_M()), SimpleGreedyDecoder)
+    t3 = SpeechRecognitionEspressoTask.setup_task(SpeechRecognitionEspressoConfig(criterion_name="transducer_loss", dict=str(dpath)))
+    class _TM:
+        def eval(self):
+            return self
+    dec = t3.build_generator([_TM()], type("A", (), dict(beam=1, transducer_max_num_expansions_per_step=3))())
+    assert isinstance(dec, TransducerGreedyDecoder) and dec.blank == 0 and dec.bos == t3.target_dictionary.eos()
+    assert dec.max_num_expansions_per_step == 3
