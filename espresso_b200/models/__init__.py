@@ -7,3 +7,4 @@ from .transformer import (  # noqa: F401
     SpeechTransformerModelBase,
     SpeechTransformerTransducerModelBase,
 )
+from .speech_lstm import SpeechLSTMModel, SpeechLSTMModelConfig  # noqa: F401,E402

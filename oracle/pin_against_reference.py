@@ -788,7 +788,79 @@ def pin_dictionary():
     print("dictionary: AsrDictionary layout, string() and encode_line identical to the reference")
 
 
-SECTIONS = {"dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_speech_lstm():
+    """The reference `speech_lstm` model (espresso/models/speech_lstm.py; BASELINE configs[0] family: conv front, BiLSTM
+    encoder, attention LSTM decoder with input feeding and residuals) + label_smoothed_nll_loss: teacher-forced logits,
+    loss and every parameter gradient -> tests/golden/speech_lstm.npz for espresso_b200.models.SpeechLSTMModel."""
+    from argparse import Namespace
+
+    from espresso.criterions.label_smoothed_cross_entropy_v2 import label_smoothed_nll_loss
+    from espresso.models.speech_lstm import SpeechLSTMModel
+
+    V, pad_idx, eos_idx = 50, 1, 2
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return pad_idx
+
+        def eos(self):
+            return eos_idx
+
+    class _Task:
+        feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+        cfg = Namespace(num_batch_buckets=0)
+
+    args = Namespace(
+        dropout=0.0, encoder_conv_channels="[64, 64, 128, 128]", encoder_conv_kernel_sizes="[(3, 3), (3, 3), (3, 3), (3, 3)]",
+        encoder_conv_strides="[(1, 1), (2, 2), (1, 1), (2, 2)]", encoder_rnn_hidden_size=32, encoder_rnn_layers=2,
+        encoder_rnn_bidirectional=True, encoder_rnn_residual=True, encoder_multilayer_rnn_as_single_module=False,
+        decoder_embed_path=None, decoder_embed_dim=24, decoder_freeze_embed=False, decoder_hidden_size=32, decoder_layers=2,
+        decoder_out_embed_dim=40, decoder_rnn_residual=True, attention_type="bahdanau", attention_dim=16, need_attention=False,
+        adaptive_softmax_cutoff=None, share_decoder_input_output_embed=False, pretrained_lm_checkpoint=None,
+        encoder_rnn_dropout_in=0.0, encoder_rnn_dropout_out=0.0, decoder_dropout_in=0.0, decoder_dropout_out=0.0,
+        scheduled_sampling_probs=[1.0], start_scheduled_sampling_epoch=1, criterion_name="label_smoothed_cross_entropy_v2",
+        max_source_positions=3600, max_target_positions=200)
+    torch.manual_seed(11)
+    m = SpeechLSTMModel.build_model(args, _Task())
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    rs = np.random.RandomState(19)
+    B, T = 3, 61
+    lens = torch.tensor([61, 50, 37])
+    feats = torch.from_numpy(rs.randn(B, T, 80).astype(np.float32))
+    for b in range(B):
+        feats[b, lens[b]:] = 0.0
+    U = 6
+    tgt = torch.full((B, U + 1), pad_idx, dtype=torch.long)
+    prev = torch.full((B, U + 1), pad_idx, dtype=torch.long)
+    for b, u in enumerate((6, 4, 2)):
+        toks = torch.from_numpy(rs.randint(4, V, size=u))
+        tgt[b, :u], tgt[b, u] = toks, eos_idx
+        prev[b, 0], prev[b, 1:u + 1] = eos_idx, toks
+    out = {"sd." + k: v.clone().numpy() for k, v in m.state_dict().items()}
+    m.train()
+    m.zero_grad()
+    logits, _ = m(feats, lens, prev)
+    lp = torch.log_softmax(logits.float(), dim=-1)
+    loss, nll = label_smoothed_nll_loss(lp.view(-1, V), tgt.view(-1, 1), 0.1, ignore_index=pad_idx, reduce=True)
+    loss.backward()
+    out.update({"grad." + n: p_.grad.numpy() for n, p_ in m.named_parameters()})
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            out["after." + k] = v.numpy()
+    out.update(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), prev_output_tokens=prev.numpy(),
+               logits=logits.detach().numpy(), loss=np.float64(loss.item()), nll=np.float64(nll.item()))
+    np.savez_compressed(os.path.join(GOLDEN, "speech_lstm.npz"), **out)
+    print("speech_lstm: loss %.6f, %d parameters -> tests/golden/speech_lstm.npz" % (loss.item(), sum(p_.numel() for p_ in m.parameters())))
+
+
+SECTIONS = {"speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

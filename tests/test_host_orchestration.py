@@ -430,3 +430,59 @@ def test_task_mirror_builds_models_criterions_and_decoders(tmp_path, golden_dir,
     dec = t3.build_generator([_TM()], type("A", (), dict(beam=1, transducer_max_num_expansions_per_step=3))())
     assert isinstance(dec, TransducerGreedyDecoder) and dec.blank == 0 and dec.bos == t3.target_dictionary.eos()
     assert dec.max_num_expansions_per_step == 3
+
+
+# ---------------------------------------------------------------------------------------------------
+# speech_lstm (BASELINE configs[0] family) vs the reference fixture
+# ---------------------------------------------------------------------------------------------------
+def _build_speech_lstm(g):
+    from espresso_b200.models import SpeechLSTMModel, SpeechLSTMModelConfig
+
+    cfg = SpeechLSTMModelConfig(dropout=0.0, encoder_rnn_hidden_size=32, encoder_rnn_layers=2, encoder_rnn_bidirectional=True,
+                                encoder_rnn_residual=True, decoder_embed_dim=24, decoder_hidden_size=32, decoder_layers=2,
+                                decoder_out_embed_dim=40, decoder_rnn_residual=True, attention_dim=16, max_source_positions=3600,
+                                max_target_positions=200)
+    m = SpeechLSTMModel.build_model(cfg, _Task(50))
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    return m
+
+
+def test_speech_lstm_keys_forward_backward_vs_reference_fixture(golden_dir, cpu_ops):
+    from espresso_b200.criterions import LabelSmoothedCrossEntropyV2Criterion
+
+    g = np.load(os.path.join(golden_dir, "speech_lstm.npz"))
+    m = _build_speech_lstm(g)
+    assert sorted(m.state_dict().keys()) == sorted(k[3:] for k in g.files if k.startswith("sd."))
+    m.finalize_(torch.device("cpu"))
+    crit = LabelSmoothedCrossEntropyV2Criterion(_Task(50), label_smoothing=0.1)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"]),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"])},
+              "target": torch.from_numpy(g["target"])}
+    m.train()
+    m.flat.zero_grad()
+    loss, sample_size, log = crit(m, sample)
+    assert abs(loss.item() - float(g["loss"])) < 0.03 * float(g["loss"])
+    assert abs(float(log["nll_loss"]) - float(g["nll"])) < 0.03 * float(g["nll"])
+    loss.backward()
+    m.sync_torch_grads_()
+    worst = []
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[len("grad."):]
+        if "pre_encoder.convolutions" in name and name.endswith(".bias"):
+            continue  # bias in front of a batch-statistics BatchNorm: analytically zero
+        refg = g[k]
+        worst.append((np.linalg.norm(m.flat.grad(name).numpy() - refg) / max(np.linalg.norm(refg), 1e-3), name))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 0.25, worst[:5]
+    assert np.median([w[0] for w in worst]) < 0.05, worst[:5]
+    m.eval()
+    with torch.no_grad():
+        logits, _ = m(**sample["net_input"])
+    m.train()
+    with torch.no_grad():
+        logits_t, _ = m(**sample["net_input"])
+    ref = g["logits"]
+    assert logits_t.shape == ref.shape
+    assert np.abs(logits_t.float().numpy() - ref).max() < 0.06 * np.abs(ref).max()
