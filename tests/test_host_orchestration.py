@@ -486,3 +486,27 @@ def test_speech_lstm_keys_forward_backward_vs_reference_fixture(golden_dir, cpu_
     ref = g["logits"]
     assert logits_t.shape == ref.shape
     assert np.abs(logits_t.float().numpy() - ref).max() < 0.06 * np.abs(ref).max()
+
+
+def test_speech_lstm_trains_through_the_flat_buffer_trainer(golden_dir, cpu_ops):
+    """speech_lstm + LS-CE through espresso_b200.trainer.Trainer: flat gradients, clipping, fused Adam update the
+    cuDNN-executed LSTM weights too (they are views of the flat bf16 buffer); the loss goes down on a repeated batch."""
+    from espresso_b200.criterions import LabelSmoothedCrossEntropyV2Criterion
+    from espresso_b200.optim import NoamLRScheduler
+    from espresso_b200.trainer import Trainer
+
+    g = np.load(os.path.join(golden_dir, "speech_lstm.npz"))
+    m = _build_speech_lstm(g).finalize_(torch.device("cpu"))
+    crit = LabelSmoothedCrossEntropyV2Criterion(_Task(50), label_smoothing=0.1)
+    tr = Trainer(m, crit, NoamLRScheduler(0.05, 4, 32, 1e-6), clip_norm=2.0)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"]),
+                            "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"])},
+              "target": torch.from_numpy(g["target"]), "ntokens": 15}
+    w0 = m.encoder.lstm[0].weight_ih_l0.detach().float().clone()
+    losses = []
+    for _ in range(6):
+        tail = tr.train_step([sample])
+        losses.append(float(tail[3]))
+    assert np.isfinite(losses).all() and min(losses[-2:]) < 0.9 * losses[0], losses
+    assert (m.encoder.lstm[0].weight_ih_l0.detach().float() - w0).abs().max() > 0
+    assert m.encoder.lstm[0].weight_ih_l0.data_ptr() == m.flat.param("encoder.lstm.0.weight_ih_l0").data_ptr()
