@@ -35,8 +35,7 @@ class SequenceGenerator:
                  normalize_scores=True, len_penalty=1.0, unk_penalty=0.0, temperature=1.0, lm_model=None, lm_weight=1.0,
                  eos_factor=None, eos=None, **unused):
         self.models = models if isinstance(models, (list, tuple)) else [models]
-        if len(self.models) != 1:
-            raise NotImplementedError("ensembles are not on the B200 path yet")
+        assert len(self.models) >= 1
         self.tgt_dict = tgt_dict
         self.pad, self.unk = tgt_dict.pad(), tgt_dict.unk()
         self.eos = tgt_dict.eos() if eos is None else eos
@@ -74,13 +73,18 @@ class SequenceGenerator:
         assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"
         N, L = bsz * beam, max_len + 2
 
-        for m_ in (model, self.lm_model):
+        for m_ in tuple(self.models) + (self.lm_model,):
             if m_ is not None and hasattr(m_, "t_max_hint"):
                 m_.t_max_hint = max_len + 1
-        enc = model.forward_encoder(net_input)
-        state = model.init_incremental_state(enc, bsz, beam)
+        # an ensemble = one encoder pass and one incremental state per model; their step log-probs are averaged in the
+        # probability domain (EnsembleModel.forward_decoder, fairseq/sequence_generator.py:836-901)
+        states = []
+        for m_ in self.models:
+            enc = m_.forward_encoder(net_input)
+            states.append(m_.init_incremental_state(enc, bsz, beam))
+        state = states[0]
         lm_state = self.lm_model.init_incremental_state(None, bsz, beam) if self.lm_model is not None else None
-        for s_ in (state, lm_state):  # models may size their caches from this
+        for s_ in states + [lm_state]:  # models may size their caches from this
             if isinstance(s_, dict):
                 s_["max_len"] = max_len
 
@@ -105,12 +109,21 @@ class SequenceGenerator:
         new_order = None
         for step in range(max_len + 1):  # one extra step for the eos marker
             values, is_logits = model.decode_step(step, st.tokens, state, new_order)
+            if len(self.models) > 1:
+                lps = []
+                for m_, s_ in zip(self.models, states):
+                    v_, il_ = (values, is_logits) if m_ is model else m_.decode_step(step, st.tokens, s_, new_order)
+                    v_ = v_[:, :V].float()
+                    lps.append(torch.log_softmax(v_ / self.temperature, dim=-1) if il_ else v_)
+                values = torch.logsumexp(torch.stack(lps, dim=0), dim=0) - math.log(len(self.models))
+                is_logits = False  # temperature already applied per model (sequence_generator.py:866-870)
             lm_vals, lm_logits = (None, True)
             if self.lm_model is not None:
                 lm_vals, lm_logits = self.lm_model.decode_step(step, st.tokens, lm_state, new_order)
             if step > 0:
                 prev.copy_(st.scores[:, step - 1])
-            _ops.beam_merge(values, V, is_logits, cand, prev_scores=prev if step > 0 else None, temperature=self.temperature,
+            _ops.beam_merge(values, V, is_logits, cand, prev_scores=prev if step > 0 else None,
+                            temperature=self.temperature if (is_logits or len(self.models) == 1) else 1.0,
                             lm=lm_vals, lm_is_logits=lm_logits, lm_weight=self.lm_weight, pad=self.pad, unk=self.unk,
                             unk_penalty=self.unk_penalty, eos=self.eos, force_eos=step >= max_len,
                             eos_factor=self.eos_factor, ban_eos=step < self.min_len)

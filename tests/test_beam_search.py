@@ -224,3 +224,32 @@ def test_product_generator_matches_reference_generator(golden_dir, cpu_ops):
             for h, (toks, score) in zip(hs, rs):
                 assert h["tokens"].tolist() == toks, (c, toks, h["tokens"].tolist())
                 assert abs(float(h["score"]) - score) < 1e-4
+
+
+def test_ensemble_averages_probabilities_like_the_reference(cpu_ops):
+    """Two models: per-step log-probs are averaged in the probability domain (logsumexp - log N,
+    fairseq/sequence_generator.py:895-897) before LM fusion and the search; checked against the oracle driven with the
+    averaged tables."""
+    from espresso_b200.sequence_generator import SequenceGenerator
+
+    Vn, bsz, beam = 17, 3, 4
+
+    class D(_Dict):
+        def __len__(self):
+            return Vn
+
+    m1, m2, lm = _RandomModel(Vn, 21), _RandomModel(Vn, 22), _RandomModel(Vn, 23)
+    kw = dict(beam_size=beam, max_len_a=0.0, max_len_b=10, min_len=2, unk_penalty=0.2, eos_factor=1.5)
+    gen = SequenceGenerator([m1, m2], D(), lm_model=lm, lm_weight=0.4, **kw)
+    sample = {"net_input": {"src_tokens": torch.zeros(bsz, 7, dtype=torch.long), "src_lengths": torch.full((bsz,), 7)}}
+    got = gen.generate([m1, m2], sample)
+
+    def fn(step, tokens, ro):
+        avg = torch.logsumexp(torch.stack([m1.lprobs(step, tokens), m2.lprobs(step, tokens)]), dim=0) - math.log(2)
+        return avg + 0.4 * lm.lprobs(step, tokens)
+
+    ref = OB.generate(fn, bsz, 7, Vn, PAD, UNK, EOS, model_max_len=m1.max_pos, **kw)
+    for hs, rs in zip(got, ref):
+        assert len(hs) == len(rs)
+        for h, r in zip(hs, rs):
+            assert h["tokens"].tolist() == r["tokens"].tolist() and abs(float(h["score"]) - float(r["score"])) < 1e-4
