@@ -8,3 +8,4 @@ from .transformer import (  # noqa: F401
     SpeechTransformerTransducerModelBase,
 )
 from .speech_lstm import SpeechLSTMModel, SpeechLSTMModelConfig  # noqa: F401,E402
+from .lstm_lm import LSTMLanguageModelEspresso, LSTMLanguageModelEspressoConfig  # noqa: F401,E402

@@ -140,7 +140,8 @@ class SpeechLSTMDecoder(nn.Module):
         self.layers = nn.ModuleList([
             _uniform_(nn.LSTMCell(encoder_output_units + (embed_dim if i == 0 else hidden_size), hidden_size))
             for i in range(num_layers)])
-        self.attention = _BahdanauAttention(hidden_size, encoder_output_units, attn_dim)
+        # encoder_output_units == 0: no attention / input feeding (the language-model case, espresso/models/lstm_lm.py)
+        self.attention = _BahdanauAttention(hidden_size, encoder_output_units, attn_dim) if encoder_output_units > 0 else None
         if hidden_size + encoder_output_units != out_embed_dim:
             self.additional_fc = _uniform_(nn.Linear(hidden_size + encoder_output_units, out_embed_dim))
         if not share_input_output_embed:
@@ -149,36 +150,46 @@ class SpeechLSTMDecoder(nn.Module):
     def max_positions(self):
         return self.max_target_positions
 
-    def forward(self, prev_output_tokens, encoder_out):
-        enc = encoder_out["encoder_out"][0]                                         # T x B x C
-        mask = encoder_out["encoder_padding_mask"][0] if encoder_out["encoder_padding_mask"] else None
-        keys = self.attention.keys(enc)
-        B, U = prev_output_tokens.shape
-        x = F.dropout(self.embed_tokens(prev_output_tokens), self.dropout_in, self.training).transpose(0, 1)
-        hs = [x.new_zeros(B, self.hidden_size) for _ in self.layers]
-        cs = [x.new_zeros(B, self.hidden_size) for _ in self.layers]
-        feed = x.new_zeros(B, self.encoder_output_units)
-        outs = []
-        for j in range(U):
-            inp = torch.cat((x[j], feed), dim=1)  # input feeding: previous step's context
-            context = feed
-            for i, cell in enumerate(self.layers):
-                h, c = cell(inp, (hs[i], cs[i]))
-                below = inp[:, : self.hidden_size] if (self.residual and i > 0) else None
-                if i == 0:
-                    context, _ = self.attention(h, enc, keys, mask)
-                inp = F.dropout(torch.cat((h, context), dim=1), self.dropout_out, self.training)
-                if below is not None:
-                    inp = torch.cat((inp[:, : self.hidden_size] + below, inp[:, self.hidden_size:]), dim=1)
-                hs[i], cs[i] = h, c
-            feed = context
-            outs.append(inp)
-        y = torch.stack(outs, dim=1)                                                 # B x U x (H + C)
+    def step(self, x_j, hs, cs, feed, enc=None, keys=None, mask=None):
+        """One time step of the LSTMCell stack.  Returns (features of the top layer [B, H + C], hs, cs, feed)."""
+        attend = self.attention is not None
+        inp = torch.cat((x_j, feed), dim=1) if attend else x_j  # input feeding: previous step's context
+        context = feed
+        hs, cs = list(hs), list(cs)
+        for i, cell in enumerate(self.layers):
+            h, c = cell(inp, (hs[i], cs[i]))
+            below = inp[:, : self.hidden_size] if (self.residual and i > 0) else None
+            if attend and i == 0:  # attention is driven by the FIRST layer's hidden state
+                context, _ = self.attention(h, enc, keys, mask)
+            inp = F.dropout(torch.cat((h, context), dim=1) if attend else h, self.dropout_out, self.training)
+            if below is not None:
+                inp = torch.cat((inp[:, : self.hidden_size] + below, inp[:, self.hidden_size:]), dim=1) if attend else inp + below
+            hs[i], cs[i] = h, c
+        return inp, hs, cs, context
+
+    def output_layer(self, y):
         if hasattr(self, "additional_fc"):
             y = F.dropout(self.additional_fc(y), self.dropout_out, self.training)
         if self.share_input_output_embed:
             return F.linear(y, self.embed_tokens.weight)
         return self.fc_out(y)
+
+    def forward(self, prev_output_tokens, encoder_out=None):
+        enc = mask = keys = None
+        if self.attention is not None:
+            enc = encoder_out["encoder_out"][0]                                     # T x B x C
+            mask = encoder_out["encoder_padding_mask"][0] if encoder_out["encoder_padding_mask"] else None
+            keys = self.attention.keys(enc)
+        B, U = prev_output_tokens.shape
+        x = F.dropout(self.embed_tokens(prev_output_tokens), self.dropout_in, self.training).transpose(0, 1)
+        hs = [x.new_zeros(B, self.hidden_size) for _ in self.layers]
+        cs = [x.new_zeros(B, self.hidden_size) for _ in self.layers]
+        feed = x.new_zeros(B, self.encoder_output_units) if self.attention is not None else None
+        outs = []
+        for j in range(U):
+            y, hs, cs, feed = self.step(x[j], hs, cs, feed, enc, keys, mask)
+            outs.append(y)
+        return self.output_layer(torch.stack(outs, dim=1))                          # B x U x V
 
 
 @register_model("speech_lstm", dataclass=SpeechLSTMModelConfig)

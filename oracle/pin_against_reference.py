@@ -860,7 +860,52 @@ def pin_speech_lstm():
     print("speech_lstm: loss %.6f, %d parameters -> tests/golden/speech_lstm.npz" % (loss.item(), sum(p_.numel() for p_ in m.parameters())))
 
 
-SECTIONS = {"speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_lstm_lm():
+    """The reference LSTM language model (espresso/models/lstm_lm.py, the LM the LibriSpeech recipe fuses): teacher-forced
+    logits with residual layers, additional_fc and shared / separate output embeddings -> tests/golden/lstm_lm.npz."""
+    from argparse import Namespace
+
+    from espresso.models.lstm_lm import LSTMLanguageModelEspresso
+
+    V = 50
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return 1
+
+        def eos(self):
+            return 2
+
+    class _Task:
+        source_dictionary = target_dictionary = _Dict()
+
+    out = {}
+    for name, kw in (("shared", dict(decoder_embed_dim=32, decoder_hidden_size=32, decoder_out_embed_dim=32, share_embed=True,
+                                     decoder_rnn_residual=True)),
+                     ("proj", dict(decoder_embed_dim=24, decoder_hidden_size=32, decoder_out_embed_dim=40, share_embed=False,
+                                   decoder_rnn_residual=False))):
+        args = Namespace(dropout=0.0, decoder_embed_path=None, decoder_freeze_embed=False, decoder_layers=2,
+                         adaptive_softmax_cutoff=None, is_wordlm=False, decoder_dropout_in=0.0, decoder_dropout_out=0.0,
+                         criterion_name="cross_entropy", max_target_positions=64, tokens_per_sample=64, **kw)
+        torch.manual_seed(31)
+        m = LSTMLanguageModelEspresso.build_model(args, _Task())
+        m.eval()
+        rs = np.random.RandomState(8)
+        toks = torch.from_numpy(rs.randint(2, V, size=(3, 9)))
+        with torch.no_grad():
+            logits = m(toks)[0]
+        for k, v in m.state_dict().items():
+            out["%s.sd.%s" % (name, k)] = v.numpy()
+        out[name + ".tokens"], out[name + ".logits"] = toks.numpy(), logits.numpy()
+        print("lstm_lm %-6s: logits %s, %d parameters" % (name, tuple(logits.shape), sum(p_.numel() for p_ in m.parameters())))
+    np.savez_compressed(os.path.join(GOLDEN, "lstm_lm.npz"), **out)
+    print("lstm_lm pinned -> tests/golden/lstm_lm.npz")
+
+
+SECTIONS = {"lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

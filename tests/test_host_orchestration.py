@@ -510,3 +510,66 @@ def test_speech_lstm_trains_through_the_flat_buffer_trainer(golden_dir, cpu_ops)
     assert np.isfinite(losses).all() and min(losses[-2:]) < 0.9 * losses[0], losses
     assert (m.encoder.lstm[0].weight_ih_l0.detach().float() - w0).abs().max() > 0
     assert m.encoder.lstm[0].weight_ih_l0.data_ptr() == m.flat.param("encoder.lstm.0.weight_ih_l0").data_ptr()
+
+
+@pytest.mark.parametrize("name,kw", [("shared", dict(decoder_embed_dim=32, decoder_hidden_size=32, decoder_out_embed_dim=32,
+                                                    share_embed=True, decoder_rnn_residual=True)),
+                                     ("proj", dict(decoder_embed_dim=24, decoder_hidden_size=32, decoder_out_embed_dim=40,
+                                                   share_embed=False, decoder_rnn_residual=False))])
+def test_lstm_lm_matches_reference_and_fuses(name, kw, golden_dir, cpu_ops):
+    """LSTM language model (the recipe's fusion LM): reference state-dict keys, teacher-forced logits equal to the
+    reference fixture (fp32), incremental decode_step == teacher forcing under beam reordering, and shallow fusion
+    through SequenceGenerator == the oracle driven with the LM's teacher-forced log-probs."""
+    from espresso_b200.models import LSTMLanguageModelEspresso, LSTMLanguageModelEspressoConfig
+    from espresso_b200.sequence_generator import SequenceGenerator
+    from oracle import beam as OB
+    from test_beam_search import EOS, PAD, UNK, _RandomModel
+
+    g = np.load(os.path.join(golden_dir, "lstm_lm.npz"))
+    lm = LSTMLanguageModelEspresso.build_model(LSTMLanguageModelEspressoConfig(dropout=0.0, decoder_layers=2, max_target_positions=64, **kw),
+                                               _Task(50))
+    sd = {k[len(name) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + ".sd.")}
+    assert sorted(lm.state_dict().keys()) == sorted(sd.keys())
+    lm.load_state_dict(sd, strict=True)
+    lm.finalize_(torch.device("cpu"), dtype=torch.float32)
+    toks = torch.from_numpy(g[name + ".tokens"])
+    with torch.no_grad():
+        full = lm(toks)[0]
+    assert np.abs(full.numpy() - g[name + ".logits"]).max() < 1e-5
+    # incremental steps with the two beams of every sentence swapped each step
+    B, U = toks.shape
+    beam, N = 2, B * 2
+    rows = torch.arange(N)
+    state = lm.init_incremental_state(None, B, beam)
+    buf = torch.full((N, U + 1), 1, dtype=torch.int32)
+    perm = None
+    for step in range(U):
+        buf[:, : step + 1] = toks[rows // beam, : step + 1].to(torch.int32)
+        out, is_logits = lm.decode_step(step, buf, state, perm)
+        assert is_logits and (out[:, :50] - full[rows // beam, step]).abs().max() < 1e-5
+        perm = (rows ^ 1).to(torch.int32)
+    # shallow fusion: product generator with this LM vs the oracle with the LM's teacher-forced log-probs
+    Vn = 50
+
+    class D(_Dict):
+        def __len__(self):
+            return Vn
+
+        def unk(self):
+            return UNK
+
+    m = _RandomModel(Vn, 41)
+    kw2 = dict(beam_size=3, max_len_a=0.0, max_len_b=8, min_len=1, eos_factor=1.5)
+    got = SequenceGenerator([m], D(50), lm_model=lm, lm_weight=0.5, **kw2).generate(
+        [m], {"net_input": {"src_tokens": torch.zeros(2, 5, dtype=torch.long), "src_lengths": torch.full((2,), 5)}})
+
+    def fn(step, tokens, ro):
+        with torch.no_grad():
+            lml = torch.log_softmax(lm(tokens[:, : step + 1].long())[0][:, -1].float(), dim=-1)
+        return m.lprobs(step, tokens) + 0.5 * lml
+
+    ref = OB.generate(fn, 2, 5, Vn, PAD, UNK, EOS, model_max_len=m.max_pos, **kw2)
+    for hs, rs in zip(got, ref):
+        assert len(hs) == len(rs)
+        for h, r in zip(hs, rs):
+            assert h["tokens"].tolist() == r["tokens"].tolist() and abs(float(h["score"]) - float(r["score"])) < 1e-4
