@@ -1,6 +1,7 @@
 """Frame-synchronous greedy decoder for transducer models, the reference's validation / 1-best decoder
 (espresso/tools/transducer_greedy_decoder.py:21-251, base class espresso/tools/transducer_base_decoder.py:17-190),
-without LM fusion.
+with optional shallow fusion of an LSTM language model (espresso_b200.models.LSTMLanguageModelEspresso; like the
+reference, fusion needs an LM whose cached state can be rolled back per hypothesis).
 
 Per encoder frame at most `max_num_expansions_per_step` non-blank tokens are emitted; a hypothesis that emits blank
 moves to the next frame with its predictor state rolled back (`masked_copy_cached_state`), the last slot of a frame
@@ -36,8 +37,17 @@ class TransducerGreedyDecoder:
         assert temperature > 0, "--temperature must be greater than 0"
         self.temperature = temperature
         self.print_alignment = print_alignment
+        self.lm_model, self.lm_weight = lm_model, lm_weight
+        self.no_blank_in_lm = False
         if lm_model is not None:
-            raise NotImplementedError("LM fusion in the transducer greedy decoder is not on the B200 path yet")
+            dec = getattr(lm_model, "decoder", None)
+            if dec is None or not hasattr(dec, "step"):
+                raise NotImplementedError("transducer LM fusion needs an LSTM LM with a per-row cached state "
+                                          "(masked_copy_cached_state in the reference)")
+            n_lm = dec.embed_tokens.num_embeddings
+            # an LM vocabulary one symbol short = the ASR vocabulary without blank (transducer_base_decoder.py:93-104)
+            assert n_lm in (self.vocab_size, self.vocab_size - 1)
+            self.no_blank_in_lm = n_lm == self.vocab_size - 1
 
     # ---- one predictor (LSTMCell stack) step from cached state --------------------------------------
     def _predictor_step(self, prev, hs, cs):
@@ -89,6 +99,13 @@ class TransducerGreedyDecoder:
         hid = [l.weight_hh.shape[1] for l in m.decoder.layers]
         hs = [torch.zeros(B, h, dtype=torch.bfloat16, device=dev) for h in hid]
         cs = [torch.zeros(B, h, dtype=torch.float32, device=dev) for h in hid]
+        lm = self.lm_model
+        if lm is not None:
+            lm.eval()
+            lst = lm.init_incremental_state(None, B, 1)
+            lhs, lcs = lst["h"], lst["c"]
+            nonblank = torch.ones(V, dtype=torch.bool, device=dev)
+            nonblank[self.blank] = False
         for t in range(max_len):
             blank_mask = t >= enc_lens
             k = 0
@@ -102,6 +119,18 @@ class TransducerGreedyDecoder:
                     torch.empty(B, ldV, dtype=torch.bfloat16, device=dev)
                 _ops.gemm(f, W, logits, B, V, J, J, J, ldV, bias=P("fc_out.bias"))
                 lp = torch.log_softmax(logits[:, :V].float() / self.temperature, dim=-1)
+                if lm is not None:
+                    # shallow fusion over the non-blank symbols, renormalised so that the transducer's blank / non-blank
+                    # split is untouched (transducer_greedy_decoder.py:165-201)
+                    lm_prev = torch.where(prev > self.blank, prev - 1, prev) if self.no_blank_in_lm else prev
+                    ly, lnh, lnc, _ = lm.decoder.step(lm.decoder.embed_tokens(lm_prev), lhs, lcs, None)
+                    lm_lp = torch.log_softmax(lm.decoder.output_layer(ly).float(), dim=-1)
+                    if not self.no_blank_in_lm:
+                        lm_lp = lm_lp[:, nonblank]
+                    lp_nb = lp[:, nonblank]
+                    fused = lp_nb + self.lm_weight * lm_lp
+                    fused = fused + (lp_nb.exp().sum(1).log() - fused.exp().sum(1).log())[:, None]
+                    lp[:, nonblank] = fused
                 if self.model_predicts_eos:
                     # move the eos mass onto blank: mitigates early stops (transducer_greedy_decoder.py:203-208)
                     lp[:, self.blank] = torch.logaddexp(lp[:, self.blank], lp[:, self.eos])
@@ -118,6 +147,9 @@ class TransducerGreedyDecoder:
                 keep_old = blank_mask[:, None]  # masked_copy_cached_state: blank keeps the previous predictor state
                 hs = [torch.where(keep_old, o, n) for o, n in zip(hs, nh)]
                 cs = [torch.where(keep_old, o, n) for o, n in zip(cs, nc)]
+                if lm is not None:
+                    lhs = [torch.where(keep_old, o, n) for o, n in zip(lhs, lnh)]
+                    lcs = [torch.where(keep_old, o, n) for o, n in zip(lcs, lnc)]
                 k += 1
         alignments = tokens if self.print_alignment else None
         return tokens.view(B, -1), scores.view(B, -1).sum(-1), alignments

@@ -429,6 +429,47 @@ def pin_transducer():
         print("transducer greedy %-7s: tokens identical (%d non-blank), |score diff| %.3g"
               % (name, int((r_tok != blank).sum()), (o_sc - r_sc).abs().max().item()))
         gout["tokens_" + name], gout["scores_" + name], gout["margins_" + name] = r_tok.numpy(), r_sc.numpy(), o_mar.numpy()
+    # ---- with LSTM-LM shallow fusion (the reference requires an LSTM LM here: masked_copy_cached_state)
+    from argparse import Namespace
+
+    from espresso.models.lstm_lm import LSTMLanguageModelEspresso
+
+    class _LmTask:
+        source_dictionary = target_dictionary = _DDict()
+
+    largs = Namespace(dropout=0.0, decoder_embed_path=None, decoder_freeze_embed=False, decoder_layers=2, decoder_embed_dim=24,
+                      decoder_hidden_size=32, decoder_out_embed_dim=40, share_embed=False, decoder_rnn_residual=False,
+                      adaptive_softmax_cutoff=None, is_wordlm=False, decoder_dropout_in=0.0, decoder_dropout_out=0.0,
+                      criterion_name="cross_entropy", max_target_positions=64, tokens_per_sample=64)
+    chosen = None
+    for lm_seed in range(70, 130):  # pick an LM whose fusion changes many decisions while none of them is a near-tie
+        torch.manual_seed(lm_seed)
+        lm = LSTMLanguageModelEspresso.build_model(largs, _LmTask())
+        with torch.no_grad():
+            for p_ in lm.parameters():
+                p_.mul_(6.0)
+            lm.decoder.fc_out.weight.mul_(12.0)  # a peaky LM, so that fusion actually changes decisions
+        lm_sd = {k: v.clone() for k, v in lm.state_dict().items()}
+        with torch.no_grad():
+            o_tok, o_sc, o_mar = OT.greedy_decode(sde, enc_e, ol_e, 2, pad_idx, blank, eos_idx, eos_idx, max_num_expansions_per_step=2,
+                                                  lm_sd=lm_sd, lm_weight=1.0)
+        fin = o_mar[torch.isfinite(o_mar)]
+        changed = int((o_tok != torch.from_numpy(gout["tokens_e2"])).sum())
+        if float(fin.min()) > 0.3 and changed >= 20:
+            chosen = lm_seed
+            break
+    assert chosen is not None, "no LM seed with clear margins found"
+    lm.decoder.dictionary = _DDict()
+    lm.eval()
+    dec = TransducerGreedyDecoder([m], _DDict(), blank=blank, max_num_expansions_per_step=2, lm_model=lm, lm_weight=1.0)
+    r_tok, r_sc, _ = dec.decode([m], {"net_input": {"src_tokens": feats, "src_lengths": lens}})
+    assert torch.equal(o_tok, r_tok), (o_tok, r_tok)
+    assert (o_sc - r_sc).abs().max().item() < 1e-3
+    print("transducer greedy + LM fusion (LM seed %d): tokens identical (%d non-blank, %d differ from no-LM), min margin %.3f"
+          % (chosen, int((r_tok != blank).sum()), changed, float(fin.min())))
+    gout["tokens_lm"], gout["scores_lm"], gout["margins_lm"] = r_tok.numpy(), r_sc.numpy(), o_mar.numpy()
+    for k, v in lm_sd.items():
+        gout["lm.sd." + k] = v.numpy()
     np.savez_compressed(os.path.join(GOLDEN, "transducer_greedy.npz"), **gout)
     print("transducer greedy decoder pinned -> tests/golden/transducer_greedy.npz")
 

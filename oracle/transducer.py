@@ -45,8 +45,31 @@ def transducer_loss(logits, enc_lens, target, pad, eos, blank):
                                            clamp=-1.0, reduction="sum")
 
 
+def lstm_lm_step(lm_sd, prev, hs, cs, pad):
+    """One step of the attention-free LSTM LM (espresso/models/lstm_lm.py -> SpeechLSTMDecoder without encoder):
+    returns (log-probs [B, V_lm], new hs, new cs)."""
+    x = F.embedding(prev, lm_sd["decoder.embed_tokens.weight"], padding_idx=pad)
+    nh, nc = [], []
+    for i in range(len(hs)):
+        p = "decoder.layers.%d." % i
+        gates = F.linear(x, lm_sd[p + "weight_ih"], lm_sd[p + "bias_ih"]) + F.linear(hs[i], lm_sd[p + "weight_hh"], lm_sd[p + "bias_hh"])
+        i_, f_, g_, o_ = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f_) * cs[i] + torch.sigmoid(i_) * torch.tanh(g_)
+        h = torch.sigmoid(o_) * torch.tanh(c)
+        nh.append(h)
+        nc.append(c)
+        x = h
+    if "decoder.additional_fc.weight" in lm_sd:
+        x = F.linear(x, lm_sd["decoder.additional_fc.weight"], lm_sd["decoder.additional_fc.bias"])
+    if "decoder.fc_out.weight" in lm_sd:
+        logits = F.linear(x, lm_sd["decoder.fc_out.weight"], lm_sd["decoder.fc_out.bias"])
+    else:
+        logits = F.linear(x, lm_sd["decoder.embed_tokens.weight"])
+    return torch.log_softmax(logits, dim=-1), nh, nc
+
+
 def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_expansions_per_step=2, temperature=1.0,
-                  model_predicts_eos=False, max_len=0):
+                  model_predicts_eos=False, max_len=0, lm_sd=None, lm_weight=1.0):
     """Restates espresso/tools/transducer_greedy_decoder.py:91-251 (no LM): frame-synchronous greedy search, at most
     `max_num_expansions_per_step` non-blank tokens per encoder frame, predictor state rolled back on blank.
     enc [B, T, d] (eval-mode encoder output), enc_lens [B].
@@ -62,6 +85,12 @@ def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_exp
     hid = [sd["decoder.layers.%d.weight_hh" % i].shape[1] for i in range(n_layers)]
     hs = [torch.zeros(B, h) for h in hid]
     cs = [torch.zeros(B, h) for h in hid]
+    if lm_sd is not None:  # LM shallow fusion (transducer_greedy_decoder.py:165-201), LM vocabulary = ASR vocabulary
+        n_lm = len([k for k in lm_sd if k.endswith("weight_hh")])
+        lhs = [torch.zeros(B, lm_sd["decoder.layers.%d.weight_hh" % i].shape[1]) for i in range(n_lm)]
+        lcs = [torch.zeros_like(h) for h in lhs]
+        nonblank = torch.ones(sd["fc_out.bias"].numel(), dtype=torch.bool)
+        nonblank[blank] = False
     for t in range(T):
         blank_mask = t >= enc_lens
         k = 0
@@ -80,6 +109,14 @@ def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_exp
                 x = h
             logits = joint_logits(sd, enc[:, t:t + 1], x[:, None, :])[:, 0, 0]  # [B, V]
             lp = torch.log_softmax(logits / temperature, dim=-1)
+            if lm_sd is not None:
+                lm_lp, lnh, lnc = lstm_lm_step(lm_sd, prev, lhs, lcs, pad)
+                lp_nb = lp[:, nonblank]
+                fused = lp_nb + lm_weight * lm_lp[:, nonblank]
+                # the non-blank probability mass stays what the transducer assigned
+                fused = fused + (lp_nb.exp().sum(1).log() - fused.exp().sum(1).log())[:, None]
+                lp = lp.clone()
+                lp[:, nonblank] = fused
             if model_predicts_eos:
                 lp[:, blank] = torch.logaddexp(lp[:, blank], lp[:, eos])
                 lp[:, eos] = float("-inf")
@@ -98,5 +135,8 @@ def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_exp
             keep_old = blank_mask[:, None]
             hs = [torch.where(keep_old, o, n) for o, n in zip(hs, nh)]
             cs = [torch.where(keep_old, o, n) for o, n in zip(cs, nc)]
+            if lm_sd is not None:
+                lhs = [torch.where(keep_old, o, n) for o, n in zip(lhs, lnh)]
+                lcs = [torch.where(keep_old, o, n) for o, n in zip(lcs, lnc)]
             k += 1
     return tokens.view(B, -1), scores.view(B, -1).sum(-1), margins

@@ -573,3 +573,33 @@ def test_lstm_lm_matches_reference_and_fuses(name, kw, golden_dir, cpu_ops):
         assert len(hs) == len(rs)
         for h, r in zip(hs, rs):
             assert h["tokens"].tolist() == r["tokens"].tolist() and abs(float(h["score"]) - float(r["score"])) < 1e-4
+
+
+def test_transducer_greedy_decoder_with_lstm_lm_fusion_matches_reference_tokens(golden_dir, cpu_ops):
+    """Transducer greedy search with LSTM-LM shallow fusion vs the REAL reference decoder + reference LSTM LM on the
+    fixture (tests/golden/transducer_greedy.npz: fusion changes all 78 emitted tokens, every decision's top-2 margin is
+    above 0.4): identical token sequences."""
+    from espresso_b200.models import LSTMLanguageModelEspresso, LSTMLanguageModelEspressoConfig
+    from espresso_b200.tools.transducer_greedy_decoder import TransducerGreedyDecoder
+
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    assert (gg["tokens_lm"] != gg["tokens_e2"]).sum() > 20
+    fin = gg["margins_lm"][np.isfinite(gg["margins_lm"])]
+    assert fin.min() > 0.3
+    m = _build_transducer(g).finalize_(torch.device("cpu"))
+    lm = LSTMLanguageModelEspresso.build_model(
+        LSTMLanguageModelEspressoConfig(dropout=0.0, decoder_layers=2, decoder_embed_dim=24, decoder_hidden_size=32,
+                                        decoder_out_embed_dim=40, share_embed=False, max_target_positions=64), _Task(50))
+    lm.load_state_dict({k[len("lm.sd."):]: torch.from_numpy(gg[k]) for k in gg.files if k.startswith("lm.sd.")}, strict=True)
+    lm.finalize_(torch.device("cpu"), dtype=torch.float32)
+
+    class D(_Dict):
+        def bos(self):
+            return 0
+
+    dec = TransducerGreedyDecoder([m], D(50), blank=0, max_num_expansions_per_step=2, lm_model=lm, lm_weight=1.0)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"])}}
+    tokens, scores, _ = dec.decode([m], sample)
+    assert np.array_equal(tokens.numpy(), gg["tokens_lm"])
+    assert np.abs(scores.numpy() - gg["scores_lm"]).max() < 0.03 * np.abs(gg["scores_lm"]).max()
