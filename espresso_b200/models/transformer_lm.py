@@ -3,7 +3,6 @@ branch of espresso/speech_recognize.py:111-165; model fairseq/models/transformer
 espresso/tasks/language_modeling_for_asr.py:29).  Parameter names follow fairseq's `decoder.*` keys (layers without
 encoder attention).  Only incremental scoring (the generator protocol) is implemented: training the LM is an
 offline step of the recipe and out of scope."""
-import math
 
 import torch
 import torch.nn as nn

@@ -18,7 +18,7 @@ import math
 import torch
 
 from .. import ops as _ops
-from ..lib import ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_SILU, ACT_SILU_BWD
+from ..lib import ACT_RELU, ACT_RELU_BWD, ACT_SILU, ACT_SILU_BWD
 
 LN_EPS = 1e-5
 BN_EPS = 1e-5

@@ -1,7 +1,6 @@
 """Which Python lines launch the non-native (ATen / cuDNN) kernels of one eager training step?
 torch.profiler with stacks; prints, per ATen op that launched CUDA kernels, the count, CUDA time and the innermost
 repo frame.   python profiles/find_torch_kernels.py"""
-import collections
 import os
 import sys
 
