@@ -94,10 +94,14 @@ class SpeechRecognitionEspressoTask:
         if self.cfg.criterion_name == "transducer_loss":
             from ..tools.transducer_greedy_decoder import TransducerGreedyDecoder
 
+            from ..tools.transducer_beam_search_decoder import TransducerBeamSearchDecoder
+
             if seq_gen_cls is None:
-                if g("beam", 1) != 1:
-                    raise NotImplementedError("transducer beam search is not on the B200 path yet (greedy: --beam 1)")
-                seq_gen_cls = TransducerGreedyDecoder
+                seq_gen_cls = TransducerGreedyDecoder if g("beam", 1) == 1 else TransducerBeamSearchDecoder
+            if seq_gen_cls is TransducerBeamSearchDecoder:
+                extra.update(beam_size=g("beam", 1), normalize_scores=not g("unnormalized", False),
+                             expansion_beta=g("transducer_expansion_beta", 0), expansion_gamma=g("transducer_expansion_gamma", None),
+                             prefix_alpha=g("transducer_prefix_alpha", None))
             return seq_gen_cls(
                 models, self.target_dictionary, temperature=g("temperature", 1.0),
                 max_num_expansions_per_step=g("transducer_max_num_expansions_per_step", 20),

@@ -468,6 +468,34 @@ def pin_transducer():
     print("transducer greedy + LM fusion (LM seed %d): tokens identical (%d non-blank, %d differ from no-LM), min margin %.3f"
           % (chosen, int((r_tok != blank).sum()), changed, float(fin.min())))
     gout["tokens_lm"], gout["scores_lm"], gout["margins_lm"] = r_tok.numpy(), r_sc.numpy(), o_mar.numpy()
+
+    # ---- beam search ("adaptive expansion search", the recipes' decoder): the reference TransducerBeamSearchDecoder vs
+    # espresso_b200's host search driven by fp32 oracle callbacks -- n-best token sequences and scores must be identical
+    from espresso.tools.transducer_beam_search_decoder import TransducerBeamSearchDecoder as RefBeam
+
+    from espresso_b200.tools.transducer_beam_search_decoder import AdaptiveExpansionSearch
+
+    for name, kw, use_lm in (("beam5", dict(beam_size=5, max_num_expansions_per_step=3, expansion_beta=2, expansion_gamma=2.3,
+                                            prefix_alpha=1, temperature=1.3), False),
+                             ("beam3_lm", dict(beam_size=3, max_num_expansions_per_step=2, expansion_beta=1, expansion_gamma=4.0,
+                                               prefix_alpha=2, temperature=1.0), True),
+                             ("beam4_eos", dict(beam_size=4, max_num_expansions_per_step=2, expansion_beta=0, expansion_gamma=None,
+                                                prefix_alpha=None, temperature=1.0, model_predicts_eos=True), False)):
+        rdec = RefBeam([m], _DDict(), blank=blank, lm_model=lm if use_lm else None, lm_weight=0.3, **kw)
+        r_seqs, r_scores, _ = rdec._generate({"net_input": {"src_tokens": feats, "src_lengths": lens}})
+        core = AdaptiveExpansionSearch(V, blank, pad_idx, eos_idx, eos_idx, kw["beam_size"], kw["max_num_expansions_per_step"],
+                                       kw["expansion_beta"], kw["expansion_gamma"], kw["prefix_alpha"], True,
+                                       kw.get("model_predicts_eos", False), 0.3, False)
+        n_h = 0
+        for b in range(feats.size(0)):
+            cb = OT.search_callbacks(sde, enc_e[b], 2, pad_idx, temperature=kw["temperature"], lm_sd=lm_sd if use_lm else None)
+            with torch.no_grad():
+                seqs, scores = core.search(int(ol_e[b]), cb, torch.device("cpu"), use_lm=use_lm)
+            assert seqs.shape == r_seqs[b].shape and torch.equal(seqs, r_seqs[b]), (name, b, seqs, r_seqs[b])
+            assert (scores - r_scores[b]).abs().max().item() < 1e-4, (name, b)
+            gout["%s_b%d_seqs" % (name, b)], gout["%s_b%d_scores" % (name, b)] = r_seqs[b].numpy(), r_scores[b].numpy()
+            n_h += seqs.size(0)
+        print("transducer beam search %-9s: %d hypotheses identical to the reference (tokens and scores)" % (name, n_h))
     for k, v in lm_sd.items():
         gout["lm.sd." + k] = v.numpy()
     np.savez_compressed(os.path.join(GOLDEN, "transducer_greedy.npz"), **gout)

@@ -140,3 +140,54 @@ def greedy_decode(sd, enc, enc_lens, n_layers, pad, blank, bos, eos, max_num_exp
                 lcs = [torch.where(keep_old, o, n) for o, n in zip(lcs, lnc)]
             k += 1
     return tokens.view(B, -1), scores.view(B, -1).sum(-1), margins
+
+
+def search_callbacks(sd, enc_b, n_layers, pad, temperature=1.0, lm_sd=None):
+    """fp32 model callbacks for espresso_b200.tools.transducer_beam_search_decoder.AdaptiveExpansionSearch (one utterance,
+    enc_b [T, d]): the prediction network / joint / LM of this module behind the search's callback protocol, so the
+    host search can be checked against the reference decoder without any bf16 noise."""
+    hid = [sd["decoder.layers.%d.weight_hh" % i].shape[1] for i in range(n_layers)]
+    assert len(set(hid)) == 1
+
+    def cell_stack(prefix, weights, x, hs, cs, n):
+        nh, nc = [], []
+        for i in range(n):
+            p = prefix + "layers.%d." % i
+            gates = F.linear(x, weights[p + "weight_ih"], weights[p + "bias_ih"]) + F.linear(hs[:, i], weights[p + "weight_hh"], weights[p + "bias_hh"])
+            i_, f_, g_, o_ = gates.chunk(4, dim=1)
+            c = torch.sigmoid(f_) * cs[:, i] + torch.sigmoid(i_) * torch.tanh(g_)
+            h = torch.sigmoid(o_) * torch.tanh(c)
+            nh.append(h)
+            nc.append(c)
+            x = h
+        return x, torch.stack(nh, dim=1), torch.stack(nc, dim=1)
+
+    def pred_step(prev, hs, cs):
+        x = F.embedding(prev, sd["decoder.embed_tokens.weight"], padding_idx=pad)
+        return cell_stack("decoder.", sd, x, hs, cs, n_layers)
+
+    def joint_lprobs(t, out):
+        n = out.size(0)
+        logits = joint_logits(sd, enc_b[None, t:t + 1].expand(n, -1, -1), out[:, None, :])[:, 0, 0]
+        return torch.log_softmax(logits / temperature, dim=-1)
+
+    cb = dict(pred_step=pred_step, joint_lprobs=joint_lprobs,
+              init_state=lambda n: (torch.zeros(n, n_layers, hid[0]), torch.zeros(n, n_layers, hid[0])))
+    if lm_sd is not None:
+        n_lm = len([k for k in lm_sd if k.endswith("weight_hh")])
+        lh = lm_sd["decoder.layers.0.weight_hh"].shape[1]
+
+        def lm_step(prev, lhs, lcs):
+            x = F.embedding(prev, lm_sd["decoder.embed_tokens.weight"], padding_idx=pad)
+            return cell_stack("decoder.", lm_sd, x, lhs, lcs, n_lm)
+
+        def lm_lprobs(feat):
+            x = feat
+            if "decoder.additional_fc.weight" in lm_sd:
+                x = F.linear(x, lm_sd["decoder.additional_fc.weight"], lm_sd["decoder.additional_fc.bias"])
+            w = lm_sd["decoder.fc_out.weight"] if "decoder.fc_out.weight" in lm_sd else lm_sd["decoder.embed_tokens.weight"]
+            b = lm_sd.get("decoder.fc_out.bias") if "decoder.fc_out.weight" in lm_sd else None
+            return torch.log_softmax(F.linear(x, w, b), dim=-1)
+
+        cb.update(lm_step=lm_step, lm_lprobs=lm_lprobs, lm_init_state=lambda n: (torch.zeros(n, n_lm, lh), torch.zeros(n, n_lm, lh)))
+    return cb

@@ -430,6 +430,12 @@ def test_task_mirror_builds_models_criterions_and_decoders(tmp_path, golden_dir,
     dec = t3.build_generator([_TM()], type("A", (), dict(beam=1, transducer_max_num_expansions_per_step=3))())
     assert isinstance(dec, TransducerGreedyDecoder) and dec.blank == 0 and dec.bos == t3.target_dictionary.eos()
     assert dec.max_num_expansions_per_step == 3
+    from espresso_b200.tools.transducer_beam_search_decoder import TransducerBeamSearchDecoder
+    bdec = t3.build_generator([_TM()], type("A", (), dict(beam=5, temperature=1.3, transducer_max_num_expansions_per_step=20,
+                                                         transducer_expansion_beta=2, transducer_expansion_gamma=2.3,
+                                                         transducer_prefix_alpha=1))())
+    assert isinstance(bdec, TransducerBeamSearchDecoder) and bdec.core.beam == 5 and bdec.core.beta == 2
+    assert bdec.core.gamma == 2.3 and bdec.core.alpha == 1 and bdec.temperature == 1.3
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -603,3 +609,77 @@ def test_transducer_greedy_decoder_with_lstm_lm_fusion_matches_reference_tokens(
     tokens, scores, _ = dec.decode([m], sample)
     assert np.array_equal(tokens.numpy(), gg["tokens_lm"])
     assert np.abs(scores.numpy() - gg["scores_lm"]).max() < 0.03 * np.abs(gg["scores_lm"]).max()
+
+
+_BEAM_CASES = [("beam5", dict(beam_size=5, max_num_expansions_per_step=3, expansion_beta=2, expansion_gamma=2.3, prefix_alpha=1,
+                              temperature=1.3), False),
+               ("beam3_lm", dict(beam_size=3, max_num_expansions_per_step=2, expansion_beta=1, expansion_gamma=4.0, prefix_alpha=2,
+                                 temperature=1.0), True),
+               ("beam4_eos", dict(beam_size=4, max_num_expansions_per_step=2, expansion_beta=0, expansion_gamma=None,
+                                  prefix_alpha=None, temperature=1.0, model_predicts_eos=True), False)]
+
+
+def _lm_from_fixture(gg, dtype=torch.float32):
+    from espresso_b200.models import LSTMLanguageModelEspresso, LSTMLanguageModelEspressoConfig
+
+    lm = LSTMLanguageModelEspresso.build_model(
+        LSTMLanguageModelEspressoConfig(dropout=0.0, decoder_layers=2, decoder_embed_dim=24, decoder_hidden_size=32,
+                                        decoder_out_embed_dim=40, share_embed=False, max_target_positions=64), _Task(50))
+    lm.load_state_dict({k[len("lm.sd."):]: torch.from_numpy(gg[k]) for k in gg.files if k.startswith("lm.sd.")}, strict=True)
+    return lm.finalize_(torch.device("cpu"), dtype=dtype)
+
+
+@pytest.mark.parametrize("name,kw,use_lm", _BEAM_CASES)
+def test_adaptive_expansion_search_matches_reference_nbest(name, kw, use_lm, golden_dir):
+    """The host search (prefix merge, k-expansions, prune by value, LM fusion, eos folding) driven by fp32 oracle model
+    callbacks reproduces the n-best of the REAL reference TransducerBeamSearchDecoder recorded in
+    tests/golden/transducer_greedy.npz: identical token sequences, scores to 1e-4."""
+    from espresso_b200.tools.transducer_beam_search_decoder import AdaptiveExpansionSearch
+    from oracle import conformer as OC
+    from oracle import transducer as OT
+
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    lm_sd = {k[len("lm.sd."):]: torch.from_numpy(gg[k]) for k in gg.files if k.startswith("lm.sd.")}
+    ecfg = dict(embed_dim=64, ffn_dim=128, heads=4, layers=2, layer_type="conformer", dw_kernel=31, dropout=0.0,
+                attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, final_layer_norm=False, vocab=None)
+    with torch.no_grad():
+        enc, ol, _ = OC.encoder_forward(sd, ecfg, torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"]), training=False)
+        core = AdaptiveExpansionSearch(50, 0, 1, 2, 2, kw["beam_size"], kw["max_num_expansions_per_step"], kw["expansion_beta"],
+                                       kw["expansion_gamma"], kw["prefix_alpha"], True, kw.get("model_predicts_eos", False), 0.3, False)
+        for b in range(enc.size(0)):
+            cb = OT.search_callbacks(sd, enc[b], 2, 1, temperature=kw["temperature"], lm_sd=lm_sd if use_lm else None)
+            seqs, scores = core.search(int(ol[b]), cb, torch.device("cpu"), use_lm=use_lm)
+            assert np.array_equal(seqs.numpy(), gg["%s_b%d_seqs" % (name, b)])
+            assert np.abs(scores.numpy() - gg["%s_b%d_scores" % (name, b)]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,kw,use_lm", _BEAM_CASES)
+def test_transducer_beam_search_decoder_product_path(name, kw, use_lm, golden_dir, cpu_ops):
+    """The product decoder (bf16 model through the host orchestration): its best hypothesis scores within bf16
+    tolerance of the reference's best, and equals the reference's best tokens whenever the reference's own top-2 gap
+    is clear; the API returns what the reference's decode()/generate() return."""
+    from espresso_b200.tools.transducer_beam_search_decoder import TransducerBeamSearchDecoder
+
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    m = _build_transducer(g).finalize_(torch.device("cpu"))
+
+    class D(_Dict):
+        def bos(self):
+            return 0
+
+    dec = TransducerBeamSearchDecoder([m], D(50), blank=0, lm_model=_lm_from_fixture(gg) if use_lm else None, lm_weight=0.3, **kw)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"])}}
+    tokens, scores, _ = dec.decode([m], sample)
+    hyps = dec.generate([m], sample)
+    assert tokens.size(0) == 3 and len(hyps) == 3
+    for b in range(3):
+        ref_seqs, ref_scores = gg["%s_b%d_seqs" % (name, b)], gg["%s_b%d_scores" % (name, b)]
+        assert abs(float(scores[b]) - float(ref_scores[0])) < 0.05 * abs(float(ref_scores[0])) + 0.02
+        sc = [float(h["score"]) for h in hyps[b]]
+        assert sc == sorted(sc, reverse=True) and 1 <= len(sc) <= kw["beam_size"]
+        if len(ref_scores) > 1 and ref_scores[0] - ref_scores[1] > 0.1:
+            ref_best = [t for t in ref_seqs[0].tolist() if t != 1]
+            assert tokens[b][tokens[b] != 1].tolist() == ref_best, (name, b)
