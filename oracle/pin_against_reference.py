@@ -974,7 +974,35 @@ def pin_lstm_lm():
     print("lstm_lm pinned -> tests/golden/lstm_lm.npz")
 
 
-SECTIONS = {"lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+def pin_text():
+    """Character tokenisation (espresso/tools/utils.py:36-58, espresso/data/encoders/characters_asr.py) and the word /
+    character error counting behind validation WER (espresso/tools/utils.py:265-330 edit_distance) vs
+    espresso_b200.data.encoders / espresso_b200.tasks.speech_recognition.edit_counts."""
+    from espresso.data.encoders.characters_asr import CharactersAsr as RefChars
+    from espresso.tools.utils import edit_distance
+
+    from espresso_b200.data.encoders import CharactersAsr
+    from espresso_b200.tasks.speech_recognition import edit_counts
+
+    nls = ["<noise>", "[laughter]", "<unk>"]
+    sents = ["hello  world", " a <noise> b[laughter]c ", "", "x", "<noise><noise> y  z ", "it's <unk> o'clock"]
+    for ends in (True, False):
+        for syms in (None, [], nls):
+            a, b = RefChars(None, ends_with_space=ends, non_lang_syms=syms), CharactersAsr(ends_with_space=ends, non_lang_syms=syms)
+            for s_ in sents:
+                assert a.encode(s_) == b.encode(s_), (s_, a.encode(s_), b.encode(s_))
+                assert a.decode(a.encode(s_)) == b.decode(b.encode(s_))
+    rs = np.random.RandomState(2)
+    vocab = ["a", "b", "c", "dd", "e"]
+    for _ in range(200):
+        ref = [vocab[i] for i in rs.randint(0, 5, size=rs.randint(0, 12))]
+        hyp = [vocab[i] for i in rs.randint(0, 5, size=rs.randint(0, 12))]
+        _, _, counter = edit_distance(ref, hyp)
+        assert edit_counts(ref, hyp) == (counter["sub"] + counter["ins"] + counter["del"], counter["words"]), (ref, hyp)
+    print("text: characters_asr encode/decode and edit-distance error counts identical to the reference")
+
+
+SECTIONS = {"text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

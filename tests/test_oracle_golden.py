@@ -208,3 +208,17 @@ def test_asr_dictionary_layout(tmp_path):
     out = tmp_path / "saved.txt"
     db.save(str(out))
     assert AsrDictionary.load(str(out), enable_bos=True).symbols == db.symbols
+
+
+def test_character_encoder_and_edit_counts():
+    """Known answers for the text utilities pinned against the reference by oracle/pin_against_reference.py::pin_text."""
+    from espresso_b200.data.encoders import CharactersAsr, tokenize
+    from espresso_b200.tasks.speech_recognition import edit_counts
+
+    assert tokenize("ab c") == "a b <space> c"
+    enc = CharactersAsr(non_lang_syms=["<noise>"])
+    assert enc.encode(" hi <noise> yo ") == "h i <space> <noise> <space> y o <space>"
+    assert enc.decode(enc.encode("hi <noise> yo")) == "hi <noise> yo"
+    assert CharactersAsr(ends_with_space=False).encode("a b") == "a <space> b"
+    assert edit_counts(list("kitten"), list("sitting")) == (3, 6)
+    assert edit_counts([], ["a", "b"]) == (2, 0) and edit_counts(["a"], []) == (1, 1)
