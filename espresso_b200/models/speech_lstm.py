@@ -275,3 +275,37 @@ class SpeechLSTMModel(nn.Module):
     def get_normalized_probs(self, net_output, log_probs, sample=None):
         x = net_output[0].float()
         return F.log_softmax(x, dim=-1) if log_probs else F.softmax(x, dim=-1)
+
+    # ---- generator protocol (espresso_b200/sequence_generator.py): incremental decoding with cached (h, c, context) ---
+    def forward_encoder(self, net_input):
+        src = net_input["src_tokens"].to(self.decoder.embed_tokens.weight.dtype)
+        return self.encoder(src, net_input["src_lengths"], src_lengths_cpu=net_input.get("src_lengths_cpu"))
+
+    def init_incremental_state(self, encoder_out, bsz, beam):
+        """Encoder outputs (and the attention keys, computed once) are replicated per hypothesis; a search step only
+        permutes hypotheses inside a sentence, so they never need reordering (reorder_encoder_out in the reference)."""
+        dec = self.decoder
+        enc = encoder_out["encoder_out"][0].repeat_interleave(beam, dim=1)            # T x N x C
+        mask = encoder_out["encoder_padding_mask"][0].repeat_interleave(beam, dim=1) if encoder_out["encoder_padding_mask"] else None
+        N = bsz * beam
+        z = lambda w: [enc.new_zeros(N, w) for _ in dec.layers]  # noqa: E731
+        return {"enc": enc, "mask": mask, "keys": dec.attention.keys(enc), "h": z(dec.hidden_size), "c": z(dec.hidden_size),
+                "feed": enc.new_zeros(N, dec.encoder_output_units)}
+
+    @torch.no_grad()
+    def decode_step(self, step, tokens, state, new_order):
+        dec = self.decoder
+        if new_order is not None:  # reorder_incremental_state (speech_lstm.py:974-1000)
+            idx = new_order.long()
+            state["h"] = [h.index_select(0, idx) for h in state["h"]]
+            state["c"] = [c.index_select(0, idx) for c in state["c"]]
+            state["feed"] = state["feed"].index_select(0, idx)
+        x = dec.embed_tokens(tokens[:, step].long())
+        y, state["h"], state["c"], state["feed"] = dec.step(x, state["h"], state["c"], state["feed"], state["enc"], state["keys"],
+                                                             state["mask"])
+        logits = dec.output_layer(y)
+        V = logits.size(-1)
+        ldV = (V + 7) // 8 * 8
+        if logits.dtype == torch.bfloat16 and ldV != V:
+            logits = F.pad(logits, (0, ldV - V))
+        return logits.contiguous(), True

@@ -683,3 +683,38 @@ def test_transducer_beam_search_decoder_product_path(name, kw, use_lm, golden_di
         if len(ref_scores) > 1 and ref_scores[0] - ref_scores[1] > 0.1:
             ref_best = [t for t in ref_seqs[0].tolist() if t != 1]
             assert tokens[b][tokens[b] != 1].tolist() == ref_best, (name, b)
+
+
+def test_speech_lstm_incremental_decoding_and_beam_search(golden_dir, cpu_ops):
+    """speech_lstm behind the generator protocol: one-token steps (cached h / c / context, beams swapped every step)
+    reproduce the teacher-forced logits, and a beam-3 search runs end to end."""
+    from espresso_b200.sequence_generator import SequenceGenerator
+
+    g = np.load(os.path.join(golden_dir, "speech_lstm.npz"))
+    m = _build_speech_lstm(g).finalize_(torch.device("cpu"))
+    m.eval()
+    feats, lens = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"])
+    prev = torch.from_numpy(g["prev_output_tokens"])
+    B, U = prev.shape
+    with torch.no_grad():
+        full, _ = m(feats, lens, prev)
+        enc = m.forward_encoder({"src_tokens": feats, "src_lengths": lens})
+        beam, N = 2, B * 2
+        rows = torch.arange(N)
+        state = m.init_incremental_state(enc, B, beam)
+        buf = torch.full((N, U + 1), 1, dtype=torch.int32)
+        perm = None
+        for step in range(U):
+            buf[:, : step + 1] = prev[rows // beam, : step + 1].to(torch.int32)
+            out, is_logits = m.decode_step(step, buf, state, perm)
+            ref = full[rows // beam, step].float()
+            assert is_logits and (out[:, :50].float() - ref).abs().max() < 0.05 * ref.abs().max() + 1e-3, step
+            perm = (rows ^ 1).to(torch.int32)
+
+    class D(_Dict):
+        def unk(self):
+            return 3
+
+    hyps = SequenceGenerator([m], D(50), beam_size=3, max_len_a=0.0, max_len_b=6).generate(
+        [m], {"net_input": {"src_tokens": feats, "src_lengths": lens}})
+    assert len(hyps) == B and all(1 <= len(h) <= 3 and int(h[0]["tokens"][-1]) == 2 for h in hyps)
