@@ -42,7 +42,7 @@ def compact_targets(target, pad_idx, eos_idx):
 @register_criterion("ctc_loss")
 class CtcLossCriterion(torch.nn.Module):
     def __init__(self, task=None, zero_infinity=True, sentence_avg=True, pad_idx=None, eos_idx=None, blank_idx=None,
-                 unit_grad_output=True):
+                 unit_grad_output=False):
         super().__init__()
         d = getattr(task, "target_dictionary", None)
         self.pad_idx = pad_idx if pad_idx is not None else d.pad()
@@ -61,7 +61,8 @@ class CtcLossCriterion(torch.nn.Module):
         targets, tgt_lens = compact_targets(sample["target"], self.pad_idx, self.eos_idx)
         loss_b = _CtcFn.apply(out, V, in_lens, targets, tgt_lens, self.blank_idx, self.zero_infinity, self.unit_grad_output)
         loss = loss_b.sum() if reduce else loss_b
-        ntokens = sample["ntokens"] if "ntokens" in sample else tgt_lens.sum()  # device scalar when not given
+        # collate's count: every non-pad target token, eos included (espresso/data/asr_dataset.py:110-125); device scalar
+        ntokens = sample["ntokens"] if "ntokens" in sample else sample["target"].ne(self.pad_idx).sum()
         nsent = sample["target"].size(0)
         sample_size = nsent if self.sentence_avg else ntokens
         logging_output = {"loss": loss.detach(), "ntokens": ntokens, "nsentences": nsent, "sample_size": sample_size}

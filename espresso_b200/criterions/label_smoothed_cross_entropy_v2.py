@@ -35,7 +35,7 @@ class LabelSmoothedCrossEntropyV2Criterion(torch.nn.Module):
     _SMOOTHING = {"uniform": 0, "unigram": 1, "temporal": 2}
 
     def __init__(self, task=None, sentence_avg=False, label_smoothing=0.1, smoothing_type="uniform", pad_idx=None,
-                 unit_grad_output=True, unigram_pseudo_count=1.0, unigram_counts=None):
+                 unit_grad_output=False, unigram_pseudo_count=1.0, unigram_counts=None):
         """unigram smoothing builds the distribution like the reference (:151-155): dictionary.count (or
         `unigram_counts`) + pseudo count, normalised."""
         super().__init__()

@@ -28,7 +28,7 @@ class _RnntFn(torch.autograd.Function):
 
 @register_criterion("transducer_loss")
 class TransducerLossCriterion(torch.nn.Module):
-    def __init__(self, task=None, sentence_avg=True, pad_idx=None, eos_idx=None, blank_idx=None, unit_grad_output=True):
+    def __init__(self, task=None, sentence_avg=True, pad_idx=None, eos_idx=None, blank_idx=None, unit_grad_output=False):
         super().__init__()
         d = getattr(task, "target_dictionary", None)
         self.pad_idx = pad_idx if pad_idx is not None else d.pad()
@@ -46,7 +46,7 @@ class TransducerLossCriterion(torch.nn.Module):
         tg = target[:, :-1].to(torch.int32).contiguous()
         loss_b = _RnntFn.apply(out, V, enc_lens.to(torch.int32), u_lens, tg, self.blank_idx, self.unit_grad_output)
         loss = loss_b.sum() if reduce else loss_b
-        ntokens = sample["ntokens"] if "ntokens" in sample else u_lens.sum()
+        ntokens = sample["ntokens"] if "ntokens" in sample else sample["target"].ne(self.pad_idx).sum()
         nsent = target.size(0)
         sample_size = nsent if self.sentence_avg else ntokens
         return loss, sample_size, {"loss": loss.detach(), "ntokens": ntokens, "nsentences": nsent, "sample_size": sample_size}

@@ -19,7 +19,8 @@ from . import ops as _ops
 
 class Trainer:
     def __init__(self, model, criterion, lr_scheduler, adam_betas=(0.9, 0.98), adam_eps=1e-8, weight_decay=0.0,
-                 clip_norm=2.0, process_group=None, use_cuda_graphs=False):
+                 clip_norm=2.0, process_group=None, use_cuda_graphs=False, bucket_frames=64, bucket_tokens=16,
+                 max_graphs=96):
         self.model = model
         self.criterion = criterion
         self.lr_scheduler = lr_scheduler
@@ -32,6 +33,10 @@ class Trainer:
         self.num_updates = 0
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        # the hand-written backward assumes d(sum loss) = 1: the trainer is the one caller that guarantees it
+        if hasattr(criterion, "unit_grad_output"):
+            criterion.unit_grad_output = True
         self.last_stats = None
         # schedule scalars and the dropout seed live in device memory (written from a pinned staging buffer once
         # per update) so that a captured CUDA graph of the whole step can be replayed with fresh values
@@ -42,7 +47,13 @@ class Trainer:
         self._hyper_host = torch.zeros(2, dtype=torch.float32, pin_memory=pin)
         self._seed_host = torch.zeros(1, dtype=torch.int64, pin_memory=pin)
         _ops.set_seed_tensor(self._seed)
+        # CUDA graphs are keyed on BUCKETED shapes: waveform length padded to a multiple of `bucket_frames` feature
+        # frames, target length to a multiple of `bucket_tokens`, SpecAugment descriptor counts to multiples of 4,
+        # so real (every-batch-different) length distributions hit a small set of graphs; least-recently-used graphs
+        # are dropped beyond `max_graphs`.
+        self.bucket_frames, self.bucket_tokens, self.max_graphs = bucket_frames, bucket_tokens, max_graphs
         self._graphs, self._seen, self._pool = {}, {}, None
+        self.graph_hits = self.graph_misses = 0
 
     def get_lr(self):
         return self.lr_scheduler.lr
@@ -51,7 +62,8 @@ class Trainer:
         lr = self.lr_scheduler.step_update(self.num_updates)
         self._hyper_host[0] = lr
         self._hyper_host[1] = float(self.num_updates + 1)
-        self._seed_host[0] = (self.num_updates + 1) * 1000003
+        # one dropout stream per (update, rank); micro-batches of an update are separated in _fwd_bwd
+        self._seed_host[0] = (self.num_updates + 1) * 1000003 + self.rank * 7919
         self._hyper.copy_(self._hyper_host, non_blocking=True)
         self._seed.copy_(self._seed_host, non_blocking=True)
 
@@ -61,9 +73,12 @@ class Trainer:
         model, flat = self.model, self.flat
         flat.zero_grad()
         tail = flat.tail
-        for sample in samples:
+        enc = getattr(model, "encoder", model)
+        for i, sample in enumerate(samples):
             if not sample:
                 continue
+            if hasattr(enc, "dropout_seed"):
+                enc.dropout_seed = 1 + i  # update_freq > 1: every micro-batch draws its own masks
             loss, sample_size, log = self.criterion(model, sample)
             loss.backward()
             (model.sync_torch_grads_ if hasattr(model, "sync_torch_grads_") else model.encoder.sync_torch_grads_)()
@@ -88,29 +103,90 @@ class Trainer:
         self._fwd_bwd(samples)
         self._reduce_and_update()
 
+    # ---- shape bucketing -------------------------------------------------------------------------------------
     @staticmethod
-    def _signature(sample):
+    def _round_up(n, m):
+        return (n + m - 1) // m * m
+
+    def _bucket_shapes(self, sample):
+        """Padded ("bucket") shapes of one micro-batch: {net_input key or 'target': shape}."""
         ni = sample["net_input"]
-        lens_cpu = ni.get("src_lengths_cpu")
-        full = bool((lens_cpu == lens_cpu.max()).all()) if lens_cpu is not None else None
-        sig = [("pads", full)]
-        for k in sorted(ni):
-            if torch.is_tensor(ni[k]) and ni[k].is_cuda:
-                sig.append((k, tuple(ni[k].shape), str(ni[k].dtype)))
-        sig.append(("target", tuple(sample["target"].shape)))
-        return tuple(sig)
+        shapes = {}
+        for k, v in ni.items():
+            if not (torch.is_tensor(v) and v.is_cuda):
+                continue
+            shp = list(v.shape)
+            if k == "src_tokens":
+                if v.dim() == 2:    # raw waveform [B, N]: N -> samples of the next multiple of bucket_frames frames
+                    frames = 1 + max(shp[1] - 400, 0) // 160
+                    shp[1] = max(shp[1], 400 + (self._round_up(frames, self.bucket_frames) - 1) * 160)
+                elif v.dim() == 3:  # features [B, T, F]
+                    shp[1] = self._round_up(shp[1], self.bucket_frames)
+            elif k in ("freq_masks", "time_masks"):
+                shp[1] = self._round_up(shp[1], 4)
+            elif k == "prev_output_tokens":
+                shp[1] = self._round_up(shp[1], self.bucket_tokens)
+            shapes[k] = tuple(shp)
+        t = list(sample["target"].shape)
+        if len(t) == 2:
+            t[1] = self._round_up(t[1], self.bucket_tokens)
+        shapes["target"] = tuple(t)
+        return shapes
+
+    def _has_pads(self, sample, shapes):
+        """The predicate the model bakes into the captured kernels' arguments (length masking on/off): any utterance
+        shorter than the (bucketed) encoder time axis, evaluated AFTER the conv front's subsampling."""
+        ni = sample["net_input"]
+        lens = ni["src_lengths_cpu"]
+        T = shapes["src_tokens"][1]
+        if len(shapes["src_tokens"]) == 2:
+            lens = torch.where(lens >= 400, 1 + (lens - 400) // 160, torch.zeros_like(lens))
+            T = 1 + (T - 400) // 160
+        out = self.model.output_lengths(lens)
+        Tp = int(self.model.output_lengths(torch.tensor([T]))[0])
+        return bool((out < Tp).any())
+
+    def _signature(self, sample):
+        shapes = self._bucket_shapes(sample)
+        sig = [("pads", self._has_pads(sample, shapes))]
+        sig += [(k, shapes[k], str(sample["net_input"][k].dtype)) for k in sorted(shapes) if k != "target"]
+        sig.append(("target", shapes["target"]))
+        return tuple(sig), shapes
+
+    def _pad_value(self, key):
+        if key in ("target", "prev_output_tokens"):
+            return getattr(self.criterion, "pad_idx", getattr(self.criterion, "padding_idx", 1))
+        return 0  # waveform samples / feature frames beyond src_lengths are never read; width-0 masks are no-ops
+
+    def _fill_static(self, static, sample):
+        for k, v in list(sample["net_input"].items()) + [("target", sample["target"])]:
+            if not (torch.is_tensor(v) and v.is_cuda):
+                continue
+            dst = static["target"] if k == "target" else static["net_input"][k]
+            if dst.shape == v.shape:
+                dst.copy_(v, non_blocking=True)
+            else:
+                if k != "src_tokens" or v.dim() != 2:
+                    # token / descriptor / feature-frame tails carry meaning (pad symbol, no-op mask, zero frames as
+                    # collate_frames pads them); only raw-waveform samples beyond src_lengths are never read
+                    dst.fill_(self._pad_value(k))
+                dst[tuple(slice(0, n) for n in v.shape)].copy_(v, non_blocking=True)
 
     def _graphed_step(self, sample):
-        key = self._signature(sample)
+        key, shapes = self._signature(sample)
         entry = self._graphs.get(key)
         if entry is None:
+            self.graph_misses += 1
             self._seen[key] = self._seen.get(key, 0) + 1
-            if self._seen[key] < 2:  # first sight of this shape: plain eager step (also warms every kernel up)
+            if self._seen[key] < 2:  # first sight of this bucket: plain eager step (also warms every kernel up)
                 self._step_body([sample])
                 return
-            static = {"net_input": {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v)
-                                    for k, v in sample["net_input"].items()},
-                      "target": sample["target"].clone()}
+            ni = sample["net_input"]
+            static = {"net_input": {k: (torch.full(shapes[k], self._pad_value(k), dtype=v.dtype, device=v.device)
+                                        if k in shapes else v) for k, v in ni.items()},
+                      "target": torch.full(shapes["target"], self._pad_value("target"), dtype=sample["target"].dtype,
+                                           device=sample["target"].device)}
+            self._fill_static(static, sample)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             n0 = _lib.launch_count()
@@ -120,13 +196,17 @@ class Trainer:
             _lib.load().esp_note_graph_replay(-n_kernels)  # capture itself executed nothing
             if self._pool is None:
                 self._pool = graph.pool()
-            entry = (graph, static, n_kernels)
+            entry = [graph, static, n_kernels, 0]
             self._graphs[key] = entry
-        graph, static, n_kernels = entry
-        for k, v in sample["net_input"].items():
-            if torch.is_tensor(v) and v.is_cuda:
-                static["net_input"][k].copy_(v, non_blocking=True)
-        static["target"].copy_(sample["target"], non_blocking=True)
+            if len(self._graphs) > self.max_graphs:  # drop the least recently used graph
+                old = min((k for k in self._graphs if k != key), key=lambda k: self._graphs[k][3])
+                del self._graphs[old]
+        else:
+            self.graph_hits += 1
+        graph, static, n_kernels, _ = entry
+        entry[3] = self.num_updates
+        self._fill_static(static, sample)
+        # host-side lengths are not part of the graph, but the model reads them while CAPTURING only
         graph.replay()
         _lib.load().esp_note_graph_replay(n_kernels)
         self._reduce_and_update()
