@@ -111,6 +111,44 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair, one 256-row UMMA across two SMs) ------------------------------------------------
+// Shared::cluster addresses carry the CTA rank in bit 24; clearing it makes an mbarrier address name the LEADER
+// (even) CTA's barrier at the same offset (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_cg2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -245,12 +283,12 @@ __device__ __forceinline__ void dropout32(float* v, unsigned long long seed, uns
   }
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, bool CG2 = false>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (CG2 ? BN / 2 : BN) * BK * 2;  // cta_group::2: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && !CG2) ? 4 : 6;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
@@ -258,11 +296,22 @@ struct SmemLayout {
 // MC = 2: the kernel runs as 2-CTA clusters along M.  The two CTAs of a cluster work on M-adjacent tiles of the same
 // (N tile, batch, K split), so they need the SAME B tile: each loads half of it and multicasts it to both, which cuts
 // the L2->SM operand traffic per CTA from (128 + BN) to (128 + BN/2) rows per k-block -- the bound of these tiles.
+//
+// MC = 3: cta_group::2.  The pair computes ONE 256 x BN tile with tcgen05.mma.cta_group::2 (UMMA_M = 256): each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader CTA's MMA thread issues for both SMs, each
+// CTA's TMEM receives the accumulator of its own 128 rows and its own epilogue warps drain it.  Per k-block and SM the
+// operand ingress drops from (128 + BN) to (128 + BN/2) rows for the same 128 x BN outputs per SM -- the bound of the
+// cta_group::1 kernel.  Barrier protocol (cutlass sm100 2-SM pipelines restated): both
+// producers' TMA transactions signal the LEADER's full barrier (peer bit cleared), which expects the bytes of both
+// CTAs; the MMA thread's commits are multicast to both CTAs' empty / accumulator-full barriers; the epilogue warps of
+// both CTAs arrive on the leader's accumulator-empty barrier.
 template <int BN, bool A_K, bool B_K, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const KParams p) {
-  using L = SmemLayout<BN, A_K, B_K>;
+  constexpr bool CG2 = (MC == 3);
+  constexpr int CL = MC > 1 ? 2 : 1;  // cluster size
+  using L = SmemLayout<BN, A_K, B_K, CG2>;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -282,13 +331,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // With MC = 2 a work item is a PAIR of M tiles: "tiles_m" counts pairs and this CTA owns tile 2*pair + rank
   // (a missing odd tile is all out-of-bounds rows: TMA zero-fills, the epilogue's row guard drops it).
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
-  const int tiles_m = ((p.M + BM - 1) / BM + MC - 1) / MC;
+  const int tiles_m = ((p.M + BM - 1) / BM + CL - 1) / CL;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int nbatch = p.nb1 * p.nb2;
   const int num_kb_all = (p.K + BK - 1) / BK;
   const int kb_per = (num_kb_all + p.ksplit - 1) / p.ksplit;
   const int total_tiles = tiles_m * tiles_n * nbatch * p.ksplit;  // work items = output tiles (pairs) x K splits
-  const int work0 = blockIdx.x / MC, work_stride = gridDim.x / MC;
+  const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
 
   esp_pdl_trigger();  // the next kernel may be scheduled behind this grid's CTAs (it waits for our completion itself)
   if (warp == 0 && lane == 0) {
@@ -298,20 +347,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), MC);  // MC > 1: the peer's producer also writes this slot, so both consumers free it
+      // MC = 2: the peer's producer also writes this slot, so both consumers free it; MC = 3: one (multicast) commit
+      mbar_init(empty_bar(s), MC == 2 ? 2 : 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), CG2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     constexpr int kCols = kAccStages * BN;  // 128 / 256 / 512: all powers of two >= 32
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(kCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (CG2) {  // the same warp of BOTH CTAs allocates (cute::TMEM::Allocator2Sm contract)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -332,7 +387,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb0 = ks * kb_per;
         const int kb1 = min(num_kb_all, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K split (all three roles skip it identically)
-        const int mt = (tile % tiles_m) * MC + crank;
+        const int mt = (tile % tiles_m) * CL + crank;
         const int rest = tile / tiles_m;
         const int nt = rest % tiles_n;
         const int bt = rest / tiles_n;
@@ -341,9 +396,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), L::kStageBytes);
           const uint32_t sa = smem_base + s * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
+          if (CG2) {
+            // both CTAs' transactions complete on the leader's barrier, which expects the bytes of the pair
+            if (crank == 0) mbar_expect_tx(full_bar(s), 2 * L::kStageBytes);
+            if (A_K) {
+              tma_load_4d_cg2(sa, &tmA, full_bar(s), kb * BK, mt * BM, b1 * p.a_b1, b2 * p.a_b2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_4d_cg2(sa + j * (BK * 128), &tmA, full_bar(s), mt * BM + 64 * j, kb * BK, b1 * p.a_b1,
+                                b2 * p.a_b2);
+            }
+            const int n0 = nt * BN + crank * (BN / 2);  // this CTA's half of the B tile
+            if (B_K) {
+              tma_load_4d_cg2(sb, &tmB, full_bar(s), kb * BK, n0, b1 * p.b_b1, b2 * p.b_b2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_4d_cg2(sb + j * (BK * 128), &tmB, full_bar(s), n0 + 64 * j, kb * BK, b1 * p.b_b1,
+                                b2 * p.b_b2);
+            }
+            continue;
+          }
+          mbar_expect_tx(full_bar(s), L::kStageBytes);
           if (A_K) {
             tma_load_4d(sa, &tmA, full_bar(s), kb * BK, mt * BM, b1 * p.a_b1, b2 * p.a_b2);
           } else {
@@ -352,7 +429,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(s), mt * BM + 64 * j, kb * BK,
                           b1 * p.a_b1, b2 * p.a_b2);
           }
-          if (MC == 1) {
+          if (MC != 2) {
             if (B_K) {
               tma_load_4d(sb, &tmB, full_bar(s), kb * BK, nt * BN, b1 * p.b_b1, b2 * p.b_b2);
             } else {
@@ -381,11 +458,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =======================================
-    if (lane == 0) {
+    if (lane == 0 && (!CG2 || crank == 0)) {  // cta_group::2: the leader CTA issues for the pair
       // Instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=bf16.
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_K ? 0u : 1u) << 15) |
                              ((B_K ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)((CG2 ? 2 * BM : BM) >> 4) << 24);
       uint32_t it = 0, ti = 0;
       for (int work = work0; work < total_tiles; work += work_stride) {
         const int ks = work % p.ksplit;
@@ -414,13 +491,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     : make_sdesc(sa + k * 2048, BK * 128, 1024);
             const uint64_t db = B_K ? make_sdesc(sb + k * 32, 16, 1024)
                                     : make_sdesc(sb + k * 2048, BK * 128, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if (CG2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          // frees the smem slot when these MMAs retire (in both CTAs of a multicast pair)
-          if (MC > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)0x3);
+          // frees the smem slot when these MMAs retire (in both CTAs of a pair)
+          if (CG2) tcgen05_commit_cg2_mc(empty_bar(s), (uint16_t)0x3);
+          else if (MC > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)0x3);
           else tcgen05_commit(empty_bar(s));
         }
-        tcgen05_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs in cta_group::2 mode)
+        if (CG2) tcgen05_commit_cg2_mc(tfull_bar(as), (uint16_t)0x3);
+        else tcgen05_commit(tfull_bar(as));
       }
     }
   } else if (warp >= 4) {
@@ -439,7 +520,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int kb0 = ks * kb_per;
       const int kb1 = min(num_kb_all, kb0 + kb_per);
       if (kb0 >= kb1) continue;
-      const int mt = (tile % tiles_m) * MC + crank;
+      const int mt = (tile % tiles_m) * CL + crank;
       const int rest = tile / tiles_m;
       const int nt = rest % tiles_n;
       const int bt = rest / tiles_n;
@@ -592,7 +673,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(tempty_bar(as), 0u);  // the leader's MMA thread waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
@@ -602,7 +686,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tcgen05_fence_after();
     constexpr int kCols = kAccStages * BN;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols));
+    if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols));
   }
 }
 
@@ -668,42 +753,54 @@ int make_tmap(CUtensorMap* tm, const void* base, long inner, long rows, long ld,
   return 0;
 }
 
+bool esp_gemm_cg2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ESP_GEMM_CG2");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// co-resident 2-CTA clusters of a kernel variant (clusters sit inside one GPC: with odd SM counts per GPC fewer than
+// SMs/2 pairs fit at once -- ask the runtime instead of assuming)
+template <typename K>
+int cluster_slots(K kfn, int smem_bytes) {
+  int slots = esp_num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(esp_num_sms() / 2 * 2);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) == cudaSuccess && n > 0 && n < slots) slots = n;
+  (void)cudaGetLastError();
+  return slots;
+}
+
 template <int BN, bool A_K, bool B_K, int MC>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t st) {
-  using L = SmemLayout<BN, A_K, B_K>;
+  constexpr int CL = MC > 1 ? 2 : 1;
+  using L = SmemLayout<BN, A_K, B_K, MC == 3>;
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC>;
   if (!configured) {
     ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int tiles_m = (((kp.M + BM - 1) / BM) + MC - 1) / MC;
+  const int tiles_m = (((kp.M + BM - 1) / BM) + CL - 1) / CL;
   const int work = tiles_m * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2 * kp.ksplit;
-  // persistent grid = what is co-resident.  Clusters must sit inside one GPC, so with odd SM counts per GPC fewer
-  // than SMs/2 pairs fit at once: ask the runtime instead of assuming.
-  static int slots = 0;
-  if (slots == 0) {
-    slots = esp_num_sms() / MC;
-    if (MC > 1) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(esp_num_sms() / MC * MC);
-      cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = L::kTotal;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = MC;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) == cudaSuccess && n > 0 && n < slots) slots = n;
-      (void)cudaGetLastError();
-    }
-  }
-  int grid = (work < slots ? work : slots) * MC;
+  static int slots = 0;  // persistent grid = what is co-resident
+  if (slots == 0) slots = CL > 1 ? cluster_slots(kfn, L::kTotal) : esp_num_sms();
+  int grid = (work < slots ? work : slots) * CL;
   if (grid < 1) return 0;
-  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, MC, ta, tb, kp);
+  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, CL, ta, tb, kp);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
@@ -736,16 +833,27 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   auto tiles_for = [&](int w) { return tm * ((g->N + w - 1) / w) * (long)nb1 * nb2; };
   int bn;
   int ksplit = 1;
+  int mode = 1;  // 1: single CTA, 2: multicast pair, 3: cta_group::2 pair
   const int num_kb = (int)((g->K + BK - 1) / BK);
+  const bool cg2_ok = esp_gemm_cg2_enabled() && tm >= 2 && g->N > 128 && g->K >= 256;  // K = 64 attention tiles are epilogue-bound: no gain
+  const int pairs = sms / 2;  // upper bound of co-resident clusters (the launch clamps to the real number)
+  // utilisation of `slots` persistent workers by `items` equal work items
+  auto eff = [](long items, long slots) {
+    const long waves = (items + slots - 1) / slots;
+    return (double)items / (double)(waves * slots);
+  };
   if (g->accumulate) {
     // gradient GEMMs: long reduction (K = rows of the batch), small output -> split K across CTAs and
     // accumulate with vector reductions; keep >= 4 k-blocks per split.
     bn = g->N >= 192 ? 256 : (g->N > 64 ? 128 : 64);
-    const long t = tiles_for(bn);
-    if (t < sms) {
-      ksplit = (int)((sms + t - 1) / t);
-      const int max_split = num_kb / 4 > 0 ? num_kb / 4 : 1;
-      if (ksplit > max_split) ksplit = max_split;
+    if (bn == 256 && cg2_ok) mode = 3;
+    const long t = mode == 3 ? ((tm + 1) / 2) * ((g->N + 255) / 256) * (long)nb1 * nb2 : tiles_for(bn);
+    const long slots = mode == 3 ? pairs : sms;
+    const int max_split = num_kb / 4 > 0 ? num_kb / 4 : 1;
+    double best = -1.0;
+    for (int ks = 1; ks <= max_split && (long)(ks - 1) * t < slots; ++ks) {
+      const double e = eff(t * ks, slots) - 0.01 * ks;  // prefer fewer splits at equal utilisation (less red traffic)
+      if (e > best) { best = e; ksplit = ks; }
     }
   } else {
     if (g->N <= 64) bn = 64;
@@ -753,11 +861,22 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
     else if (g->N > 64 && tiles_for(128) * 10 >= (long)sms * 6) bn = 128;
     else if (g->N >= 192 && tiles_for(256) * 2 >= tiles_for(128)) bn = 128;
     else bn = g->N > 128 ? 128 : (g->N > 64 && tiles_for(64) < sms ? 64 : 128);
+    // cta_group::2 (256 x 256 per CTA pair): whenever the output is wide enough and the pairs fill at least ~60 % of
+    // the machine -- halving the per-SM operand ingress outweighs some tile-quantisation loss
+    if (cg2_ok && g->N >= 192) {
+      const long t2 = ((tm + 1) / 2) * ((g->N + 255) / 256) * (long)nb1 * nb2;
+      if (eff(t2, pairs) >= 0.6 || t2 >= 4 * pairs) { bn = 256; mode = 3; }
+    }
   }
-  if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) bn = g->tile_n;
+  if (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) { bn = g->tile_n; mode = 1; }
+  if (g->tile_n == 512) {  // forced cta_group::2 (tests, microbenchmarks)
+    ESP_CHECK(tm >= 1 && g->N >= 1, "bad shape");
+    bn = 256;
+    mode = 3;
+  }
   // 2-CTA multicast pairs along M: worth it when the pairing wastes (almost) no tile
-  int mc = 1;
-  if (bn >= 128 && esp_gemm_multicast_enabled() && (tm % 2 == 0 || tm >= 16)) mc = 2;
+  if (mode == 1 && bn >= 128 && esp_gemm_multicast_enabled() && (tm % 2 == 0 || tm >= 16)) mode = 2;
+  const int mc = mode == 1 ? 1 : 2;
   int rc;
   if (ak) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, nb1, g->sA1, nb2, g->sA2, BM);
   else    rc = make_tmap(&ta, g->A, g->M, g->K, g->lda, nb1, g->sA1, nb2, g->sA2, BK);
@@ -787,6 +906,9 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   ESP_CHECK(!g->accumulate || g->c_f32, "accumulate (atomic) output must be fp32");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
   if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, kp, st);
-  if (bn == 256) return mc == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, kp, st);
-  return mc == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, kp, st);
+  if (bn == 256) {
+    if (mode == 3) return dispatch_major<256, 3>(ak, bk, ta, tb, kp, st);
+    return mode == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, kp, st);
+  }
+  return mode == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, kp, st);
 }

@@ -177,15 +177,20 @@ class Trainer:
         entry = self._graphs.get(key)
         if entry is None:
             self.graph_misses += 1
-            self._seen[key] = self._seen.get(key, 0) + 1
-            if self._seen[key] < 2:  # first sight of this bucket: plain eager step (also warms every kernel up)
-                self._step_body([sample])
+            static = self._seen.get(key)
+            if static is None:
+                # first sight of this bucket: a plain eager step ON THE BUCKET-SHAPED buffers, so that every
+                # shape-dependent cache (position tables, workspaces, kernel attributes) exists before capture
+                ni = sample["net_input"]
+                static = {"net_input": {k: (torch.full(shapes[k], self._pad_value(k), dtype=v.dtype, device=v.device)
+                                            if k in shapes else v) for k, v in ni.items()},
+                          "target": torch.full(shapes["target"], self._pad_value("target"), dtype=sample["target"].dtype,
+                                               device=sample["target"].device)}
+                self._seen[key] = static
+                self._fill_static(static, sample)
+                self._step_body([static])
                 return
-            ni = sample["net_input"]
-            static = {"net_input": {k: (torch.full(shapes[k], self._pad_value(k), dtype=v.dtype, device=v.device)
-                                        if k in shapes else v) for k, v in ni.items()},
-                      "target": torch.full(shapes["target"], self._pad_value("target"), dtype=sample["target"].dtype,
-                                           device=sample["target"].device)}
+            del self._seen[key]
             self._fill_static(static, sample)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()

@@ -62,7 +62,7 @@ typedef struct EspGemm {
   int32_t act;
   int32_t drop_mode; /* 0 none, 1 after activation (forward), 2 before activation (backward) */
   int32_t skew_r;    /* 0, or T: read R with relative-position skew */
-  int32_t tile_n;    /* 0 auto, or 64/128/256 */
+  int32_t tile_n;    /* 0 auto, or 64/128/256 (single-CTA tiles), 512 = 256-wide tile on a cta_group::2 CTA pair */
   int32_t accumulate; /* 1: C (fp32) += alpha*acc with L2 vector reductions; enables split-K (weight gradients) */
   float alpha, beta, drop_p;
   uint64_t seed;

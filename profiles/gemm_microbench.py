@@ -39,7 +39,7 @@ def rnd(*s):
 
 x = rnd(R, d)
 h = rnd(R, ffn)
-for tn in (0, 128, 256):
+for tn in (0, 256, 512):  # 0 = heuristic, 256 = single-CTA/multicast 128x256, 512 = cta_group::2 256x256 per CTA pair
     W1, b1 = rnd(ffn, d), rnd(ffn)
     U = torch.empty(R, ffn, device=dev, dtype=BF)
     out = torch.empty(R, ffn, device=dev, dtype=BF)

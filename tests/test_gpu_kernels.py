@@ -145,7 +145,7 @@ def _ref_mm(a, b):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 72, 96), (1000, 512, 512), (333, 2048, 520), (6500, 5008, 512),
                                    (77, 40, 2560), (1, 8, 8)])
-@pytest.mark.parametrize("tile_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 256, 512])  # 512 = forced cta_group::2 (256 x 256 per CTA pair)
 def test_gemm_kmajor(dev, M, N, K, tile_n):
     from espresso_b200 import ops
 
@@ -160,7 +160,7 @@ def test_gemm_kmajor(dev, M, N, K, tile_n):
 
 
 @pytest.mark.parametrize("ak,bk", [(True, False), (False, True), (False, False)])
-@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("tile_n", [64, 128, 256, 512])
 def test_gemm_mn_major(dev, ak, bk, tile_n):
     from espresso_b200 import ops
 
@@ -175,11 +175,16 @@ def test_gemm_mn_major(dev, ak, bk, tile_n):
     assert (c - _ref_mm(a, b)).abs().max().item() < 0.05
 
 
-def test_gemm_epilogues(dev):
-    from espresso_b200 import ops
+@pytest.mark.parametrize("tile_n,M,N,K", [(0, 400, 264, 136), (512, 400, 264, 136), (512, 1000, 520, 328)])
+def test_gemm_epilogues(dev, tile_n, M, N, K):
+    from espresso_b200 import ops as _o
+    import functools
+    import types
 
+    # every ops.linear below runs with the parametrised tile mode
+    ops = types.SimpleNamespace(**{k: getattr(_o, k) for k in dir(_o) if not k.startswith("__")})
+    ops.linear = functools.partial(_o.linear, tile_n=tile_n)
     torch.manual_seed(1)
-    M, N, K = 400, 264, 136
     a = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.2).bfloat16()
     bias = torch.randn(N, device=dev).bfloat16()
@@ -242,7 +247,8 @@ def test_gemm_batched_and_skew(dev):
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 512, 6500), (2048, 512, 3000), (5004, 512, 1806), (512, 2560, 777), (64, 31 * 8, 4000)])
-def test_gemm_accumulate_splitk(dev, M, N, K):
+@pytest.mark.parametrize("tile_n", [0, 512])
+def test_gemm_accumulate_splitk(dev, M, N, K, tile_n):
     """Weight-gradient form: C(fp32) += A^T B with both operands MN-major, split-K + vector reductions."""
     from espresso_b200 import ops
 
@@ -251,8 +257,8 @@ def test_gemm_accumulate_splitk(dev, M, N, K):
     dy = torch.randn(K, ldm, device=dev).bfloat16()[:, :M]  # [rows, N_out] view with padded row stride (A = dy^T)
     x = torch.randn(K, N, device=dev).bfloat16()
     c = torch.full((M, N), 2.0, device=dev, dtype=torch.float32)
-    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True)
+    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, tile_n=tile_n)
     ref = 2.0 + dy.float().t() @ x.float()
     assert (c - ref).abs().max().item() <= 3e-3 * K ** 0.5 + 1e-2
-    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, alpha=-1.0)
+    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, alpha=-1.0, tile_n=tile_n)
     assert (c - 2.0).abs().max().item() <= 6e-3 * K ** 0.5 + 2e-2
