@@ -187,7 +187,7 @@ class OracleStep:
         self.OC, self.dev, self.bf16 = OC, device, bf16
         dt = torch.bfloat16 if bf16 else torch.float32
         sd = OC.random_state_dict(ORACLE_CFG, seed=1)
-        self.sd = {k: v.to(device=device, dtype=(torch.float32 if "running_" in k else dt)) for k, v in sd.items()}
+        self.sd = {k: v.to(device=device, dtype=dt) for k, v in sd.items()}  # model.bfloat16() casts the BN buffers too
         self.params = [v.requires_grad_(True) for k, v in self.sd.items() if "running_" not in k]
         self.master = [p.detach().float().clone() for p in self.params] if bf16 else self.params
         self.opt = torch.optim.Adam(self.master, lr=1e-4, betas=(0.9, 0.98), eps=1e-8)

@@ -817,6 +817,12 @@ int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& t
 
 }  // namespace
 
+// bf16 SWIZZLE_128B tensor map (64-element boxes) for the other tcgen05 kernels of the library (attn_fused.cu)
+int esp_make_tmap_bf16(CUtensorMap* tm, const void* base, long inner, long rows, long ld, int nb1, long s1, int nb2,
+                       long s2, int box_rows) {
+  return make_tmap(tm, base, inner, rows, ld, nb1, s1, nb2, s2, box_rows);
+}
+
 extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ESP_CHECK(g != nullptr, "null gemm descriptor");

@@ -14,6 +14,7 @@ module's backward mirrors its forward line by line and accumulates parameter gra
 the flat fp32 gradient buffer.
 """
 import math
+import os
 
 import torch
 
@@ -63,6 +64,10 @@ class EncoderEngine:
         self.bn_state = None  # {layer: (running_mean fp32, running_var fp32)} provided by the module
         self.training = True
         self.seed = 0
+        # rel-pos attention forward as one fused tcgen05 kernel (csrc/attn_fused.cu); ESP_FUSED_ATTN=0 restores the
+        # round-1 chain (BD GEMM -> QK^T+skew GEMM -> softmax -> P V GEMM) for A/B comparisons
+        self.fused_attention = os.environ.get("ESP_FUSED_ATTN", "1") != "0"
+        self._save_probs = True
 
     # ------------------------------------------------------------------------------------------
     def P(self, name):
@@ -173,17 +178,23 @@ class EncoderEngine:
             Pp = _ops.linear(pe, self.P(lp + "self_attn.pos_proj.weight"))  # [2T-1, d], batch independent
         E = Pp.shape[1]
         ph = hd if E == d else 0  # head stride of the position operand
-        ldt, ldp = _r8(T), _r8(2 * T - 1)
-        BD = torch.empty(H, B, T, ldp, device=x.device, dtype=torch.bfloat16)
-        _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, E, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(ph, 0),
-                  sC=(B * T * ldp, T * ldp))
-        S = torch.empty(H, B, T, ldt, device=x.device, dtype=torch.bfloat16)
-        _ops.gemm(qu, k, S, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
-                  sC=(B * T * ldt, T * ldt), R=BD, ldr=ldp, sR=(B * T * ldp, T * ldp), skew_r=T)
-        Pr, Pd = _ops.attn_softmax_fwd(S, T, lens, self._drop("attention_dropout"), self._seed(li, 10))
-        ctx = torch.empty(R, d, device=x.device, dtype=torch.bfloat16)
-        _ops.gemm(Pd, v, ctx, T, hd, T, ldt, 3 * d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
-                  sB=(hd, T * 3 * d), sC=(hd, T * d))
+        if self.fused_attention and hd == 64:
+            # scores, relative-position logits, skew, softmax and P v in ONE kernel (csrc/attn_fused.cu); only the
+            # probabilities the backward pass needs go to HBM
+            ctx, Pr, Pd = _ops.attn_fused_fwd(qu, qv, k, v, Pp, B, T, H, lens, self._drop("attention_dropout"),
+                                              self._seed(li, 10), save_probs=self._save_probs, pos_hstride=ph)
+        else:
+            ldt, ldp = _r8(T), _r8(2 * T - 1)
+            BD = torch.empty(H, B, T, ldp, device=x.device, dtype=torch.bfloat16)
+            _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, E, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(ph, 0),
+                      sC=(B * T * ldp, T * ldp))
+            S = torch.empty(H, B, T, ldt, device=x.device, dtype=torch.bfloat16)
+            _ops.gemm(qu, k, S, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
+                      sC=(B * T * ldt, T * ldt), R=BD, ldr=ldp, sR=(B * T * ldp, T * ldp), skew_r=T)
+            Pr, Pd = _ops.attn_softmax_fwd(S, T, lens, self._drop("attention_dropout"), self._seed(li, 10))
+            ctx = torch.empty(R, d, device=x.device, dtype=torch.bfloat16)
+            _ops.gemm(Pd, v, ctx, T, hd, T, ldt, 3 * d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
+                      sB=(hd, T * 3 * d), sC=(hd, T * d))
         y = _ops.linear(ctx, self.P(lp + "self_attn.out_proj.weight"), self.P(lp + "self_attn.out_proj.bias"),
                         drop_p=self._drop("dropout"), drop_mode=1, seed=self._seed(li, 11), R=x, ldr=x.stride(0), beta=1.0)
         return y, (x, mean, rstd, ln, qkv, qu, qv, Pp, Pr, Pd, ctx)
@@ -318,6 +329,7 @@ class EncoderEngine:
         R = B * T
         cfg = self.cfg
         lens_k = lens if has_pads else None
+        self._save_probs = bool(save)  # inference: the fused attention kernel writes no probabilities at all
         pdrop = self._drop("dropout")
         xin = xc.reshape(R, Fin)
         if pdrop > 0:

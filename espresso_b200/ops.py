@@ -251,6 +251,29 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
     return p, (pd if pd is not None else p)
 
 
+def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None):
+    """Fused relative-position attention forward (esp_attn_fused_fwd): qu, qv [B*T, d]; k, v [B*T, d] views with a common
+    row stride (the fused q/k/v buffer); pos [2T-1, E] projected positions (E == d: head h at column h*hd; E == hd: one
+    table for all heads).  Returns (ctx [B*T, d], p, p_drop) with p / p_drop [H, B, T, ld] bf16 or None."""
+    _need_cuda(qu, qv, k, v, pos, lens)
+    _bf(qu, qv, k, v, pos)
+    R, d = qu.shape
+    hd = d // H
+    assert R == B * T and qv.shape == qu.shape and qu.stride(0) == qv.stride(0) and qu.stride(1) == 1
+    assert k.stride(0) == v.stride(0) and k.stride(1) == 1 and v.stride(1) == 1 and pos.stride(1) == 1
+    assert lens is None or lens.dtype == torch.int32
+    if pos_hstride is None:
+        pos_hstride = hd if pos.shape[1] == d else 0
+    ld = (T + 7) // 8 * 8
+    ctx = torch.empty(R, d, device=qu.device, dtype=torch.bfloat16)
+    p = torch.empty(H, B, T, ld, device=qu.device, dtype=torch.bfloat16) if save_probs else None
+    pd = torch.empty_like(p) if (save_probs and drop_p > 0) else None
+    _lib.check(_lib.load().esp_attn_fused_fwd(_ptr(qu), _ptr(qv), qu.stride(0), _ptr(k), _ptr(v), k.stride(0), _ptr(pos),
+                                              pos.stride(0), pos_hstride, B, T, H, hd, _ptr(lens), _ptr(ctx), d, _ptr(p),
+                                              _ptr(pd), ld, drop_p, seed, _seed_ptr(), _stream()))
+    return ctx, p, (pd if pd is not None else p)
+
+
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     """Returns (dS [H,B,Tq,ld], dBD [H,B,T,ldp] in skewed relative-position layout or None)."""
     _need_cuda(p, dp_drop)

@@ -150,6 +150,37 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
     return p, p
 
 
+def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None):
+    """fairseq/modules/multihead_attention.py:788-897 (rel-pos branch) in fp32: AC + skew(BD), key-padding mask, softmax,
+    P v.  Same return convention as espresso_b200.ops.attn_fused_fwd."""
+    assert drop_p == 0.0
+    R, d = qu.shape
+    hd = d // H
+    if pos_hstride is None:
+        pos_hstride = hd if pos.shape[1] == d else 0
+    quh = qu.float().view(B, T, H, hd).permute(2, 0, 1, 3)                    # [H, B, T, hd]
+    qvh = qv.float().view(B, T, H, hd).permute(2, 0, 1, 3)
+    kh = k.float().reshape(B, T, H, hd).permute(2, 0, 1, 3)
+    vh = v.float().reshape(B, T, H, hd).permute(2, 0, 1, 3)
+    ph = torch.stack([pos.float()[:, h * pos_hstride: h * pos_hstride + hd] for h in range(H)])   # [H, 2T-1, hd]
+    ac = quh @ kh.transpose(-1, -2)
+    bd_full = (qvh @ ph[:, None].transpose(-1, -2)).to(BF).float()           # the reference keeps BD in the model dtype
+    i = torch.arange(T)[:, None]
+    j = torch.arange(T)[None, :]
+    s = ac + bd_full.gather(-1, ((T - 1) - i + j).expand(H, B, T, T))
+    if lens is not None:
+        km = torch.arange(T)[None, :] >= lens[:, None]
+        s = s.masked_fill(km[None, :, None, :], float("-inf"))
+    pr = torch.softmax(s, dim=-1).to(BF)
+    ctx = (pr.float() @ vh).permute(1, 2, 0, 3).reshape(R, d).to(BF)
+    ld = (T + 7) // 8 * 8
+    p = None
+    if save_probs:
+        p = torch.zeros(H, B, T, ld, dtype=BF)
+        p[..., :T] = pr
+    return ctx, p, p
+
+
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     assert drop_p == 0.0
     H, B, Tq, ld = p.shape

@@ -296,3 +296,76 @@ def test_joint_kernels(dev):
     der, ddr = O.joint_bwd(df, fr)
     _close(de, der, 0.02, "joint denc")
     _close(dd, ddr, 0.01, "joint ddec")
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused relative-position attention forward (csrc/attn_fused.cu) vs the fp32 statement of
+# fairseq/modules/multihead_attention.py:788-897
+# ---------------------------------------------------------------------------------------------------
+def _attn_inputs(B, T, H, seed, dev, shared_pos=False):
+    torch.manual_seed(seed)
+    d = H * 64
+    qkv = (torch.randn(B * T, 3 * d, device=dev) * 0.7).bfloat16()
+    qu = (torch.randn(B * T, d, device=dev) * 0.3).bfloat16()
+    qv = (torch.randn(B * T, d, device=dev) * 0.3).bfloat16()
+    pos = (torch.randn(2 * T - 1, 64 if shared_pos else d, device=dev) * 0.7).bfloat16()
+    return qu, qv, qkv[:, d:2 * d], qkv[:, 2 * d:], pos
+
+
+@pytest.mark.parametrize("B,T,H,lens,shared", [
+    (2, 25, 2, None, False),                 # one partial tile (1 s utterances)
+    (3, 128, 2, [128, 77, 1], False),        # exactly one tile, padded keys, a single-key utterance
+    (2, 129, 4, [129, 128], False),          # one row / key spills into a second tile
+    (3, 407, 8, [407, 333, 150], False),     # the bench's typical T' (4 x 4 tiles)
+    (1, 875, 2, None, False),                # 35 s utterance: 7 x 7 tiles
+    (2, 200, 4, [200, 64], True),            # learned positions shared by all heads (head stride 0)
+])
+def test_attn_fused_fwd_vs_reference(dev, B, T, H, lens, shared):
+    from espresso_b200 import ops
+    from oracle import ops_ref
+
+    qu, qv, k, v, pos = _attn_inputs(B, T, H, 100 + T, dev, shared)
+    lens_t = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=dev)
+    ctx, p, pd = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens_t)
+    torch.cuda.synchronize()
+    rc, rp, _ = ops_ref.attn_fused_fwd(qu.cpu(), qv.cpu(), k.cpu(), v.cpu(), pos.cpu(), B, T, H,
+                                       None if lens is None else lens_t.cpu())
+    assert pd is p
+    perr = (p.float().cpu()[..., :T] - rp.float()[..., :T]).abs().max().item()
+    cerr = (ctx.float().cpu() - rc.float()).abs().max().item()
+    print("attn fused fwd B=%d T=%d H=%d: max |dP| %.2e, max |dctx| %.2e" % (B, T, H, perr, cerr))
+    # probabilities are bf16 (<= 2^-9 relative on values <= 1); logits differ by the bf16 rounding of BD only
+    assert perr < 1.5e-2, perr
+    assert cerr < 2e-2 * max(1.0, rc.float().abs().max().item()), cerr
+    ld = p.shape[-1]
+    assert ld % 8 == 0 and (p[..., T:] == 0).all()
+    assert torch.allclose(p.float()[..., :T].sum(-1), torch.ones(H, B, T, device=dev), atol=2e-2)
+    if lens is not None:  # masked keys get exactly zero probability
+        for b, l in enumerate(lens):
+            assert (p[:, b, :, l:] == 0).all()
+    # inference mode: same context, nothing else written
+    ctx2, p2, _ = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens_t, save_probs=False)
+    assert p2 is None and torch.equal(ctx2, ctx)
+
+
+def test_attn_fused_fwd_dropout_stream_matches_softmax_kernels(dev):
+    """The dropped probabilities use the same counter-RNG stream as esp_attn_softmax_fwd / _bwd (the backward pass
+    regenerates the mask with esp_attn_softmax_bwd), and ctx == Pd v."""
+    from espresso_b200 import ops
+
+    B, T, H = 2, 203, 4
+    qu, qv, k, v, pos = _attn_inputs(B, T, H, 7, dev)
+    ctx, p, pd = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, None, drop_p=0.25, seed=4242)
+    ld = p.shape[-1]
+    # reference mask: the unfused kernel on arbitrary scores of the same shape with the same seed
+    _, pd_ref = ops.attn_softmax_fwd(torch.zeros(H, B, T, ld, device=dev, dtype=torch.bfloat16), T, None, drop_p=0.25, seed=4242)
+    keep_ref = pd_ref[..., :T] != 0
+    keep = pd[..., :T] != 0
+    nz = p[..., :T] != 0          # a probability that underflowed to 0 says nothing about its mask bit
+    assert torch.equal(keep[nz], keep_ref[nz])
+    kept = pd[..., :T][keep].float()
+    assert torch.allclose(kept, (p[..., :T][keep].float() * (1 / 0.75)).bfloat16().float(), rtol=1e-2, atol=1e-6)
+    assert abs(keep_ref.float().mean().item() - 0.75) < 0.01
+    d = H * 64
+    ref = torch.einsum("hbij,bjhe->bihe", pd[..., :T].float(), v.float().reshape(B, T, H, 64)).reshape(B * T, d)
+    assert (ctx.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
