@@ -1002,7 +1002,75 @@ def pin_text():
     print("text: characters_asr encode/decode and edit-distance error counts identical to the reference")
 
 
-SECTIONS = {"text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+from oracle.fullsize import (FULLSIZE_CFG, FULLSIZE_GRADS, FULLSIZE_GRADS_SUB, fullsize_cotangent,  # noqa: E402
+                             fullsize_inputs)
+
+
+def pin_fullsize():
+    """The BENCHMARKED configuration (17 x 512 Conformer, ffn 2048, 8 heads, conv-k31, V = 5004) through the REAL
+    reference model in fp32 and in bf16 (`model.bfloat16()`, fairseq --bf16 semantics, fairseq/trainer.py:105-107).
+    Weights come from oracle.conformer.random_state_dict(FULLSIZE_CFG, seed=1) -- reproducible on the GPU box, so the
+    fixture only stores outputs: sub-sampled logits, per-frame log-normalisers, the CTC loss and a set of gradients (small
+    tensors whole, matrices sub-sampled), each from the fp32 run (truth) and from the bf16 run (the reference's own
+    bf16 error, the yardstick for ours)."""
+    import torch.nn.functional as F
+
+    from oracle import conformer as O
+
+    feats_np, lens_np, tgt_np = fullsize_inputs()
+    feats, lens, tgt = torch.from_numpy(feats_np), torch.from_numpy(lens_np), torch.from_numpy(tgt_np)
+    sd = O.random_state_dict(FULLSIZE_CFG, seed=1)
+    out = {}
+    for mode in ("fp32", "bf16"):
+        m = _ref_model("conformer", layers=17, d=512, ffn=2048, heads=8, V=5004)
+        # plain nn.Module loading: the reference's upgrade_state_dict hook does not exist on its Conformer layers
+        missing = torch.nn.Module.load_state_dict(m, {k: v.clone() for k, v in sd.items()}, strict=False)
+        assert not missing.unexpected_keys and all("num_batches_tracked" in k or k.endswith("version") or k.endswith("_float_tensor") for k in missing.missing_keys), missing
+        if mode == "bf16":
+            m = m.bfloat16()
+        m.train()
+        x = feats.bfloat16() if mode == "bf16" else feats
+        net = m(x, lens)
+        logits = net["encoder_out"][0]                      # T' x B x V
+        olens = net["src_lengths"][0]
+        lprobs = m.get_normalized_probs(net, log_probs=True).contiguous()
+        assert lprobs.dtype == torch.float32
+        keep = (tgt != 1) & (tgt != 2)
+        with torch.backends.cudnn.flags(enabled=False):
+            loss = F.ctc_loss(lprobs, tgt.masked_select(keep), olens, keep.sum(-1), blank=0, reduction="sum", zero_infinity=True)
+        # gradients: of the linear functional sum(G * logits) (well conditioned; see fullsize_cotangent), not of the CTC
+        # loss -- the CTC value itself is stored and its kernel gradient is tested against autograd on identical logits
+        G = torch.from_numpy(fullsize_cotangent(olens.tolist()))
+        (logits.transpose(0, 1).float() * G).sum().backward()
+        lg = logits.detach().float().transpose(0, 1)        # B x T' x V
+        out["logits_sub_" + mode] = lg[:, ::5, ::11].numpy()
+        out["lse_" + mode] = torch.logsumexp(lg, dim=-1).numpy()
+        out["loss_" + mode] = np.float64(loss.item())
+        grads = dict(m.named_parameters())
+        for n in FULLSIZE_GRADS:
+            out["grad_%s.%s" % (mode, n)] = grads[n].grad.float().numpy()
+        for n in FULLSIZE_GRADS_SUB:
+            g = grads[n].grad.float()
+            g2 = g.reshape(g.shape[0], -1)
+            out["gradsub_%s.%s" % (mode, n)] = g2[::8, ::8].contiguous().numpy()
+        out["gnorm_" + mode] = np.float64(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in m.parameters())).item())
+        print("fullsize/%s: loss %.6f  |g| %.5f  out_lens %s" % (mode, loss.item(), out["gnorm_" + mode], olens.tolist()))
+        if mode == "fp32":
+            out["out_lens"] = olens.numpy()
+            # the oracle restatement at this size too (forward only: it is what bench.py times as the baselines)
+            with torch.no_grad():
+                o_logits, o_lens, _ = O.encoder_forward({k: v.clone() for k, v in sd.items()}, FULLSIZE_CFG, feats, lens, training=True)
+            d_log = (o_logits - lg).abs().max().item()
+            print("   oracle vs reference |logits diff| = %.3g" % d_log)
+            assert d_log < 5e-3 and torch.equal(o_lens, olens)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    print("   reference bf16 vs fp32: logits rel-Frobenius %.3g, loss rel %.3g" % (
+        rel(out["logits_sub_bf16"], out["logits_sub_fp32"]), abs(out["loss_bf16"] - out["loss_fp32"]) / out["loss_fp32"]))
+    np.savez_compressed(os.path.join(GOLDEN, "fullsize_conformer.npz"), **out)
+    print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
+
+
+SECTIONS = {"fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

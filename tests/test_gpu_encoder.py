@@ -355,3 +355,15 @@ def test_transducer_vs_reference_fixture(golden_dir):
     worst.sort(reverse=True)
     assert worst[0][0] < 0.25, worst[:5]
     assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.12, worst[:8]
+
+
+def test_full_size_encoder_value_parity(golden_dir):
+    """VALUE parity at the benchmarked configuration (17 x 512 Conformer, V = 5004, 3.1 / 6.4 / 10 s utterances) on the CUDA
+    path: logits, log-normalisers, CTC loss and a spread of gradients are as close to the fp32 reference as the
+    reference's own bf16 run (tests/fullsize_util.py states the contract; achieved errors are printed)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fullsize_util import run_and_check
+
+    run_and_check("cuda:0", golden_dir)

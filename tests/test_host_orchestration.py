@@ -718,3 +718,14 @@ def test_speech_lstm_incremental_decoding_and_beam_search(golden_dir, cpu_ops):
     hyps = SequenceGenerator([m], D(50), beam_size=3, max_len_a=0.0, max_len_b=6).generate(
         [m], {"net_input": {"src_tokens": feats, "src_lengths": lens}})
     assert len(hyps) == B and all(1 <= len(h) <= 3 and int(h[0]["tokens"][-1]) == 2 for h in hyps)
+
+
+def test_full_size_encoder_host_path_vs_reference(golden_dir, cpu_ops):
+    """The benchmarked configuration (17 x 512, V = 5004, head_dim 64 -> the fused-attention call path) through the
+    host orchestration with the per-op oracle, against the real reference's fp32 / bf16 outputs."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fullsize_util import run_and_check
+
+    run_and_check("cpu", golden_dir)
