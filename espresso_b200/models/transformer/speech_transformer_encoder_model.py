@@ -230,6 +230,11 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         dxc = ctx.engine.backward(dout.contiguous())
+        # a host that drives plain autograd (fairseq's trainer through espresso_b200_plugin) asks to be called once the
+        # WHOLE backward pass is over, to publish the flat fp32 gradients as .grad
+        cb = getattr(ctx.engine, "after_backward", None)
+        if cb is not None:
+            torch.autograd.Variable._execution_engine.queue_callback(cb)
         return dxc, None, None, None, None
 
 

@@ -66,7 +66,12 @@ class OmegaConf:
 
     @staticmethod
     def merge(*cfgs):
-        return cfgs[0]
+        """Later configs override earlier ones.  The shim only ever merges a default-constructed dataclass with a fully
+        populated config of the same class (fairseq/dataclass/utils.py merge_with_parent), so "the last one wins"."""
+        import copy
+
+        out = [c for c in cfgs if c is not None][-1]
+        return copy.copy(out)
 
     @staticmethod
     def structured(obj):
