@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kTile = 128;      // query rows per CTA = key columns per step
 constexpr int kHd = 64;         // head dim (one SWIZZLE_128B row of bf16)
-constexpr int kThreads = 160;   // warps 0-3: softmax (TMEM lane quarters), warp 4: TMA + MMA issue + TMEM alloc
+constexpr int kThreads = 288;   // warps 0-7: softmax (TMEM lane quarter x column half), warp 8: TMA + MMA issue + TMEM alloc
 constexpr int kTileBytes = kTile * kHd * 2;  // 16 KB
 constexpr int kWRowBytes = 336;              // 160 bf16 + 16 B pad (bank-conflict-free 16-byte row stores)
 constexpr int kOffQu = 0;
@@ -43,7 +43,7 @@ constexpr int kOffP = kOffV + 2 * kTileBytes;      // 3 relative-position blocks
 constexpr int kOffA = kOffP + 3 * kTileBytes;      // dropped probabilities, A operand of P V: 128 x 128 bf16 = 2 chunks
 constexpr int kOffW = kOffA + 2 * kTileBytes;      // W staging, 128 rows x 336 B
 constexpr int kOffBar = kOffW + kTile * kWRowBytes;
-constexpr int kSmemBytes = kOffBar + 128 + 1024;   // + alignment slack
+constexpr int kSmemBytes = kOffBar + 128 + 2 * kTile * 2 * 4 + 1024;   // barriers, (m, l) exchange, alignment slack
 constexpr int kColS = 0, kColW = 128, kColO = 384, kTmemCols = 512;
 
 struct Params {
@@ -136,6 +136,13 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool b_mn_major) {
          ((uint32_t)(kTile >> 4) << 24);
 }
 
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Thread layout: warps 0-7 are softmax warps -- warp w owns TMEM lane quarter (w & 3) (rows 32 (w & 3) .. + 31 of the
+// query tile) and column half (w >> 2) of the 128-key tile, so every query row is shared by two threads; warp 8 is the
+// control warp (TMA + MMA issue + TMEM allocation).  The softmax warps release S / W as soon as they hold the logits in
+// registers, so the tensor core works on tile it + 1 while they exponentiate tile it.
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -144,9 +151,11 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar0 = sb + kOffBar;
-  // barriers: 0 Q loaded | 1,2 stage loads | 3 S/W ready | 4 tile consumed by the softmax warps | 5 P V done
-  const uint32_t barQ = bar0, barL0 = bar0 + 8, barS = bar0 + 24, barC = bar0 + 32, barO = bar0 + 40;
-  uint32_t* tmem_slot = (uint32_t*)(smem + kOffBar + 64);
+  // mbarriers: Q | K+positions stage 0,1 | V stage 0,1 | S/W ready | S/W read (TMEM free) | A operand written | P V done
+  const uint32_t barQ = bar0, barK0 = bar0 + 8, barV0 = bar0 + 24, barS = bar0 + 40, barT = bar0 + 48, barP = bar0 + 56,
+                 barO = bar0 + 64;
+  uint32_t* tmem_slot = (uint32_t*)(smem + kOffBar + 96);
+  float* xch = (float*)(smem + kOffBar + 128);  // [2][128][2] (m, l) exchange between the two threads of a row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -157,19 +166,22 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
   const int wbase = (T - 1) - i0 - (kTile - 1);  // relative position seen by (row 127, key 0); block a = wbase + 128 a
 
   esp_pdl_trigger();
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == 256) {
     mbar_init(barQ, 1);
-    mbar_init(barL0, 1);
-    mbar_init(barL0 + 8, 1);
+    mbar_init(barK0, 1);
+    mbar_init(barK0 + 8, 1);
+    mbar_init(barV0, 1);
+    mbar_init(barV0 + 8, 1);
     mbar_init(barS, 1);
-    mbar_init(barC, 4);  // one arrive per softmax warp
+    mbar_init(barT, 8);  // one arrive per softmax warp
+    mbar_init(barP, 8);
     mbar_init(barO, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQu) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -180,38 +192,26 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
   const uint32_t tmem = *tmem_slot;
   esp_pdl_wait();
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== control: TMA loads + MMA issue (one thread) ==================================
     if (lane == 0) {
       const int pcol = h * p.pos_hstride;
-      // loads of iteration `it`: K tile (+ V tile in pass 2) and the relative-position blocks it needs that are not
-      // resident yet.  Block a lives in ring slot a % 3; within a pass tile jt needs blocks jt (loaded by the previous
-      // iteration) and jt + 1.
-      auto issue_loads = [&](int it) {
+      // K tile + relative-position blocks of iteration `it`.  Block a lives in ring slot a % 3; within a pass tile jt needs
+      // blocks jt (loaded by the previous iteration) and jt + 1.
+      auto load_k = [&](int it) {
         const int jt = it % nkt, st = it & 1;
-        const bool pass2 = it >= nkt;
         const bool first = jt == 0;
-        const uint32_t bar = barL0 + 8 * st;
-        mbar_expect_tx(bar, (uint32_t)kTileBytes * (1 + (pass2 ? 1 : 0) + (first ? 2 : 1)));
+        const uint32_t bar = barK0 + 8 * st;
+        mbar_expect_tx(bar, (uint32_t)kTileBytes * (first ? 3 : 2));
         tma_load_4d(sb + kOffK + st * kTileBytes, &tmK, bar, h * kHd, jt * kTile, b, 0);
-        if (pass2) tma_load_4d(sb + kOffV + st * kTileBytes, &tmV, bar, h * kHd, jt * kTile, b, 0);
         if (first) tma_load_4d(sb + kOffP + (jt % 3) * kTileBytes, &tmP, bar, pcol, wbase + jt * kTile, 0, 0);
         tma_load_4d(sb + kOffP + ((jt + 1) % 3) * kTileBytes, &tmP, bar, pcol, wbase + (jt + 1) * kTile, 0, 0);
       };
-      mbar_expect_tx(barQ, 2 * kTileBytes);
-      tma_load_4d(sb + kOffQu, &tmQu, barQ, h * kHd, i0, b, 0);
-      tma_load_4d(sb + kOffQv, &tmQv, barQ, h * kHd, i0, b, 0);
-      issue_loads(0);
-      mbar_wait(barQ, 0);
       const uint32_t id128 = make_idesc(128, false), id64 = make_idesc(kHd, true);
-      for (int it = 0; it < total; ++it) {
+      auto issue_sw = [&](int it) {
         const int jt = it % nkt, st = it & 1;
-        const bool pass2 = it >= nkt;
-        // prefetch the next iteration's operands while this one computes -- except across the pass boundary, where the
-        // position ring restarts at block 0 and would overwrite blocks this iteration still reads
-        const bool boundary = (it + 1) % nkt == 0;
-        if (it + 1 < total && !boundary) issue_loads(it + 1);
-        mbar_wait(barL0 + 8 * st, (it >> 1) & 1);
+        mbar_wait(barK0 + 8 * st, (it >> 1) & 1);
+        if (it > 0) mbar_wait(barT, (it - 1) & 1);  // the softmax warps hold tile it-1's logits in registers
         tcgen05_fence_after();
         const uint32_t sk = sb + kOffK + st * kTileBytes;
         const uint32_t plo = sb + kOffP + (jt % 3) * kTileBytes, phi = sb + kOffP + ((jt + 1) % 3) * kTileBytes;
@@ -226,44 +226,72 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
           umma_bf16(tmem + kColW + 128, make_sdesc(sb + kOffQv + k * 32, 16, 1024), make_sdesc(phi + k * 32, 16, 1024),
                     id128, k);
         tcgen05_commit(barS);
-        mbar_wait(barC, it & 1);  // softmax warps are done with S / W (and, in pass 2, wrote the A operand)
+      };
+      auto issue_pv = [&](int jt) {
+        mbar_wait(barV0 + 8 * (jt & 1), (jt >> 1) & 1);
+        mbar_wait(barP, jt & 1);  // the dropped probabilities of tile jt are in shared memory
         tcgen05_fence_after();
-        if (pass2) {
-          const uint32_t sv = sb + kOffV + st * kTileBytes;
+        const uint32_t sv = sb + kOffV + (jt & 1) * kTileBytes;
 #pragma unroll
-          for (int k = 0; k < kTile / 16; ++k)
-            umma_bf16(tmem + kColO, make_sdesc(sb + kOffA + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                      make_sdesc(sv + k * 2048, kTileBytes, 1024), id64, (jt > 0 || k > 0) ? 1u : 0u);
-          tcgen05_commit(barO);
-          mbar_wait(barO, jt & 1);  // A operand and the V stage are free again; O is complete after the last tile
+        for (int k = 0; k < kTile / 16; ++k)
+          umma_bf16(tmem + kColO, make_sdesc(sb + kOffA + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                    make_sdesc(sv + k * 2048, kTileBytes, 1024), id64, (jt > 0 || k > 0) ? 1u : 0u);
+        tcgen05_commit(barO);
+      };
+      mbar_expect_tx(barQ, 2 * kTileBytes);
+      tma_load_4d(sb + kOffQu, &tmQu, barQ, h * kHd, i0, b, 0);
+      tma_load_4d(sb + kOffQv, &tmQv, barQ, h * kHd, i0, b, 0);
+      load_k(0);
+      mbar_wait(barQ, 0);
+      for (int it = 0; it < total; ++it) {
+        issue_sw(it);
+        if (it + 1 < total) {
+          // K stage (it+1)&1 and ring slot (jt+2)%3 were last read by the S/W MMAs of iteration it-1, which completed
+          // before barT(it-1) could be observed.  Across the pass boundary the ring restarts at block 0 and would
+          // overwrite blocks the MMAs of THIS iteration read: wait for them first.
+          if ((it + 1) % nkt == 0) mbar_wait(barT, it & 1);
+          load_k(it + 1);
         }
-        if (it + 1 < total && boundary) issue_loads(it + 1);
+        if (it >= nkt) {
+          // V tile of this pass-2 tile (consumed by its P V one iteration later); its stage was last read by P V(jt-2)
+          const int jt = it - nkt;
+          if (jt >= 2) mbar_wait(barO, (jt - 2) & 1);
+          const uint32_t bar = barV0 + 8 * (jt & 1);
+          mbar_expect_tx(bar, kTileBytes);
+          tma_load_4d(sb + kOffV + (jt & 1) * kTileBytes, &tmV, bar, h * kHd, jt * kTile, b, 0);
+        }
+        if (it > nkt) issue_pv(it - 1 - nkt);
       }
+      issue_pv(nkt - 1);
     }
   } else {
-    // ============================== softmax warps: thread = query row = TMEM lane ================================
-    const int r = threadIdx.x;  // 0..127
+    // ============================== softmax warps ===============================================================
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;  // query row inside the tile = TMEM lane
     const int qi = i0 + r;
     const bool row_ok = qi < T;
     const int klen = p.lens ? min(p.lens[b], T) : T;
     const unsigned long long seed = p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull);
     const float dscale = p.drop_p > 0.f ? 65536.f / (65536.f - (float)p.thresh) : 1.f;
     const long prow = ((long)h * p.B + b) * T + qi;  // row of the probability tensors
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint8_t* wrow = smem + kOffW + r * kWRowBytes;
-    const int c_lo = 96 - 32 * warp;  // first W column this warp stages; the thread's window starts 31 - lane further
+    const int c_lo = 96 - 32 * q;  // first W column this lane quarter stages (160 columns from there)
     float m_run = -INFINITY, l_run = 0.f, inv_l = 0.f;
     const float kLog2e = 1.4426950408889634f;
+    constexpr int kHalf = kTile / 2;
 
     for (int it = 0; it < total; ++it) {
       const int jt = it % nkt;
       const bool pass2 = it >= nkt;
-      const int j0 = jt * kTile;
+      const int j0 = jt * kTile + hf * kHalf;  // first key of this thread's half tile
       mbar_wait(barS, it & 1);
       tcgen05_fence_after();
-      // ---- stage this row's slice of W (160 columns starting at c_lo) in shared memory as bf16 ----
+      // ---- stage the row's slice of W in shared memory as bf16: half 0 stages chunks 0-2 (all it reads itself),
+      //      half 1 stages chunks 3-4 and additionally needs chunk 2 from its partner warp ----
+      const int cb = hf ? 3 : 0, ce = hf ? 5 : 3;
 #pragma unroll 1
-      for (int c = 0; c < 5; ++c) {
+      for (int c = cb; c < ce; ++c) {
         uint32_t w[32];
         tmem_ld32(lane_base + (uint32_t)(kColW + c_lo + 32 * c), w);
         tmem_ld_wait();
@@ -277,17 +305,19 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
           *reinterpret_cast<uint4*>(wrow + c * 64 + q4 * 16) = o;
         }
       }
-      // ---- logits of the row: s[c] = S[r, c] + W[r, 127 - r + c], masked beyond the utterance's keys ----
-      // the window starts (31 - lane) bf16 into the staged slice: odd offsets are re-aligned with a funnel shift
-      const int woff = 31 - lane;
+      if (hf == 0) named_arrive(1 + q, 64);
+      else named_sync(1 + q, 64);
+      // ---- logits of the half row: s[c] = S[r, c] + W[r, 127 - r + c], masked beyond the utterance's keys ----
+      // the window starts (31 - lane) + 64 hf bf16 into the staged slice: odd offsets are re-aligned with a funnel shift
+      const int woff = 31 - lane + hf * kHalf;
       const uint32_t* wwords = reinterpret_cast<const uint32_t*>(wrow) + (woff >> 1);
       const bool odd = (woff & 1) != 0;
-      float s[kTile];
+      float s[kHalf];
       float tmax = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t sr[32];
-        tmem_ld32(lane_base + (uint32_t)(kColS + 32 * c), sr);
+        tmem_ld32(lane_base + (uint32_t)(kColS + hf * kHalf + 32 * c), sr);
         uint32_t ww[17];
 #pragma unroll
         for (int x = 0; x < 17; ++x) ww[x] = wwords[16 * c + x];
@@ -305,26 +335,44 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
           tmax = fmaxf(tmax, fmaxf(a0, a1));
         }
       }
+      // S / W (TMEM) and the staged slice are consumed: the tensor core may start the next tile
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barT);
       if (!pass2) {
-        // ---- pass 1: online row maximum and normaliser ----
+        // ---- pass 1: online maximum and normaliser of this thread's half of the row ----
         const float m_new = fmaxf(m_run, tmax);
         if (m_new > -INFINITY) {
           float acc = 0.f;
           const float mb = m_new * kLog2e;
 #pragma unroll
-          for (int c = 0; c < kTile; ++c) acc += exp2f(fmaf(s[c], kLog2e, -mb));  // exp2(-inf) = 0 for masked keys
+          for (int c = 0; c < kHalf; ++c) acc += exp2f(fmaf(s[c], kLog2e, -mb));  // exp2(-inf) = 0 for masked keys
           l_run = l_run * exp2f((m_run - m_new) * kLog2e) + acc;
           m_run = m_new;
         }
-        if (it == nkt - 1) inv_l = 1.f / l_run;
+        if (it == nkt - 1) {
+          // merge the two halves of the row
+          xch[(hf * kTile + r) * 2] = m_run;
+          xch[(hf * kTile + r) * 2 + 1] = l_run;
+          named_sync(5 + q, 64);
+          const float m_o = xch[((hf ^ 1) * kTile + r) * 2], l_o = xch[((hf ^ 1) * kTile + r) * 2 + 1];
+          const float m_all = fmaxf(m_run, m_o);
+          float l_all = 0.f;
+          if (m_run > -INFINITY) l_all += l_run * exp2f((m_run - m_all) * kLog2e);
+          if (m_o > -INFINITY) l_all += l_o * exp2f((m_o - m_all) * kLog2e);
+          m_run = m_all;
+          inv_l = l_all > 0.f ? 1.f / l_all : 0.f;
+        }
       } else {
         // ---- pass 2: normalised probabilities, dropout, A operand of P V ----
         const float mb = m_run * kLog2e;
         bf16* prp = p.p_out ? p.p_out + prow * p.ld + j0 : nullptr;
         bf16* pdp = p.pd_out ? p.pd_out + prow * p.ld + j0 : nullptr;
-        uint8_t* arow = smem + kOffA + r * 128;
+        uint8_t* arow = smem + kOffA + hf * kTileBytes + r * 128;  // 64-column chunk hf of the K-major A operand
+        const int tj = it - nkt;
+        if (tj > 0) mbar_wait(barO, (tj - 1) & 1);  // P V of the previous tile has finished reading the A operand
 #pragma unroll
-        for (int g = 0; g < kTile / 8; ++g) {
+        for (int g = 0; g < kHalf / 8; ++g) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -349,25 +397,23 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
           v4.x = pack_bf16x2(o[0], o[1]); v4.y = pack_bf16x2(o[2], o[3]);
           v4.z = pack_bf16x2(o[4], o[5]); v4.w = pack_bf16x2(o[6], o[7]);
           if (pdp && in_ld) *reinterpret_cast<uint4*>(pdp + 8 * g) = v4;
-          // K-major SWIZZLE_128B: 64-column chunk (g >> 3), 16-byte unit (g & 7) XOR (row & 7)
-          *reinterpret_cast<uint4*>(arow + (g >> 3) * kTileBytes + (((g & 7) ^ (r & 7)) << 4)) = v4;
+          // K-major SWIZZLE_128B: 16-byte unit g XOR (row & 7) inside the row's 128 bytes
+          *reinterpret_cast<uint4*>(arow + ((g ^ (r & 7)) << 4)) = v4;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(barP);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(barC);
     }
-    // ---- epilogue: O (already normalised) -> ctx ----
+    // ---- epilogue: O (already normalised) -> ctx; this thread stores 32 of the row's 64 values ----
     mbar_wait(barO, (nkt - 1) & 1);
     tcgen05_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t o[32];
-      tmem_ld32(lane_base + (uint32_t)(kColO + 32 * c), o);
+      tmem_ld32(lane_base + (uint32_t)(kColO + 32 * hf), o);
       tmem_ld_wait();
       if (row_ok) {
-        bf16* dst = p.ctx + ((long)b * T + qi) * p.d + h * kHd + 32 * c;
+        bf16* dst = p.ctx + ((long)b * T + qi) * p.d + h * kHd + 32 * hf;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint4 v4;
@@ -383,7 +429,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
   }

@@ -9,9 +9,10 @@
 //   fairseq/data/audio/feature_transforms/global_cmvn.py:26-29
 //   espresso/data/feature_transforms/adaptive_specaugment.py:77-136
 //
-// Data movement: every waveform sample is read from HBM exactly once (a CTA stages the samples of
-// 32 consecutive frames in shared memory, so the 2.5x frame overlap is served on-chip); each
-// output element is written once (+ once more inside SpecAugment masks).  Algorithmic bytes per
+// Data movement: every waveform sample is read from HBM exactly once with 16-byte loads (a CTA stages the samples of
+// 64 consecutive frames in shared memory, so the 2.5x frame overlap is served on-chip); each
+// output element is written once (+ once more inside SpecAugment masks, painted by a second grid-wide kernel once the
+// utterance means are known).  Algorithmic bytes per
 // audio-second: 16000*4 (fp32 wave) + 100*80*2 (bf16 feats) = 80 000 B.
 #include "common.cuh"
 #include "espresso_b200.h"
@@ -23,7 +24,7 @@ namespace {
 constexpr int kFrameLen = 400;
 constexpr int kShift = 160;
 constexpr int kBins = 80;
-constexpr int kFramesPerCta = 32;
+constexpr int kFramesPerCta = 64;  // per-CTA table staging (8 KB) amortised over 64 frames; 42 KB of samples
 constexpr int kWarps = 8;
 constexpr int kSamplesPerCta = (kFramesPerCta - 1) * kShift + kFrameLen;  // 5360
 constexpr int kMaxMelW = 640;  // total non-zero triangular weights (actual ~ 510)
@@ -89,13 +90,12 @@ void build_tables(Tables& t) {
 }
 
 struct Smem {
-  float samples[kSamplesPerCta];
+  alignas(16) float samples[kSamplesPerCta];
   Tables t;
   float re[kWarps][256];
   float im[kWarps][256];
   float pw[kWarps][256];
   double red[kWarps];
-  int is_last;
 };
 
 template <typename WaveT>
@@ -131,9 +131,30 @@ frontend_kernel(const WaveT* __restrict__ wave, long wave_ld, const int* __restr
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     const long s0 = (long)f_begin * kShift;
     const WaveT* wrow = wave + (long)b * wave_ld;
-    for (int i = threadIdx.x; i < kSamplesPerCta; i += blockDim.x) {
-      const long s = s0 + i;
-      sm.samples[i] = (s < n) ? load_sample<WaveT>(wrow + s) : 0.f;
+    // fp32 waveforms: 16-byte vector loads (s0 is a multiple of 4 samples) whenever the row is 16-byte aligned
+    bool vec = false;
+    if (sizeof(WaveT) == 4) vec = ((reinterpret_cast<uintptr_t>(wrow) & 15) == 0);
+    if (vec) {
+      const float4* w4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wrow) + s0);
+      float4* d4 = reinterpret_cast<float4*>(sm.samples);
+      for (int i = threadIdx.x; i < kSamplesPerCta / 4; i += blockDim.x) {
+        const long s = s0 + 4 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s + 3 < n) {
+          v = __ldg(w4 + i);
+        } else {
+          const float* wf = reinterpret_cast<const float*>(wrow);
+          if (s < n) v.x = wf[s];
+          if (s + 1 < n) v.y = wf[s + 1];
+          if (s + 2 < n) v.z = wf[s + 2];
+        }
+        d4[i] = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < kSamplesPerCta; i += blockDim.x) {
+        const long s = s0 + i;
+        sm.samples[i] = (s < n) ? load_sample<WaveT>(wrow + s) : 0.f;
+      }
     }
   }
   __syncthreads();
@@ -222,7 +243,8 @@ frontend_kernel(const WaveT* __restrict__ wave, long wave_ld, const int* __restr
     __syncwarp();
   }
 
-  // ---- SpecAugment: the last CTA of the utterance knows the utterance mean and paints the masks ---
+  // ---- SpecAugment needs the utterance mean (fill value): accumulate it; specaug_paint_kernel (same stream, next
+  //      launch) paints the masks with every CTA of the grid in parallel ----------------------------------------
   const bool have_masks = (freq_masks && n_freq_masks > 0) || (time_masks && max_time_masks > 0);
   if (!have_masks || m == 0) return;  // uniform per CTA (depends on b only)
   local_sum = warp_sum_d(local_sum);
@@ -232,46 +254,62 @@ frontend_kernel(const WaveT* __restrict__ wave, long wave_ld, const int* __restr
     double tot = 0.0;
     for (int w = 0; w < kWarps; ++w) tot += sm.red[w];
     atomicAdd(&ws_sum[b], tot);
-    __threadfence();
-    const unsigned ticket = atomicAdd(&ws_cnt[b], 1u);
-    sm.is_last = (ticket == (unsigned)(n_chunks - 1));
+  }
+}
+
+// Adaptive SpecAugment masks (espresso/data/feature_transforms/adaptive_specaugment.py:111-134): every CTA owns 32 frames
+// of one utterance and overwrites the elements that fall inside ANY of the utterance's frequency / time masks with the
+// utterance mean -- the features themselves are not read.  The last CTA of an utterance (ticket) clears the workspace.
+constexpr int kMaxMasks = 64;
+__global__ void __launch_bounds__(256)
+specaug_paint_kernel(const int* __restrict__ n_samples, const int* __restrict__ freq_masks, int n_freq_masks,
+                     const int* __restrict__ time_masks, int max_time_masks, void* __restrict__ out, int out_f32, int t_max,
+                     double* __restrict__ ws_sum, unsigned int* __restrict__ ws_cnt) {
+  esp_pdl();
+  __shared__ int s_f0[kMaxMasks], s_f1[kMaxMasks], s_t0[kMaxMasks], s_t1[kMaxMasks];
+  __shared__ int s_nf, s_nt;
+  const int b = blockIdx.y;
+  const int n = n_samples[b];
+  const int m = n >= kFrameLen ? 1 + (n - kFrameLen) / kShift : 0;
+  if (m == 0) return;
+  if (threadIdx.x == 0) {
+    int nf = 0, nt = 0;
+    for (int i = 0; i < n_freq_masks && nf < kMaxMasks; ++i) {
+      const int f0 = freq_masks[((long)b * n_freq_masks + i) * 2], fw = freq_masks[((long)b * n_freq_masks + i) * 2 + 1];
+      if (fw > 0) { s_f0[nf] = f0; s_f1[nf] = min(f0 + fw, kBins); ++nf; }
+    }
+    for (int i = 0; i < max_time_masks && nt < kMaxMasks; ++i) {
+      const int t0 = time_masks[((long)b * max_time_masks + i) * 2], tw = time_masks[((long)b * max_time_masks + i) * 2 + 1];
+      if (tw > 0) { s_t0[nt] = t0; s_t1[nt] = min(t0 + tw, m); ++nt; }
+    }
+    s_nf = nf;
+    s_nt = nt;
   }
   __syncthreads();
-  if (!sm.is_last) return;
-  __threadfence();
-  const double total = *((volatile double*)&ws_sum[b]);
-  const float fill = (float)(total / ((double)m * (double)kBins));
+  const float fill = (float)(ws_sum[b] / ((double)m * (double)kBins));
   const bf16 fill_bf = f2bf(fill);
-  for (int i = 0; i < n_freq_masks; ++i) {
-    const int f0 = freq_masks[((long)b * n_freq_masks + i) * 2];
-    const int fw = freq_masks[((long)b * n_freq_masks + i) * 2 + 1];
-    if (fw <= 0) continue;
-    const long total_el = (long)m * fw;
-    for (long e = threadIdx.x; e < total_el; e += blockDim.x) {
-      const int t = (int)(e / fw), j = f0 + (int)(e % fw);
-      if (j >= kBins) continue;
+  const int f_begin = blockIdx.x * kFramesPerCta;
+  const int nf = s_nf, nt = s_nt;
+  for (int e = threadIdx.x; e < kFramesPerCta * kBins; e += blockDim.x) {
+    const int t = f_begin + e / kBins, j = e % kBins;
+    if (t >= m) break;  // e is monotone in t
+    bool hit = false;
+    for (int i = 0; i < nt; ++i) hit |= (t >= s_t0[i]) & (t < s_t1[i]);
+    for (int i = 0; i < nf; ++i) hit |= (j >= s_f0[i]) & (j < s_f1[i]);
+    if (hit) {
       const long o = ((long)b * t_max + t) * kBins + j;
       if (out_f32) ((float*)out)[o] = fill;
       else ((bf16*)out)[o] = fill_bf;
     }
   }
-  for (int i = 0; i < max_time_masks; ++i) {
-    const int t0 = time_masks[((long)b * max_time_masks + i) * 2];
-    const int tw = time_masks[((long)b * max_time_masks + i) * 2 + 1];
-    if (tw <= 0) continue;
-    const long total_el = (long)tw * kBins;
-    for (long e = threadIdx.x; e < total_el; e += blockDim.x) {
-      const int t = t0 + (int)(e / kBins);
-      if (t >= m) continue;
-      const long o = ((long)b * t_max + t) * kBins + (e % kBins);
-      if (out_f32) ((float*)out)[o] = fill;
-      else ((bf16*)out)[o] = fill_bf;
-    }
-  }
-  __syncthreads();
+  __syncthreads();  // every thread has read ws_sum[b]
   if (threadIdx.x == 0) {  // leave the workspace clean for the next launch
-    ws_sum[b] = 0.0;
-    ws_cnt[b] = 0u;
+    __threadfence();
+    const unsigned ticket = atomicAdd(&ws_cnt[b], 1u);
+    if (ticket == gridDim.x - 1) {
+      ws_sum[b] = 0.0;
+      ws_cnt[b] = 0u;
+    }
   }
 }
 
@@ -326,5 +364,13 @@ extern "C" int esp_frontend_fbank(const void* wave, int32_t wave_i16, int64_t wa
   }
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
+  const bool have_masks = (freq_masks && n_freq_masks > 0) || (time_masks && max_time_masks > 0);
+  if (have_masks) {
+    ESP_CHECK(n_freq_masks <= kMaxMasks && max_time_masks <= kMaxMasks, "at most %d masks of each kind per utterance", kMaxMasks);
+    esp_launch(specaug_paint_kernel, grid, 256, 0, st, n_samples, freq_masks, n_freq_masks, time_masks, max_time_masks, out,
+               out_f32, t_max, ws_sum, ws_cnt);
+    ESP_LAUNCH_CHECK();
+    esp_count_launch(1);
+  }
   return 0;
 }

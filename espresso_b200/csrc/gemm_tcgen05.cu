@@ -49,6 +49,8 @@ struct EpiParams {
 
 struct KParams {
   int M, N, K, nb1, nb2, ksplit;
+  int debug;  // ESP_GEMM_DEBUG bit mask for bottleneck experiments (0 in production): 1 no epilogue stores, 2 no MMA,
+              // 4 no TMA loads, 8 no TMEM reads either
   int a_b1, a_b2, b_b1, b_b2;  // 0 => operand is broadcast along that batch dim
   EpiParams ep;
 };
@@ -398,6 +400,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
+          if (p.debug & 4) {  // experiment: no operand traffic at all
+            if (!CG2 || crank == 0) mbar_arrive(full_bar(s));
+            continue;
+          }
           if (CG2) {
             // both CTAs' transactions complete on the leader's barrier, which expects the bytes of the pair
             if (crank == 0) mbar_expect_tx(full_bar(s), 2 * L::kStageBytes);
@@ -491,6 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     : make_sdesc(sa + k * 2048, BK * 128, 1024);
             const uint64_t db = B_K ? make_sdesc(sb + k * 32, 16, 1024)
                                     : make_sdesc(sb + k * 2048, BK * 128, 1024);
+            if (p.debug & 2) continue;  // experiment: barriers only
             if (CG2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             else umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
@@ -543,6 +550,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int c = half * kChunksPerWarp + cc;
         const int n0 = nt * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
+        if (p.debug & 8) break;  // experiment: the epilogue only hands the accumulator back
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);  // asynchronous
         const int valid = p.N - n0;  // >= 1; >= 32 for a full chunk
@@ -572,7 +580,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 17; ++j) sk[j] = __ldg(wp + j);
         }
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok || (p.debug & 1)) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -892,6 +900,10 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   if (rc) return rc;
 
   KParams kp;
+  {
+    const char* dbg = getenv("ESP_GEMM_DEBUG");
+    kp.debug = dbg ? atoi(dbg) : 0;
+  }
   kp.M = (int)g->M; kp.N = (int)g->N; kp.K = (int)g->K; kp.nb1 = nb1; kp.nb2 = nb2; kp.ksplit = ksplit;
   kp.a_b1 = (nb1 > 1 && g->sA1 != 0) ? 1 : 0;
   kp.a_b2 = (nb2 > 1 && g->sA2 != 0) ? 1 : 0;
