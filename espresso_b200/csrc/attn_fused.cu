@@ -136,6 +136,17 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool b_mn_major) {
          ((uint32_t)(kTile >> 4) << 24);
 }
 
+// two adjacent 16-byte groups of a probability row: one 32-byte store when aligned, guarded per group against the row end
+__device__ __forceinline__ void store_2x16(bf16* dst, const uint4 (&v)[2], int j, int ld) {
+  if (j + 16 <= ld && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0)) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0].x), "r"(v[0].y), "r"(v[0].z),
+                 "r"(v[0].w), "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w)
+                 : "memory");
+  } else {
+    if (j < ld) *reinterpret_cast<uint4*>(dst) = v[0];
+    if (j + 8 < ld) *reinterpret_cast<uint4*>(dst + 8) = v[1];
+  }
+}
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -372,33 +383,36 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
         const int tj = it - nkt;
         if (tj > 0) mbar_wait(barO, (tj - 1) & 1);  // P V of the previous tile has finished reading the A operand
 #pragma unroll
-        for (int g = 0; g < kHalf / 8; ++g) {
-          float o[8];
+        for (int g2 = 0; g2 < kHalf / 16; ++g2) {
+          // 16 keys per iteration so that every global store is one full 32-byte sector (sub-sector writes are slow)
+          uint4 pr4[2], pd4[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float pv = exp2f(fmaf(s[8 * g + e], kLog2e, -mb)) * inv_l;
-            o[e] = bf2f(f2bf(pv));  // softmax in fp32, cast to the model dtype (fairseq/utils.py:514-525 + .type_as)
-          }
-          const int j = j0 + 8 * g;
-          const bool in_ld = row_ok && j < p.ld;
-          if (prp && in_ld) {
-            uint4 v4;
-            v4.x = pack_bf16x2(o[0], o[1]); v4.y = pack_bf16x2(o[2], o[3]);
-            v4.z = pack_bf16x2(o[4], o[5]); v4.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(prp + 8 * g) = v4;
-          }
-          if (p.drop_p > 0.f) {
-            bool keep[8];
-            esp_keep8(seed, (unsigned long long)prow * p.ld + j, p.thresh, keep);
+          for (int u = 0; u < 2; ++u) {
+            const int g = 2 * g2 + u;
+            float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = keep[e] ? o[e] * dscale : 0.f;
+            for (int e = 0; e < 8; ++e) {
+              const float pv = exp2f(fmaf(s[8 * g + e], kLog2e, -mb)) * inv_l;
+              o[e] = bf2f(f2bf(pv));  // softmax in fp32, cast to the model dtype (fairseq/utils.py:514-525 + .type_as)
+            }
+            pr4[u].x = pack_bf16x2(o[0], o[1]); pr4[u].y = pack_bf16x2(o[2], o[3]);
+            pr4[u].z = pack_bf16x2(o[4], o[5]); pr4[u].w = pack_bf16x2(o[6], o[7]);
+            if (p.drop_p > 0.f) {
+              bool keep[8];
+              esp_keep8(seed, (unsigned long long)prow * p.ld + j0 + 8 * g, p.thresh, keep);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = keep[e] ? o[e] * dscale : 0.f;
+            }
+            pd4[u].x = pack_bf16x2(o[0], o[1]); pd4[u].y = pack_bf16x2(o[2], o[3]);
+            pd4[u].z = pack_bf16x2(o[4], o[5]); pd4[u].w = pack_bf16x2(o[6], o[7]);
+            // K-major SWIZZLE_128B: 16-byte unit g XOR (row & 7) inside the row's 128 bytes
+            *reinterpret_cast<uint4*>(arow + ((g ^ (r & 7)) << 4)) = pd4[u];
           }
-          uint4 v4;
-          v4.x = pack_bf16x2(o[0], o[1]); v4.y = pack_bf16x2(o[2], o[3]);
-          v4.z = pack_bf16x2(o[4], o[5]); v4.w = pack_bf16x2(o[6], o[7]);
-          if (pdp && in_ld) *reinterpret_cast<uint4*>(pdp + 8 * g) = v4;
-          // K-major SWIZZLE_128B: 16-byte unit g XOR (row & 7) inside the row's 128 bytes
-          *reinterpret_cast<uint4*>(arow + ((g ^ (r & 7)) << 4)) = v4;
+          const int j = j0 + 16 * g2;
+          if (row_ok) {
+            if (prp) store_2x16(prp + 16 * g2, pr4, j, p.ld);
+            if (pdp) store_2x16(pdp + 16 * g2, pd4, j, p.ld);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
         __syncwarp();

@@ -142,12 +142,14 @@ __device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, 
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  RELAXED: the only thing handed over is "this
+// warp's tcgen05.ld of the accumulator has completed", which tcgen05.fence::before_thread_sync orders; a release at cluster
+// scope would additionally drain the warp's outstanding global stores (stall_membar was the hottest epilogue stall).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(rank)
       : "memory");
 }
@@ -250,8 +252,23 @@ __device__ __forceinline__ void load32(const bf16* p, int valid, float* v) {
     for (int j = 0; j < 32; ++j) v[j] = j < valid ? bf2f(p[j]) : 0.f;
   }
 }
+// 32-byte (one full L2 sector) global store: sm_100 has 256-bit st.global.  A row-per-thread epilogue that writes 16 bytes
+// per instruction leaves every sector half-written per request; the sub-sector writes were the dominant cost of the whole
+// GEMM (profiles/r02_gemm_bottleneck.txt: 7.3 of 22.5 us).
+__device__ __forceinline__ void stg256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                       uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
 __device__ __forceinline__ void store32_bf16(bf16* p, int valid, const float* v) {
-  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(p) & 31) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 16)
+      stg256(p + j, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
+             pack_bf16x2(v[j + 6], v[j + 7]), pack_bf16x2(v[j + 8], v[j + 9]), pack_bf16x2(v[j + 10], v[j + 11]),
+             pack_bf16x2(v[j + 12], v[j + 13]), pack_bf16x2(v[j + 14], v[j + 15]));
+  } else if (valid >= 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       uint4 o;
@@ -667,7 +684,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (e.c_f32) {
           float* cp = (float*)e.C + c_off + n0;
-          if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+          if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 31) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              stg256(cp + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                     __float_as_uint(v[j + 3]), __float_as_uint(v[j + 4]), __float_as_uint(v[j + 5]),
+                     __float_as_uint(v[j + 6]), __float_as_uint(v[j + 7]));
+          } else if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
