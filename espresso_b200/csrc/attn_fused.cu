@@ -12,9 +12,12 @@
 //     2-stage ring (K, V) and a 3-slot ring of 128-row relative-position blocks;
 //   * per key tile three tcgen05.mma groups write TMEM: S = Qu K^T (128 columns) and W = Qv [Pblk_lo; Pblk_hi]^T
 //     (2 x 128 columns) -- the 255 relative positions this (query tile, key tile) pair can see;
-//   * four softmax warps (thread = query row = TMEM lane) read S with tcgen05.ld, stage their W row in shared memory
-//     and read it back shifted by (127 - row): BD[r, c] = W[r, 127 - r + c] -- the skew is a column re-index, the thread
-//     re-reads only the row it wrote itself, so no inter-thread synchronisation is needed;
+//   * eight softmax warps (two threads per query row = TMEM lane, each owning 64 of the 128 keys) read S with
+//     tcgen05.ld, stage the row's slice of W in shared memory (bf16, as the reference keeps BD) and read it back shifted
+//     by (127 - row): BD[r, c] = W[r, 127 - r + c] -- the skew is a column re-index through a per-row staging buffer, the
+//     only synchronisation is a 64-thread named barrier between the two warps that share a lane quarter; S / W are
+//     handed back to the tensor core as soon as the logits sit in registers, so the MMAs of tile i+1 overlap the
+//     exponentials of tile i;
 //   * two passes over the key tiles: pass 1 accumulates the row maximum and the normaliser online, pass 2 recomputes the
 //     logits, forms the NORMALISED probabilities in registers, writes them (bf16) for the backward pass, applies the
 //     counter-RNG dropout (same stream as esp_attn_softmax_fwd/bwd), stores the dropped tile as the K-major A operand in
@@ -429,13 +432,17 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
       if (row_ok) {
         bf16* dst = p.ctx + ((long)b * T + qi) * p.d + h * kHd + 32 * hf;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 v4;
-          v4.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]), __uint_as_float(o[8 * q4 + 1]));
-          v4.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]), __uint_as_float(o[8 * q4 + 3]));
-          v4.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]), __uint_as_float(o[8 * q4 + 5]));
-          v4.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]), __uint_as_float(o[8 * q4 + 7]));
-          *reinterpret_cast<uint4*>(dst + 8 * q4) = v4;
+        for (int q2 = 0; q2 < 2; ++q2) {
+          uint4 v4[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int o0 = 16 * q2 + 8 * u;
+            v4[u].x = pack_bf16x2(__uint_as_float(o[o0 + 0]), __uint_as_float(o[o0 + 1]));
+            v4[u].y = pack_bf16x2(__uint_as_float(o[o0 + 2]), __uint_as_float(o[o0 + 3]));
+            v4[u].z = pack_bf16x2(__uint_as_float(o[o0 + 4]), __uint_as_float(o[o0 + 5]));
+            v4[u].w = pack_bf16x2(__uint_as_float(o[o0 + 6]), __uint_as_float(o[o0 + 7]));
+          }
+          store_2x16(dst + 16 * q2, v4, 0, 1 << 30);
         }
       }
     }
