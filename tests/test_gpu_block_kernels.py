@@ -319,6 +319,8 @@ def _attn_inputs(B, T, H, seed, dev, shared_pos=False):
     (3, 407, 8, [407, 333, 150], False),     # the bench's typical T' (4 x 4 tiles)
     (1, 875, 2, None, False),                # 35 s utterance: 7 x 7 tiles
     (2, 200, 4, [200, 64], True),            # learned positions shared by all heads (head stride 0)
+    (3, 250, 8, [250, 160, 77], False),      # the full-size parity fixture's shape (two tiles, second one ragged)
+    (4, 64, 8, [64, 40, 33, 1], False),      # at most 64 keys: the second half-row warps see masked keys only
 ])
 def test_attn_fused_fwd_vs_reference(dev, B, T, H, lens, shared):
     from espresso_b200 import ops
