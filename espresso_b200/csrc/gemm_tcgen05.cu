@@ -49,6 +49,7 @@ struct EpiParams {
 
 struct KParams {
   int M, N, K, nb1, nb2, ksplit;
+  int tma_c;  // the bf16 output goes through per-warp shared-memory slabs and TMA stores (tmC is valid)
   int debug;  // ESP_GEMM_DEBUG bit mask for bottleneck experiments (0 in production): 1 no epilogue stores, 2 no MMA,
               // 4 no TMA loads, 8 no TMEM reads either
   int a_b1, a_b2, b_b1, b_b2;  // 0 => operand is broadcast along that batch dim
@@ -113,6 +114,17 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
+// ---- TMA store (shared -> global, bulk async-group completion) -------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- cta_group::2 (CTA pair, one 256-row UMMA across two SMs) ------------------------------------------------
 // Shared::cluster addresses carry the CTA rank in bit 24; clearing it makes an mbarrier address name the LEADER
 // (even) CTA's barrier at the same offset (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask).
@@ -308,7 +320,10 @@ struct SmemLayout {
   static constexpr int kBBytes = (CG2 ? BN / 2 : BN) * BK * 2;  // cta_group::2: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256 && !CG2) ? 4 : 6;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  // output staging for the TMA-store epilogue: one 32-row x 64-column bf16 slab (SWIZZLE_128B, 4 KB) per epilogue warp
+  static constexpr int kSlabBytes = 32 * 128;
+  static constexpr int kSlabOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kSlabOffset + (BN >= 128 ? kEpiWarps * kSlabBytes : 0);
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
 
@@ -327,7 +342,7 @@ struct SmemLayout {
 template <int BN, bool A_K, bool B_K, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const KParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const KParams p) {
   constexpr bool CG2 = (MC == 3);
   constexpr int CL = MC > 1 ? 2 : 1;  // cluster size
   using L = SmemLayout<BN, A_K, B_K, CG2>;
@@ -537,6 +552,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kChunksPerWarp = kChunks / 2;
     const EpiParams& e = p.ep;
     const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
+    const bool use_slab = BN >= 128 && p.tma_c != 0;
+    uint8_t* slab = smem + L::kSlabOffset + (warp - 4) * L::kSlabBytes;
     uint32_t ti = 0;
     for (int work = work0; work < total_tiles; work += work_stride) {
       const int ks = work % p.ksplit;
@@ -597,7 +614,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 17; ++j) sk[j] = __ldg(wp + j);
         }
         tmem_ld_wait();
-        if (!row_ok || (p.debug & 1)) continue;
+        if (row_ok && !(p.debug & 1)) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -612,8 +629,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (j < valid) atomicAdd(cp + j, v[j] * e.alpha);
           }
-          continue;
-        }
+        } else {
         if (bias_p) {
           float bv[32];
           if (f_bias) unpack32(pk_bias, bv);
@@ -698,8 +714,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (j < valid) cp[j] = v[j];
           }
+        } else if (use_slab) {
+          // this row's 64 bytes of the chunk -> the warp's SWIZZLE_128B slab (16-byte unit u of row `lane` lives at
+          // unit u ^ (lane & 7)); the pair of chunks leaves as ONE bulk tensor store of full 128-byte lines
+          uint8_t* srow = slab + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(srow + ((((cc & 1) * 4 + j) ^ (lane & 7)) << 4)) = o;
+          }
         } else {
           store32_bf16((bf16*)e.C + c_off + n0, valid, v);
+        }
+        }  // !atomic
+        }  // row_ok
+        if (use_slab && ((cc & 1) || cc == kChunksPerWarp - 1 || n0 + 32 >= p.N)) {
+          // hand the slab to the TMA engine (rows >= M and columns >= N are clipped by the tensor map); the slab is
+          // reusable as soon as the engine has READ it
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmC, smem_u32(slab), nt * BN + (half * kChunksPerWarp + (cc & ~1)) * 32, mt * BM + q * 32, b1, b2);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          __syncwarp();
         }
       }
       tcgen05_fence_before();
@@ -709,6 +752,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else mbar_arrive(tempty_bar(as));
       }
     }
+    if (use_slab && lane == 0) tma_store_wait_all();  // every bulk store of this warp has been written
   }
 
   tcgen05_fence_before();
@@ -816,7 +860,7 @@ int cluster_slots(K kfn, int smem_bytes) {
 }
 
 template <int BN, bool A_K, bool B_K, int MC>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KParams& kp, cudaStream_t st) {
   constexpr int CL = MC > 1 ? 2 : 1;
   using L = SmemLayout<BN, A_K, B_K, MC == 3>;
   static bool configured = false;
@@ -831,19 +875,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cuda
   if (slots == 0) slots = CL > 1 ? cluster_slots(kfn, L::kTotal) : esp_num_sms();
   int grid = (work < slots ? work : slots) * CL;
   if (grid < 1) return 0;
-  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, CL, ta, tb, kp);
+  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, CL, ta, tb, tc, kp);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
 template <int BN, int MC>
-int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp,
-                   cudaStream_t st) {
-  if (ak && bk) return launch<BN, true, true, MC>(ta, tb, kp, st);
-  if (ak && !bk) return launch<BN, true, false, MC>(ta, tb, kp, st);
-  if (!ak && bk) return launch<BN, false, true, MC>(ta, tb, kp, st);
-  return launch<BN, false, false, MC>(ta, tb, kp, st);
+int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                   const KParams& kp, cudaStream_t st) {
+  if (ak && bk) return launch<BN, true, true, MC>(ta, tb, tc, kp, st);
+  if (ak && !bk) return launch<BN, true, false, MC>(ta, tb, tc, kp, st);
+  if (!ak && bk) return launch<BN, false, true, MC>(ta, tb, tc, kp, st);
+  return launch<BN, false, false, MC>(ta, tb, tc, kp, st);
 }
 
 }  // namespace
@@ -946,10 +990,29 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
   ESP_CHECK(!g->accumulate || g->c_f32, "accumulate (atomic) output must be fp32");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
-  if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, kp, st);
-  if (bn == 256) {
-    if (mode == 3) return dispatch_major<256, 3>(ak, bk, ta, tb, kp, st);
-    return mode == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, kp, st);
+  // bf16 outputs of the wide-tile variants leave through shared-memory slabs + TMA stores (full 128-byte lines, clipped at
+  // the matrix edges by the tensor map) whenever the output is TMA-addressable; ESP_GEMM_TMA_STORE=0 keeps direct stores
+  CUtensorMap tc = ta;
+  kp.tma_c = 0;
+  {
+    static int tma_on = -1;
+    if (tma_on < 0) {
+      const char* ev = getenv("ESP_GEMM_TMA_STORE");
+      tma_on = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    const bool ok = tma_on && bn >= 128 && !g->c_f32 && !g->accumulate && ((uintptr_t)g->C & 15) == 0 && g->ldc % 8 == 0 &&
+                    (nb1 <= 1 || g->sC1 % 8 == 0) && (nb2 <= 1 || g->sC2 % 8 == 0) && (nb1 <= 1 || g->sC1 != 0) &&
+                    (nb2 <= 1 || g->sC2 != 0);
+    if (ok) {
+      rc = make_tmap(&tc, g->C, g->N, g->M, g->ldc, nb1, g->sC1, nb2, g->sC2, 32);
+      if (rc) return rc;
+      kp.tma_c = 1;
+    }
   }
-  return mode == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, kp, st);
+  if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, tc, kp, st);
+  if (bn == 256) {
+    if (mode == 3) return dispatch_major<256, 3>(ak, bk, ta, tb, tc, kp, st);
+    return mode == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, tc, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, tc, kp, st);
+  }
+  return mode == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, tc, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, tc, kp, st);
 }

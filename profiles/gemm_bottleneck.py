@@ -29,7 +29,7 @@ x = (torch.randn(M, K, device=dev) * 0.1).bfloat16()
 W = (torch.randn(N, K, device=dev) * 0.1).bfloat16()
 out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
 names = {0: "full kernel", 1: "no epilogue stores", 8: "no epilogue at all (hand TMEM back)", 2: "no MMA", 4: "no TMA loads",
-         6: "no MMA, no TMA (barriers + epilogue)", 14: "barrier skeleton only", 12: "MMA only (no TMA, no epilogue)",
+         14: "barrier skeleton only", 12: "MMA only (no TMA, no epilogue)",
          10: "TMA only (no MMA, no epilogue)"}
 for tn in (256, 512):
     for dbg, nm in names.items():
