@@ -990,15 +990,18 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   ESP_CHECK(g->C != nullptr, "GEMM output pointer is null");
   ESP_CHECK(!g->accumulate || g->c_f32, "accumulate (atomic) output must be fp32");
   ESP_CHECK(!(e.act >= ESP_ACT_RELU_BWD) || e.aux != nullptr, "activation-gradient epilogue needs aux");
-  // bf16 outputs of the wide-tile variants leave through shared-memory slabs + TMA stores (full 128-byte lines, clipped at
-  // the matrix edges by the tensor map) whenever the output is TMA-addressable; ESP_GEMM_TMA_STORE=0 keeps direct stores
+  // Optional (ESP_GEMM_TMA_STORE=1): bf16 outputs of the wide-tile variants leave through shared-memory slabs + TMA stores
+  // (full 128-byte lines, clipped at the matrix edges by the tensor map).  Correct (the whole GPU suite passes with it) but
+  // measured SLOWER than the 32-byte row stores on the bench shapes (profiles/r02_gemm_microbench_v4.txt: FFN1 20.9 vs
+  // 19.6 us; step 23.1 vs 22.5 ms): the epilogue is bound by TMEM read-out and per-element math, not by the store
+  // pattern, and the slab hand-off adds a serial wait per chunk pair.  Kept as an experiment switch, off by default.
   CUtensorMap tc = ta;
   kp.tma_c = 0;
   {
     static int tma_on = -1;
     if (tma_on < 0) {
       const char* ev = getenv("ESP_GEMM_TMA_STORE");
-      tma_on = (ev && ev[0] == '0') ? 0 : 1;
+      tma_on = (ev && ev[0] == '1') ? 1 : 0;
     }
     const bool ok = tma_on && bn >= 128 && !g->c_f32 && !g->accumulate && ((uintptr_t)g->C & 15) == 0 && g->ldc % 8 == 0 &&
                     (nb1 <= 1 || g->sC1 % 8 == 0) && (nb2 <= 1 || g->sC2 % 8 == 0) && (nb1 <= 1 || g->sC1 != 0) &&
