@@ -153,7 +153,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
               const unsigned long long* __restrict__ seed_ptr) {
   esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
-  extern __shared__ float sm_red[];  // [2][d]
+  extern __shared__ float sm_red[];  // [warps][2][NV * 256]: per-warp partial column sums, transposed
   const int lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
   const long warp0 = (long)blockIdx.x * nw + (threadIdx.x >> 5);
@@ -165,8 +165,6 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
   for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm_red[i] = 0.f;
-  __syncthreads();
   uint4 gq[NV];  // gamma stays in registers (packed) for every row of this warp
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -247,24 +245,30 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       }
     }
   }
-  // block reduce of the per-column partial sums in shared memory, then the contention-free cross-CTA reduction
+  // Block reduce of the per-column partial sums WITHOUT shared-memory atomics (64 conflicting atomics per thread were the
+  // tail of this kernel): every warp parks its partials transposed ([value index][lane] -> conflict-free), then each
+  // thread adds the 8 warps' values of 4 (gamma) + 4 (beta) columns and sends them to the cross-CTA slots.
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  {
+    const int warp = threadIdx.x >> 5;
+    float* mine = sm_red + (size_t)warp * (2 * NV * 256);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sm_red[vi * 8 + j], ag[i][j]);
-        atomicAdd(&sm_red[d + vi * 8 + j], ab[i][j]);
+        mine[(i * 8 + j) * 32 + lane] = ag[i][j];
+        mine[NV * 256 + (i * 8 + j) * 32 + lane] = ab[i][j];
       }
-    }
   }
   __syncthreads();
-  if (dgamma == nullptr && dbeta == nullptr) return;
   const int slot = blockIdx.x % kRedSlots;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(&g_red_slots[0][slot][i], sm_red[i]);
-    atomicAdd(&g_red_slots[1][slot][i], sm_red[d + i]);
+  for (int pidx = threadIdx.x; pidx < 2 * NV * 256; pidx += blockDim.x) {
+    float acc = 0.f;
+    for (int w = 0; w < nw; ++w) acc += sm_red[(size_t)w * (2 * NV * 256) + pidx];
+    const int which = pidx / (NV * 256), q = pidx % (NV * 256);
+    const int ln = q & 31, ij = q >> 5;
+    const int col = (ln + 32 * (ij >> 3)) * 8 + (ij & 7);
+    if (col < d) atomicAdd(&g_red_slots[which][slot][col], acc);
   }
   __shared__ int s_last;
   __threadfence();
@@ -1072,12 +1076,18 @@ extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* me
   if (R == 0) return 0;
   ESP_CHECK(d <= kRedMaxCols, "LayerNorm backward: at most %d columns", kRedMaxCols);
 #define ESP_LN_BWD(NV)                                                                                             \
-  esp_launch(ln_bwd_kernel<NV>, grid_for(R, 8, 2), 256, 2 * d * sizeof(float), st,                                           \
+  {                                                                                                                \
+    if (NV > 2) {                                                                                                  \
+      ESP_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                    (int)(8 * 2 * NV * 256 * sizeof(float))));                                     \
+    }                                                                                                              \
+    esp_launch(ln_bwd_kernel<NV>, grid_for(R, 8, 2), 256, 8 * 2 * NV * 256 * sizeof(float), st,                                           \
       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
-      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr)
-  if (d <= 512) ESP_LN_BWD(2);
-  else if (d <= 1024) ESP_LN_BWD(4);
-  else ESP_LN_BWD(8);
+      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr);              \
+  }
+  if (d <= 512) ESP_LN_BWD(2)
+  else if (d <= 1024) ESP_LN_BWD(4)
+  else ESP_LN_BWD(8)
 #undef ESP_LN_BWD
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);

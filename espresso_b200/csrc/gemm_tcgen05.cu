@@ -49,6 +49,8 @@ struct EpiParams {
 
 struct KParams {
   int M, N, K, nb1, nb2, ksplit;
+  float* rowsum_a;     // optional: rowsum_a[m] += rowsum_scale * sum_k A[m, k] (bias gradient of a weight-gradient GEMM)
+  float rowsum_scale;
   int tma_c;  // the bf16 output goes through per-warp shared-memory slabs and TMA stores (tmC is valid)
   int debug;  // ESP_GEMM_DEBUG bit mask for bottleneck experiments (0 in production): 1 no epilogue stores, 2 no MMA,
               // 4 no TMA loads, 8 no TMEM reads either
@@ -382,7 +384,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       // MC = 2: the peer's producer also writes this slot, so both consumers free it; MC = 3: one (multicast) commit
-      mbar_init(empty_bar(s), MC == 2 ? 2 : 1);
+      // (+2: the two row-sum warps also read the A tile of every stage)
+      mbar_init(empty_bar(s), (MC == 2 ? 2 : 1) + ((!A_K && p.rowsum_a) ? 2 : 0));
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -541,6 +544,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // accumulator complete -> epilogue (of both CTAs in cta_group::2 mode)
         if (CG2) tcgen05_commit_cg2_mc(tfull_bar(as), (uint16_t)0x3);
         else tcgen05_commit(tfull_bar(as));
+      }
+    }
+  } else if (!A_K && p.rowsum_a != nullptr && (warp == 2 || warp == 3)) {
+    // ================================ bias gradient ======================================
+    // Weight-gradient GEMMs (A = dy^T, MN-major): the row sums of A over the whole reduction are the bias gradient of the
+    // same layer.  The two warps that are idle during the mainloop read every A tile from shared memory (the data the
+    // tensor core consumes anyway) and accumulate it -- the separate column-sum pass over dy disappears.
+    // A tile layout (MN-major, SWIZZLE_128B): BM/64 boxes of [BK k-rows][64 m]; row k of a box is 128 bytes, its 16-byte
+    // unit u (8 consecutive m) lives at unit u ^ (k & 7).  Lane l owns unit (l & 15) of the 16 units of a k-row pair.
+    const int u = lane & 15;
+    const uint32_t unit_base = (uint32_t)(u >> 3) * (BK * 128);
+    const int u7 = u & 7;
+    uint32_t it = 0;
+    for (int work = work0; work < total_tiles; work += work_stride) {
+      const int ks = work % p.ksplit;
+      const int tile = work / p.ksplit;
+      const int kb0 = ks * kb_per;
+      const int kb1 = min(num_kb_all, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      const int mt = (tile % tiles_m) * CL + crank;
+      const int nt = (tile / tiles_m) % tiles_n;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
+        if (nt == 0) {  // one N tile per M tile adds the sums (every CTA still takes part in the barrier protocol)
+          const uint8_t* ta_ = smem + s * L::kStageBytes + unit_base;
+          // warp 2: k rows 0-31, warp 3: k rows 32-63; two rows per iteration (lanes 0-15 / 16-31)
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int k = (warp - 2) * 32 + 2 * i + (lane >> 4);
+            const uint4 q4 = *reinterpret_cast<const uint4*>(ta_ + k * 128 + ((u7 ^ (k & 7)) << 4));
+            float lo, hi;
+            unpack_bf16x2(q4.x, lo, hi); acc[0] += lo; acc[1] += hi;
+            unpack_bf16x2(q4.y, lo, hi); acc[2] += lo; acc[3] += hi;
+            unpack_bf16x2(q4.z, lo, hi); acc[4] += lo; acc[5] += hi;
+            unpack_bf16x2(q4.w, lo, hi); acc[6] += lo; acc[7] += hi;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+      }
+      if (nt == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        if (lane < 16) {
+          const int m0 = mt * BM + u * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (m0 + e < p.M) atomicAdd(p.rowsum_a + m0 + e, acc[e] * p.rowsum_scale);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -927,7 +981,8 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
     // gradient GEMMs: long reduction (K = rows of the batch), small output -> split K across CTAs and
     // accumulate with vector reductions; keep >= 4 k-blocks per split.
     bn = g->N >= 192 ? 256 : (g->N > 64 ? 128 : 64);
-    if (bn == 256 && cg2_ok) mode = 3;
+    // (the bias-gradient warps wait on the CTA's own full barrier: not available to the peer CTA of a cta_group::2 pair)
+    if (bn == 256 && cg2_ok && g->rowsum_a == nullptr) mode = 3;
     const long t = mode == 3 ? ((tm + 1) / 2) * ((g->N + 255) / 256) * (long)nb1 * nb2 : tiles_for(bn);
     const long slots = mode == 3 ? pairs : sms;
     const int max_split = num_kb / 4 > 0 ? num_kb / 4 : 1;
@@ -953,7 +1008,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   if (g->tile_n == 512) {  // forced cta_group::2 (tests, microbenchmarks)
     ESP_CHECK(tm >= 1 && g->N >= 1, "bad shape");
     bn = 256;
-    mode = 3;
+    mode = g->rowsum_a ? 1 : 3;
   }
   // 2-CTA multicast pairs along M: worth it when the pairing wastes (almost) no tile
   if (mode == 1 && bn >= 128 && esp_gemm_multicast_enabled() && (tm % 2 == 0 || tm >= 16)) mode = 2;
@@ -967,6 +1022,11 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   if (rc) return rc;
 
   KParams kp;
+  kp.rowsum_a = g->rowsum_a;
+  kp.rowsum_scale = g->rowsum_scale;
+  if (g->rowsum_a) {
+    ESP_CHECK(!ak && g->accumulate && nb1 == 1 && nb2 == 1, "rowsum_a needs an MN-major A operand, accumulate = 1, no batch dims");
+  }
   {
     const char* dbg = getenv("ESP_GEMM_DEBUG");
     kp.debug = dbg ? atoi(dbg) : 0;

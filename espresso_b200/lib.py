@@ -28,6 +28,7 @@ class EspGemm(C.Structure):
         ("alpha", C.c_float), ("beta", C.c_float), ("drop_p", C.c_float),
         ("seed", C.c_uint64),
         ("seed_ptr", C.c_void_p),
+        ("rowsum_a", C.c_void_p), ("rowsum_scale", C.c_float),
     ]
 
 

@@ -119,12 +119,14 @@ class EncoderEngine:
         return _ops.gemm(dy, W, out, M, K, N, dy.stride(0), W.stride(0), K, b_kmajor=False, **kw)
 
     @staticmethod
-    def _wgrad(dy, x, gW):
-        """gW[N,K] += dy[M,N]^T @ x[M,K]   (fp32 accumulate into the flat gradient buffer)"""
+    def _wgrad(dy, x, gW, gb=None):
+        """gW[N,K] += dy[M,N]^T @ x[M,K]   (fp32 accumulate into the flat gradient buffer); with `gb` the bias gradient
+        gb[N] += sum_m dy[m, :] comes out of the same GEMM (row sums of its A operand, csrc/gemm_tcgen05.cu)."""
         M, N = dy.shape
         K = x.shape[1]
         gW2 = gW.view(N, K)
-        _ops.gemm(dy, x, gW2, N, K, M, dy.stride(0), x.stride(0), K, a_kmajor=False, b_kmajor=False, accumulate=True)
+        _ops.gemm(dy, x, gW2, N, K, M, dy.stride(0), x.stride(0), K, a_kmajor=False, b_kmajor=False, accumulate=True,
+                  rowsum_a=gb)
 
     # ---- feed-forward module ----------------------------------------------------------------------
     def ffn_fwd(self, x, lp, names, act, alpha, li, opbase):
@@ -143,13 +145,11 @@ class EncoderEngine:
         ln_n, w1_n, w2_n = names
         x, mean, rstd, ln, U, Hh = saved
         W1, W2 = self.P(lp + w1_n + ".weight"), self.P(lp + w2_n + ".weight")
-        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha,
-                          colsum_acc=self.G(lp + w2_n + ".bias"))  # bias gradient in the same pass
-        self._wgrad(dZ, Hh, self.G(lp + w2_n + ".weight"))
+        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha)
+        self._wgrad(dZ, Hh, self.G(lp + w2_n + ".weight"), self.G(lp + w2_n + ".bias"))
         dU = self._dgrad(dZ, W2, act=act_bwd, aux=U, ld_aux=U.stride(0), drop_p=self._drop("activation_dropout"),
                          drop_mode=2, seed=self._seed(li, opbase))
-        self._wgrad(dU, ln, self.G(lp + w1_n + ".weight"))
-        _ops.colsum(dU, self.G(lp + w1_n + ".bias"))
+        self._wgrad(dU, ln, self.G(lp + w1_n + ".weight"), self.G(lp + w1_n + ".bias"))
         dln = self._dgrad(dU, W1)
         return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + ln_n + ".weight"), self.G(lp + ln_n + ".weight"),
                                    self.G(lp + ln_n + ".bias"), dres=dy)
@@ -206,8 +206,8 @@ class EncoderEngine:
         k, v = qkv[:, d:2 * d], qkv[:, 2 * d:]
         ldt, ldp = _r8(T), _r8(2 * T - 1)
         dev = dy.device
-        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11), colsum_acc=self.G(lp + "self_attn.out_proj.bias"))
-        self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"))
+        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
+        self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"), self.G(lp + "self_attn.out_proj.bias"))
         dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
         dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
         _ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
@@ -244,8 +244,7 @@ class EncoderEngine:
             _ops.colsum(dqu, self.G(lp + "self_attn.pos_bias_u"), scale=self.scaling)
             _ops.colsum(dqv, self.G(lp + "self_attn.pos_bias_v"), scale=self.scaling)
         Wqkv, _, gW, gb = self._qkv(lp)
-        self._wgrad(dqkv, ln, gW)
-        _ops.colsum(dqkv, gb)
+        self._wgrad(dqkv, ln, gW, gb)
         dln = self._dgrad(dqkv, Wqkv)
         return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + "self_attn_layer_norm.weight"),
                                    self.G(lp + "self_attn_layer_norm.weight"), self.G(lp + "self_attn_layer_norm.bias"),
@@ -376,10 +375,7 @@ class EncoderEngine:
             ldV = _r8(V)
             dlog = dout.reshape(R, ldV)
             dl = dlog[:, :V] if ldV != V else dlog
-            self._wgrad(dl, s["xL"], self.G("fc_out.weight"))
-            tmp = torch.zeros(ldV, device=dlog.device, dtype=torch.float32)
-            _ops.colsum(dlog, tmp)
-            self.G("fc_out.bias").add_(tmp[:V])
+            self._wgrad(dl, s["xL"], self.G("fc_out.weight"), self.G("fc_out.bias"))
             dx = self._dgrad(dl, self.P("fc_out.weight"))
         else:
             dx = dout.reshape(R, self.d).contiguous()
@@ -400,8 +396,7 @@ class EncoderEngine:
                 de = _ops.mask_rows_(de.clone().view(B, T, -1), s["lens"]).view(R, -1)
             if pdrop > 0:
                 de = _ops.dropout(de, pdrop, self._seed(999, 1))
-        self._wgrad(de, s["xin"], self.G("fc0.weight"))
-        _ops.colsum(de, self.G("fc0.bias"))
+        self._wgrad(de, s["xin"], self.G("fc0.weight"), self.G("fc0.bias"))
         dxin = self._dgrad(de, self.P("fc0.weight"))
         if pdrop > 0:
             dxin = _ops.dropout(dxin, pdrop, self._seed(999, 0))

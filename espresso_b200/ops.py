@@ -46,7 +46,7 @@ def _need_cuda(*ts):
 def gemm(A, B, C_out, M, N, K, lda, ldb, ldc, *, a_kmajor=True, b_kmajor=True, nb1=1, nb2=1,
          sA=(0, 0), sB=(0, 0), sC=(0, 0), bias=None, act=ACT_NONE, aux=None, ld_aux=0, sAux=(0, 0),
          R=None, ldr=0, sR=(0, 0), alpha=1.0, beta=1.0, C2=None, drop_p=0.0, drop_mode=0, seed=0,
-         skew_r=0, tile_n=0, accumulate=False):
+         skew_r=0, tile_n=0, accumulate=False, rowsum_a=None, rowsum_scale=1.0):
     """C = epilogue(op(A) @ op(B)^T); see EspGemm in include/espresso_b200.h.  Strides in elements."""
     _need_cuda(A, B, C_out, bias, aux, R, C2)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -76,6 +76,9 @@ def gemm(A, B, C_out, M, N, K, lda, ldb, ldc, *, a_kmajor=True, b_kmajor=True, n
     g.alpha, g.beta, g.drop_p = alpha, beta, drop_p
     g.seed = seed
     g.seed_ptr = _SEED_T.data_ptr() if (_SEED_T is not None and drop_p > 0) else None
+    if rowsum_a is not None:
+        assert rowsum_a.dtype == torch.float32 and rowsum_a.is_cuda and rowsum_a.numel() >= M and rowsum_a.stride(-1) == 1
+        g.rowsum_a, g.rowsum_scale = rowsum_a.data_ptr(), rowsum_scale
     _lib.check(_lib.load().esp_gemm_bf16(C.byref(g), _stream()))
     return C_out
 

@@ -40,7 +40,7 @@ void esp_note_graph_replay(int64_t launches);
  * Epilogue, in order: +bias[n]; C2=bf16(pre-activation); dropout(mode 2); activation
  * (ESP_ACT_*; *_BWD multiply by act'(aux)); dropout(mode 1); *alpha; +beta*R (R optionally read with
  * the Transformer-XL skew R[m,(skew_r-1)-m+n]); store bf16 or fp32.  With `accumulate`, the epilogue is
- * C(fp32) += alpha*acc only (atomic, split-K).
+ * C(fp32) += alpha*acc only (atomic, split-K); `rowsum_a` adds the bias gradient of the same layer for free.
  * Dropout is a stateless counter RNG keyed by (seed, logical element index): the backward pass
  * regenerates the forward mask, nothing is stored. */
 enum { ESP_ACT_NONE = 0, ESP_ACT_RELU = 1, ESP_ACT_SILU = 2, ESP_ACT_RELU_BWD = 3, ESP_ACT_SILU_BWD = 4 };
@@ -67,6 +67,10 @@ typedef struct EspGemm {
   float alpha, beta, drop_p;
   uint64_t seed;
   const uint64_t* seed_ptr; /* optional DEVICE pointer: effective seed = seed + *seed_ptr (CUDA-graph replays) */
+  float* rowsum_a;   /* optional fp32 [M] (weight-gradient GEMMs: a_kmajor = 0, accumulate = 1, no batch dims):
+                        rowsum_a[m] += rowsum_scale * sum_k A[m, k] -- with A = dy^T this is the BIAS gradient, computed
+                        from the operand tiles already staged in shared memory by otherwise idle warps */
+  float rowsum_scale;
 } EspGemm;
 
 int esp_gemm_bf16(const EspGemm* g, void* stream);

@@ -28,11 +28,14 @@ def _view(t, nb2, nb1, rows, cols, s2, s1, ld, kmajor):
 
 def gemm(A, B, C_out, M, N, K, lda, ldb, ldc, *, a_kmajor=True, b_kmajor=True, nb1=1, nb2=1, sA=(0, 0), sB=(0, 0),
          sC=(0, 0), bias=None, act=ACT_NONE, aux=None, ld_aux=0, sAux=(0, 0), R=None, ldr=0, sR=(0, 0), alpha=1.0,
-         beta=1.0, C2=None, drop_p=0.0, drop_mode=0, seed=0, skew_r=0, tile_n=0, accumulate=False):
+         beta=1.0, C2=None, drop_p=0.0, drop_mode=0, seed=0, skew_r=0, tile_n=0, accumulate=False, rowsum_a=None,
+         rowsum_scale=1.0):
     assert drop_p == 0.0, "oracle gemm emulates dropout only for p == 0"
     a = _view(A, nb2, nb1, M, K, sA[1], sA[0], lda, a_kmajor).float()
     b = _view(B, nb2, nb1, N, K, sB[1], sB[0], ldb, b_kmajor).float()
     v = a @ b.transpose(-1, -2)
+    if rowsum_a is not None:
+        rowsum_a[:M] += rowsum_scale * a.sum(dim=(0, 1, 3))
     if accumulate:
         cv = _view(C_out, nb2, nb1, M, N, sC[1], sC[0], ldc, True)
         cv += (alpha * v).to(C_out.dtype)

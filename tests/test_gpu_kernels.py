@@ -257,8 +257,11 @@ def test_gemm_accumulate_splitk(dev, M, N, K, tile_n):
     dy = torch.randn(K, ldm, device=dev).bfloat16()[:, :M]  # [rows, N_out] view with padded row stride (A = dy^T)
     x = torch.randn(K, N, device=dev).bfloat16()
     c = torch.full((M, N), 2.0, device=dev, dtype=torch.float32)
-    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, tile_n=tile_n)
+    gb = torch.full((M,), -1.0, device=dev, dtype=torch.float32)   # bias gradient from the same GEMM (row sums of A = dy^T)
+    ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, tile_n=tile_n,
+             rowsum_a=gb, rowsum_scale=0.5)
     ref = 2.0 + dy.float().t() @ x.float()
     assert (c - ref).abs().max().item() <= 3e-3 * K ** 0.5 + 1e-2
+    assert (gb - (-1.0 + 0.5 * dy.float().sum(0))).abs().max().item() <= 2e-3 * K ** 0.5 + 1e-3
     ops.gemm(dy, x, c, M, N, K, dy.stride(0), N, N, a_kmajor=False, b_kmajor=False, accumulate=True, alpha=-1.0, tile_n=tile_n)
     assert (c - 2.0).abs().max().item() <= 6e-3 * K ** 0.5 + 2e-2
