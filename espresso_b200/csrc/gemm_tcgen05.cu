@@ -556,6 +556,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int u = lane & 15;
     const uint32_t unit_base = (uint32_t)(u >> 3) * (BK * 128);
     const int u7 = u & 7;
+    const int parts = tiles_n >= 4 ? 4 : (tiles_n >= 2 ? 2 : 1);  // CTAs per M tile that share the summing
+    const int rows_per = 32 / parts;                              // k rows per warp, CTA and k-block
     uint32_t it = 0;
     for (int work = work0; work < total_tiles; work += work_stride) {
       const int ks = work % p.ksplit;
@@ -569,24 +571,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % S;
         mbar_wait(full_bar(s), (it / S) & 1);
-        if (nt == 0) {  // one N tile per M tile adds the sums (every CTA still takes part in the barrier protocol)
+        if (nt < parts) {
+          // The CTAs that share this M tile (one per N tile) split the k rows of every tile between them, so each of the
+          // two warps reads 16 / parts row pairs per k-block (every CTA still takes part in the barrier protocol).
           const uint8_t* ta_ = smem + s * L::kStageBytes + unit_base;
-          // warp 2: k rows 0-31, warp 3: k rows 32-63; two rows per iteration (lanes 0-15 / 16-31)
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int k = (warp - 2) * 32 + 2 * i + (lane >> 4);
-            const uint4 q4 = *reinterpret_cast<const uint4*>(ta_ + k * 128 + ((u7 ^ (k & 7)) << 4));
-            float lo, hi;
-            unpack_bf16x2(q4.x, lo, hi); acc[0] += lo; acc[1] += hi;
-            unpack_bf16x2(q4.y, lo, hi); acc[2] += lo; acc[3] += hi;
-            unpack_bf16x2(q4.z, lo, hi); acc[4] += lo; acc[5] += hi;
-            unpack_bf16x2(q4.w, lo, hi); acc[6] += lo; acc[7] += hi;
+          const int kbase = (warp - 2) * 32 + nt * rows_per + (lane >> 4);
+          uint4 q4[8];
+#pragma unroll 1
+          for (int i0 = 0; i0 < rows_per / 2; i0 += 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // 8 independent 16-byte loads in flight
+              const int k = kbase + 2 * (i0 + i);
+              q4[i] = (i0 + i < rows_per / 2) ? *reinterpret_cast<const uint4*>(ta_ + k * 128 + ((u7 ^ (k & 7)) << 4))
+                                              : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // bf16 -> fp32 is a shift / mask of the packed word
+              acc[0] += __uint_as_float(q4[i].x << 16); acc[1] += __uint_as_float(q4[i].x & 0xFFFF0000u);
+              acc[2] += __uint_as_float(q4[i].y << 16); acc[3] += __uint_as_float(q4[i].y & 0xFFFF0000u);
+              acc[4] += __uint_as_float(q4[i].z << 16); acc[5] += __uint_as_float(q4[i].z & 0xFFFF0000u);
+              acc[6] += __uint_as_float(q4[i].w << 16); acc[7] += __uint_as_float(q4[i].w & 0xFFFF0000u);
+            }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));
       }
-      if (nt == 0) {
+      if (nt < parts) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
         if (lane < 16) {

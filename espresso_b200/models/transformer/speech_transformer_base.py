@@ -227,16 +227,21 @@ class SpeechTransformerModelBase(nn.Module):
             src_tokens, src_lengths = self.frontend(src_tokens, src_lengths, None, None)
         return self.encoder(src_tokens, src_lengths, src_lengths_cpu=net_input.get("src_lengths_cpu"))
 
-    def init_incremental_state(self, encoder_out, bsz, beam):
+    def init_incremental_state(self, encoder_out, bsz, beam, reuse=None):
         enc = encoder_out["b200_out"]
         has_pad = len(encoder_out["encoder_padding_mask"]) > 0
         lens = encoder_out["src_lengths"][0].to(torch.int32) if has_pad else None
         self.decoder.engine.training = False
-        inc = IncrementalDecoder(self.decoder.engine)
-        return {"inc": inc, "st": inc.init_state(enc, lens, bsz, beam, min(self.decoder.max_positions(), self.t_max_hint) + 2)}
+        inc = reuse["inc"] if reuse is not None else IncrementalDecoder(self.decoder.engine)
+        t_max = min(self.decoder.max_positions(), self.t_max_hint) + 2
+        return {"inc": inc, "st": inc.init_state(enc, lens, bsz, beam, t_max, reuse=reuse["st"] if reuse is not None else None)}
 
     def decode_step(self, step, tokens, state, new_order):
         return state["inc"].step(step, tokens, state["st"], new_order), True
+
+    @staticmethod
+    def advance_state_without_compute(state):
+        state["inc"].advance_without_compute(state["st"])
 
 
 # legacy class name kept by the reference (espresso/models/transformer/speech_transformer_legacy.py:23-24)

@@ -67,9 +67,14 @@ class TransformerLanguageModel(nn.Module):
     def max_decoder_positions(self):
         return self.max_target_positions
 
-    def init_incremental_state(self, encoder_out, bsz, beam):
-        inc = IncrementalDecoder(self.engine)
-        return {"inc": inc, "st": inc.init_state(None, None, bsz, beam, min(self.max_target_positions, self.t_max_hint) + 2)}
+    def init_incremental_state(self, encoder_out, bsz, beam, reuse=None):
+        inc = reuse["inc"] if reuse is not None else IncrementalDecoder(self.engine)
+        t_max = min(self.max_target_positions, self.t_max_hint) + 2
+        return {"inc": inc, "st": inc.init_state(None, None, bsz, beam, t_max, reuse=reuse["st"] if reuse is not None else None)}
 
     def decode_step(self, step, tokens, state, new_order):
         return state["inc"].step(step, tokens, state["st"], new_order), True
+
+    @staticmethod
+    def advance_state_without_compute(state):
+        state["inc"].advance_without_compute(state["st"])

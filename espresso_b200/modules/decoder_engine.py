@@ -241,26 +241,44 @@ class IncrementalDecoder:
     def __init__(self, engine: DecoderEngine):
         self.e = engine
 
-    def init_state(self, enc, enc_lens, bsz, beam, t_max):
-        """enc bf16 [bsz, Tk, d] or None (language model: no encoder attention)."""
+    def init_state(self, enc, enc_lens, bsz, beam, t_max, reuse=None):
+        """enc bf16 [bsz, Tk, d] or None (language model: no encoder attention).
+
+        `reuse`: a state returned earlier for the SAME shapes -- its buffers are re-initialised in place (KV caches keep
+        their addresses, ancestry tables are zeroed and put back in their initial roles, the encoder-attention K/V are
+        recomputed into the same tensors), which is what lets a search step be replayed from a CUDA graph."""
         e = self.e
         d, Lr = e.d, e.cfg["layers"]
         N = bsz * beam
         dev = e.flat.p16.device
-        st = dict(N=N, beam=beam, bsz=bsz, enc_lens=enc_lens, t_max=t_max)
-        st["kv"] = [torch.empty(t_max, N, 2 * d, device=dev, dtype=torch.bfloat16) for _ in range(Lr)]
-        st["anc"] = torch.zeros(t_max, N, device=dev, dtype=torch.int32)
-        st["anc_alt"] = torch.zeros_like(st["anc"])
-        st["cross"] = None
+        Tk = enc.shape[1] if enc is not None else 0
+        sig = (N, beam, bsz, t_max, Tk, enc_lens is not None)
+        if reuse is not None and reuse.get("sig") == sig:
+            st = reuse
+            st["anc"], st["anc_alt"] = st["anc0"], st["anc1"]
+            st["anc"].zero_()
+            st["anc_alt"].zero_()
+            if enc_lens is not None:
+                st["enc_lens"].copy_(enc_lens)
+        else:
+            st = dict(N=N, beam=beam, bsz=bsz, t_max=t_max, sig=sig)
+            st["enc_lens"] = enc_lens.clone() if enc_lens is not None else None
+            st["kv"] = [torch.empty(t_max, N, 2 * d, device=dev, dtype=torch.bfloat16) for _ in range(Lr)]
+            st["anc0"] = torch.zeros(t_max, N, device=dev, dtype=torch.int32)
+            st["anc1"] = torch.zeros_like(st["anc0"])
+            st["anc"], st["anc_alt"] = st["anc0"], st["anc1"]
+            st["cross"] = [torch.empty(bsz, Tk, 2 * d, device=dev, dtype=torch.bfloat16) for _ in range(Lr)] if enc is not None else None
         if enc is not None:
-            Tk = enc.shape[1]
             enc2 = enc.reshape(bsz * Tk, d)
-            cross = []
             for li in range(Lr):
                 Wkv, bkv, _, _ = e._proj("layers.%d." % li, "encoder_attn", "kv")
-                cross.append(_ops.linear(enc2, Wkv, bkv).view(bsz, Tk, 2 * d))
-            st["cross"] = cross
+                _ops.linear(enc2, Wkv, bkv, out=st["cross"][li].view(bsz * Tk, 2 * d))
         return st
+
+    @staticmethod
+    def advance_without_compute(st):
+        """Host-side effect of step() when its device work is replayed from a CUDA graph: the ancestry tables swap."""
+        st["anc"], st["anc_alt"] = st["anc_alt"], st["anc"]
 
     def step(self, step, tokens, st, new_order):
         """tokens int32 [N, L] (column `step` is the newest token) -> logits bf16 [N, ldV]."""

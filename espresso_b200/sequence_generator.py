@@ -33,7 +33,7 @@ class _SearchState:
 class SequenceGenerator:
     def __init__(self, models, tgt_dict, beam_size=1, max_len_a=0, max_len_b=200, max_len=0, min_len=1,
                  normalize_scores=True, len_penalty=1.0, unk_penalty=0.0, temperature=1.0, lm_model=None, lm_weight=1.0,
-                 eos_factor=None, eos=None, **unused):
+                 eos_factor=None, eos=None, use_cuda_graphs=True, **unused):
         self.models = models if isinstance(models, (list, tuple)) else [models]
         assert len(self.models) >= 1
         self.tgt_dict = tgt_dict
@@ -49,6 +49,12 @@ class SequenceGenerator:
         self.lm_model, self.lm_weight = lm_model, lm_weight
         self.eos_factor = eos_factor
         assert eos_factor is None or eos_factor >= 1.0, "--eos-factor must be >= 1.0 if set"
+        # One search step (decoder + LM step, merge, top-k, bookkeeping: ~140 kernel launches) is host-bound when launched
+        # from Python.  With use_cuda_graphs every step index gets its own CUDA graph over PERSISTENT search / decoder state
+        # (first batch of a shape: eager, second: capture, then replay); the per-step "all sentences finished?" read stays
+        # outside the graphs.  Single-model search only (ensembles run eagerly).
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graph_cache = {}
 
     @torch.no_grad()
     def generate(self, models, sample, **kwargs):
@@ -76,38 +82,81 @@ class SequenceGenerator:
         for m_ in tuple(self.models) + (self.lm_model,):
             if m_ is not None and hasattr(m_, "t_max_hint"):
                 m_.t_max_hint = max_len + 1
+        graphs_on = (self.use_cuda_graphs and dev.type == "cuda" and len(self.models) == 1
+                     and hasattr(model, "advance_state_without_compute")
+                     and (self.lm_model is None or hasattr(self.lm_model, "advance_state_without_compute")))
+        enc = model.forward_encoder(net_input)
+        cache = None
+        if graphs_on:
+            enc_T = enc["b200_out"].shape[1] if isinstance(enc, dict) and "b200_out" in enc else -1
+            has_pad = isinstance(enc, dict) and len(enc.get("encoder_padding_mask", [])) > 0
+            key = (bsz, beam, max_len, enc_T, has_pad, bos_token, str(dev))
+            cache = self._graph_cache.get(key)
+            if cache is None:
+                if len(self._graph_cache) >= 4:  # bounded: search shapes come in a handful of buckets
+                    self._graph_cache.pop(next(iter(self._graph_cache)))
+                cache = self._graph_cache[key] = {"calls": 0, "graphs": {}, "pool": None, "state": None, "lm_state": None,
+                                                  "search": None}
         # an ensemble = one encoder pass and one incremental state per model; their step log-probs are averaged in the
         # probability domain (EnsembleModel.forward_decoder, fairseq/sequence_generator.py:836-901)
-        states = []
-        for m_ in self.models:
-            enc = m_.forward_encoder(net_input)
-            states.append(m_.init_incremental_state(enc, bsz, beam))
+        if graphs_on:
+            states = [model.init_incremental_state(enc, bsz, beam, reuse=cache["state"])]
+            cache["state"] = states[0]
+        else:
+            states = [model.init_incremental_state(enc, bsz, beam)]
+            for m_ in self.models[1:]:
+                states.append(m_.init_incremental_state(m_.forward_encoder(net_input), bsz, beam))
         state = states[0]
-        lm_state = self.lm_model.init_incremental_state(None, bsz, beam) if self.lm_model is not None else None
+        lm_state = None
+        if self.lm_model is not None:
+            if graphs_on:
+                lm_state = cache["lm_state"] = self.lm_model.init_incremental_state(None, bsz, beam, reuse=cache["lm_state"])
+            else:
+                lm_state = self.lm_model.init_incremental_state(None, bsz, beam)
         for s_ in states + [lm_state]:  # models may size their caches from this
             if isinstance(s_, dict):
                 s_["max_len"] = max_len
 
-        st = _SearchState()
-        st.tokens = torch.full((N, L), self.pad, dtype=torch.int32, device=dev)
+        st = cache["search"] if graphs_on else None
+        if st is None:
+            st = _SearchState()
+            st.buf_tokens = [torch.empty((N, L), dtype=torch.int32, device=dev) for _ in range(2)]
+            st.buf_scores = [torch.empty(N, L - 1, dtype=torch.float32, device=dev) for _ in range(2)]
+            st.ignore = torch.empty(N, dtype=torch.uint8, device=dev)
+            st.finished = torch.empty(bsz, dtype=torch.uint8, device=dev)
+            st.nfin = torch.empty(bsz, dtype=torch.int32, device=dev)
+            st.fin_tokens = torch.empty((bsz, beam, L - 1), dtype=torch.int32, device=dev)
+            st.fin_len = torch.empty(bsz, beam, dtype=torch.int32, device=dev)
+            st.fin_score = torch.empty(bsz, beam, dtype=torch.float32, device=dev)
+            st.fin_pos = torch.empty(bsz, beam, L - 1, dtype=torch.float32, device=dev)
+            st.new_order = torch.empty(N, dtype=torch.int32, device=dev)
+            st.n_unfinished = torch.empty((1,), dtype=torch.int32, device=dev)
+            st.cand = torch.empty(N, V, dtype=torch.float32, device=dev)
+            st.prev = torch.empty(N, dtype=torch.float32, device=dev)
+            st.arange = torch.arange(N, dtype=torch.int32, device=dev)
+            if graphs_on:
+                cache["search"] = st
+        # (re-)initialise in place: the same buffers, in the same ping-pong roles, for every batch of this shape
+        st.tokens, st.tokens_alt = st.buf_tokens
+        st.scores, st.scores_alt = st.buf_scores
+        st.tokens.fill_(self.pad)
         st.tokens[:, 0] = self.eos if bos_token is None else bos_token
-        st.tokens_alt = torch.empty_like(st.tokens)
-        st.scores = torch.zeros(N, L - 1, dtype=torch.float32, device=dev)
-        st.scores_alt = torch.zeros_like(st.scores)
-        st.ignore = torch.zeros(N, dtype=torch.uint8, device=dev)
-        st.finished = torch.zeros(bsz, dtype=torch.uint8, device=dev)
-        st.nfin = torch.zeros(bsz, dtype=torch.int32, device=dev)
-        st.fin_tokens = torch.full((bsz, beam, L - 1), self.pad, dtype=torch.int32, device=dev)
-        st.fin_len = torch.zeros(bsz, beam, dtype=torch.int32, device=dev)
-        st.fin_score = torch.zeros(bsz, beam, dtype=torch.float32, device=dev)
-        st.fin_pos = torch.zeros(bsz, beam, L - 1, dtype=torch.float32, device=dev)
-        st.new_order = torch.arange(N, dtype=torch.int32, device=dev)
-        st.n_unfinished = torch.full((1,), bsz, dtype=torch.int32, device=dev)
-        cand = torch.empty(N, V, dtype=torch.float32, device=dev)
-        prev = torch.empty(N, dtype=torch.float32, device=dev)
+        st.scores.zero_()
+        st.scores_alt.zero_()
+        st.ignore.zero_()
+        st.finished.zero_()
+        st.nfin.zero_()
+        st.fin_tokens.fill_(self.pad)
+        st.fin_len.zero_()
+        st.fin_score.zero_()
+        st.fin_pos.zero_()
+        st.new_order.copy_(st.arange)
+        st.n_unfinished.fill_(bsz)
+        cand, prev = st.cand, st.prev
 
-        new_order = None
-        for step in range(max_len + 1):  # one extra step for the eos marker
+        def device_step(step):
+            """All device work of search step `step` (this is what a step graph records)."""
+            new_order = st.new_order if step > 0 else None
             values, is_logits = model.decode_step(step, st.tokens, state, new_order)
             if len(self.models) > 1:
                 lps = []
@@ -132,9 +181,36 @@ class SequenceGenerator:
             cs, ct, cb = _ops.beam_topk(cand, bsz, beam * V, n_cand, K, V)
             _ops.beam_bookkeep(step, max_len, bsz, beam, K, self.eos, self.pad, self.normalize_scores, self.len_penalty,
                                cs, ct, cb, st)
-            new_order = st.new_order
+
+        def host_swaps():
+            """What device_step changes on the host side (ping-pong roles); replays must repeat it."""
+            st.tokens, st.tokens_alt = st.tokens_alt, st.tokens
+            st.scores, st.scores_alt = st.scores_alt, st.scores
+            model.advance_state_without_compute(state)
+            if self.lm_model is not None:
+                self.lm_model.advance_state_without_compute(lm_state)
+
+        for step in range(max_len + 1):  # one extra step for the eos marker
+            graph = cache["graphs"].get(step) if graphs_on else None
+            if graph is not None:
+                graph.replay()
+                host_swaps()
+            elif graphs_on and cache["calls"] >= 1:
+                # second batch of this shape: record the step (recording executes nothing), then run it by replaying
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph, pool=cache["pool"]):
+                    device_step(step)
+                if cache["pool"] is None:
+                    cache["pool"] = graph.pool()
+                cache["graphs"][step] = graph
+                graph.replay()
+            else:
+                device_step(step)
             if int(st.n_unfinished.item()) == 0:  # the step's single host sync
                 break
+        if graphs_on:
+            cache["calls"] += 1
 
         # ---- collect (:611-620): sort each sentence's hypotheses by score, descending
         nfin = st.nfin.cpu().tolist()
