@@ -178,6 +178,25 @@ def test_incremental_decoding_and_beam_search_with_real_model(golden_dir):
         for x, y in zip(a, b):
             assert x["tokens"].tolist() == y["tokens"].tolist() and int(x["tokens"][-1]) == 2
             assert abs(float(x["positional_scores"].sum()) / len(x["tokens"]) - float(x["score"])) < 1e-4
+    # CUDA-graphed search steps: call 1 ran eagerly, call 2 recorded one graph per step, call 3 only replays.  A replay must
+    # follow NEW inputs (different utterances through the same graphs) and agree with a generator that never uses graphs.
+    eager = SequenceGenerator([m], D(50), beam_size=5, max_len_a=0.5, max_len_b=4, lm_model=lm, lm_weight=0.47, eos_factor=1.5,
+                              use_cuda_graphs=False)
+    torch.manual_seed(11)
+    feats2 = feats.roll(1, dims=0) + 0.3 * torch.randn_like(feats)
+    for inp in (feats, feats2, feats):
+        smp = {"net_input": {"src_tokens": inp, "src_lengths": lens}}
+        hg = gen.generate([m], smp)
+        he = eager.generate([m], smp)
+        assert len(gen._graph_cache) == 1 and len(next(iter(gen._graph_cache.values()))["graphs"]) > 0
+        for a, b in zip(hg, he):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert x["tokens"].tolist() == y["tokens"].tolist()
+                assert abs(float(x["score"]) - float(y["score"])) < 1e-5
+    h3 = gen.generate([m], sample)
+    for a, b in zip(h1, h3):
+        assert [x["tokens"].tolist() for x in a] == [x["tokens"].tolist() for x in b]
 
 
 def test_ctc_greedy_decoder(golden_dir):
