@@ -20,7 +20,7 @@ from . import ops as _ops
 class Trainer:
     def __init__(self, model, criterion, lr_scheduler, adam_betas=(0.9, 0.98), adam_eps=1e-8, weight_decay=0.0,
                  clip_norm=2.0, process_group=None, use_cuda_graphs=False, bucket_frames=64, bucket_tokens=16,
-                 max_graphs=96):
+                 max_graphs=96, reduce_dtype="bf16"):
         self.model = model
         self.criterion = criterion
         self.lr_scheduler = lr_scheduler
@@ -38,6 +38,13 @@ class Trainer:
         if hasattr(criterion, "unit_grad_output"):
             criterion.unit_grad_output = True
         self.last_stats = None
+        # Gradient exchange dtype.  "bf16" = what the reference sends (fairseq --bf16: bf16 .grad tensors through
+        # legacy_distributed_data_parallel.py:76-165), half the NVLink bytes of the fp32 flat buffer; the 8 logging /
+        # normalisation scalars of the tail travel in a second, 32-byte fp32 all-reduce.  "fp32": one all-reduce of the
+        # flat fp32 buffer including its tail.
+        assert reduce_dtype in ("bf16", "fp32")
+        self.reduce_dtype = reduce_dtype
+        self._g16 = None
         # schedule scalars and the dropout seed live in device memory (written from a pinned staging buffer once
         # per update) so that a captured CUDA graph of the whole step can be replayed with fresh values
         self.use_cuda_graphs = use_cuda_graphs and dev.type == "cuda"
@@ -93,7 +100,16 @@ class Trainer:
         memory.  Kept outside the CUDA graph: the NCCL call stays an ordinary stream operation."""
         flat = self.flat
         if self.world > 1:
-            dist.all_reduce(flat.g32, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.reduce_dtype == "bf16":
+                if self._g16 is None:
+                    self._g16 = torch.empty(flat.numel, dtype=torch.bfloat16, device=flat.g32.device)
+                _ops.cast_f32_bf16(flat.grads, self._g16)
+                w1 = dist.all_reduce(flat.tail, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                dist.all_reduce(self._g16, op=dist.ReduceOp.SUM, group=self.pg)
+                w1.wait()
+                _ops.cast_bf16_f32(self._g16, flat.grads)
+            else:
+                dist.all_reduce(flat.g32, op=dist.ReduceOp.SUM, group=self.pg)
         _ops.sumsq(flat.grads, self._sumsq)
         _ops.adam_step(flat.p32, flat.m, flat.v, flat.grads, flat.p16, 0.0, self.betas[0], self.betas[1], self.eps,
                        self.weight_decay, 1, self._sumsq, denom_dev=flat.tail[0:1], clip_norm=self.clip_norm,

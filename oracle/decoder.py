@@ -71,8 +71,9 @@ def decoder_forward(sd, cfg, prev_output_tokens, enc_out, enc_pad, training=Fals
         p = pre + "layers.%d." % i
         h = F.layer_norm(x, (d,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"])
         x = x + _drop(mha(sd, p + "self_attn.", h, h, H, self_pad, True, adr, training), dr, training)
-        h = F.layer_norm(x, (d,), sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"])
-        x = x + _drop(mha(sd, p + "encoder_attn.", h, enc_out, H, enc_pad, False, adr, training), dr, training)
+        if enc_out is not None:  # enc_out None: decoder-only language model (fairseq transformer_lm layers)
+            h = F.layer_norm(x, (d,), sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"])
+            x = x + _drop(mha(sd, p + "encoder_attn.", h, enc_out, H, enc_pad, False, adr, training), dr, training)
         h = F.layer_norm(x, (d,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
         h = _drop(F.relu(F.linear(h, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), acdr, training)
         x = x + _drop(F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"]), dr, training)

@@ -23,7 +23,7 @@ def _patch_ops():
             setattr(ops, name, getattr(ops_ref, name))
 
 
-def _make(golden_dir):
+def _make(golden_dir, reduce_dtype="fp32"):
     for pth in (ROOT, os.path.join(ROOT, "tests")):
         if pth not in sys.path:
             sys.path.insert(0, pth)
@@ -34,19 +34,19 @@ def _make(golden_dir):
 
     g = np.load(os.path.join(golden_dir, "encoder_conformer.npz"))
     m = _build("conformer", g).finalize_(torch.device("cpu"))
-    tr = Trainer(m, CtcLossCriterion(_Task(50)), NoamLRScheduler(5.0, 100, 64, 1e-6), clip_norm=2.0)
+    tr = Trainer(m, CtcLossCriterion(_Task(50)), NoamLRScheduler(5.0, 100, 64, 1e-6), clip_norm=2.0, reduce_dtype=reduce_dtype)
     feats, lens, tgt = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"]), torch.from_numpy(g["target"])
     s0 = {"net_input": {"src_tokens": feats[:2], "src_lengths": lens[:2]}, "target": tgt[:2]}
     s1 = {"net_input": {"src_tokens": feats[2:, :40].contiguous(), "src_lengths": lens[2:].clamp(max=40)}, "target": tgt[2:]}
     return tr, m, (s0, s1)
 
 
-def _worker(rank, world, port, golden_dir, out_dir):
+def _worker(rank, world, port, golden_dir, out_dir, reduce_dtype):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     _patch_ops()
-    tr, m, samples = _make(golden_dir)
+    tr, m, samples = _make(golden_dir, reduce_dtype)
     tail = tr.train_step([samples[rank]])
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), p32=m.flat.p32.numpy(), tail=tail.numpy())
     dist.destroy_process_group()
@@ -61,8 +61,11 @@ def _free_port():
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_update_equals_accumulated_update(golden_dir, tmp_path):
-    mp.spawn(_worker, args=(2, _free_port(), golden_dir, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("reduce_dtype", ["fp32", "bf16"])
+def test_two_rank_update_equals_accumulated_update(golden_dir, tmp_path, reduce_dtype):
+    """fp32: one all-reduce of the flat fp32 buffer (+ stats tail); bf16: the reference's exchange dtype (bf16 gradients,
+    fp32 stats in a second tiny all-reduce)."""
+    mp.spawn(_worker, args=(2, _free_port(), golden_dir, str(tmp_path), reduce_dtype), nprocs=2, join=True)
     r0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
     r1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
     assert np.array_equal(r0["p32"], r1["p32"])  # both ranks hold the same parameters after the update
@@ -86,7 +89,8 @@ def test_two_rank_update_equals_accumulated_update(golden_dir, tmp_path):
     diff = np.abs(r0["p32"] - ref)
     lr = tr.get_lr()
     assert diff.max() <= 2.0 * lr, (diff.max(), lr)
-    assert (diff > 1e-6).mean() < 2e-3, (diff > 1e-6).mean()
+    # (bf16 exchange rounds every gradient once more: a few more sign flips at the rounding floor)
+    assert (diff > 1e-6).mean() < (2e-3 if reduce_dtype == "fp32" else 1e-2), (diff > 1e-6).mean()
 
 
 def test_shard_batches_round_robin_with_padding():
