@@ -3,7 +3,8 @@ step) -> profiles/r01_gemm_traffic.json, which bench.py reads to fill roofline.t
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
         -k regex:gemm_tcgen05 --csv --log-file gpurun_out/gemm_dram.csv python bench.py --steps 1 --warmup 1 --eager ...
-    python profiles/gemm_traffic_from_ncu.py gpurun_out/gemm_dram.csv 601
+    python profiles/gemm_traffic_from_ncu.py gpurun_out/gemm_dram.csv 601 [profiles/r02_gemm_traffic.json]
+(round 2: the capture comes from profiles/one_step.py under `ncu --profile-from-start off`, i.e. exactly one step)
 """
 import csv
 import json
@@ -32,5 +33,5 @@ us = sum(launch[i].get("gpu__time_duration.sum", 0.0) for i in ids)
 out = {"launches": len(ids), "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_launch": (rd + wr) / max(len(ids), 1),
        "kernel_us_under_ncu": us,
        "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum (cache control: flush between launches)"}
-json.dump(out, open("profiles/r01_gemm_traffic.json", "w"), indent=1)
+json.dump(out, open(sys.argv[3] if len(sys.argv) > 3 else "profiles/r01_gemm_traffic.json", "w"), indent=1)
 print(json.dumps(out))
