@@ -692,13 +692,13 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
     }
   }
   float s1 = 0.f, s2 = 0.f;
+  __syncthreads();  // every thread has consumed its inputs: the tile is reused to collect the outputs
 #pragma unroll
   for (int i = 0; i < kDwPerThr; ++i) {
     const int t = t0 + tb + i;
+    const float of = bf2f(f2bf(acc[i]));
+    tile[tb + i][cl] = of;
     if (t < T) {
-      const bf16 ob = f2bf(acc[i]);
-      y[((long)b * T + t) * Cn + c0 + cl] = ob;
-      const float of = bf2f(ob);
       s1 += of;
       s2 += of * of;
     }
@@ -706,6 +706,16 @@ glu_dwconv_fwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ w, in
   red[0][tg][cl] = s1;
   red[1][tg][cl] = s2;
   __syncthreads();
+  // 16-byte stores: one task = 8 channels of one row (instead of sixteen 2-byte stores per thread)
+  for (int i = threadIdx.x; i < kDwT * (kDwC / 8); i += blockDim.x) {
+    const int r = i >> 3, cv = (i & 7) * 8;
+    const int t = t0 + r;
+    if (t >= T) continue;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = tile[r][cv + j];
+    store8(y + ((long)b * T + t) * Cn + c0 + cv, o);
+  }
   if (stats && tg == 0) {
     const float a = red[0][0][cl] + red[0][1][cl] + red[0][2][cl] + red[0][3][cl];
     const float q = red[1][0][cl] + red[1][1][cl] + red[1][2][cl] + red[1][3][cl];
@@ -774,19 +784,37 @@ glu_dwconv_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ g, c
         }
       }
     }
+    // park dglu in shared memory (the dwred area is free until the weight-gradient pass) ...
+    float (*dgl)[kDwC + 1] = reinterpret_cast<float (*)[kDwC + 1]>(dwred);
 #pragma unroll
-    for (int i = 0; i < kDwPerThr; ++i) {
-      const int t = t0 + tb + i;
-      if (t < T) {
-        const bf16* row = g + ((long)b * T + t) * 2 * Cn;
-        const float a = bf2f(row[c0 + cl]);
-        const float sg = sigmoidf_(bf2f(row[Cn + c0 + cl]));
-        bf16* orow = dg + ((long)b * T + t) * 2 * Cn;
-        orow[c0 + cl] = f2bf(acc[i] * sg);
-        orow[Cn + c0 + cl] = f2bf(acc[i] * a * sg * (1.f - sg));
+    for (int i = 0; i < kDwPerThr; ++i) dgl[tb + i][cl] = acc[i];
+  }
+  __syncthreads();
+  // ... and write both halves of dg with 16-byte vectors: one task = 8 channels of one row (a and the gate are re-read
+  // with 16-byte loads; the scalar 2-byte loads / stores of this epilogue were the bulk of the kernel's memory instructions)
+  {
+    float (*dgl)[kDwC + 1] = reinterpret_cast<float (*)[kDwC + 1]>(dwred);
+    for (int i = threadIdx.x; i < kDwT * (kDwC / 8); i += blockDim.x) {
+      const int r = i >> 3, cv = (i & 7) * 8;
+      const int t = t0 + r;
+      if (t >= T) continue;
+      const bf16* row = g + ((long)b * T + t) * 2 * Cn + c0 + cv;
+      float a[8], gate[8], o1[8], o2[8];
+      load8(row, a);
+      load8(row + Cn, gate);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sg = sigmoidf_(gate[j]);
+        const float d = dgl[r][cv + j];
+        o1[j] = d * sg;
+        o2[j] = d * a[j] * sg * (1.f - sg);
       }
+      bf16* orow = dg + ((long)b * T + t) * 2 * Cn + c0 + cv;
+      store8(orow, o1);
+      store8(orow + Cn, o2);
     }
   }
+  __syncthreads();
   // ---- weight gradient: dw[k] += sum_i dy[tb+i] * glu[tb + i + k - half] = dyt[tb+i+half] * glt[tb+i+k]
   {
     float acc[kDwMaxK];

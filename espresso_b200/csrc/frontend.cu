@@ -289,14 +289,27 @@ specaug_paint_kernel(const int* __restrict__ n_samples, const int* __restrict__ 
   const float fill = (float)(ws_sum[b] / ((double)m * (double)kBins));
   const bf16 fill_bf = f2bf(fill);
   const int f_begin = blockIdx.x * kFramesPerCta;
-  const int nf = s_nf, nt = s_nt;
+  // per-row / per-column flags first (64 + 80 small loops), then every element tests two flags instead of every mask
+  __shared__ unsigned char s_trow[kFramesPerCta], s_fcol[kBins];
+  for (int i = threadIdx.x; i < kFramesPerCta + kBins; i += blockDim.x) {
+    if (i < kFramesPerCta) {
+      const int t = f_begin + i;
+      bool hit = false;
+      for (int k = 0; k < s_nt; ++k) hit |= (t >= s_t0[k]) & (t < s_t1[k]);
+      s_trow[i] = hit && t < m;
+    } else {
+      const int j = i - kFramesPerCta;
+      bool hit = false;
+      for (int k = 0; k < s_nf; ++k) hit |= (j >= s_f0[k]) & (j < s_f1[k]);
+      s_fcol[j] = hit;
+    }
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < kFramesPerCta * kBins; e += blockDim.x) {
-    const int t = f_begin + e / kBins, j = e % kBins;
+    const int r = e / kBins, j = e % kBins;
+    const int t = f_begin + r;
     if (t >= m) break;  // e is monotone in t
-    bool hit = false;
-    for (int i = 0; i < nt; ++i) hit |= (t >= s_t0[i]) & (t < s_t1[i]);
-    for (int i = 0; i < nf; ++i) hit |= (j >= s_f0[i]) & (j < s_f1[i]);
-    if (hit) {
+    if (s_trow[r] | s_fcol[j]) {
       const long o = ((long)b * t_max + t) * kBins + j;
       if (out_f32) ((float*)out)[o] = fill;
       else ((bf16*)out)[o] = fill_bf;
