@@ -136,6 +136,66 @@ beam_topk_kernel(const float* __restrict__ cand, long sent_stride, int n_cand, i
   }
 }
 
+// Small K (2 x beam <= 16, i.e. every recipe's beam): ONE pass over the candidates.  Each thread keeps the KMAX best of its
+// strided slice in registers (sorted, static indices), then the block runs K rounds of "every thread offers the head of its
+// list, block arg-best, the winner advances" -- exact, same total order (value desc, index asc) as the K-pass kernel.
+template <int KMAX>
+__global__ void __launch_bounds__(kT)
+beam_topk_small_kernel(const float* __restrict__ cand, long sent_stride, int n_cand, int K, int V, float* __restrict__ out_s,
+                       int* __restrict__ out_tok, int* __restrict__ out_beam) {
+  __shared__ float sv[kT / 32];
+  __shared__ int si[kT / 32];
+  __shared__ int s_win;
+  const float* c = cand + (long)blockIdx.x * sent_stride;
+  float lv[KMAX];
+  int li[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { lv[k] = kNegInf; li[k] = 0x7fffffff; }
+  for (int i = threadIdx.x; i < n_cand; i += kT) {
+    const float v = c[i];
+    if (better(v, i, lv[KMAX - 1], li[KMAX - 1])) {
+      lv[KMAX - 1] = v;
+      li[KMAX - 1] = i;
+#pragma unroll
+      for (int k = KMAX - 1; k > 0; --k) {
+        if (better(lv[k], li[k], lv[k - 1], li[k - 1])) {
+          const float tv = lv[k]; lv[k] = lv[k - 1]; lv[k - 1] = tv;
+          const int ti = li[k]; li[k] = li[k - 1]; li[k - 1] = ti;
+        }
+      }
+    }
+  }
+  for (int r = 0; r < K; ++r) {
+    float bv = lv[0];
+    int bi = li[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kT / 32; ++w)
+        if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+      if (bi == 0x7fffffff) { bv = kNegInf; bi = 0; }
+      s_win = bi;
+      out_s[(long)blockIdx.x * K + r] = bv;
+      out_tok[(long)blockIdx.x * K + r] = bi % V;
+      out_beam[(long)blockIdx.x * K + r] = bi / V;
+    }
+    __syncthreads();
+    if (li[0] == s_win) {  // the winner pops its head (indices are unique, so exactly one thread does)
+#pragma unroll
+      for (int k = 0; k < KMAX - 1; ++k) { lv[k] = lv[k + 1]; li[k] = li[k + 1]; }
+      lv[KMAX - 1] = kNegInf;
+      li[KMAX - 1] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+
 struct BK {
   int step, max_len, beam, K, eos, pad, L;  // L = row length of tokens (max_len + 2) ; scores rows have L - 1
   int normalize;
@@ -275,7 +335,10 @@ extern "C" int esp_beam_topk(const float* cand, int64_t sent_stride, int32_t bsz
   cudaStream_t st = (cudaStream_t)stream;
   ESP_CHECK(K >= 1 && K <= n_cand, "top-k size %d out of range (n_cand=%d)", K, n_cand);
   if (bsz == 0) return 0;
-  beam_topk_kernel<<<bsz, kT, 0, st>>>(cand, sent_stride, n_cand, K, V, out_scores, out_tokens, out_beams);
+  if (K <= 16)
+    beam_topk_small_kernel<16><<<bsz, kT, 0, st>>>(cand, sent_stride, n_cand, K, V, out_scores, out_tokens, out_beams);
+  else
+    beam_topk_kernel<<<bsz, kT, 0, st>>>(cand, sent_stride, n_cand, K, V, out_scores, out_tokens, out_beams);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;

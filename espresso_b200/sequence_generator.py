@@ -190,6 +190,13 @@ class SequenceGenerator:
             if self.lm_model is not None:
                 self.lm_model.advance_state_without_compute(lm_state)
 
+        # "all sentences finished?" is read one step LATE through pinned memory: the host never waits for the step it has
+        # just queued (finished sentences are inert, so at most one surplus step runs after the last hypothesis ended)
+        lagged = dev.type == "cuda"
+        if lagged:
+            if not hasattr(self, "_nu_host"):
+                self._nu_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+                self._nu_ev = [torch.cuda.Event() for _ in range(2)]
         for step in range(max_len + 1):  # one extra step for the eos marker
             graph = cache["graphs"].get(step) if graphs_on else None
             if graph is not None:
@@ -207,7 +214,15 @@ class SequenceGenerator:
                 graph.replay()
             else:
                 device_step(step)
-            if int(st.n_unfinished.item()) == 0:  # the step's single host sync
+            if lagged:
+                k = step & 1
+                self._nu_host[k].copy_(st.n_unfinished, non_blocking=True)
+                self._nu_ev[k].record()
+                if step > 0:
+                    self._nu_ev[1 - k].synchronize()
+                    if int(self._nu_host[1 - k][0]) == 0:
+                        break
+            elif int(st.n_unfinished.item()) == 0:
                 break
         if graphs_on:
             cache["calls"] += 1
