@@ -13,7 +13,7 @@ parameter / gradient buffers with the single all-reduce and the fused Adam of th
             state; every deeper layer sees [hidden, context]; optional residuals; additional_fc; output projection"""
 import math
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -49,6 +49,22 @@ class SpeechLSTMModelConfig:
     decoder_dropout_out: Optional[float] = None
     max_source_positions: int = 10240
     max_target_positions: int = 1024
+    # P_1, P_2, ...: probability of feeding the TRUTH token per epoch from start_scheduled_sampling_epoch on, the last value
+    # for all later epochs (espresso/models/speech_lstm.py:150-165; asr_wsj / asr_swbd recipes)
+    scheduled_sampling_probs: Tuple[float, ...] = (1.0,)
+    start_scheduled_sampling_epoch: int = 1
+
+
+class ScheduledSamplingRateScheduler:
+    """espresso/tools/scheduled_sampling_rate_scheduler.py:10-45."""
+
+    def __init__(self, scheduled_sampling_probs=(1.0,), start_scheduled_sampling_epoch=1):
+        self.probs, self.start = list(scheduled_sampling_probs), start_scheduled_sampling_epoch
+
+    def step(self, epoch):
+        if (len(self.probs) > 1 or self.probs[0] < 1.0) and epoch >= self.start:
+            return self.probs[min(epoch - self.start, len(self.probs) - 1)]
+        return 1.0
 
 
 def _uniform_(m, a=0.1):
@@ -127,8 +143,10 @@ class SpeechLSTMEncoder(nn.Module):
 
 class SpeechLSTMDecoder(nn.Module):
     def __init__(self, dictionary, embed_dim, hidden_size, out_embed_dim, num_layers, dropout_in, dropout_out,
-                 encoder_output_units, attn_dim, residual, share_input_output_embed, max_target_positions):
+                 encoder_output_units, attn_dim, residual, share_input_output_embed, max_target_positions,
+                 scheduled_sampling_rate_scheduler=None):
         super().__init__()
+        self.scheduled_sampling_rate_scheduler = scheduled_sampling_rate_scheduler
         V, pad = len(dictionary), dictionary.pad()
         self.hidden_size, self.encoder_output_units, self.residual = hidden_size, encoder_output_units, residual
         self.dropout_in, self.dropout_out = dropout_in, dropout_out
@@ -174,7 +192,13 @@ class SpeechLSTMDecoder(nn.Module):
             return F.linear(y, self.embed_tokens.weight)
         return self.fc_out(y)
 
-    def forward(self, prev_output_tokens, encoder_out=None):
+    def forward(self, prev_output_tokens, encoder_out=None, epoch=1):
+        """Teacher forcing, or -- in training, when the scheduler's probability of feeding the truth is < 1 -- scheduled
+        sampling exactly as espresso/models/speech_lstm.py:735-764: at every step > 0 a per-sentence coin decides between
+        the truth token and the arg-max of the previous step's output."""
+        sampling_prob = 1.0
+        if self.training and self.scheduled_sampling_rate_scheduler is not None:
+            sampling_prob = self.scheduled_sampling_rate_scheduler.step(epoch)
         enc = mask = keys = None
         if self.attention is not None:
             enc = encoder_out["encoder_out"][0]                                     # T x B x C
@@ -186,10 +210,23 @@ class SpeechLSTMDecoder(nn.Module):
         cs = [x.new_zeros(B, self.hidden_size) for _ in self.layers]
         feed = x.new_zeros(B, self.encoder_output_units) if self.attention is not None else None
         outs = []
+        if sampling_prob >= 1.0:
+            for j in range(U):
+                y, hs, cs, feed = self.step(x[j], hs, cs, feed, enc, keys, mask)
+                outs.append(y)
+            return self.output_layer(torch.stack(outs, dim=1))                      # B x U x V
+        logits, pred = [], None
         for j in range(U):
-            y, hs, cs, feed = self.step(x[j], hs, cs, feed, enc, keys, mask)
-            outs.append(y)
-        return self.output_layer(torch.stack(outs, dim=1))                          # B x U x V
+            tok = prev_output_tokens[:, j]
+            if j > 0:
+                use_truth = torch.rand(B, device=tok.device).lt(sampling_prob)
+                tok = torch.where(use_truth, tok, pred)
+            x_j = F.dropout(self.embed_tokens(tok), self.dropout_in, self.training)
+            y, hs, cs, feed = self.step(x_j, hs, cs, feed, enc, keys, mask)
+            lj = self.output_layer(y)                                               # B x V
+            logits.append(lj)
+            pred = lj.argmax(-1)
+        return torch.stack(logits, dim=1)
 
 
 @register_model("speech_lstm", dataclass=SpeechLSTMModelConfig)
@@ -223,7 +260,10 @@ class SpeechLSTMModel(nn.Module):
         dec = SpeechLSTMDecoder(task.target_dictionary, cfg.decoder_embed_dim, cfg.decoder_hidden_size, cfg.decoder_out_embed_dim,
                                 cfg.decoder_layers, d(cfg.decoder_dropout_in), d(cfg.decoder_dropout_out), enc.output_units,
                                 cfg.attention_dim, cfg.decoder_rnn_residual, cfg.share_decoder_input_output_embed,
-                                cfg.max_target_positions)
+                                cfg.max_target_positions,
+                                scheduled_sampling_rate_scheduler=ScheduledSamplingRateScheduler(
+                                    getattr(cfg, "scheduled_sampling_probs", (1.0,)),
+                                    getattr(cfg, "start_scheduled_sampling_epoch", 1)))
         return cls(enc, dec)
 
     # ---- B200 wiring: flat buffers (one all-reduce, fused Adam), native BatchNorm in the conv front ----------------
@@ -266,7 +306,7 @@ class SpeechLSTMModel(nn.Module):
 
     def forward(self, src_tokens, src_lengths, prev_output_tokens, epoch=1, src_lengths_cpu=None, **unused):
         enc = self.encoder(src_tokens.to(self.decoder.embed_tokens.weight.dtype), src_lengths, src_lengths_cpu=src_lengths_cpu)
-        logits = self.decoder(prev_output_tokens, enc)                               # B x U x V
+        logits = self.decoder(prev_output_tokens, enc, epoch=epoch)                  # B x U x V
         V = logits.size(-1)
         ldV = (V + 7) // 8 * 8
         padded = F.pad(logits, (0, ldV - V)) if ldV != V else logits

@@ -518,6 +518,46 @@ def test_speech_lstm_trains_through_the_flat_buffer_trainer(golden_dir, cpu_ops)
     assert m.encoder.lstm[0].weight_ih_l0.data_ptr() == m.flat.param("encoder.lstm.0.weight_ih_l0").data_ptr()
 
 
+def test_speech_lstm_scheduled_sampling(golden_dir, cpu_ops):
+    """espresso/models/speech_lstm.py:700-764: below probability 1 (scheduler: per epoch, from the start epoch on) the
+    decoder feeds its own arg-max instead of the truth token, decided per sentence and step.  P = 1 is teacher forcing;
+    P = 0 equals feeding the model's greedy continuation explicitly; eval mode never samples."""
+    from espresso_b200.models.speech_lstm import ScheduledSamplingRateScheduler
+
+    sch = ScheduledSamplingRateScheduler((0.9, 0.8, 0.7), 6)     # the asr_wsj recipe's shape
+    assert [sch.step(e) for e in (1, 5, 6, 7, 8, 9)] == [1.0, 1.0, 0.9, 0.8, 0.7, 0.7]
+    g = np.load(os.path.join(golden_dir, "speech_lstm.npz"))
+    m = _build_speech_lstm(g).finalize_(torch.device("cpu"))
+    ni = {"src_tokens": torch.from_numpy(g["feats"]), "src_lengths": torch.from_numpy(g["lens"]),
+          "prev_output_tokens": torch.from_numpy(g["prev_output_tokens"])}
+    m.train()
+    with torch.no_grad():
+        tf, _ = m(**ni)                                          # default scheduler: probability 1 = teacher forcing
+        m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((0.0,), 1)
+        own, _ = m(**ni, epoch=1)                                # always the model's own prediction
+        # reference semantics restated: token j+1 = argmax of step j, step 0 = the truth's first token
+        prev = ni["prev_output_tokens"].clone()
+        for j in range(1, prev.shape[1]):
+            lg, _ = m.__class__.forward(m, ni["src_tokens"], ni["src_lengths"], prev, epoch=0)   # epoch 0 < start: P = 1
+            prev[:, j] = lg[:, j - 1].argmax(-1)
+        chk, _ = m.__class__.forward(m, ni["src_tokens"], ni["src_lengths"], prev, epoch=0)
+        assert torch.allclose(own.float(), chk.float(), atol=2e-2 * float(chk.float().abs().max()))
+        assert torch.equal(own[:, 0], tf[:, 0]) and not torch.equal(own, tf)
+        m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((0.5,), 3)
+        e2, _ = m(**ni, epoch=2)
+        assert torch.equal(e2, tf)                               # before the start epoch: teacher forcing
+        m.eval()
+        ev, _ = m(**ni, epoch=5)
+        m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((1.0,), 1)
+        ev1, _ = m(**ni, epoch=5)
+        assert torch.equal(ev, ev1)                              # eval never samples
+    m.train()
+    m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((0.5,), 1)
+    out, _ = m(**ni, epoch=1)
+    out.float().sum().backward()                                 # gradients flow through the sampled-input path
+    assert m.decoder.fc_out.weight.grad is not None and torch.isfinite(m.decoder.fc_out.weight.grad.float()).all()
+
+
 @pytest.mark.parametrize("name,kw", [("shared", dict(decoder_embed_dim=32, decoder_hidden_size=32, decoder_out_embed_dim=32,
                                                     share_embed=True, decoder_rnn_residual=True)),
                                      ("proj", dict(decoder_embed_dim=24, decoder_hidden_size=32, decoder_out_embed_dim=40,
