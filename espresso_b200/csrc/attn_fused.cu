@@ -53,6 +53,8 @@ struct Params {
   int B, T, H, d, ld;       // ld: row stride of the probability tensors (multiple of 8, >= T)
   int pos_hstride;          // head stride (elements) inside a projected-position row: hd, or 0 (table shared by heads)
   const int* lens;          // valid keys per utterance or nullptr
+  const int* key_lo;        // optional per-query-row visible key range [key_lo[i], key_hi[i]) (streaming / context masks)
+  const int* key_hi;
   bf16* ctx;                // [B*T, d]
   bf16* p_out;              // [H, B, T, ld] or nullptr
   bf16* pd_out;             // [H, B, T, ld] or nullptr (no dropout)
@@ -285,6 +287,12 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
     const int qi = i0 + r;
     const bool row_ok = qi < T;
     const int klen = p.lens ? min(p.lens[b], T) : T;
+    int kmin = 0, kmax = T;
+    if (p.key_lo) {  // chunk-streaming / limited-context attention: a contiguous key range per query row
+      const int qr = min(qi, T - 1);
+      kmin = p.key_lo[qr];
+      kmax = p.key_hi[qr];
+    }
     const unsigned long long seed = p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull);
     const float dscale = p.drop_p > 0.f ? 65536.f / (65536.f - (float)p.thresh) : 1.f;
     const long prow = ((long)h * p.B + b) * T + qi;  // row of the probability tensors
@@ -342,8 +350,16 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
           float lo, hi;
           unpack_bf16x2(wv, lo, hi);
           const int j = j0 + 32 * c + 2 * x;
-          const float a0 = (j < klen) ? __uint_as_float(sr[2 * x]) + lo : -INFINITY;
-          const float a1 = (j + 1 < klen) ? __uint_as_float(sr[2 * x + 1]) + hi : -INFINITY;
+          float a0 = __uint_as_float(sr[2 * x]) + lo, a1 = __uint_as_float(sr[2 * x + 1]) + hi;
+          if (p.key_lo) {
+            // hidden keys: the reference ADDS bf16(-1e4) to its bf16 scores (transformer_layer.py:189-192,
+            // multihead_attention.py:835-839) -- finite, so a row whose visible keys are all padding still
+            // normalises over the hidden ones
+            if (j < kmin || j >= kmax) a0 = __bfloat162float(__float2bfloat16_rn(a0 - 9984.f));
+            if (j + 1 < kmin || j + 1 >= kmax) a1 = __bfloat162float(__float2bfloat16_rn(a1 - 9984.f));
+          }
+          a0 = (j < klen) ? a0 : -INFINITY;      // key padding: -inf (:841-859)
+          a1 = (j + 1 < klen) ? a1 : -INFINITY;
           s[32 * c + 2 * x] = a0;
           s[32 * c + 2 * x + 1] = a1;
           tmax = fmaxf(tmax, fmaxf(a0, a1));
@@ -463,9 +479,9 @@ int esp_make_tmap_bf16(CUtensorMap* tm, const void* base, long inner, long rows,
 
 extern "C" int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                                   const void* pos, int64_t ldpos, int32_t pos_hstride, int32_t B, int32_t T, int32_t H,
-                                  int32_t head_dim, const int32_t* lens, void* ctx, int64_t ldctx, void* p_out,
-                                  void* pd_out, int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
-                                  void* stream) {
+                                  int32_t head_dim, const int32_t* lens, const int32_t* key_lo, const int32_t* key_hi,
+                                  void* ctx, int64_t ldctx, void* p_out, void* pd_out, int32_t ldp, float drop_p,
+                                  uint64_t seed, const uint64_t* seed_ptr, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ESP_CHECK(head_dim == kHd, "fused attention is built for head_dim 64 (got %d)", head_dim);
   ESP_CHECK(B >= 0 && T >= 0 && H > 0, "bad attention shape");
@@ -485,6 +501,8 @@ extern "C" int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, c
   if ((rc = esp_make_tmap_bf16(&tp, pos, pos_cols, 2L * T - 1, ldpos, 1, 0, 1, 0, kTile))) return rc;
   Params pr;
   pr.B = B; pr.T = T; pr.H = H; pr.d = (int)ldctx; pr.ld = ldp; pr.pos_hstride = pos_hstride;
+  ESP_CHECK((key_lo == nullptr) == (key_hi == nullptr), "key_lo and key_hi must be given together");
+  pr.key_lo = key_lo; pr.key_hi = key_hi;
   pr.lens = lens; pr.ctx = (bf16*)ctx; pr.p_out = (bf16*)p_out; pr.pd_out = drop_p > 0.f ? (bf16*)pd_out : nullptr;
   pr.drop_p = drop_p; pr.thresh = esp_dropout_thresh(drop_p); pr.seed = seed;
   pr.seed_ptr = (const unsigned long long*)seed_ptr;

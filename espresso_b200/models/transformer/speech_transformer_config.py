@@ -30,7 +30,9 @@ class SpeechEncoderConfig(SpeechEncDecBaseConfig):
     layer_type: str = "transformer"  # "transformer" | "conformer"
     depthwise_conv_kernel_size: int = 31
     transformer_context: Optional[str] = None
-    chunk_size: int = 0
+    chunk_size: int = 0  # > 0: chunk-streaming self-attention (speech_transformer_config.py:85-100)
+    chunk_left_window: int = 0
+    chunk_right_window: int = 0
 
 
 @dataclass

@@ -12,6 +12,8 @@ The modules below are *containers*: they own parameters (re-homed into one flat 
 """
 import math
 
+import numpy as np
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -19,7 +21,9 @@ import torch.nn.functional as F
 from ... import ops as _ops
 from ...flat import FlatParams
 from ...modules.encoder_engine import EncoderEngine
+from ...data.specaugment import numpy_seed
 from ...registry import register_model
+from ...tools.utils import chunk_streaming_bounds, context_bounds
 from .speech_transformer_config import DEFAULT_MAX_SOURCE_POSITIONS, SpeechTransformerConfig, eval_str_nested_list_or_tuple
 
 
@@ -280,6 +284,15 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
             raise NotImplementedError(e.layer_type)
         self.vocab_size = vocab_size
         self.fc_out = _Linear(d, vocab_size, xavier=1.0) if vocab_size is not None else None
+        # limited self-attention context, "(left, right)" in frames (speech_transformer_encoder.py:179-190)
+        ctx_ = e.transformer_context
+        if isinstance(ctx_, str):
+            ctx_ = eval_str_nested_list_or_tuple(ctx_, type=int)
+        if ctx_ is not None:
+            if len(ctx_) != 2 or any(c is not None and (not isinstance(c, int) or c < 0) for c in ctx_):
+                raise ValueError("transformer_context must be a pair of None / non-negative ints, got %r" % (ctx_,))
+            ctx_ = tuple(ctx_)
+        self.transformer_context = ctx_
         self.num_updates = 0
         self.flat = None
         self.flat_prefix = ""
@@ -354,6 +367,29 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
     def max_positions(self):
         return self.max_source_positions
 
+    @property
+    def has_attn_mask(self):
+        c = self.transformer_context
+        return self.cfg.encoder.chunk_size > 0 or (c is not None and (c[0] is not None or c[1] is not None))
+
+    def attn_key_bounds(self, max_len, T):
+        """The reference's get_attn_mask (speech_transformer_encoder.py:226-263) as per-row key ranges: numpy int32
+        (lo, hi) of length T, or None.  Chunk streaming takes precedence over transformer_context, and its first-or-last
+        partial chunk coin is drawn under numpy_seed(num_updates) exactly like the reference."""
+        e = self.cfg.encoder
+        if e.chunk_size > 0:
+            with numpy_seed(self.num_updates):
+                lo, hi = chunk_streaming_bounds(max_len, e.chunk_size, e.chunk_left_window, e.chunk_right_window,
+                                                always_partial_in_last=not self.training)
+        elif self.has_attn_mask:
+            lo, hi = context_bounds(max_len, *self.transformer_context)
+        else:
+            return None
+        if T > max_len:  # rows beyond the longest utterance (shape bucketing) are padding: any non-empty range does
+            lo = np.concatenate([lo, np.zeros(T - max_len, np.int32)])
+            hi = np.concatenate([hi, np.full(T - max_len, max_len, np.int32)])
+        return lo, hi
+
     def forward(self, src_tokens, src_lengths, return_all_hiddens: bool = False, src_lengths_cpu=None):
         if self.engine is None:
             raise RuntimeError("call finalize_(device) before running the B200 encoder")
@@ -373,6 +409,13 @@ class SpeechTransformerEncoderForPrediction(nn.Module):
         eng.training = self.training
         # per-update variation comes from the device seed tensor when a trainer installed one (graph-replay safe)
         eng.seed = self.dropout_seed if _ops._SEED_T is not None else self.dropout_seed * 7919 + self.num_updates
+        eng.key_bounds = None
+        if self.has_attn_mask:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("streaming / limited-context attention masks change per update; run without CUDA graphs")
+            lo, hi = self.attn_key_bounds(int(out_lens_cpu.max()), T)
+            eng.key_bounds = (torch.from_numpy(lo).to(x.device, non_blocking=True),
+                              torch.from_numpy(hi).to(x.device, non_blocking=True))
         if self.training:
             for l in self.layers:
                 if hasattr(l, "conv_module"):

@@ -68,6 +68,7 @@ class EncoderEngine:
         # round-1 chain (BD GEMM -> QK^T+skew GEMM -> softmax -> P V GEMM) for A/B comparisons
         self.fused_attention = os.environ.get("ESP_FUSED_ATTN", "1") != "0"
         self._save_probs = True
+        self.key_bounds = None  # (lo, hi) int32 [T] device tensors: per-row visible key range (streaming masks)
 
     # ------------------------------------------------------------------------------------------
     def P(self, name):
@@ -182,8 +183,12 @@ class EncoderEngine:
             # scores, relative-position logits, skew, softmax and P v in ONE kernel (csrc/attn_fused.cu); only the
             # probabilities the backward pass needs go to HBM
             ctx, Pr, Pd = _ops.attn_fused_fwd(qu, qv, k, v, Pp, B, T, H, lens, self._drop("attention_dropout"),
-                                              self._seed(li, 10), save_probs=self._save_probs, pos_hstride=ph)
+                                              self._seed(li, 10), save_probs=self._save_probs, pos_hstride=ph,
+                                              key_bounds=self.key_bounds)
         else:
+            if self.key_bounds is not None:
+                raise NotImplementedError("chunk-streaming / limited-context masks run in the fused attention kernel only "
+                                          "(head_dim 64, ESP_FUSED_ATTN unset)")
             ldt, ldp = _r8(T), _r8(2 * T - 1)
             BD = torch.empty(H, B, T, ldp, device=x.device, dtype=torch.bfloat16)
             _ops.gemm(qv, Pp, BD, T, 2 * T - 1, hd, d, E, ldp, nb1=H, nb2=B, sA=(hd, T * d), sB=(ph, 0),

@@ -254,11 +254,16 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
     return p, (pd if pd is not None else p)
 
 
-def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None):
+def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None, key_bounds=None):
     """Fused relative-position attention forward (esp_attn_fused_fwd): qu, qv [B*T, d]; k, v [B*T, d] views with a common
     row stride (the fused q/k/v buffer); pos [2T-1, E] projected positions (E == d: head h at column h*hd; E == hd: one
-    table for all heads).  Returns (ctx [B*T, d], p, p_drop) with p / p_drop [H, B, T, ld] bf16 or None."""
+    table for all heads); key_bounds: optional (lo, hi) int32 [T] device vectors, query row i attends keys lo[i] <= j < hi[i].
+    Returns (ctx [B*T, d], p, p_drop) with p / p_drop [H, B, T, ld] bf16 or None."""
     _need_cuda(qu, qv, k, v, pos, lens)
+    klo, khi = key_bounds if key_bounds is not None else (None, None)
+    if klo is not None:
+        _need_cuda(klo, khi)
+        assert klo.dtype == torch.int32 and khi.dtype == torch.int32 and klo.numel() == T and khi.numel() == T
     _bf(qu, qv, k, v, pos)
     R, d = qu.shape
     hd = d // H
@@ -272,7 +277,7 @@ def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_pr
     p = torch.empty(H, B, T, ld, device=qu.device, dtype=torch.bfloat16) if save_probs else None
     pd = torch.empty_like(p) if (save_probs and drop_p > 0) else None
     _lib.check(_lib.load().esp_attn_fused_fwd(_ptr(qu), _ptr(qv), qu.stride(0), _ptr(k), _ptr(v), k.stride(0), _ptr(pos),
-                                              pos.stride(0), pos_hstride, B, T, H, hd, _ptr(lens), _ptr(ctx), d, _ptr(p),
+                                              pos.stride(0), pos_hstride, B, T, H, hd, _ptr(lens), _ptr(klo), _ptr(khi), _ptr(ctx), d, _ptr(p),
                                               _ptr(pd), ld, drop_p, seed, _seed_ptr(), _stream()))
     return ctx, p, (pd if pd is not None else p)
 

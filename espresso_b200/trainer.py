@@ -242,7 +242,9 @@ class Trainer:
         model.train()
         model.set_num_updates(self.num_updates)
         self._stage_scalars()
-        if self.use_cuda_graphs and len(samples) == 1 and samples[0] and "src_lengths_cpu" in samples[0]["net_input"]:
+        streaming = getattr(getattr(model, "encoder", None), "has_attn_mask", False)  # masks change per update: eager
+        if (self.use_cuda_graphs and not streaming and len(samples) == 1 and samples[0]
+                and "src_lengths_cpu" in samples[0]["net_input"]):
             self._graphed_step(samples[0])
         else:
             self._step_body(samples)

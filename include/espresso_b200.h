@@ -157,13 +157,16 @@ int esp_attn_softmax_bwd(const void* p, const void* dp_drop, int32_t H, int32_t 
  * TMEM / registers / shared memory.  qu, qv: [B*T, H*64] bf16 (row stride ldq), already (q + pos_bias) * scaling
  * (:679-688); k, v: [B*T, H*64] bf16 with row stride ldkv (views into the fused q/k/v projection buffer); pos:
  * projected positions [2T-1, ldpos] bf16, head h at column h * pos_hstride (pos_hstride = 0: one table for all heads);
- * lens: valid keys per utterance (int32 [B]) or NULL.  ctx: [B*T, H*64] bf16.  p_out / pd_out: optional
+ * lens: valid keys per utterance (int32 [B]) or NULL; key_lo / key_hi: optional int32 [T] per-query-row visible key range
+ * (chunk-streaming and limited-context masks, espresso/tools/utils.py:131-194, speech_transformer_encoder.py:232-263 --
+ * contiguous per row, so two vectors replace the [T,T] mask).  ctx: [B*T, H*64] bf16.  p_out / pd_out: optional
  * [H, B, T, ldp] bf16 probabilities / dropped probabilities for the backward pass (pd_out only when drop_p > 0) --
  * same contents and dropout stream as esp_attn_softmax_fwd. */
 int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                        const void* pos, int64_t ldpos, int32_t pos_hstride, int32_t B, int32_t T, int32_t H,
-                       int32_t head_dim, const int32_t* lens, void* ctx, int64_t ldctx, void* p_out, void* pd_out,
-                       int32_t ldp, float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+                       int32_t head_dim, const int32_t* lens, const int32_t* key_lo, const int32_t* key_hi, void* ctx,
+                       int64_t ldctx, void* p_out, void* pd_out, int32_t ldp, float drop_p, uint64_t seed,
+                       const uint64_t* seed_ptr, void* stream);
 /* Conformer convolution module body (fairseq/modules/conformer_layer.py:88-96):
  *   y = depthwise_conv_k(GLU(g)) with 'same' zero padding over the padded length T, g [B,T,2C], w [C,k];
  *   stats (double [2,C], +=): per-channel sum and sum of squares of y for BatchNorm1d batch statistics.

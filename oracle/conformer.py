@@ -61,7 +61,7 @@ def conv_front(sd, pre, x, lens, strides, training):
     return h, ol, pad
 
 
-def relpos_mha(sd, p, x, pad_mask, H, attn_drop, training):
+def relpos_mha(sd, p, x, pad_mask, H, attn_drop, training, attn_mask=None):
     """x [B, T, d] (batch-major here; the reference is time-major, the math is identical)."""
     B, T, d = x.shape
     hd = d // H
@@ -92,6 +92,8 @@ def relpos_mha(sd, p, x, pad_mask, H, attn_drop, training):
     j = torch.arange(T, device=x.device)[None, :]
     bd = bd_full.gather(-1, ((T - 1) - i + j).expand(B, H, T, T))               # skew: r = j - i
     w = ac + bd
+    if attn_mask is not None:   # [T, T] additive mask (multihead_attention.py:835-839)
+        w = w + attn_mask.to(w.dtype)
     if pad_mask is not None:
         w = w.masked_fill(pad_mask[:, None, None, :], float("-inf"))
     w = torch.softmax(w.float(), dim=-1).to(w.dtype)
@@ -121,28 +123,29 @@ def conv_module(sd, p, x, drop, training):
     return _drop(h, drop, training).transpose(1, 2)
 
 
-def conformer_layer(sd, p, x, pad_mask, cfg, training):
+def conformer_layer(sd, p, x, pad_mask, cfg, training, attn_mask=None):
     dr, adr, acdr = cfg["dropout"], cfg["attention_dropout"], cfg["activation_dropout"]
     x = x + 0.5 * ffn_module(sd, p + "ffn1.", x, acdr, dr, training)
     h = F.layer_norm(x, (x.size(-1),), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"])
-    x = x + _drop(relpos_mha(sd, p + "self_attn.", h, pad_mask, cfg["heads"], adr, training), dr, training)
+    x = x + _drop(relpos_mha(sd, p + "self_attn.", h, pad_mask, cfg["heads"], adr, training, attn_mask), dr, training)
     x = x + conv_module(sd, p + "conv_module.", x, dr, training)
     x = x + 0.5 * ffn_module(sd, p + "ffn2.", x, acdr, dr, training)
     return F.layer_norm(x, (x.size(-1),), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
 
 
-def transformer_layer(sd, p, x, pad_mask, cfg, training):
+def transformer_layer(sd, p, x, pad_mask, cfg, training, attn_mask=None):
     dr, adr, acdr = cfg["dropout"], cfg["attention_dropout"], cfg["activation_dropout"]
     h = F.layer_norm(x, (x.size(-1),), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"])
-    x = x + _drop(relpos_mha(sd, p + "self_attn.", h, pad_mask, cfg["heads"], adr, training), dr, training)
+    x = x + _drop(relpos_mha(sd, p + "self_attn.", h, pad_mask, cfg["heads"], adr, training, attn_mask), dr, training)
     h = F.layer_norm(x, (x.size(-1),), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
     h = _drop(F.relu(F.linear(h, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), acdr, training)
     return x + _drop(F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"]), dr, training)
 
 
-def encoder_forward(sd, cfg, feats, lens, training=False, pre="encoder.", skip_conv_front=False):
+def encoder_forward(sd, cfg, feats, lens, training=False, pre="encoder.", skip_conv_front=False, attn_mask=None):
     """feats [B, T, 80] (or the conv-front output if skip_conv_front), lens [B] ->
-    (out [B, T', V or d], out_lens, padding_mask)."""
+    (out [B, T', V or d], out_lens, padding_mask).  attn_mask: optional [T', T'] bool, True = HIDDEN key
+    (speech_transformer_encoder.py:368-379; the layers turn it into an additive -1e8 / -1e4 mask)."""
     if skip_conv_front:
         x, ol = feats, lens
         pad = torch.arange(x.size(1), device=x.device)[None, :] >= ol[:, None]
@@ -157,8 +160,11 @@ def encoder_forward(sd, cfg, feats, lens, training=False, pre="encoder.", skip_c
     if has_pads:
         x = x * (~pad)[:, :, None].to(x.dtype)
     layer_fn = conformer_layer if cfg["layer_type"] == "conformer" else transformer_layer
+    # transformer_layer.py:189-192 / conformer_with_relative_positional_embedding_encoder_layer.py:107-110
+    add_mask = None if attn_mask is None else attn_mask.to(x.dtype).masked_fill(
+        attn_mask, -1e8 if x.dtype == torch.float32 else -1e4)
     for i in range(cfg["layers"]):
-        x = layer_fn(sd, pre + "layers.%d." % i, x, pad if has_pads else None, cfg, training)
+        x = layer_fn(sd, pre + "layers.%d." % i, x, pad if has_pads else None, cfg, training, add_mask)
     if cfg.get("final_layer_norm", False):
         x = F.layer_norm(x, (x.size(-1),), sd[pre + "layer_norm.weight"], sd[pre + "layer_norm.bias"])
     if cfg.get("vocab"):

@@ -153,7 +153,7 @@ def attn_softmax_fwd(scores, T, lens, drop_p=0.0, seed=0, causal=False):
     return p, p
 
 
-def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None):
+def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_probs=True, pos_hstride=None, key_bounds=None):
     """fairseq/modules/multihead_attention.py:788-897 (rel-pos branch) in fp32: AC + skew(BD), key-padding mask, softmax,
     P v.  Same return convention as espresso_b200.ops.attn_fused_fwd."""
     assert drop_p == 0.0
@@ -171,6 +171,10 @@ def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_pr
     i = torch.arange(T)[:, None]
     j = torch.arange(T)[None, :]
     s = ac + bd_full.gather(-1, ((T - 1) - i + j).expand(H, B, T, T))
+    if key_bounds is not None:   # attn_mask: bf16(-1e4) ADDED on the hidden keys in the model dtype
+        lo, hi = key_bounds      # (transformer_layer.py:189-192, multihead_attention.py:835-839)
+        hidden = (j < lo.long()[:, None]) | (j >= hi.long()[:, None])
+        s = torch.where(hidden.expand_as(s), (s - 9984.0).to(BF).float(), s)
     if lens is not None:
         km = torch.arange(T)[None, :] >= lens[:, None]
         s = s.masked_fill(km[None, :, None, :], float("-inf"))

@@ -100,14 +100,15 @@ def pin_ctc():
     print("ctc pinned -> tests/golden/ctc.npz")
 
 
-def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50, learned_pos=False, share_heads=False):
+def _ref_model(layer_type, layers=2, d=64, ffn=128, heads=4, V=50, learned_pos=False, share_heads=False,
+               conv_channels="[64, 64, 128, 128]"):
     from espresso.models.transformer.speech_transformer_config import SpeechTransformerConfig
     from espresso.models.transformer.speech_transformer_encoder_model import SpeechTransformerEncoderModel
 
     cfg = SpeechTransformerConfig()
     cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
     e = cfg.encoder
-    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_channels = conv_channels
     e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
     e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
     e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = d, ffn, layers, heads
@@ -230,7 +231,7 @@ def pin_encdec():
     cfg = SpeechTransformerConfig()
     cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
     e = cfg.encoder
-    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_channels = conv_channels
     e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
     e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
     e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = 64, 128, 2, 4
@@ -327,7 +328,7 @@ def pin_transducer():
     cfg = SpeechTransformerTransducerConfig()
     cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
     e = cfg.encoder
-    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_channels = conv_channels
     e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
     e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
     e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = 64, 128, 2, 4
@@ -1006,6 +1007,129 @@ from oracle.fullsize import (FULLSIZE_CFG, FULLSIZE_GRADS, FULLSIZE_GRADS_SUB, f
                              fullsize_inputs)
 
 
+def pin_streaming():
+    """Chunk-streaming / limited-context self-attention.  (1) espresso_b200.tools.utils.chunk_streaming_bounds and
+    context_bounds against the reference's chunk_streaming_mask (espresso/tools/utils.py:131-194) and get_attn_mask
+    (speech_transformer_encoder.py:226-263) over a grid, same numpy seeds; (2) the reference encoder model with
+    chunk_size > 0 (train at two num_updates -> both coin outcomes, and eval) against oracle/conformer.py with the mask,
+    stored as tests/golden/encoder_streaming.npz for the GPU parity test."""
+    import types
+
+    import torch.nn.functional as F
+    from espresso.models.transformer.speech_transformer_encoder import SpeechTransformerEncoder
+    from espresso.tools import utils as RU
+    from fairseq.data import data_utils
+
+    from espresso_b200.tools.utils import bounds_to_mask, chunk_streaming_bounds, context_bounds
+    from oracle import conformer as O
+
+    n = 0
+    for max_len in (1, 2, 7, 18, 37, 64, 131):
+        for chunk in (1, 4, 18, 40):
+            for lw, rw in ((0, 0), (1, 0), (2, 1), (0, 3), (100, 100)):
+                for partial_last in (True, False):
+                    for seed in range(4):
+                        with data_utils.numpy_seed(seed):
+                            ref = RU.chunk_streaming_mask(torch.tensor([max_len, max(max_len // 2, 1)]), chunk, left_window=lw,
+                                                          right_window=rw, always_partial_in_last=partial_last).numpy()
+                        with data_utils.numpy_seed(seed):
+                            lo, hi = chunk_streaming_bounds(max_len, chunk, lw, rw, always_partial_in_last=partial_last)
+                        assert np.array_equal(bounds_to_mask(lo, hi), ref), (max_len, chunk, lw, rw, partial_last, seed)
+                        n += 1
+    class _Lengths(torch.Tensor):
+        """speech_transformer_encoder.py:255 calls `in_lengths.ones(...)`, which torch.Tensor does not have (the
+        reference raises AttributeError there, so `transformer_context` is dead upstream); supplying the evidently
+        intended new_ones lets the rest of the reference's band-mask expression run unmodified."""
+        def ones(self, *a, **k):
+            return torch.ones(*a, **k)
+
+    for max_len in (1, 5, 33):
+        for ctx in ((None, 0), (0, None), (3, 2), (0, 0), (40, 1), (2, 50)):
+            fake = types.SimpleNamespace(cfg=types.SimpleNamespace(encoder=types.SimpleNamespace(chunk_size=0)),
+                                         transformer_context=ctx)
+            ref = SpeechTransformerEncoder.get_attn_mask(fake, torch.tensor([max_len, 1]).as_subclass(_Lengths)).numpy()   # True = hidden
+            lo, hi = context_bounds(max_len, *ctx)
+            assert np.array_equal(~bounds_to_mask(lo, hi), ref), (max_len, ctx)
+            n += 1
+    print("streaming masks: %d reference masks reproduced as key ranges" % n)
+
+    # (2) model-level fixture: head_dim 64 (the fused attention kernel's shape)
+    V, pad_idx, eos_idx, blank = 50, 1, 2, 0
+    m = _ref_model("conformer", d=128, ffn=128, heads=2, V=V, conv_channels="[16, 16, 32, 32]")
+    enc_cfg = m.encoder.cfg.encoder
+    enc_cfg.chunk_size, enc_cfg.chunk_left_window, enc_cfg.chunk_right_window = 6, 2, 1
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for _, p_ in m.named_parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    rs = np.random.RandomState(12)
+    B, T = 3, 163
+    lens = torch.tensor([163, 140, 75])
+    feats = torch.from_numpy(rs.randn(B, T, 80).astype(np.float32))
+    for b in range(B):
+        feats[b, lens[b]:] = 0.0
+    tgt = torch.full((B, 9), pad_idx, dtype=torch.long)
+    for b, u in enumerate((8, 6, 3)):
+        tgt[b, :u] = torch.from_numpy(rs.randint(4, V, size=u))
+        tgt[b, u] = eos_idx
+    cfg = dict(embed_dim=128, ffn_dim=128, heads=2, layers=2, layer_type="conformer", dw_kernel=31, dropout=0.0,
+               attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, final_layer_norm=False, vocab=V)
+    out = dict(feats=feats.numpy(), lens=lens.numpy(), target=tgt.numpy(), chunk=np.array([6, 2, 1]))
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    coins = set()
+    # num_updates 0 and 1 give different first-or-last-partial coins under numpy_seed(num_updates)
+    cases = [("train", 0), ("train", 1), ("eval", 7)]
+    for mode, nu in cases:
+        torch.nn.Module.load_state_dict(m, sd0)   # the Conformer layer has no upgrade_state_dict_named upstream
+        m.train(mode == "train")
+        m.set_num_updates(nu)
+        m.zero_grad()
+        net = m(feats, lens)
+        logits = net["encoder_out"][0]
+        olens = net["src_lengths"][0]
+        hidden = m.encoder.get_attn_mask(olens)                      # deterministic given num_updates
+        if mode == "train":
+            coins.add(int((~hidden[0]).sum()))
+        lprobs = m.get_normalized_probs(net, log_probs=True).contiguous()
+        keep = (tgt != pad_idx) & (tgt != eos_idx)
+        loss = F.ctc_loss(lprobs, tgt.masked_select(keep), olens, keep.sum(-1), blank=blank, reduction="sum",
+                          zero_infinity=True)
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and k in dict(m.named_parameters())) for k, v in sd0.items()}
+        o_logits, o_lens, _ = O.encoder_forward(sd, cfg, feats, lens, training=(mode == "train"), attn_mask=hidden)
+        o_loss = O.ctc_criterion(o_logits, o_lens, tgt, pad_idx, eos_idx, blank)
+        d_log = (o_logits.transpose(0, 1) - logits).abs().max().item()
+        assert d_log < 2e-4 and abs(o_loss.item() - loss.item()) < 1e-3 * abs(loss.item()), (mode, nu, d_log)
+        tag = "%s%d" % (mode, nu)
+        if mode == "train":
+            loss.backward()
+            o_loss.backward()
+            worst = max((sd[k].grad - p_.grad).abs().max().item() / max(p_.grad.abs().max().item(), 1e-3)
+                        for k, p_ in m.named_parameters())
+            assert worst < 2e-3, worst
+            if nu == 0:   # one gradient set keeps the fixture small; train1 is covered through loss + logits
+                for k, p_ in m.named_parameters():
+                    out["grad_%s.%s" % (tag, k)] = p_.grad.numpy().copy()
+        # the unmasked model must differ visibly, or the fixture would not test the mask
+        enc_cfg.chunk_size = 0
+        with torch.no_grad():
+            torch.nn.Module.load_state_dict(m, sd0)
+            free = m(feats, lens)["encoder_out"][0]
+        enc_cfg.chunk_size = 6
+        sep = (free - logits).abs().max().item() / logits.abs().max().item()
+        assert sep > 0.05, sep
+        out["hidden_" + tag] = hidden.numpy()
+        out["logits_" + tag] = logits.detach().transpose(0, 1).numpy()
+        out["loss_" + tag] = np.float64(loss.item())
+        out["out_lens"] = olens.numpy()
+        print("streaming %s: |logits diff|=%.3g loss %.5f, masked vs free logits differ by %.2f of range" % (tag, d_log, loss.item(), sep))
+    assert len(coins) == 2, "both partial-chunk placements must be covered"
+    for k, v in sd0.items():
+        out["sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "encoder_streaming.npz"), **out)
+    print("streaming encoder pinned -> tests/golden/encoder_streaming.npz")
+
+
 def pin_fullsize():
     """The BENCHMARKED configuration (17 x 512 Conformer, ffn 2048, 8 heads, conv-k31, V = 5004) through the REAL
     reference model in fp32 and in bf16 (`model.bfloat16()`, fairseq --bf16 semantics, fairseq/trainer.py:105-107).
@@ -1070,7 +1194,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

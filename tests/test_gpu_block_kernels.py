@@ -350,6 +350,54 @@ def test_attn_fused_fwd_vs_reference(dev, B, T, H, lens, shared):
     assert p2 is None and torch.equal(ctx2, ctx)
 
 
+@pytest.mark.parametrize("B,T,lens,chunk,lw,rw,last,ctx", [
+    (2, 203, [203, 150], 16, 1, 0, True, None),     # causal-ish chunks, one chunk of history
+    (3, 407, [407, 333, 150], 40, 2, 1, False, None),  # training layout (coin decides which end is partial)
+    (2, 130, None, 7, 0, 0, True, None),            # chunks smaller than a warp's column group, two key tiles
+    (2, 64, [64, 20], 200, 0, 0, True, None),       # one chunk covers everything (mask is a no-op)
+    (3, 250, [250, 160, 77], 0, 0, 0, True, (10, 3)),  # transformer_context band
+    (2, 129, [129, 40], 0, 0, 0, True, (None, 0)),  # causal
+    (2, 90, [90, 31], 30, 0, 0, True, None),        # rows of the short utterance whose visible chunk is all padding
+])
+def test_attn_fused_fwd_streaming_masks(dev, B, T, lens, chunk, lw, rw, last, ctx):
+    """Per-row visible key ranges (chunk streaming, espresso/tools/utils.py:131-194; limited context,
+    speech_transformer_encoder.py:250-263) inside the fused kernel vs the oracle's additive-mask statement."""
+    from espresso_b200 import ops
+    from espresso_b200.tools.utils import chunk_streaming_bounds, context_bounds
+    from oracle import ops_ref
+
+    H = 2
+    qu, qv, k, v, pos = _attn_inputs(B, T, H, 300 + T, dev)
+    np.random.seed(T)
+    lo, hi = chunk_streaming_bounds(T, chunk, lw, rw, always_partial_in_last=last) if chunk else context_bounds(T, *ctx)
+    lo_t, hi_t = torch.from_numpy(lo), torch.from_numpy(hi)
+    lens_t = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=dev)
+    out, p, _ = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens_t, key_bounds=(lo_t.to(dev), hi_t.to(dev)))
+    torch.cuda.synchronize()
+    rc, rp, _ = ops_ref.attn_fused_fwd(qu.cpu(), qv.cpu(), k.cpu(), v.cpu(), pos.cpu(), B, T, H,
+                                       None if lens is None else lens_t.cpu(), key_bounds=(lo_t, hi_t))
+    j = torch.arange(T)[None, :]
+    hidden = (j < lo_t[:, None]) | (j >= hi_t[:, None])                       # [T, T]
+    # rows whose visible keys are all padding normalise over the hidden keys (finite -1e4 mask): the reference's bf16
+    # score arithmetic there is only reproduced approximately, compare everything else tightly
+    L = torch.full((B,), T) if lens is None else torch.tensor(lens)
+    vis = (~hidden)[None] & (j[None] < L[:, None, None])                      # [B, T, T]
+    ok_rows = vis.any(-1)                                                      # [B, T]
+    pg = p.float().cpu()[..., :T]
+    perr = (pg - rp.float()[..., :T])[:, ok_rows].abs().max().item()
+    cg, cr = out.float().cpu().view(B, T, -1), rc.float().view(B, T, -1)
+    cerr = (cg - cr)[ok_rows].abs().max().item()
+    assert perr < 1.5e-2 and cerr < 2e-2 * max(1.0, cr.abs().max().item()), (perr, cerr)
+    # hidden keys carry exactly zero probability wherever a visible key exists
+    assert (pg.permute(1, 2, 3, 0)[(ok_rows[:, :, None] & hidden[None])] == 0).all()
+    assert torch.allclose(pg.sum(-1), torch.ones(H, B, T), atol=2e-2)
+    if (~ok_rows).any():   # degenerate rows: still a proper distribution over the unpadded keys, never NaN
+        assert torch.isfinite(cg).all()
+        bad = (~ok_rows).nonzero()
+        b0, i0 = bad[0].tolist()
+        assert (pg[:, b0, i0, L[b0]:] == 0).all()
+
+
 def test_attn_fused_fwd_dropout_stream_matches_softmax_kernels(dev):
     """The dropped probabilities use the same counter-RNG stream as esp_attn_softmax_fwd / _bwd (the backward pass
     regenerates the mask with esp_attn_softmax_bwd), and ctx == Pd v."""

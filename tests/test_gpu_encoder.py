@@ -367,3 +367,66 @@ def test_full_size_encoder_value_parity(golden_dir):
     from fullsize_util import run_and_check
 
     run_and_check("cuda:0", golden_dir)
+
+
+def test_chunk_streaming_encoder_vs_reference_fixture(golden_dir):
+    """Chunk-streaming Conformer (chunk_size / chunk_left_window / chunk_right_window) against the REAL reference model
+    (tests/golden/encoder_streaming.npz, oracle/pin_against_reference.py::pin_streaming): training at num_updates 0
+    and 1 (the reference draws the first-or-last partial chunk under numpy_seed(num_updates); the fixture holds both
+    outcomes) and eval (always partial in last).  The masks run inside the fused attention kernel as key ranges."""
+    from espresso_b200.criterions import CtcLossCriterion
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerEncoderModel
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "encoder_streaming.npz"))
+    chunk, lw, rw = (int(c) for c in g["chunk"])
+    cfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=True, max_source_positions=3600,
+        encoder=dict(embed_dim=128, ffn_embed_dim=128, layers=2, attention_heads=2, normalize_before=True,
+                     relative_positional_embeddings=True, layer_type="conformer", depthwise_conv_kernel_size=31,
+                     conv_channels="[16, 16, 32, 32]", chunk_size=chunk, chunk_left_window=lw, chunk_right_window=rw)))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    crit = CtcLossCriterion(_Task(50))
+    sample = _sample(g, dev)
+    for mode, nu in (("train", 0), ("train", 1), ("eval", 7)):
+        tag = "%s%d" % (mode, nu)
+        m = SpeechTransformerEncoderModel.build_model(cfg, _Task(50))
+        m.load_state_dict(sd, strict=True)
+        m.finalize_(dev)
+        m.train(mode == "train")
+        m.set_num_updates(nu)
+        assert m.encoder.has_attn_mask
+        if mode == "train":
+            m.flat.zero_grad()
+            loss, _, _ = crit(m, sample)
+            loss.backward()
+            m.encoder.sync_torch_grads_()
+        else:
+            with torch.no_grad():
+                loss, _, _ = crit(m, sample)
+        ref_loss = float(g["loss_" + tag])
+        assert abs(loss.item() - ref_loss) < 0.03 * ref_loss, (tag, loss.item(), ref_loss)
+        # the two training coins give different losses in the fixture; ours must follow the right one
+        lo, hi = m.encoder.attn_key_bounds(int(g["out_lens"].max()), int(g["out_lens"].max()))
+        j = np.arange(len(lo))[None, :]
+        assert np.array_equal((j < lo[:, None]) | (j >= hi[:, None]), g["hidden_" + tag]), tag
+        if mode == "train" and nu == 0:
+            worst = []
+            for k in g.files:
+                if not k.startswith("grad_train0.encoder."):
+                    continue
+                name = k[len("grad_train0."):]
+                if ("pre_encoder.convolutions" in name and name.endswith(".bias")) or name.endswith("k_proj.bias"):
+                    continue
+                ours = m.flat.grad(name).cpu().numpy()
+                worst.append((np.linalg.norm(ours - g[k]) / max(np.linalg.norm(g[k]), 1e-3), name))
+            worst.sort(reverse=True)
+            assert worst[0][0] < 0.25, worst[:5]
+            assert max(w[0] for w in worst if "pre_encoder" not in w[1]) < 0.1, worst[:8]
+            assert np.median([w[0] for w in worst]) < 0.03
+        if mode == "eval":
+            with torch.no_grad():
+                net = m(**sample["net_input"])
+            logits = net["encoder_out"][0].transpose(0, 1).float().cpu().numpy()
+            ref = g["logits_" + tag]
+            assert np.abs(logits - ref).max() < 0.06 * np.abs(ref).max()
