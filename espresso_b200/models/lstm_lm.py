@@ -27,24 +27,27 @@ class LSTMLanguageModelEspressoConfig:
     decoder_rnn_residual: bool = False
     share_embed: bool = False
     max_target_positions: int = 1024
+    is_wordlm: bool = False  # word LM (look-ahead / multi-level fusion at decoding time), espresso/models/lstm_lm.py:64-70
 
 
 @register_model("lstm_lm_espresso", dataclass=LSTMLanguageModelEspressoConfig)
 class LSTMLanguageModelEspresso(nn.Module):
-    def __init__(self, decoder):
+    def __init__(self, decoder, is_wordlm=False):
         super().__init__()
         self.decoder = decoder
+        self.is_wordlm = is_wordlm
 
     @classmethod
     def build_model(cls, cfg, task):
         if cfg.share_embed and cfg.decoder_embed_dim != cfg.decoder_out_embed_dim:
             raise ValueError("--share-embed requires --decoder-embed-dim to match --decoder-out-embed-dim")
-        d = task.target_dictionary
+        # a word LM uses the task's word dictionary when there is one (lstm_lm.py:155-158)
+        d = task.word_dictionary if getattr(cfg, "is_wordlm", False) and hasattr(task, "word_dictionary") else task.target_dictionary
         dec = SpeechLSTMDecoder(d, cfg.decoder_embed_dim, cfg.decoder_hidden_size, cfg.decoder_out_embed_dim, cfg.decoder_layers,
                                 cfg.dropout, cfg.dropout, encoder_output_units=0, attn_dim=0,
                                 residual=False,  # the reference does not forward decoder_rnn_residual to the decoder (lstm_lm.py:175-191)
                                 share_input_output_embed=cfg.share_embed, max_target_positions=cfg.max_target_positions)
-        return cls(dec)
+        return cls(dec, is_wordlm=getattr(cfg, "is_wordlm", False))
 
     def finalize_(self, device, dtype=torch.bfloat16):
         self.to(device=device, dtype=dtype)

@@ -147,6 +147,7 @@ class SpeechLSTMDecoder(nn.Module):
                  scheduled_sampling_rate_scheduler=None):
         super().__init__()
         self.scheduled_sampling_rate_scheduler = scheduled_sampling_rate_scheduler
+        self.dictionary = dictionary
         V, pad = len(dictionary), dictionary.pad()
         self.hidden_size, self.encoder_output_units, self.residual = hidden_size, encoder_output_units, residual
         self.dropout_in, self.dropout_out = dropout_in, dropout_out

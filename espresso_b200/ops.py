@@ -497,6 +497,54 @@ def beam_bookkeep(step, max_len, bsz, beam, K, eos, pad, normalize, len_penalty,
     st.scores, st.scores_alt = st.scores_alt, st.scores
 
 
+def lookahead_words(nodes_in, new_order, node_word, word_unk, nodes_out, words):
+    """Look-ahead LM fusion, part 1: nodes_out = nodes_in[new_order]; words = word completed at each node (or <unk>)."""
+    _need_cuda(nodes_in, node_word, nodes_out, words)
+    _lib.check(_lib.load().esp_lookahead_words(_ptr(nodes_in), _ptr(new_order) if new_order is not None else None, _ptr(node_word),
+                                               word_unk, nodes_in.numel(), _ptr(nodes_out), _ptr(words), _stream()))
+
+
+def wordlm_cumsum(logits, Vw, prev_tokens, tok_stride, space_idx, first, cum_in, new_order, cum_out, eos_logprob, word_eos,
+                  log_mode=False):
+    """Part 2: rows after a <space> (all rows if first) get cumsum(softmax(logits[:, :Vw])) -- or log_softmax with
+    log_mode -- the rest inherit cum_in[new_order].  logits bf16 / fp32 [N, >= Vw]; prev_tokens: int32 view with element
+    stride tok_stride."""
+    _need_cuda(logits, cum_in, cum_out, eos_logprob)
+    assert logits.dtype in (torch.bfloat16, torch.float32) and logits.stride(1) == 1 and prev_tokens.dtype == torch.int32
+    assert cum_out.is_contiguous() and cum_in.is_contiguous() and cum_out.shape[1] == Vw
+    _lib.check(_lib.load().esp_wordlm_cumsum(
+        _ptr(logits), int(logits.dtype == torch.float32), logits.stride(0), logits.shape[0], Vw, _ptr(prev_tokens), tok_stride,
+        space_idx, int(first), _ptr(cum_in), _ptr(new_order) if new_order is not None else None, _ptr(cum_out), _ptr(eos_logprob),
+        word_eos, int(log_mode), _stream()))
+
+
+def lookahead_step(prev_tokens, tok_stride, first, nodes_in, nodes_out, cum, Vw, eos_logprob, tree, space_idx, eos_idx, pad_idx,
+                   word_unk, oov_penalty, open_vocab, zero, out, Vs):
+    """Part 3: prefix-tree transition and the fp32 subword log-probability rows out[:, :Vs] (tree: dict of device int32
+    arrays from TensorizedPrefixTree.to)."""
+    _need_cuda(nodes_in, nodes_out, cum, out)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and cum.is_contiguous()
+    _lib.check(_lib.load().esp_lookahead_step(
+        _ptr(prev_tokens), tok_stride, nodes_in.numel(), int(first), _ptr(nodes_in), _ptr(nodes_out), _ptr(cum), Vw, _ptr(eos_logprob),
+        _ptr(tree["child_off"]), _ptr(tree["child_tok"]), _ptr(tree["child_node"]), _ptr(tree["node_word"]), _ptr(tree["node_lo"]),
+        _ptr(tree["node_hi"]), space_idx, eos_idx, pad_idx, word_unk, oov_penalty, int(open_vocab), zero, _ptr(out), out.stride(0), Vs,
+        _stream()))
+
+
+def multilevel_step(prev_tokens, tok_stride, first, nodes_in, nodes_out, new_order, wlp, Vw, sub, sub_is_logits, sub_weight, out_prev,
+                    cumlp_in, cumlp_out, tree, space_idx, eos_idx, word_unk, word_eos, log_oov_penalty, open_vocab, logzero, out, Vs):
+    """Multi-level (subword + word) LM step: see esp_multilevel_step in include/espresso_b200.h."""
+    _need_cuda(nodes_in, nodes_out, wlp, sub, out)
+    assert sub.dtype in (torch.bfloat16, torch.float32) and sub.stride(1) == 1 and out.dtype == torch.float32 and wlp.is_contiguous()
+    assert out_prev.stride() == out.stride()
+    _lib.check(_lib.load().esp_multilevel_step(
+        _ptr(prev_tokens), tok_stride, nodes_in.numel(), int(first), _ptr(nodes_in), _ptr(nodes_out),
+        _ptr(new_order) if new_order is not None else None, _ptr(wlp), Vw, _ptr(sub), int(sub.dtype == torch.float32), sub.stride(0),
+        int(sub_is_logits), sub_weight, _ptr(out_prev), _ptr(cumlp_in), _ptr(cumlp_out), _ptr(tree["child_off"]),
+        _ptr(tree["child_tok"]), _ptr(tree["child_node"]), _ptr(tree["node_word"]), space_idx, eos_idx, word_unk, word_eos,
+        log_oov_penalty, int(open_vocab), logzero, _ptr(out), out.stride(0), Vs, _stream()))
+
+
 def gather_rows(src, idx, out=None):
     """out[i] = src[idx[i]] along dim 0 (rows must be multiples of 16 bytes)."""
     _need_cuda(src, idx)

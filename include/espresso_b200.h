@@ -250,6 +250,46 @@ int esp_beam_bookkeep(int32_t step, int32_t max_len, int32_t bsz, int32_t beam, 
                       void* stream);
 int esp_gather_rows(const void* src, const int32_t* idx, int64_t row_bytes, int64_t n_rows, void* dst, void* stream);
 
+/* ---- look-ahead word-LM fusion (espresso/models/tensorized_lookahead_language_model.py:84-262) -------------
+ * A word LM scores subword hypotheses through a lexical prefix tree (espresso/tools/tensorized_prefix_tree.py:15-108,
+ * here in CSR form: node 0 = "outside the lexicon", node 1 = root, edges sorted by subword id; node_lo/node_hi =
+ * (first word id - 1, last word id) of the words below a node, node_word = word id ending at the node or -1).
+ * One search step = three calls:
+ *   lookahead_words: nodes_out[n] = nodes_in[new_order[n]] (new_order NULL = identity); words[n] = the word the
+ *     hypothesis has just completed (word_unk if none) -- the word LM's input (:126-130).
+ *   wordlm_cumsum: rows whose previous subword (prev_tokens[n * tok_stride]) is <space>, or all rows when first != 0:
+ *     cum_out[n, :] = inclusive cumsum(softmax(logits[n, :Vw])) (fp32) and eos_logprob[n] = log softmax[word_eos];
+ *     every other row copies cum_in[new_order[n], :] (the reference's reorder_incremental_state, :264-272).
+ *     logits: bf16 or fp32 [N, ld]; cum_in != cum_out.  log_mode != 0: the rows hold log_softmax instead (no scan) --
+ *     the per-word log-probabilities the multi-level LM keeps (external_language_model.py:425-436).
+ *   lookahead_step: tree transition on prev_tokens (nodes_in -> nodes_out, :150-164) and the subword log-probability row
+ *     out[n, :Vs] (fp32, Eqn. 15 cases 1-4 of arXiv:1808.02608 as implemented at :173-263; columns Vs..ld_out-1 = -inf).
+ *     open_vocab = 0: probability `zero` outside the lexicon; zero = 1e-10 in the reference. */
+int esp_lookahead_words(const int32_t* nodes_in, const int32_t* new_order, const int32_t* node_word, int32_t word_unk,
+                        int32_t N, int32_t* nodes_out, int32_t* words, void* stream);
+int esp_wordlm_cumsum(const void* logits, int32_t logits_f32, int64_t ld, int32_t N, int32_t Vw, const int32_t* prev_tokens,
+                      int64_t tok_stride, int32_t space_idx, int32_t first, const float* cum_in, const int32_t* new_order,
+                      float* cum_out, float* eos_logprob, int32_t word_eos, int32_t log_mode, void* stream);
+int esp_lookahead_step(const int32_t* prev_tokens, int64_t tok_stride, int32_t N, int32_t first, const int32_t* nodes_in,
+                       int32_t* nodes_out, const float* cum, int32_t Vw, const float* eos_logprob, const int32_t* child_off,
+                       const int32_t* child_tok, const int32_t* child_node, const int32_t* node_word, const int32_t* node_lo,
+                       const int32_t* node_hi, int32_t space_idx, int32_t eos_idx, int32_t pad_idx, int32_t word_unk,
+                       float oov_penalty, int32_t open_vocab, float zero, float* out, int64_t ld_out, int32_t Vs,
+                       void* stream);
+
+/* multilevel_step (MultiLevelLanguageModel, espresso/models/external_language_model.py:385-555): the subword LM's row
+ * (sub: bf16 / fp32 [N, ld_sub], logits or log-probs) is scaled by sub_weight; <space> gets the word LM's log-probability
+ * of the completed word minus what the subword LM accumulated inside it (cumlp), or the <unk> score + log_oov_penalty
+ * outside the lexicon; </s> adds the word-level </s>.  out_prev / cumlp_in are the previous step's out / cumlp_out
+ * (read at row new_order[n]); nodes_in is already reordered (esp_lookahead_words).  logzero = -10 in the reference. */
+int esp_multilevel_step(const int32_t* prev_tokens, int64_t tok_stride, int32_t N, int32_t first, const int32_t* nodes_in,
+                        int32_t* nodes_out, const int32_t* new_order, const float* wordlm_logprobs, int32_t Vw, const void* sub,
+                        int32_t sub_f32, int64_t ld_sub, int32_t sub_is_logits, float sub_weight, const float* out_prev,
+                        const float* cumlp_in, float* cumlp_out, const int32_t* child_off, const int32_t* child_tok,
+                        const int32_t* child_node, const int32_t* node_word, int32_t space_idx, int32_t eos_idx,
+                        int32_t word_unk, int32_t word_eos, float log_oov_penalty, int32_t open_vocab, float logzero, float* out,
+                        int64_t ld_out, int32_t Vs, void* stream);
+
 /* ---- incremental decoding (fairseq/modules/multihead_attention.py:639-760,878-897,964-989) --------------
  * One query per hypothesis.  Self-attention: kv_cache [T_max, N, 2d] (k | v) is written in place by the K/V
  * projection GEMM of each step; anc [T_max, N] maps (time, hypothesis) -> cache row, so beam reordering never

@@ -615,3 +615,101 @@ def rnnt_loss(logits, V, t_lens, u_lens, targets, blank, grad_scale=1.0, want_gr
             grad[..., :V] = x.grad * grad_scale
             grad = grad.to(BF)
     return loss.detach(), grad
+
+
+# ---- look-ahead word-LM fusion (csrc/lookahead.cu): same call signatures as espresso_b200.ops ---------------------------
+def lookahead_words(nodes_in, new_order, node_word, word_unk, nodes_out, words):
+    n = nodes_in if new_order is None else nodes_in[new_order.long()]
+    w = node_word[n.long()]
+    nodes_out.copy_(n)
+    words.copy_(torch.where(w < 0, torch.full_like(w, word_unk), w))
+
+
+def wordlm_cumsum(logits, Vw, prev_tokens, tok_stride, space_idx, first, cum_in, new_order, cum_out, eos_logprob, word_eos,
+                  log_mode=False):
+    x = logits[:, :Vw].double()
+    lp = torch.log_softmax(x, -1)
+    new = lp.float() if log_mode else lp.exp().cumsum(-1).float()
+    if first:
+        cum_out.copy_(new)
+    else:
+        old = cum_in if new_order is None else cum_in[new_order.long()]
+        cum_out.copy_(torch.where((prev_tokens == space_idx)[:, None], new, old))
+    eos_logprob.copy_(lp[:, word_eos].float())
+
+
+def lookahead_step(prev_tokens, tok_stride, first, nodes_in, nodes_out, cum, Vw, eos_logprob, tree, space_idx, eos_idx, pad_idx,
+                   word_unk, oov_penalty, open_vocab, zero, out, Vs):
+    """espresso/models/tensorized_lookahead_language_model.py:150-263 on the CSR tree, one hypothesis at a time."""
+    off, tok, child = tree["child_off"].tolist(), tree["child_tok"].tolist(), tree["child_node"].tolist()
+    word, lo, hi = tree["node_word"].tolist(), tree["node_lo"].tolist(), tree["node_hi"].tolist()
+    cs_all = cum.double()
+    out.fill_(float("-inf"))
+    for n in range(nodes_in.numel()):
+        prev = int(prev_tokens[n])
+        after_space = (not first) and prev == space_idx
+        if first or after_space:
+            node = 1
+        else:
+            cur, node = int(nodes_in[n]), 0
+            for e in range(off[cur], off[cur + 1]):
+                if tok[e] == prev:
+                    node = child[e]
+        nodes_out[n] = node
+        cs = cs_all[n]
+        if not open_vocab:
+            row = torch.full((Vs,), zero, dtype=torch.float64)
+        elif node == 0:
+            row = torch.ones(Vs, dtype=torch.float64)
+        else:
+            row = torch.full((Vs,), float(oov_penalty * (cs[word_unk] - cs[word_unk - 1])), dtype=torch.float64)
+            if after_space or prev == eos_idx:
+                row[space_idx] = zero
+            if not after_space:
+                row[eos_idx] = zero
+        sum_p = float(cs[hi[node]] - cs[lo[node]]) if node > 1 else 1.0
+        for e in range(off[node], off[node + 1]):
+            c = child[e]
+            row[tok[e]] = zero if sum_p < zero else float(cs[hi[c]] - cs[lo[c]]) / sum_p
+        row[pad_idx] = zero
+        if word[node] >= 0:
+            row[space_idx] = zero if sum_p < zero else float(cs[word[node]] - cs[word[node] - 1]) / sum_p
+        lp = row.clamp(min=zero).log().float()
+        if after_space:
+            lp[eos_idx] = eos_logprob[n]
+        out[n, :Vs] = lp
+
+
+def multilevel_step(prev_tokens, tok_stride, first, nodes_in, nodes_out, new_order, wlp, Vw, sub, sub_is_logits, sub_weight, out_prev,
+                    cumlp_in, cumlp_out, tree, space_idx, eos_idx, word_unk, word_eos, log_oov_penalty, open_vocab, logzero, out, Vs):
+    """espresso/models/external_language_model.py:437-533 on the CSR tree."""
+    off, tok, child, word = (tree[k].tolist() for k in ("child_off", "child_tok", "child_node", "node_word"))
+    rows = torch.log_softmax(sub[:, :Vs].float(), -1) if sub_is_logits else sub[:, :Vs].float()
+    out.fill_(float("-inf"))
+    for n in range(nodes_in.numel()):
+        prev = int(prev_tokens[n])
+        after_space = (not first) and prev == space_idx
+        src = n if new_order is None else int(new_order[n])
+        if first or after_space:
+            node = 1
+        else:
+            cur, node = int(nodes_in[n]), 0
+            for e in range(off[cur], off[cur + 1]):
+                if tok[e] == prev:
+                    node = child[e]
+        is_child = (not first) and (not after_space) and node != 0
+        cum = 0.0
+        if not first and ((not after_space) if open_vocab else is_child):
+            cum = float(cumlp_in[src]) + float(out_prev[src, prev])
+        row = rows[n] * sub_weight
+        if (not open_vocab) and (not first) and (not after_space) and (not is_child):
+            row = torch.full_like(row, logzero)
+        w = word[node]
+        v_space = float(wlp[n, w if w >= 0 else word_unk]) + (-cum if w >= 0 else log_oov_penalty)
+        if after_space or prev == eos_idx:
+            v_space = logzero
+        row[space_idx] = v_space
+        row[eos_idx] = row[eos_idx] + wlp[n, word_eos] if after_space else logzero
+        out[n, :Vs] = row
+        nodes_out[n] = node
+        cumlp_out[n] = cum

@@ -1130,6 +1130,257 @@ def pin_streaming():
     print("streaming encoder pinned -> tests/golden/encoder_streaming.npz")
 
 
+def _lookahead_vocab():
+    """Character subwords and a word list in lexical order with shared prefixes, words ending inside other words, a word
+    with an unknown character (stays out of the tree) -- shared by the pin and the tests through the fixture."""
+    chars = list("abcdeghilnorst'")
+    words = sorted({"a", "an", "and", "ant", "are", "art", "as", "at", "be", "bed", "bee", "been", "best", "bet", "can",
+                    "cat", "do", "dog", "done", "door", "eat", "go", "god", "gold", "good", "he", "hen", "her", "here", "his",
+                    "in", "is", "it", "its", "no", "nor", "not", "note", "on", "one", "or", "so", "son", "the", "then",
+                    "there", "to", "toe", "ton", "too", "don't", "quiz"})    # "quiz": q, u, z are not subwords
+    return chars, words
+
+
+def pin_lookahead():
+    """Look-ahead word-LM fusion: the REAL TensorizedLookaheadLanguageModel over the reference LSTM word LM, driven step by
+    step like the beam search does (forward on the growing prefix, then reorder_incremental_state), vs (1) oracle/lookahead.py
+    fed with the reference LM's word distributions and (2) espresso_b200's prefix tree walked on the host.  Inputs, LM
+    weights, the per-step word distributions and the reference outputs -> tests/golden/lookahead_lm.npz."""
+    from argparse import Namespace
+
+    from espresso.data import AsrDictionary as RefDict
+    from espresso.models.lstm_lm import LSTMLanguageModelEspresso
+    from espresso.models.tensorized_lookahead_language_model import TensorizedLookaheadLanguageModel as RefLookahead
+
+    from espresso_b200.data.asr_dictionary import AsrDictionary as OurDict
+    from espresso_b200.tools.tensorized_prefix_tree import TensorizedPrefixTree
+    from oracle import lookahead as OL
+
+    chars, words = _lookahead_vocab()
+
+    def dicts(cls):
+        sd, wd = cls(), cls()
+        for c in chars + ["<space>"]:
+            sd.add_symbol(c)
+        for w in words:
+            wd.add_symbol(w)
+        if cls is OurDict:
+            sd.space_index = sd.indices.get(sd.space_word, -1)
+        else:
+            sd.space_index = sd.indices.get(sd.space_word, -1)
+        return sd, wd
+
+    sub, wrd = dicts(RefDict)
+    Vs, Vw = len(sub), len(wrd)
+
+    class _Task:
+        source_dictionary = target_dictionary = word_dictionary = wrd
+
+    args = Namespace(dropout=0.0, decoder_embed_path=None, decoder_freeze_embed=False, decoder_layers=2,
+                     adaptive_softmax_cutoff=None, is_wordlm=True, decoder_dropout_in=0.0, decoder_dropout_out=0.0,
+                     criterion_name="cross_entropy", max_target_positions=64, tokens_per_sample=64, decoder_embed_dim=24,
+                     decoder_hidden_size=32, decoder_out_embed_dim=32, share_embed=False, decoder_rnn_residual=False)
+    torch.manual_seed(77)
+    lm = LSTMLanguageModelEspresso.build_model(args, _Task())
+    with torch.no_grad():      # peaky word distributions: the tree ratios are far from uniform
+        for n_, p_ in lm.named_parameters():
+            if "fc_out" in n_ or "embed" in n_:
+                p_.mul_(6.0)
+    lm.eval()
+    assert lm.decoder.dictionary is wrd
+
+    # hypotheses as strings over the subword alphabet: "_" = <space>, "$" = </s>; the beam reordering between steps is
+    # explicit (new_orders[t] is applied after step t)
+    texts = ["the_cat_$", "then_go_$", "be_been_$", "xq_not_$", "goldx_a_$", "do_n't_$", "a_an_ant_$", "there_$"]
+    N = len(texts)
+    L = max(len(t) for t in texts)
+    sym = lambda ch: sub.space() if ch == "_" else sub.eos() if ch == "$" else sub.index(ch)  # noqa: E731
+    assert sub.index("x") == sub.unk()     # "x" / "q" exercise out-of-vocabulary subwords
+
+    out = {}
+    for variant, (open_vocab, oov_pen) in {"open": (True, 1e-4), "closed": (False, 1e-4), "open_pen": (True, 0.3)}.items():
+        ref = RefLookahead(lm, sub, oov_penalty=oov_pen, open_vocab=open_vocab)
+        ref.eval()
+        dec = ref.decoder
+        # capture the word distributions the reference's LM produces inside forward()
+        seen = []
+        orig = dec.lm_decoder.get_normalized_probs
+
+        def spy(net_output, log_probs, sample=None, _orig=orig):
+            r = _orig(net_output, log_probs, sample)
+            seen.append(r.detach().clone())
+            return r
+
+        dec.lm_decoder.get_normalized_probs = spy
+        rs = np.random.RandomState(3)
+        rows = [list(t) for t in texts]           # current text per hypothesis SLOT (slots get permuted)
+        inc = {}
+        toks = torch.full((N, 1), sub.eos(), dtype=torch.long)
+        tok_hist, order_hist, ref_out, lm_hist = [], [], [], []
+        tree = dec.tree
+        state = OL.LookaheadState(OL.build_tree([wrd[i] for i in range(Vw)], {wrd.pad(), wrd.eos(), wrd.unk()}, sub.index,
+                                                sub.unk()), N)
+        ours = TensorizedPrefixTree.build(*dicts(OurDict)[::-1])
+        our_nodes = [ours.root_id] * N
+        for t in range(L + 1):
+            seen.clear()
+            lp, _ = dec(toks, incremental_state=inc)                       # [N, 1, Vs]
+            lm_probs = seen[0][:, 0].numpy()                                # word distribution of this step
+            prev = toks[:, -1].numpy()
+            o = OL.step(state, prev, lm_probs, t == 0, Vs, sub.space(), sub.eos(), sub.pad(), wrd.unk(), wrd.eos(), oov_pen,
+                        open_vocab)
+            ref_lp = lp[:, 0].numpy()
+            big = ref_lp > -15          # below: differences of float32 cumulative sums are cancellation noise
+            err = np.abs(o - ref_lp)[big].max() if big.any() else 0.0
+            assert err < 2e-4 and np.abs(o - ref_lp).max() < 1.0, (variant, t, err)
+            # the oracle walked its own tree; the reference's node ids agree in the words they end / ranges they span
+            rn = dec.get_incremental_state(inc, "nodes").numpy()
+            for n in range(N):
+                nd = state.nodes[n]
+                assert (nd is None) == (rn[n] == 0)
+                if nd is not None and nd is not state.root:
+                    assert (int(tree.word_idx[rn[n]]), tuple(tree.word_set_idx[rn[n]].tolist())) == (nd.word, (nd.lo, nd.hi))
+                # and so does the product's CSR tree
+                if t > 0:
+                    our_nodes[n] = ours.root_id if prev[n] == sub.space() else ours.step(our_nodes[n], int(prev[n]))
+                assert (nd is None) == (our_nodes[n] == 0)
+                if nd is not None and nd is not state.root:
+                    k = our_nodes[n]
+                    assert (int(ours.node_word[k]), int(ours.node_lo[k]), int(ours.node_hi[k])) == (nd.word, nd.lo, nd.hi)
+            tok_hist.append(prev.copy())
+            ref_out.append(ref_lp.copy())
+            lm_hist.append(lm_probs.copy())
+            if t == L:
+                break
+            # beam-search style permutation with duplicates, then each surviving slot emits its next symbol
+            order = rs.randint(0, N, size=N) if t in (2, 4, 5) else np.arange(N)
+            order_hist.append(order.copy())
+            # the generator's entry point: walks every sub-module, i.e. also the wrapped LSTM LM's cached state
+            # (fairseq/sequence_generator.py:368-371)
+            dec.reorder_incremental_state_scripting(inc, torch.from_numpy(order))
+            state.reorder(order)
+            our_nodes = [our_nodes[i] for i in order]
+            rows = [rows[i] for i in order]
+            toks = toks[torch.from_numpy(order)]
+            nxt = [sym(r[t]) if t < len(r) else sub.eos() for r in rows]
+            toks = torch.cat([toks, torch.tensor(nxt)[:, None]], dim=1)
+        dec.lm_decoder.get_normalized_probs = orig
+        out[variant + ".prev_tokens"] = np.stack(tok_hist)                   # [L+1, N]
+        out[variant + ".new_orders"] = np.stack(order_hist)                  # [L, N]
+        out[variant + ".out"] = np.stack(ref_out).astype(np.float32)         # [L+1, N, Vs]
+        out[variant + ".lm_probs"] = np.stack(lm_hist).astype(np.float32)    # [L+1, N, Vw]
+        out[variant + ".tokens_final"] = toks.numpy()
+        print("lookahead %-8s: %d steps x %d hypotheses, oracle within %.1e of the reference" % (variant, L + 1, N, 2e-4))
+    for k, v in lm.state_dict().items():
+        out["sd." + k] = v.numpy()
+    out["chars"], out["words"] = np.array(chars), np.array(words)
+    out["lm_cfg"] = np.array([24, 32, 32, 2])
+    np.savez_compressed(os.path.join(GOLDEN, "lookahead_lm.npz"), **out)
+    print("look-ahead LM pinned -> tests/golden/lookahead_lm.npz (|subwords| %d, |words| %d)" % (Vs, Vw))
+
+
+def pin_multilevel():
+    """MultiLevelLanguageModel (subword LSTM LM + word LSTM LM): the REAL reference class driven step by step (forward, then
+    reorder_incremental_state_scripting) vs oracle/lookahead.py::multilevel_step fed with the two reference LMs' recorded
+    log-probabilities -> tests/golden/multilevel_lm.npz."""
+    from argparse import Namespace
+
+    from espresso.data import AsrDictionary as RefDict
+    from espresso.models.external_language_model import MultiLevelLanguageModel as RefML
+    from espresso.models.lstm_lm import LSTMLanguageModelEspresso
+
+    from oracle import lookahead as OL
+
+    chars, words = _lookahead_vocab()
+    sub, wrd = RefDict(), RefDict()
+    for c in chars + ["<space>"]:
+        sub.add_symbol(c)
+    sub.space_index = sub.indices.get(sub.space_word, -1)
+    for w in words:
+        wrd.add_symbol(w)
+    Vs, Vw = len(sub), len(wrd)
+
+    def build(d, seed, is_wordlm, e, h):
+        class _Task:
+            source_dictionary = target_dictionary = word_dictionary = d
+
+        args = Namespace(dropout=0.0, decoder_embed_path=None, decoder_freeze_embed=False, decoder_layers=1,
+                         adaptive_softmax_cutoff=None, is_wordlm=is_wordlm, decoder_dropout_in=0.0, decoder_dropout_out=0.0,
+                         criterion_name="cross_entropy", max_target_positions=64, tokens_per_sample=64, decoder_embed_dim=e,
+                         decoder_hidden_size=h, decoder_out_embed_dim=h, share_embed=False, decoder_rnn_residual=False)
+        torch.manual_seed(seed)
+        m = LSTMLanguageModelEspresso.build_model(args, _Task())
+        with torch.no_grad():
+            for n_, p_ in m.named_parameters():
+                if "fc_out" in n_ or "embed" in n_:
+                    p_.mul_(5.0)
+        return m.eval()
+
+    wlm, slm = build(wrd, 5, True, 16, 24), build(sub, 6, False, 12, 20)
+    texts = ["the_cat_$", "then_go_$", "be_been_$", "xq_not_$", "goldx_a_$", "do_n't_$", "a_an_ant_$", "there_$"]
+    N, L = len(texts), max(len(t) for t in texts)
+    sym = lambda ch: sub.space() if ch == "_" else sub.eos() if ch == "$" else sub.index(ch)  # noqa: E731
+    out = {}
+    for variant, (open_vocab, pen, weight) in {"open": (True, 1.0, 0.8), "open_pen": (True, 0.05, 0.5), "open_w1": (True, 0.3, 1.0)}.items():
+        # open_vocab=False cannot be recorded: the reference raises TypeError at external_language_model.py:484
+        # (`~batch_is_child_mask` on a Python list) on the first non-initial step
+        ref = RefML(wlm, slm, subwordlm_weight=weight, oov_penalty=pen, open_vocab=open_vocab).eval()
+        dec = ref.decoder
+        seen = {"w": [], "s": []}
+
+        def spy(key, orig):
+            def f(net_output, log_probs, sample=None):
+                r = orig(net_output, log_probs, sample)
+                seen[key].append(r.detach().clone())
+                return r
+            return f
+
+        ow, os_ = dec.wordlm_decoder.get_normalized_probs, dec.subwordlm_decoder.get_normalized_probs
+        dec.wordlm_decoder.get_normalized_probs, dec.subwordlm_decoder.get_normalized_probs = spy("w", ow), spy("s", os_)
+        rs = np.random.RandomState(4)
+        rows = [list(t) for t in texts]
+        inc = {}
+        toks = torch.full((N, 1), sub.eos(), dtype=torch.long)
+        state = OL.MultiLevelState(OL.build_tree([wrd[i] for i in range(Vw)], {wrd.pad(), wrd.eos(), wrd.unk()}, sub.index,
+                                                 sub.unk()), N)
+        tok_hist, order_hist, ref_out, w_hist, s_hist = [], [], [], [], []
+        for t in range(L + 1):
+            seen["w"].clear(), seen["s"].clear()
+            lp, _ = dec(toks, incremental_state=inc)
+            ref_lp = lp[:, 0].numpy().copy()        # the reference keeps mutating this tensor as state
+            wl, sl = seen["w"][0][:, 0].numpy(), seen["s"][0][:, 0].numpy()
+            prev = toks[:, -1].numpy()
+            o = OL.multilevel_step(state, prev, wl, sl, t == 0, sub.space(), sub.eos(), wrd.unk(), wrd.eos(), weight, pen, open_vocab)
+            err = np.abs(o - ref_lp).max()
+            assert err < 1e-4, (variant, t, err)
+            tok_hist.append(prev.copy()), ref_out.append(ref_lp), w_hist.append(wl.copy()), s_hist.append(sl.copy())
+            if t == L:
+                break
+            order = rs.randint(0, N, size=N) if t in (2, 4, 5) else np.arange(N)
+            order_hist.append(order.copy())
+            dec.reorder_incremental_state_scripting(inc, torch.from_numpy(order))
+            state.reorder(order)
+            rows = [rows[i] for i in order]
+            toks = toks[torch.from_numpy(order)]
+            nxt = [sym(r[t]) if t < len(r) else sub.eos() for r in rows]
+            toks = torch.cat([toks, torch.tensor(nxt)[:, None]], dim=1)
+        dec.wordlm_decoder.get_normalized_probs, dec.subwordlm_decoder.get_normalized_probs = ow, os_
+        out[variant + ".prev_tokens"], out[variant + ".new_orders"] = np.stack(tok_hist), np.stack(order_hist)
+        out[variant + ".out"] = np.stack(ref_out).astype(np.float32)
+        out[variant + ".word_logprobs"] = np.stack(w_hist).astype(np.float32)
+        out[variant + ".sub_logprobs"] = np.stack(s_hist).astype(np.float32)
+        out[variant + ".params"] = np.array([float(open_vocab), pen, weight])
+        print("multilevel %-8s: %d steps x %d hypotheses, oracle within 1e-4 of the reference" % (variant, L + 1, N))
+    for k, v in wlm.state_dict().items():
+        out["wsd." + k] = v.numpy()
+    for k, v in slm.state_dict().items():
+        out["ssd." + k] = v.numpy()
+    out["chars"], out["words"] = np.array(chars), np.array(words)
+    out["wlm_cfg"], out["slm_cfg"] = np.array([16, 24, 24, 1]), np.array([12, 20, 20, 1])
+    np.savez_compressed(os.path.join(GOLDEN, "multilevel_lm.npz"), **out)
+    print("multi-level LM pinned -> tests/golden/multilevel_lm.npz")
+
+
 def pin_fullsize():
     """The BENCHMARKED configuration (17 x 512 Conformer, ffn 2048, 8 heads, conv-k31, V = 5004) through the REAL
     reference model in fp32 and in bf16 (`model.bfloat16()`, fairseq --bf16 semantics, fairseq/trainer.py:105-107).
@@ -1194,7 +1445,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 
