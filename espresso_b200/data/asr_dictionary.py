@@ -22,6 +22,8 @@ class AsrDictionary:
         self.nspecial = len(self.symbols)
         self.space_index = -1
         self.non_lang_syms = None
+        self.tokenizer = None
+        self.bpe = None
 
     # ---- container protocol ----------------------------------------------------------------------
     def __len__(self):
@@ -105,6 +107,35 @@ class AsrDictionary:
                 return self.save(fd)
         for s, c in zip(self.symbols[self.nspecial:], self.count[self.nspecial:]):
             print("{} {}".format(s, c), file=f)
+
+    # ---- word pieces (espresso/data/asr_dictionary.py:117-142) ----------------------------------------------------
+    def build_bpe(self, bpe=None, sentencepiece_model=None, sentencepiece_enable_sampling=False, sentencepiece_alpha=None):
+        """bpe: "characters_asr" (character units with this dictionary's space symbol and non-linguistic symbols),
+        "sentencepiece" (needs sentencepiece_model), or None."""
+        from .encoders import CharactersAsr, SentencepieceBPE
+
+        if bpe in (None, "none"):
+            self.bpe = None
+        elif bpe == "characters_asr":
+            self.bpe = CharactersAsr(space_symbol=self.space_word, non_lang_syms=self.non_lang_syms)
+        elif bpe == "sentencepiece":
+            self.bpe = SentencepieceBPE(sentencepiece_model, sentencepiece_enable_sampling, sentencepiece_alpha)
+        else:
+            raise ValueError("unsupported bpe %r (the ASR recipes use characters_asr and sentencepiece)" % (bpe,))
+
+    def wordpiece_encode(self, x):
+        if self.tokenizer is not None:
+            x = self.tokenizer.encode(x)
+        if self.bpe is not None:
+            x = self.bpe.encode(x)
+        return x
+
+    def wordpiece_decode(self, x):
+        if self.bpe is not None:
+            x = self.bpe.decode(x)
+        if self.tokenizer is not None:
+            x = self.tokenizer.decode(x)
+        return x
 
     # ---- text <-> indices --------------------------------------------------------------------------------
     def unk_string(self, escape=False):

@@ -28,3 +28,20 @@ class CharactersAsr:
 
     def decode(self, x):
         return x.replace(" ", "").replace(self.space_symbol, " ").strip()
+
+
+class SentencepieceBPE:
+    """fairseq/data/encoders/sentencepiece_bpe.py:31-70 (the `sentencepiece` bpe of the LibriSpeech / SWBD recipes)."""
+
+    def __init__(self, model_path, enable_sampling=False, alpha=None):
+        import sentencepiece as spm
+
+        self.enable_sampling, self.alpha = enable_sampling, alpha
+        self.sp = spm.SentencePieceProcessor()
+        self.sp.Load(model_path)
+
+    def encode(self, x):
+        return " ".join(self.sp.Encode(x, out_type=str, enable_sampling=self.enable_sampling, alpha=self.alpha))
+
+    def decode(self, x):
+        return x.replace(" ", "").replace("\u2581", " ").strip()

@@ -5,6 +5,7 @@ registries, the generator choice per criterion (:526-596) and validation with wo
 (:598-607, 662-687; error counting restates espresso/tools/wer.py + espresso/tools/utils.py:265-330 as a plain
 Levenshtein distance).  Data loading from Kaldi/JSON manifests is out of scope: the task is built from a
 dictionary and a feature dimension, batches come from espresso_b200.data.collate."""
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -24,6 +25,16 @@ class SpeechRecognitionEspressoConfig:
     max_num_expansions_per_step: int = 2
     bpe: Optional[str] = None  # how token sequences become words for WER: None (tokens are words) | "sentencepiece" | ...
     seed: int = 1
+    # ---- data (espresso/tasks/speech_recognition.py:31-118) ----
+    data: Optional[str] = None  # directory (or ":"-separated shards) with {split}.json manifests
+    upsample_primary: int = 1
+    autoregressive: bool = False
+    specaugment_config: Optional[str] = None
+    global_cmvn_stats_path: Optional[str] = None
+    required_seq_len_multiple: int = 1
+    train_subset: str = "train"
+    valid_subset: str = "valid"
+    gen_subset: str = "test"
 
 
 def edit_counts(ref, hyp):
@@ -50,6 +61,7 @@ class SpeechRecognitionEspressoTask:
             self.blank_symbol = tgt_dict[tgt_dict.bos()]  # the bos symbol is reserved for blank
             self.extra_symbols_to_ignore.add(tgt_dict.bos())
         self.decoder_for_validation = None
+        self.datasets = {}
 
     @classmethod
     def load_dictionary(cls, filename, enable_bos=False, non_lang_syms=None):
@@ -71,6 +83,47 @@ class SpeechRecognitionEspressoTask:
 
     def max_positions(self):
         return (self.cfg.max_source_positions, self.cfg.max_target_positions)
+
+    # ---- data ------------------------------------------------------------------------------------------------
+    def load_dataset(self, split, epoch=1, combine=False, **unused):
+        """JSON manifest -> AsrDataset (speech_recognition.py:415-468).  Waveform entries stay raw: fbank, global CMVN
+        (`global_cmvn_stats_path`, applied by the model's OnTheFlyFbank) and SpecAugment masking run on the device."""
+        from ..data.asr_dataset import get_asr_dataset_from_json
+
+        paths = [p for p in (self.cfg.data or "").split(os.pathsep) if p]
+        if not paths:
+            raise ValueError("task.data is not set")
+        if split != self.cfg.train_subset:
+            paths = paths[:1]   # validation / test always come from the first shard
+        transducer = self.cfg.criterion_name == "transducer_loss"
+        self.datasets[split] = ds = get_asr_dataset_from_json(
+            paths[(epoch - 1) % len(paths)], split, self.tgt_dict, combine=combine, upsample_primary=self.cfg.upsample_primary,
+            shuffle=(split != self.cfg.gen_subset), pad_to_multiple=self.cfg.required_seq_len_multiple,
+            autoregressive=self.cfg.autoregressive,
+            prepend_bos_as_input_feeding=(transducer and self.cfg.include_eos_in_transducer_loss),
+            is_training_set=(split == self.cfg.train_subset), batch_based_on_both_src_tgt=transducer, seed=self.cfg.seed,
+            specaugment_config=self.cfg.specaugment_config)
+        if split == self.cfg.train_subset and ds.tgt is not None:  # eos / unk counts from the training text (:460-468)
+            self.tgt_dict.count[self.tgt_dict.eos()] = len(ds.tgt)
+            unk = self.tgt_dict.unk()
+            self.tgt_dict.count[unk] = int(sum(int((ds.tgt[i][0] == unk).sum()) for i in range(len(ds.tgt))))
+        return ds
+
+    def dataset(self, split):
+        if split not in self.datasets:
+            raise KeyError("Dataset not loaded: " + split)
+        return self.datasets[split]
+
+    def get_batch_iterator(self, dataset, max_tokens=None, max_sentences=None, required_batch_size_multiple=1, seed=1, num_shards=1,
+                           shard_id=0, num_workers=2, epoch=1, data_buffer_size=4):
+        """fairseq/tasks/fairseq_task.py:231-348: batches are formed once (ordered_indices -> batch_by_size) and frozen;
+        the iterator shuffles them per epoch, shards them over ranks and assembles them in background threads."""
+        from ..data.iterators import EpochBatchIterator
+
+        dataset.set_epoch(epoch)
+        batches = dataset.batch_by_size(dataset.ordered_indices(), max_tokens, max_sentences, required_batch_size_multiple)
+        return EpochBatchIterator(dataset, batches, seed=seed, num_shards=num_shards, shard_id=shard_id, num_workers=num_workers,
+                                  buffer_size=data_buffer_size, epoch=epoch)
 
     # ---- construction through the registries ----------------------------------------------------------------
     def build_model(self, model_cfg, arch="speech_transformer_encoder_model", **kw):
