@@ -127,6 +127,13 @@ inline cudaError_t esp_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
 }
 #endif
 
+#ifdef __CUDACC__
+// fire-and-forget fp32 vector reduction at L2 (one request for 4 consecutive floats; p must be 16-byte aligned)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+#endif
+
 // ---- counter-based RNG for dropout ---------------------------------------------------------------
 // Stateless: the backward pass regenerates the identical mask from (seed, logical element index), so
 // dropout masks are never stored in HBM.  One 64-bit hash (splitmix64 finaliser keyed by the seed) yields

@@ -261,38 +261,28 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       }
   }
   __syncthreads();
-  const int slot = blockIdx.x % kRedSlots;
-  for (int pidx = threadIdx.x; pidx < 2 * NV * 256; pidx += blockDim.x) {
-    float acc = 0.f;
-    for (int w = 0; w < nw; ++w) acc += sm_red[(size_t)w * (2 * NV * 256) + pidx];
-    const int which = pidx / (NV * 256), q = pidx % (NV * 256);
-    const int ln = q & 31, ij = q >> 5;
-    const int col = (ln + 32 * (ij >> 3)) * 8 + (ij & 7);
-    if (col < d) atomicAdd(&g_red_slots[which][slot][col], acc);
-  }
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&g_red_ticket[0], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f;
+  // Thread g owns 4 consecutive columns of one destination: 16-byte vector reductions at L2 straight into the (fp32,
+  // accumulating) parameter gradients -- fire and forget: no scratch slots, no ticket, no serial fold by a last CTA.
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
+  for (int g = threadIdx.x; g < 2 * NV * 64; g += blockDim.x) {
+    const int ln = g & 31, r = g >> 5;
+    const int jh = (r & 1) * 4, i = (r >> 1) % NV, which = (r >> 1) / NV;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < nw; ++w) {
+      const float* src = sm_red + (size_t)w * (2 * NV * 256) + which * (NV * 256) + (i * 8 + jh) * 32 + ln;
 #pragma unroll
-    for (int k = 0; k < kRedSlots; ++k) {
-      a0 += __ldcg(&g_red_slots[0][k][c]);
-      a1 += __ldcg(&g_red_slots[1][k][c]);
+      for (int t = 0; t < 4; ++t) a[t] += src[t * 32];
     }
+    float* dst = which == 0 ? dgamma : dbeta;
+    const int col = (ln + 32 * i) * 8 + jh;
+    if (dst == nullptr || col >= d) continue;
+    if (vec_ok) {
+      red_add_v4(dst + col, a[0], a[1], a[2], a[3]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kRedSlots; ++k) {
-      __stcg(&g_red_slots[0][k][c], 0.f);
-      __stcg(&g_red_slots[1][k][c], 0.f);
+      for (int t = 0; t < 4; ++t) atomicAdd(dst + col + t, a[t]);
     }
-    if (dgamma) dgamma[c] += a0;
-    if (dbeta) dbeta[c] += a1;
   }
-  if (threadIdx.x == 0) g_red_ticket[0] = 0u;
 }
 
 // ================================================================================================
@@ -1346,5 +1336,140 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bia
                                                                       (bf16*)dy);
   ESP_LAUNCH_CHECK();
   esp_count_launch(3);
+  return 0;
+}
+
+// ================================================================================================
+// First convolution of the conv front end: ONE input channel (the fbank "image" [B, T, F]) -> Cout.
+// espresso/modules/speech_convolutions.py:78-102 with in_channels = 1: a 3x3 convolution whose reduction is 9 long -- not
+// GEMM-shaped work.  It is HBM-bound on its OUTPUT (Cout x more bytes than the input): each thread produces 8 channels of
+// one output position from 9 cached input samples and writes one 16-byte vector; the gradient of the 9 x Cout taps reads
+// dy once (16-byte vectors) and reduces registers -> shared memory -> one atomic per tap, channel and CTA.
+// The following convolutions (64 / 128 input channels) are implicit GEMMs on the tcgen05 kernel (gemm_tcgen05.cu).
+// ================================================================================================
+namespace {
+
+constexpr int kConv1MaxCout = 256;
+
+// x [B, T, F] bf16, w [Cout, 3, 3] bf16, y [B, To, Fo, Cout] bf16
+__global__ void __launch_bounds__(256)
+conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int B, int T, int F, int Cout,
+                 int st, int sf, int To, int Fo) {
+  esp_pdl();
+  __shared__ float ws[9][kConv1MaxCout];  // tap-major: the 8 channels of a thread are contiguous
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i % 9][i / 9] = bf2f(w[i]);
+  __syncthreads();
+  const int cv = Cout >> 3;
+  const long total = (long)B * To * Fo * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    long pos = i / cv;
+    const int fo = (int)(pos % Fo);
+    pos /= Fo;
+    const int to = (int)(pos % To), b = (int)(pos / To);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int t = to * st + r - 1;
+      if (t < 0 || t >= T) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int f = fo * sf + c - 1;
+        if (f < 0 || f >= F) continue;
+        const float xv = bf2f(x[((long)b * T + t) * F + f]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ws[r * 3 + c][c8 + j], acc[j]);
+      }
+    }
+    store8(y + i * 8, acc);
+  }
+}
+
+// dw[co, tap] += sum_{b, to, fo} dy[b, to, fo, co] * x[b, to*st + r - 1, fo*sf + c - 1]
+// Thread mapping as in bn_stats: the grid stride is a multiple of Cout/8, so a thread keeps the same 8 channels.
+__global__ void __launch_bounds__(256)
+conv1_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, float* __restrict__ dw, int B, int T, int F,
+                   int Cout, int st, int sf, int To, int Fo) {
+  esp_pdl();
+  extern __shared__ float c1red[];  // [72 values][256 threads]: conflict-free
+  const int cv = Cout >> 3;
+  const long total = (long)B * To * Fo * cv;
+  float acc[9][8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long pos = i / cv;
+    const int fo = (int)(pos % Fo);
+    pos /= Fo;
+    const int to = (int)(pos % To), b = (int)(pos / To);
+    float d[8];
+    load8(dy + i * 8, d);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int t = to * st + r - 1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int f = fo * sf + c - 1;
+        const float xv = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(x[((long)b * T + t) * F + f]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r * 3 + c][j] = fmaf(d[j], xv, acc[r * 3 + c][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c1red[(k * 8 + j) * 256 + threadIdx.x] = acc[k][j];
+  __syncthreads();
+  // threads with the same (threadIdx.x % cv) hold the same channels: fold them, then one atomic per (channel, tap)
+  for (int o = threadIdx.x; o < 72 * cv; o += blockDim.x) {
+    const int g = o % cv, kj = o / cv;  // kj = tap * 8 + j
+    float sacc = 0.f;
+    for (int th = g; th < 256; th += cv) sacc += c1red[kj * 256 + th];
+    atomicAdd(dw + (g * 8 + (kj & 7)) * 9 + (kj >> 3), sacc);
+  }
+}
+
+}  // namespace
+
+extern "C" int esp_conv3x3_c1_fwd(const void* x, const void* w, void* y, int32_t B, int32_t T, int32_t F, int32_t Cout,
+                                  int32_t st, int32_t sf, void* stream) {
+  cudaStream_t st_ = (cudaStream_t)stream;
+  ESP_CHECK(Cout % 8 == 0 && Cout <= kConv1MaxCout, "conv3x3 (1 input channel): Cout must be a multiple of 8, at most %d",
+            kConv1MaxCout);
+  ESP_CHECK(st >= 1 && sf >= 1, "bad stride");
+  const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
+  const long total = (long)B * To * Fo * (Cout / 8);
+  if (total == 0) return 0;
+  long grid = (total + 255) / 256;
+  const long cap = 16L * esp_num_sms();
+  if (grid > cap) grid = cap;
+  esp_launch(conv1_fwd_kernel, (unsigned)grid, 256, 0, st_, (const bf16*)x, (const bf16*)w, (bf16*)y, B, T, F, Cout, st, sf, To, Fo);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
+  return 0;
+}
+
+extern "C" int esp_conv3x3_c1_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t F, int32_t Cout,
+                                    int32_t st, int32_t sf, void* stream) {
+  cudaStream_t st_ = (cudaStream_t)stream;
+  ESP_CHECK(Cout % 8 == 0 && 256 % (Cout / 8) == 0, "conv3x3 (1 input channel) wgrad: Cout/8 must divide 256 (got %d)", Cout);
+  const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
+  const long total = (long)B * To * Fo * (Cout / 8);
+  if (total == 0) return 0;
+  static bool configured = false;
+  const int smem = 72 * 256 * (int)sizeof(float);
+  if (!configured) {
+    ESP_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  long grid = (total + 255) / 256;
+  const long cap = 2L * esp_num_sms();  // few CTAs: each ends with 9 x Cout atomics
+  if (grid > cap) grid = cap;
+  esp_launch(conv1_wgrad_kernel, (unsigned)grid, 256, smem, st_, (const bf16*)dy, (const bf16*)x, dw, B, T, F, Cout, st, sf, To, Fo);
+  ESP_LAUNCH_CHECK();
+  esp_count_launch(1);
   return 0;
 }

@@ -47,8 +47,28 @@ struct EpiParams {
   const unsigned long long* seed_ptr;
 };
 
+// 3x3 convolutions of the conv front end as implicit GEMMs on this kernel (espresso/modules/speech_convolutions.py:78-102).
+// Activations are channels-last [B, T, F, C]; a tile of im2col rows is a (bt x bf) box of output positions, and the A
+// tile of one filter tap is that box of the INPUT shifted by the tap (and strided by the convolution stride through the
+// tensor map's element strides) -- one TMA box load, zero padding = TMA out-of-bounds fill.  Nothing is materialised.
+//   mode 1 (fprop / dgrad): A = implicit im2col (K-major), K block kb = (tap, 64-channel block); output rows are
+//           scattered back to positions (strided for the parity classes of a stride-2 dgrad);
+//   mode 2 (wgrad): the reduction runs over POSITIONS (K block = one 64-position box); A = dY^T, B = the shifted input
+//           box of the tap that owns the N chunk, both MN-major; the epilogue is the ordinary fp32 accumulate.
+struct ConvGeom {
+  int mode;
+  int bf_log2, bt;        // box of positions: bf = 1 << bf_log2 along F, bt along T  (bt * bf = 128 in mode 1, 64 in mode 2)
+  int tiles_t, tiles_f;   // boxes per utterance
+  int st, sf;             // box start in the tensor behind the shifted loads = box index * (bt * st, bf * sf) + offset[tap]
+  int cblocks;            // mode 1: 64-channel K blocks per tap
+  int cin;                // mode 2: channels per tap along N
+  int OT, OF, ost, osf, opt, opf;  // mode 1 output mapping: (t, f) -> (t * ost + opt, f * osf + opf), valid below (OT, OF)
+  signed char offt[9], offf[9], btap[9];  // per tap: offsets of the shifted box; tap coordinate in the (ci, tap, co) weight view
+};
+
 struct KParams {
   int M, N, K, nb1, nb2, ksplit;
+  ConvGeom cv;
   float* rowsum_a;     // optional: rowsum_a[m] += rowsum_scale * sum_k A[m, k] (bias gradient of a weight-gradient GEMM)
   float rowsum_scale;
   int tma_c;  // the bf16 output goes through per-warp shared-memory slabs and TMA stores (tmC is valid)
@@ -124,6 +144,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -246,9 +267,6 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return fmaf(0.5f, t, 0.5f);
 }
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 __device__ __forceinline__ void load8f(const bf16* p, float* v) {
   const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
   unpack_bf16x2(q.x, v[0], v[1]);
@@ -316,16 +334,19 @@ __device__ __forceinline__ void dropout32(float* v, unsigned long long seed, uns
   }
 }
 
-template <int BN, bool A_K, bool B_K, bool CG2 = false>
+template <int BN, bool A_K, bool B_K, bool CG2 = false, bool TS = false>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (CG2 ? BN / 2 : BN) * BK * 2;  // cta_group::2: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256 && !CG2) ? 4 : 6;
-  // output staging for the TMA-store epilogue: one 32-row x 64-column bf16 slab (SWIZZLE_128B, 4 KB) per epilogue warp
+  // TS (TMA-store epilogue): one ring stage less pays for the output slabs
+  static constexpr int kStages = TS ? (CG2 ? 5 : (BN == 256 ? 3 : 5)) : ((BN == 256 && !CG2) ? 4 : 6);
+  // output staging for the TMA-store epilogue: TWO 32-row x 64-column bf16 slabs (SWIZZLE_128B, 4 KB each) per epilogue
+  // warp, used alternately so that a warp only waits for the bulk store issued two chunk pairs ago
   static constexpr int kSlabBytes = 32 * 128;
+  static constexpr int kSlabsPerWarp = TS ? 2 : 0;
   static constexpr int kSlabOffset = kStages * kStageBytes;
-  static constexpr int kBarOffset = kSlabOffset + (BN >= 128 ? kEpiWarps * kSlabBytes : 0);
+  static constexpr int kBarOffset = kSlabOffset + kEpiWarps * kSlabsPerWarp * kSlabBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
 
@@ -341,13 +362,13 @@ struct SmemLayout {
 // producers' TMA transactions signal the LEADER's full barrier (peer bit cleared), which expects the bytes of both
 // CTAs; the MMA thread's commits are multicast to both CTAs' empty / accumulator-full barriers; the epilogue warps of
 // both CTAs arrive on the leader's accumulator-empty barrier.
-template <int BN, bool A_K, bool B_K, int MC>
+template <int BN, bool A_K, bool B_K, int MC, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
   constexpr bool CG2 = (MC == 3);
   constexpr int CL = MC > 1 ? 2 : 1;  // cluster size
-  using L = SmemLayout<BN, A_K, B_K, CG2>;
+  using L = SmemLayout<BN, A_K, B_K, CG2, TS>;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -462,6 +483,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             continue;
           }
           mbar_expect_tx(full_bar(s), L::kStageBytes);
+          if (MC == 1 && p.cv.mode == 1) {
+            // implicit im2col: the tile's box of positions, shifted by this K block's tap
+            const ConvGeom& g = p.cv;
+            const int tf = mt % g.tiles_f, tt = (mt / g.tiles_f) % g.tiles_t, cb = mt / (g.tiles_f * g.tiles_t);
+            const int tap = kb / g.cblocks, c0 = (kb - tap * g.cblocks) * 64;
+            tma_load_4d(sa, &tmA, full_bar(s), c0, (tf << g.bf_log2) * g.sf + g.offf[tap], tt * g.bt * g.st + g.offt[tap], cb);
+            if (B_K) {
+              tma_load_4d(sb, &tmB, full_bar(s), kb * BK, nt * BN, 0, 0);  // weights [Cout, (tap, ci)]
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)  // weights viewed (ci, tap, co): rows = 64 output channels of this tap
+                tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), nt * BN + 64 * j, g.btap[tap], c0, 0);
+            }
+            continue;
+          }
+          if (MC == 1 && p.cv.mode == 2) {
+            // weight gradient: K block = one box of 64 positions; A = dY^T, B = the input box shifted by the chunk's tap
+            const ConvGeom& g = p.cv;
+            const int tf = kb % g.tiles_f, tt = (kb / g.tiles_f) % g.tiles_t, cb = kb / (g.tiles_f * g.tiles_t);
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(s), mt * BM + 64 * j, tf << g.bf_log2, tt * g.bt, cb);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              const int n = nt * BN + 64 * j;
+              if (n < p.N) {
+                const int tap = n / g.cin, c0 = n - tap * g.cin;
+                tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), c0, (tf << g.bf_log2) * g.sf + g.offf[tap],
+                            tt * g.bt * g.st + g.offt[tap], cb);
+              } else {  // chunk beyond the last tap: an all-out-of-bounds box (zero fill; the bytes still arrive)
+                tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(s), g.cin, 0, 0, cb);
+              }
+            }
+            continue;
+          }
           if (A_K) {
             tma_load_4d(sa, &tmA, full_bar(s), kb * BK, mt * BM, b1 * p.a_b1, b2 * p.a_b2);
           } else {
@@ -618,8 +674,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kChunksPerWarp = kChunks / 2;
     const EpiParams& e = p.ep;
     const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
-    const bool use_slab = BN >= 128 && p.tma_c != 0;
-    uint8_t* slab = smem + L::kSlabOffset + (warp - 4) * L::kSlabBytes;
+    constexpr bool use_slab = TS;
+    uint8_t* const slab0 = smem + L::kSlabOffset + (warp - 4) * 2 * L::kSlabBytes;
+    uint8_t* slab = slab0;
+    uint32_t pair = 0;  // chunk pairs sent so far: slab (pair & 1) is the one being filled
     uint32_t ti = 0;
     for (int work = work0; work < total_tiles; work += work_stride) {
       const int ks = work % p.ksplit;
@@ -639,8 +697,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tcgen05_fence_after();
 
       const int m = mt * BM + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      const long c_off = (long)b1 * e.sC1 + (long)b2 * e.sC2 + (long)m * e.ldc;
+      bool row_ok = m < p.M;
+      long c_off = (long)b1 * e.sC1 + (long)b2 * e.sC2 + (long)m * e.ldc;
+      if (MC == 1 && p.cv.mode == 1) {
+        // row of an im2col tile -> its output position (channels-last activation; strided for dgrad parity classes)
+        const ConvGeom& g = p.cv;
+        const int tf = mt % g.tiles_f, tt = (mt / g.tiles_f) % g.tiles_t, cb = mt / (g.tiles_f * g.tiles_t);
+        const int ml = q * 32 + lane;
+        const int ot = (tt * g.bt + (ml >> g.bf_log2)) * g.ost + g.opt;
+        const int of = ((tf << g.bf_log2) + (ml & ((1 << g.bf_log2) - 1))) * g.osf + g.opf;
+        row_ok = ot < g.OT && of < g.OF;
+        c_off = (((long)cb * g.OT + ot) * g.OF + of) * e.ldc;
+      }
       const long aux_off = (long)b1 * e.sAux1 + (long)b2 * e.sAux2 + (long)m * e.ld_aux;
       const long r_off = (long)b1 * e.sR1 + (long)b2 * e.sR2 + (long)m * e.ldr;
       const unsigned long long rng_row = ((unsigned long long)bt * p.M + m) * (unsigned long long)p.N;
@@ -799,15 +867,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }  // !atomic
         }  // row_ok
         if (use_slab && ((cc & 1) || cc == kChunksPerWarp - 1 || n0 + 32 >= p.N)) {
-          // hand the slab to the TMA engine (rows >= M and columns >= N are clipped by the tensor map); the slab is
-          // reusable as soon as the engine has READ it
+          // hand the slab to the TMA engine (rows >= M and columns >= N are clipped by the tensor map) and move on to the
+          // other slab: it is free once the store issued from it two pairs ago has been READ (at most one group pending)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_4d(&tmC, smem_u32(slab), nt * BN + (half * kChunksPerWarp + (cc & ~1)) * 32, mt * BM + q * 32, b1, b2);
             tma_store_commit();
-            tma_store_wait_read();
+            tma_store_wait_read1();
           }
+          ++pair;
+          slab = slab0 + (pair & 1) * L::kSlabBytes;
           __syncwarp();
         }
       }
@@ -925,12 +995,12 @@ int cluster_slots(K kfn, int smem_bytes) {
   return slots;
 }
 
-template <int BN, bool A_K, bool B_K, int MC>
+template <int BN, bool A_K, bool B_K, int MC, bool TS = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KParams& kp, cudaStream_t st) {
   constexpr int CL = MC > 1 ? 2 : 1;
-  using L = SmemLayout<BN, A_K, B_K, MC == 3>;
+  using L = SmemLayout<BN, A_K, B_K, MC == 3, TS>;
   static bool configured = false;
-  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC>;
+  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC, TS>;
   if (!configured) {
     ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
@@ -947,13 +1017,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   return 0;
 }
 
-template <int BN, int MC>
+template <int BN, int MC, bool TS = false>
 int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const KParams& kp, cudaStream_t st) {
-  if (ak && bk) return launch<BN, true, true, MC>(ta, tb, tc, kp, st);
-  if (ak && !bk) return launch<BN, true, false, MC>(ta, tb, tc, kp, st);
-  if (!ak && bk) return launch<BN, false, true, MC>(ta, tb, tc, kp, st);
-  return launch<BN, false, false, MC>(ta, tb, tc, kp, st);
+  if (ak && bk) return launch<BN, true, true, MC, TS>(ta, tb, tc, kp, st);
+  if (ak && !bk) return launch<BN, true, false, MC, TS>(ta, tb, tc, kp, st);
+  if (!ak && bk) return launch<BN, false, true, MC, TS>(ta, tb, tc, kp, st);
+  return launch<BN, false, false, MC, TS>(ta, tb, tc, kp, st);
 }
 
 }  // namespace
@@ -1034,6 +1104,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   if (rc) return rc;
 
   KParams kp;
+  kp.cv.mode = 0;
   kp.rowsum_a = g->rowsum_a;
   kp.rowsum_scale = g->rowsum_scale;
   if (g->rowsum_a) {
@@ -1075,7 +1146,7 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
       const char* ev = getenv("ESP_GEMM_TMA_STORE");
       tma_on = (ev && ev[0] == '1') ? 1 : 0;
     }
-    const bool ok = tma_on && bn >= 128 && !g->c_f32 && !g->accumulate && ((uintptr_t)g->C & 15) == 0 && g->ldc % 8 == 0 &&
+    const bool ok = tma_on && bn == 256 && mode == 3 && !g->c_f32 && !g->accumulate && ((uintptr_t)g->C & 15) == 0 && g->ldc % 8 == 0 &&
                     (nb1 <= 1 || g->sC1 % 8 == 0) && (nb2 <= 1 || g->sC2 % 8 == 0) && (nb1 <= 1 || g->sC1 != 0) &&
                     (nb2 <= 1 || g->sC2 != 0);
     if (ok) {
@@ -1086,8 +1157,196 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
   }
   if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, tc, kp, st);
   if (bn == 256) {
+    if (mode == 3 && kp.tma_c) return dispatch_major<256, 3, true>(ak, bk, ta, tb, tc, kp, st);
     if (mode == 3) return dispatch_major<256, 3>(ak, bk, ta, tb, tc, kp, st);
     return mode == 2 ? dispatch_major<256, 2>(ak, bk, ta, tb, tc, kp, st) : dispatch_major<256, 1>(ak, bk, ta, tb, tc, kp, st);
   }
   return mode == 2 ? dispatch_major<128, 2>(ak, bk, ta, tb, tc, kp, st) : dispatch_major<128, 1>(ak, bk, ta, tb, tc, kp, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 convolutions of the conv front end (implicit GEMMs, ConvGeom above)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// 4-D bf16 tensor map over a channels-last activation [B, T, F, C] (dims innermost first: C, F, T, B) or any other 4-D
+// view; box[0] = 64 channels (one SWIZZLE_128B row), element strides > 1 make the box skip positions (strided convolution:
+// boxDim = elements spanned, the engine writes ceil(boxDim / stride) of them densely).
+int make_tmap_box(CUtensorMap* tm, const void* base, const cuuint64_t dims[4], const cuuint64_t strides_b[3],
+                  const cuuint32_t box[4], const cuuint32_t estr[4]) {
+  PFN_encodeTiled enc = get_encode();
+  ESP_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    ESP_CUDA(cudaFree(0));
+    ctx_bound = true;
+  }
+  ESP_CHECK(((uintptr_t)base & 15) == 0, "conv operand base must be 16-byte aligned");
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ESP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (conv box) failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+            box[0], box[1], box[2], box[3]);
+  return 0;
+}
+
+int act_tmap(CUtensorMap* tm, const void* base, int B, int T, int F, int C, int box_f, int box_t, int sf, int st) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)F * C * 2, (cuuint64_t)T * F * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)(box_f * sf), (cuuint32_t)(box_t * st), 1};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)sf, (cuuint32_t)st, 1};
+  return make_tmap_box(tm, base, dims, strides, box, estr);
+}
+
+// box of `n` positions: as wide along F as divides it evenly (power of two, at most 16), the rest along T
+void pick_box(int n, int Fpos, int* bf_log2, int* bt) {
+  int l = 0;
+  while (l < 4 && (1 << (l + 1)) <= n && Fpos % (1 << (l + 1)) == 0) ++l;
+  *bf_log2 = l;
+  *bt = n >> l;
+}
+
+void zero_epi(KParams& kp) {
+  EpiParams& e = kp.ep;
+  e.C = nullptr; e.C2 = nullptr; e.bias = nullptr; e.aux = nullptr; e.R = nullptr;
+  e.ldc = e.ld_aux = e.ldr = 0;
+  e.sC1 = e.sC2 = e.sAux1 = e.sAux2 = e.sR1 = e.sR2 = 0;
+  e.c_f32 = e.r_f32 = e.act = e.drop_mode = e.skew_r = e.atomic = 0;
+  e.alpha = 1.f; e.beta = 0.f; e.drop_scale = 1.f; e.drop_thresh = 0; e.seed = 0; e.seed_ptr = nullptr;
+  kp.rowsum_a = nullptr; kp.rowsum_scale = 0.f; kp.tma_c = 0; kp.debug = 0;
+  kp.nb1 = kp.nb2 = 1; kp.ksplit = 1; kp.a_b1 = kp.a_b2 = kp.b_b1 = kp.b_b2 = 0;
+}
+
+int conv_check(int B, int T, int F, int Cin, int Cout, int st, int sf) {
+  ESP_CHECK(B > 0 && T > 0 && F > 0, "conv3x3: empty input");
+  ESP_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3 (tensor-core path): channel counts must be multiples of 64 (got %d -> %d)", Cin, Cout);
+  ESP_CHECK((st == 1 || st == 2) && (sf == 1 || sf == 2), "conv3x3: strides 1 or 2 (got %d x %d)", st, sf);
+  return 0;
+}
+
+}  // namespace
+
+// y[b, to, fo, :] = sum_{r,s,ci} x[b, to*st + r - 1, fo*sf + s - 1, ci] * w[:, r, s, ci]      (zero padding 1, no bias)
+// x [B, T, F, Cin], w [Cout, 3, 3, Cin], y [B, ceil(T/st), ceil(F/sf), Cout], all bf16 channels-last.
+extern "C" int esp_conv3x3_fwd(const void* x, const void* w, void* y, int32_t B, int32_t T, int32_t F, int32_t Cin,
+                               int32_t Cout, int32_t st, int32_t sf, void* stream) {
+  cudaStream_t s_ = (cudaStream_t)stream;
+  if (int rc = conv_check(B, T, F, Cin, Cout, st, sf)) return rc;
+  const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
+  KParams kp;
+  zero_epi(kp);
+  ConvGeom& g = kp.cv;
+  g.mode = 1;
+  pick_box(128, Fo, &g.bf_log2, &g.bt);
+  const int bf = 1 << g.bf_log2;
+  g.tiles_t = (To + g.bt - 1) / g.bt;
+  g.tiles_f = (Fo + bf - 1) / bf;
+  g.st = st; g.sf = sf; g.cblocks = Cin / 64; g.cin = Cin;
+  g.OT = To; g.OF = Fo; g.ost = g.osf = 1; g.opt = g.opf = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      g.offt[r * 3 + c] = (signed char)(r - 1);
+      g.offf[r * 3 + c] = (signed char)(c - 1);
+      g.btap[r * 3 + c] = (signed char)(r * 3 + c);
+    }
+  const int bn = Cout % 128 == 0 ? 128 : 64;
+  CUtensorMap ta, tb;
+  if (int rc = act_tmap(&ta, x, B, T, F, Cin, bf, g.bt, sf, st)) return rc;
+  if (int rc = make_tmap(&tb, w, 9L * Cin, Cout, 9L * Cin, 1, 0, 1, 0, bn)) return rc;
+  kp.M = B * g.tiles_t * g.tiles_f * BM; kp.N = Cout; kp.K = 9 * Cin;
+  kp.ep.C = y; kp.ep.ldc = Cout;
+  return bn == 128 ? launch<128, true, true, 1>(ta, tb, ta, kp, s_) : launch<64, true, true, 1>(ta, tb, ta, kp, s_);
+}
+
+// dx[b, t, f, :] = sum over the taps (r, s) and output positions with to*st + r - 1 == t, fo*sf + s - 1 == f of
+//                  dy[b, to, fo, :] . w[:, r, s, :]
+// One launch per parity class (t mod st, f mod sf): inside a class every position sees the same taps, so the class is a
+// small un-strided convolution of dy whose outputs are written st x sf apart.
+extern "C" int esp_conv3x3_dgrad(const void* dy, const void* w, void* dx, int32_t B, int32_t T, int32_t F, int32_t Cin,
+                                 int32_t Cout, int32_t st, int32_t sf, void* stream) {
+  cudaStream_t s_ = (cudaStream_t)stream;
+  if (int rc = conv_check(B, T, F, Cin, Cout, st, sf)) return rc;
+  const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
+  const int bn = Cin % 128 == 0 ? 128 : 64;
+  CUtensorMap tb;
+  {
+    // weights [Cout][tap][Cin] viewed (ci, tap, co): a K block = 64 output channels of one tap, MN-major rows of 64 ci
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout, 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2, (cuuint64_t)9 * Cin * Cout * 2};
+    const cuuint32_t box[4] = {64, 1, 64, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (int rc = make_tmap_box(&tb, w, dims, strides, box, estr)) return rc;
+  }
+  for (int pt = 0; pt < st; ++pt)
+    for (int pf = 0; pf < sf; ++pf) {
+      const int U = (T - pt + st - 1) / st, V = (F - pf + sf - 1) / sf;  // positions of this class
+      if (U <= 0 || V <= 0) continue;
+      KParams kp;
+      zero_epi(kp);
+      ConvGeom& g = kp.cv;
+      g.mode = 1;
+      pick_box(128, V, &g.bf_log2, &g.bt);
+      const int bf = 1 << g.bf_log2;
+      g.tiles_t = (U + g.bt - 1) / g.bt;
+      g.tiles_f = (V + bf - 1) / bf;
+      g.st = g.sf = 1; g.cblocks = Cout / 64; g.cin = Cin;
+      g.OT = T; g.OF = F; g.ost = st; g.osf = sf; g.opt = pt; g.opf = pf;
+      int nt = 0;
+      for (int r = 0; r < 3; ++r) {
+        if ((pt + 1 - r) % st != 0) continue;  // t = to*st + r - 1  =>  to = (t + 1 - r) / st = u + (pt + 1 - r) / st
+        for (int c = 0; c < 3; ++c) {
+          if ((pf + 1 - c) % sf != 0) continue;
+          g.offt[nt] = (signed char)((pt + 1 - r) / st);
+          g.offf[nt] = (signed char)((pf + 1 - c) / sf);
+          g.btap[nt] = (signed char)(r * 3 + c);
+          ++nt;
+        }
+      }
+      ESP_CHECK(nt > 0, "conv3x3 dgrad: parity class without taps");
+      CUtensorMap ta;
+      if (int rc = act_tmap(&ta, dy, B, To, Fo, Cout, bf, g.bt, 1, 1)) return rc;
+      kp.M = B * g.tiles_t * g.tiles_f * BM; kp.N = Cin; kp.K = nt * Cout;
+      kp.ep.C = dx; kp.ep.ldc = Cin;
+      const int rc = bn == 128 ? launch<128, true, false, 1>(ta, tb, ta, kp, s_) : launch<64, true, false, 1>(ta, tb, ta, kp, s_);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+// dw[co, r, s, ci] += sum_{b, to, fo} dy[b, to, fo, co] * x[b, to*st + r - 1, fo*sf + s - 1, ci]      (fp32 accumulate)
+extern "C" int esp_conv3x3_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t F, int32_t Cin,
+                                 int32_t Cout, int32_t st, int32_t sf, void* stream) {
+  cudaStream_t s_ = (cudaStream_t)stream;
+  if (int rc = conv_check(B, T, F, Cin, Cout, st, sf)) return rc;
+  const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
+  KParams kp;
+  zero_epi(kp);
+  ConvGeom& g = kp.cv;
+  g.mode = 2;
+  pick_box(64, Fo, &g.bf_log2, &g.bt);
+  const int bf = 1 << g.bf_log2;
+  g.tiles_t = (To + g.bt - 1) / g.bt;
+  g.tiles_f = (Fo + bf - 1) / bf;
+  g.st = st; g.sf = sf; g.cblocks = Cin / 64; g.cin = Cin;
+  g.OT = To; g.OF = Fo; g.ost = g.osf = 1; g.opt = g.opf = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      g.offt[r * 3 + c] = (signed char)(r - 1);
+      g.offf[r * 3 + c] = (signed char)(c - 1);
+      g.btap[r * 3 + c] = (signed char)(r * 3 + c);
+    }
+  CUtensorMap ta, tb;
+  if (int rc = act_tmap(&ta, dy, B, To, Fo, Cout, bf, g.bt, 1, 1)) return rc;
+  if (int rc = act_tmap(&tb, x, B, T, F, Cin, bf, g.bt, sf, st)) return rc;
+  const long kblocks = (long)B * g.tiles_t * g.tiles_f;
+  kp.M = Cout; kp.N = 9 * Cin; kp.K = (int)(kblocks * BK);
+  ESP_CHECK(kblocks * BK < (1L << 31), "conv3x3 wgrad: too many positions");
+  const int tiles = ((Cout + BM - 1) / BM) * ((9 * Cin + 127) / 128);
+  int ks = esp_num_sms() / tiles;  // fill the machine; every split keeps a long reduction (>= 8 position boxes)
+  if (ks > kblocks / 8) ks = (int)(kblocks / 8);
+  if (ks < 1) ks = 1;
+  kp.ksplit = ks;
+  kp.ep.C = dw; kp.ep.ldc = 9 * Cin; kp.ep.c_f32 = 1; kp.ep.atomic = 1;
+  return launch<128, false, false, 1>(ta, tb, ta, kp, s_);
 }

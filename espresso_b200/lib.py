@@ -67,6 +67,11 @@ SIGNATURES = {
     "esp_bn_stats": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "esp_bn_act_fwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "esp_bn_act_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "esp_conv3x3_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "esp_conv3x3_dgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "esp_conv3x3_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "esp_conv3x3_c1_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "esp_conv3x3_c1_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "esp_lsce_loss": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _f32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp]),
     "esp_embed_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _i64, _i32, _vp, _f32, _u64, _vp, _vp]),
     "esp_embed_bwd": (C.c_int, [_vp, _vp, _i32, _f32, _i64, _i32, _vp, _f32, _u64, _vp, _vp]),

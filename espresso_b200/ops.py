@@ -333,6 +333,50 @@ def bn_finalize(stats, R, C_, eps, momentum, run_mean, run_var, training):
 BN_ACT_SILU, BN_ACT_RELU = 1, 2
 
 
+def conv3x3_fwd(x, w, stride):
+    """3x3 convolution, zero padding 1, no bias: x [B, T, F, Cin] (Cin = 1: [B, T, F]) bf16 channels-last, w [Cout, 3, 3, Cin]
+    -> y [B, ceil(T/st), ceil(F/sf), Cout]."""
+    _need_cuda(x, w)
+    _bf(x, w)
+    assert x.is_contiguous() and w.is_contiguous()
+    st, sf = stride
+    Cout = w.shape[0]
+    if x.dim() == 3:
+        B, T, F_ = x.shape
+        y = torch.empty(B, (T + st - 1) // st, (F_ + sf - 1) // sf, Cout, device=x.device, dtype=torch.bfloat16)
+        _lib.check(_lib.load().esp_conv3x3_c1_fwd(_ptr(x), _ptr(w), _ptr(y), B, T, F_, Cout, st, sf, _stream()))
+        return y
+    B, T, F_, Cin = x.shape
+    y = torch.empty(B, (T + st - 1) // st, (F_ + sf - 1) // sf, Cout, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_conv3x3_fwd(_ptr(x), _ptr(w), _ptr(y), B, T, F_, Cin, Cout, st, sf, _stream()))
+    return y
+
+
+def conv3x3_dgrad(dy, w, in_shape, stride):
+    """Input gradient of conv3x3_fwd: dy [B, To, Fo, Cout] -> dx [B, T, F, Cin] (in_shape)."""
+    _need_cuda(dy, w)
+    _bf(dy, w)
+    assert dy.is_contiguous() and w.is_contiguous()
+    B, T, F_, Cin = in_shape
+    dx = torch.empty(B, T, F_, Cin, device=dy.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().esp_conv3x3_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, F_, Cin, w.shape[0], stride[0], stride[1], _stream()))
+    return dx
+
+
+def conv3x3_wgrad(dy, x, dw_acc, stride):
+    """Weight gradient of conv3x3_fwd accumulated (fp32, +=) into dw_acc [Cout, 3, 3, Cin] (Cin = 1: x is [B, T, F])."""
+    _need_cuda(dy, x, dw_acc)
+    _bf(dy, x)
+    assert dy.is_contiguous() and x.is_contiguous() and dw_acc.is_contiguous() and dw_acc.dtype == torch.float32
+    Cout = dy.shape[-1]
+    if x.dim() == 3:
+        B, T, F_ = x.shape
+        _lib.check(_lib.load().esp_conv3x3_c1_wgrad(_ptr(dy), _ptr(x), _ptr(dw_acc), B, T, F_, Cout, stride[0], stride[1], _stream()))
+        return
+    B, T, F_, Cin = x.shape
+    _lib.check(_lib.load().esp_conv3x3_wgrad(_ptr(dy), _ptr(x), _ptr(dw_acc), B, T, F_, Cin, Cout, stride[0], stride[1], _stream()))
+
+
 def bn_stats(x, C_, pre_bias=None):
     """Per-channel (sum, sum of squares) of channels-last x [..., C] (+ pre_bias[c], rounded to bf16) -> double [2, C]."""
     _need_cuda(x, pre_bias)

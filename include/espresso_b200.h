@@ -193,6 +193,25 @@ int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bias, int64_t 
                    const void* gamma, const void* beta, int32_t act, double* sums, void* dy, float* dgamma,
                    float* dbeta, void* stream);
 
+/* 3x3 convolutions of the conv front end (espresso/modules/speech_convolutions.py:78-102, Convolution2d :104-132: kernel 3x3,
+ * zero padding 1, stride (st, sf) in {1, 2}); replaces F.conv2d and its dgrad / wgrad.  Activations are channels-last
+ * [B, T, F, C] bf16, weights [Cout, 3, 3, Cin] bf16 (the channels-last storage of the reference's [Cout, Cin, 3, 3]
+ * parameter), output positions To = ceil(T / st), Fo = ceil(F / sf).  The bias is NOT added here (see pre_bias above).
+ *   esp_conv3x3_fwd / _dgrad / _wgrad: Cin and Cout multiples of 64 -- implicit GEMMs on the tcgen05 kernel (im2col tiles
+ *     are TMA boxes of the activation shifted by the filter tap; nothing is materialised); dw is fp32 [Cout, 3, 3, Cin], +=.
+ *   esp_conv3x3_c1_fwd / _c1_wgrad: the first layer, ONE input channel: x [B, T, F] bf16, w [Cout, 3, 3], dw fp32 +=
+ *     (no input gradient: the features need none). */
+int esp_conv3x3_fwd(const void* x, const void* w, void* y, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t Cout,
+                    int32_t st, int32_t sf, void* stream);
+int esp_conv3x3_dgrad(const void* dy, const void* w, void* dx, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t Cout,
+                      int32_t st, int32_t sf, void* stream);
+int esp_conv3x3_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t Cout,
+                      int32_t st, int32_t sf, void* stream);
+int esp_conv3x3_c1_fwd(const void* x, const void* w, void* y, int32_t B, int32_t T, int32_t F, int32_t Cout, int32_t st,
+                       int32_t sf, void* stream);
+int esp_conv3x3_c1_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t F, int32_t Cout, int32_t st,
+                         int32_t sf, void* stream);
+
 /* ---- optimizer on flat buffers (fairseq/optim/fp16_optimizer.py:109-168, fairseq/optim/adam.py:150-239,
  *      fairseq/utils.py:347-397) ---------------------------------------------------------------- */
 int esp_sumsq_f32(const float* g, int64_t n, float* out, void* stream);

@@ -258,6 +258,31 @@ def _pre(y, pre_bias):
     return y if pre_bias is None else (y.float() + pre_bias.float()).to(BF)
 
 
+def _conv_nchw(x, w, stride):
+    xin = x.float().unsqueeze(1) if x.dim() == 3 else x.float().permute(0, 3, 1, 2)
+    wt = w.float().permute(0, 3, 1, 2) if w.dim() == 4 else w.float().reshape(w.shape[0], 1, 3, 3)
+    return xin, wt
+
+
+def conv3x3_fwd(x, w, stride):
+    xin, wt = _conv_nchw(x, w, stride)
+    return F.conv2d(xin, wt, None, tuple(stride), (1, 1)).permute(0, 2, 3, 1).contiguous().to(BF)
+
+
+def conv3x3_dgrad(dy, w, in_shape, stride):
+    B, T, F_, Cin = in_shape
+    wt = w.float().permute(0, 3, 1, 2)
+    dx = torch.nn.grad.conv2d_input((B, Cin, T, F_), wt, dy.float().permute(0, 3, 1, 2), tuple(stride), (1, 1))
+    return dx.permute(0, 2, 3, 1).contiguous().to(BF)
+
+
+def conv3x3_wgrad(dy, x, dw_acc, stride):
+    xin, _ = _conv_nchw(x, dw_acc, stride)
+    Cout, Cin = dy.shape[-1], xin.shape[1]
+    dw = torch.nn.grad.conv2d_weight(xin, (Cout, Cin, 3, 3), dy.float().permute(0, 3, 1, 2), tuple(stride), (1, 1))
+    dw_acc += dw.permute(0, 2, 3, 1).reshape(dw_acc.shape)
+
+
 def bn_stats(x, C_, pre_bias=None):
     x = _pre(x, pre_bias)
     xf = x.double().reshape(-1, C_)
