@@ -170,13 +170,45 @@ class _BNReLUFn(torch.autograd.Function):
         return dx.permute(0, 3, 1, 2), None, None, None, None, None
 
 
+class _ConvBNReLUFn(torch.autograd.Function):
+    """One conv-front layer on channels-last rows [B, T, F, C]: native 3x3 convolution (esp_conv3x3_*: implicit GEMM on the
+    tcgen05 kernel, or the direct kernel of the one-channel first layer) -> BatchNorm2d (batch statistics) -> ReLU.
+    The convolution weight and BatchNorm parameter gradients are accumulated straight into the flat fp32 buffer
+    (`gw`, `gbw`, `gbb`); the convolution bias sits inside the BatchNorm kernels (`conv_bias`, see ConvBNReLU.forward).
+    `anchor` only makes autograd call backward when the features themselves need no gradient (first layer)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, w, gw, stride, bn, gbw, gbb, training, conv_bias, need_dx):
+        y = _ops.conv3x3_fwd(x, w, stride)
+        C = y.shape[-1]
+        R = y.numel() // C
+        stats = _ops.bn_stats(y, C, pre_bias=conv_bias) if training else None
+        mr = _ops.bn_finalize(stats, R, C, 1e-5, 0.1, bn.running_mean, bn.running_var, training)
+        z = _ops.bn_act_fwd(y, mr, bn.weight.data, bn.bias.data, _ops.BN_ACT_RELU, pre_bias=conv_bias)
+        ctx.save_for_backward(x, y, mr)
+        ctx.w, ctx.gw, ctx.stride, ctx.bn, ctx.gbw, ctx.gbb, ctx.conv_bias, ctx.need_dx = w, gw, stride, bn, gbw, gbb, conv_bias, need_dx
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y, mr = ctx.saved_tensors
+        dy = _ops.bn_act_bwd(dz.contiguous(), y, mr, ctx.bn.weight.data, ctx.bn.bias.data, ctx.gbw, ctx.gbb, _ops.BN_ACT_RELU,
+                             pre_bias=ctx.conv_bias)
+        _ops.conv3x3_wgrad(dy, x, ctx.gw, ctx.stride)
+        dx = _ops.conv3x3_dgrad(dy, ctx.w, tuple(x.shape), ctx.stride) if ctx.need_dx else None
+        return (dx,) + (None,) * 10
+
+
 class ConvBNReLU(nn.Module):
     """espresso/modules/speech_convolutions.py:20-102.  (Conv2d 3x3 -> BatchNorm2d -> ReLU) x N, then
-    [B, C, T', F'] -> [B, T', C*F'].  Activations and conv weights are kept channels-last; BatchNorm + ReLU
-    (forward, backward, running statistics) run in the native kernels.  The 3x3 convolutions themselves still
-    go to cuDNN through torch this round (DESIGN.md "not yet native").  The reference's zeroing of padded
-    frames at this point (:97-100) is dropped: the encoder zeroes the same rows again after fc0 /
-    layernorm_embedding (speech_transformer_encoder.py:354-357), which makes the first one a no-op."""
+    [B, C, T', F'] -> [B, T', C*F'].  Activations and conv weights are kept channels-last ([B, T, F, C] rows, weights
+    [Cout, 3, 3, Cin] in the flat buffers); every layer runs in the native kernels: the 3x3 convolutions and their input /
+    weight gradients as implicit GEMMs on the tcgen05 kernel (csrc/gemm_tcgen05.cu ConvGeom: im2col tiles are TMA boxes of
+    the activation shifted by the filter tap), the one-input-channel first layer as a direct kernel, BatchNorm + ReLU
+    (forward, backward, running statistics) in the row kernels.  Layer shapes outside the native kernels' domain (kernel
+    other than 3x3, stride > 2, channel counts that are not multiples of 64) fall back to the library convolution.
+    The reference's zeroing of padded frames at this point (:97-100) is dropped: the encoder zeroes the same rows again
+    after fc0 / layernorm_embedding (speech_transformer_encoder.py:354-357), which makes the first one a no-op."""
 
     def __init__(self, out_channels, kernel_sizes, strides, in_channels=1):
         super().__init__()
@@ -192,6 +224,7 @@ class ConvBNReLU(nn.Module):
             cin = c
         self.flat = None
         self.flat_prefix = ""
+        self._anchor = None
 
     def output_lengths(self, in_lengths):
         out = in_lengths
@@ -200,14 +233,53 @@ class ConvBNReLU(nn.Module):
             out = torch.div(out + s0 - 1, s0, rounding_mode="floor") if torch.is_tensor(out) else (out + s0 - 1) // s0
         return out
 
+    def native_convolutions(self):
+        """True when every layer is inside the native kernels' domain (all shipped recipes: 3x3, strides 1 / 2,
+        1 -> 64 -> 64 -> 128 -> 128 channels)."""
+        cin = self.in_channels
+        for conv in self.convolutions:
+            c = conv.out_channels
+            if tuple(conv.kernel_size) != (3, 3) or any(s not in (1, 2) for s in conv.stride):
+                return False
+            if cin == 1:
+                if c % 8 or c > 256 or 256 % (c // 8):
+                    return False
+            elif cin % 64 or c % 64:
+                return False
+            cin = c
+        return True
+
     def forward(self, src, src_lengths):
-        x = src.view(src.size(0), src.size(1), self.in_channels, src.size(2) // self.in_channels).transpose(1, 2)
-        x = x.contiguous(memory_format=torch.channels_last)
+        if not self.native_convolutions():
+            return self._forward_library(src, src_lengths)
+        B, T, D = src.shape
+        cin = self.in_channels
+        # [B, T, cin * F] (channel-major feature axis, :80-86) -> channels-last rows [B, T, F, cin]; one channel: [B, T, F]
+        x = src.contiguous() if cin == 1 else src.view(B, T, cin, D // cin).transpose(2, 3).contiguous()
+        if self._anchor is None or self._anchor.device != src.device:
+            self._anchor = torch.zeros(1, device=src.device, requires_grad=True)
         for i, (conv, bn) in enumerate(zip(self.convolutions, self.batchnorms)):
+            name = self.flat_prefix + "convolutions.%d.weight" % i
+            w = self.flat.param(name).permute(0, 2, 3, 1)   # the flat storage order: [Cout, 3, 3, Cin], contiguous
+            gw = self.flat.grad(name).permute(0, 2, 3, 1)
+            gbw = self.flat.grad(self.flat_prefix + "batchnorms.%d.weight" % i)
+            gbb = self.flat.grad(self.flat_prefix + "batchnorms.%d.bias" % i)
+            if self.training:
+                bn.num_batches_tracked += 1
             # The convolution runs WITHOUT its bias: the bias is added inside the BatchNorm kernels (pre_bias), which
             # removes one full pass over the activation in forward (bias add) and one in backward (bias-gradient
             # reduction).  The gradient of a bias in front of a batch-statistics BatchNorm is identically zero
             # (the reference computes rounding noise there), so conv.bias receives no gradient.
+            x = _ConvBNReLUFn.apply(x, self._anchor, w, gw, tuple(conv.stride), bn, gbw, gbb, self.training,
+                                    conv.bias.data if conv.bias is not None else None, i > 0 or src.requires_grad)
+        # [B, T', F', C] -> [B, T', C * F']   (channel-major inner index, as in the reference :92-94)
+        x = x.transpose(2, 3).reshape(x.size(0), x.size(1), x.size(2) * x.size(3))
+        return x, self.output_lengths(src_lengths)
+
+    def _forward_library(self, src, src_lengths):
+        x = src.view(src.size(0), src.size(1), self.in_channels, src.size(2) // self.in_channels).transpose(1, 2)
+        x = x.contiguous(memory_format=torch.channels_last)
+        for i, (conv, bn) in enumerate(zip(self.convolutions, self.batchnorms)):
             x = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
             if not x.is_contiguous(memory_format=torch.channels_last):
                 x = x.contiguous(memory_format=torch.channels_last)
