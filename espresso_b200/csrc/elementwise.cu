@@ -1349,20 +1349,23 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bia
 // ================================================================================================
 namespace {
 
-constexpr int kConv1MaxCout = 256;
-
-// x [B, T, F] bf16, w [Cout, 3, 3] bf16, y [B, To, Fo, Cout] bf16
+// x [B, T, F] bf16, w [Cout, 3, 3] bf16, y [B, To, Fo, Cout] bf16.
+// The grid stride is a multiple of Cout/8, so a thread keeps the same 8 output channels: their 72 taps live in registers,
+// an output vector costs 9 cached 2-byte loads + 72 FMAs + one 16-byte store.
 __global__ void __launch_bounds__(256)
 conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int B, int T, int F, int Cout,
                  int st, int sf, int To, int Fo) {
   esp_pdl();
-  __shared__ float ws[9][kConv1MaxCout];  // tap-major: the 8 channels of a thread are contiguous
-  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i % 9][i / 9] = bf2f(w[i]);
-  __syncthreads();
   const int cv = Cout >> 3;
   const long total = (long)B * To * Fo * cv;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv) * 8;
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = (int)(i0 % cv) * 8;
+  float wr[9][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[k][j] = bf2f(w[(c8 + j) * 9 + k]);
+  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
     long pos = i / cv;
     const int fo = (int)(pos % Fo);
     pos /= Fo;
@@ -1371,14 +1374,12 @@ conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* _
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int t = to * st + r - 1;
-      if (t < 0 || t >= T) continue;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int f = fo * sf + c - 1;
-        if (f < 0 || f >= F) continue;
-        const float xv = bf2f(x[((long)b * T + t) * F + f]);
+        const float xv = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(x[((long)b * T + t) * F + f]) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ws[r * 3 + c][c8 + j], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[r * 3 + c][j], acc[j]);
       }
     }
     store8(y + i * 8, acc);
@@ -1386,36 +1387,57 @@ conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* _
 }
 
 // dw[co, tap] += sum_{b, to, fo} dy[b, to, fo, co] * x[b, to*st + r - 1, fo*sf + c - 1]
-// Thread mapping as in bn_stats: the grid stride is a multiple of Cout/8, so a thread keeps the same 8 channels.
-__global__ void __launch_bounds__(256)
+// Same thread mapping (fixed 8 channels per thread, 72 register accumulators).  One trip covers kC1Pos ADJACENT output
+// positions along F: their dy vectors are loaded first (kC1Pos 16-byte loads in flight per thread) and they share one
+// 3 x ((kC1Pos - 1) * SF + 3) window of input samples.
+constexpr int kC1Pos = 4;
+template <int SF>
+__global__ void __launch_bounds__(256, 2)
 conv1_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, float* __restrict__ dw, int B, int T, int F,
-                   int Cout, int st, int sf, int To, int Fo) {
+                   int Cout, int st, int To, int Fo) {
   esp_pdl();
   extern __shared__ float c1red[];  // [72 values][256 threads]: conflict-free
+  constexpr int W = (kC1Pos - 1) * SF + 3;
   const int cv = Cout >> 3;
-  const long total = (long)B * To * Fo * cv;
+  const int Fo4 = (Fo + kC1Pos - 1) / kC1Pos;
+  const long total = (long)B * To * Fo4 * cv;
   float acc[9][8];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const int c8 = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) % cv) * 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long pos = i / cv;
-    const int fo = (int)(pos % Fo);
-    pos /= Fo;
+    const int f4 = (int)(pos % Fo4) * kC1Pos;
+    pos /= Fo4;
     const int to = (int)(pos % To), b = (int)(pos / To);
-    float d[8];
-    load8(dy + i * 8, d);
+    uint4 dq[kC1Pos];
+    const bf16* drow = dy + (((long)b * To + to) * Fo + f4) * Cout + c8;
+#pragma unroll
+    for (int u = 0; u < kC1Pos; ++u)
+      dq[u] = (f4 + u < Fo) ? *reinterpret_cast<const uint4*>(drow + (long)u * Cout) : make_uint4(0, 0, 0, 0);
+    float xw[3][W];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int t = to * st + r - 1;
+      const bf16* xr = x + ((long)b * T + t) * F;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int f = fo * sf + c - 1;
-        const float xv = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(x[((long)b * T + t) * F + f]) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r * 3 + c][j] = fmaf(d[j], xv, acc[r * 3 + c][j]);
+      for (int c = 0; c < W; ++c) {
+        const int f = f4 * SF + c - 1;
+        xw[r][c] = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(xr[f]) : 0.f;
       }
+    }
+#pragma unroll
+    for (int u = 0; u < kC1Pos; ++u) {
+      float d[8];
+      unpack8(dq[u], d);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r * 3 + c][j] = fmaf(d[j], xw[r][u * SF + c], acc[r * 3 + c][j]);
     }
   }
 #pragma unroll
@@ -1437,8 +1459,7 @@ conv1_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, floa
 extern "C" int esp_conv3x3_c1_fwd(const void* x, const void* w, void* y, int32_t B, int32_t T, int32_t F, int32_t Cout,
                                   int32_t st, int32_t sf, void* stream) {
   cudaStream_t st_ = (cudaStream_t)stream;
-  ESP_CHECK(Cout % 8 == 0 && Cout <= kConv1MaxCout, "conv3x3 (1 input channel): Cout must be a multiple of 8, at most %d",
-            kConv1MaxCout);
+  ESP_CHECK(Cout % 8 == 0 && 256 % (Cout / 8) == 0, "conv3x3 (1 input channel): Cout/8 must divide 256 (got %d)", Cout);
   ESP_CHECK(st >= 1 && sf >= 1, "bad stride");
   const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
   const long total = (long)B * To * Fo * (Cout / 8);
@@ -1456,19 +1477,24 @@ extern "C" int esp_conv3x3_c1_wgrad(const void* dy, const void* x, float* dw, in
                                     int32_t st, int32_t sf, void* stream) {
   cudaStream_t st_ = (cudaStream_t)stream;
   ESP_CHECK(Cout % 8 == 0 && 256 % (Cout / 8) == 0, "conv3x3 (1 input channel) wgrad: Cout/8 must divide 256 (got %d)", Cout);
+  ESP_CHECK(sf == 1 || sf == 2, "conv3x3 (1 input channel) wgrad: frequency stride 1 or 2 (got %d)", sf);
   const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
-  const long total = (long)B * To * Fo * (Cout / 8);
+  const long total = (long)B * To * ((Fo + kC1Pos - 1) / kC1Pos) * (Cout / 8);
   if (total == 0) return 0;
   static bool configured = false;
   const int smem = 72 * 256 * (int)sizeof(float);
   if (!configured) {
-    ESP_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ESP_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ESP_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   long grid = (total + 255) / 256;
-  const long cap = 2L * esp_num_sms();  // few CTAs: each ends with 9 x Cout atomics
+  const long cap = 2L * esp_num_sms();  // one wave of resident CTAs: each ends with 9 x Cout atomics
   if (grid > cap) grid = cap;
-  esp_launch(conv1_wgrad_kernel, (unsigned)grid, 256, smem, st_, (const bf16*)dy, (const bf16*)x, dw, B, T, F, Cout, st, sf, To, Fo);
+  if (sf == 1)
+    esp_launch(conv1_wgrad_kernel<1>, (unsigned)grid, 256, smem, st_, (const bf16*)dy, (const bf16*)x, dw, B, T, F, Cout, st, To, Fo);
+  else
+    esp_launch(conv1_wgrad_kernel<2>, (unsigned)grid, 256, smem, st_, (const bf16*)dy, (const bf16*)x, dw, B, T, F, Cout, st, To, Fo);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;

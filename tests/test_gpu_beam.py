@@ -273,6 +273,46 @@ def test_transducer_greedy_decoder_on_gpu(variant, kw, golden_dir):
     assert np.abs(scores.cpu().numpy() - gg["scores_" + variant]).max() < 0.03 * np.abs(gg["scores_" + variant]).max()
 
 
+@pytest.mark.parametrize("case", range(3))
+def test_transducer_beam_search_decoder_on_gpu(case, golden_dir):
+    """CUDA path of the transducer beam search decoder (adaptive expansion search: encoder, predictor, joint and LM steps on
+    the device, the hypothesis bookkeeping of espresso/tools/transducer_beam_search_decoder.py:21-601 on the host): the best
+    hypothesis scores within bf16 tolerance of the REAL reference decoder's n-best recorded in
+    tests/golden/transducer_greedy.npz and carries the reference's best tokens whenever its own top-2 gap is clear."""
+    from test_host_orchestration import _BEAM_CASES, _build_transducer, _Dict, _lm_from_fixture
+    from espresso_b200.tools.transducer_beam_search_decoder import TransducerBeamSearchDecoder
+
+    if case >= len(_BEAM_CASES):
+        pytest.skip("no such case")
+    name, kw, use_lm = _BEAM_CASES[case]
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "transducer_conformer.npz"))
+    gg = np.load(os.path.join(golden_dir, "transducer_greedy.npz"))
+    m = _build_transducer(g).finalize_(dev)
+
+    class D(_Dict):
+        def bos(self):
+            return 0
+
+    lm = None
+    if use_lm:
+        lm = _lm_from_fixture(gg).finalize_(dev, torch.float32)
+    dec = TransducerBeamSearchDecoder([m], D(50), blank=0, lm_model=lm, lm_weight=0.3, **kw)
+    sample = {"net_input": {"src_tokens": torch.from_numpy(g["feats"]).to(dev), "src_lengths": torch.from_numpy(g["lens"]).to(dev)}}
+    tokens, scores, _ = dec.decode([m], sample)
+    hyps = dec.generate([m], sample)
+    assert tokens.size(0) == 3 and len(hyps) == 3
+    for b in range(3):
+        ref_seqs, ref_scores = gg["%s_b%d_seqs" % (name, b)], gg["%s_b%d_scores" % (name, b)]
+        assert abs(float(scores[b]) - float(ref_scores[0])) < 0.05 * abs(float(ref_scores[0])) + 0.02
+        sc = [float(h["score"]) for h in hyps[b]]
+        assert sc == sorted(sc, reverse=True) and 1 <= len(sc) <= kw["beam_size"]
+        if len(ref_scores) > 1 and ref_scores[0] - ref_scores[1] > 0.1:
+            ref_best = [t for t in ref_seqs[0].tolist() if t != 1]
+            tb = tokens[b].cpu()
+            assert tb[tb != 1].tolist() == ref_best, (name, b)
+
+
 def test_cuda_generator_matches_reference_generator(golden_dir):
     """CUDA beam search (esp_beam_merge / _topk / _bookkeep) vs the hypotheses of the REAL reference SequenceGenerator
     recorded in tests/golden/beam_reference.npz: LM shallow fusion, eos_factor, unk penalty, min_len, length penalty.
