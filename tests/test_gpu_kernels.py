@@ -15,6 +15,11 @@ def dev():
 
 
 # ------------------------------------------------------------------------------------------ front end
+# max abs error on log-mel values (|x| up to ~20): two fp32 FFT implementations differ by a few 1e-4 on low-energy bins
+# (log amplifies); achieved values are written to gpurun_out/parity_report.txt by every run
+FE_TOL = 1e-3  # achieved on the B200: 6e-6 ... 7.1e-4 (profiles/r02_parity_report_gpu.txt); the numpy oracle itself is 2.7e-4 from torchaudio
+
+
 def _run_frontend(dev, waves, mean, std, fms, tms, out_dtype=torch.float32, i16=False):
     from espresso_b200 import ops
     from espresso_b200.data import specaugment as SA
@@ -38,7 +43,7 @@ def _run_frontend(dev, waves, mean, std, fms, tms, out_dtype=torch.float32, i16=
     return out.float().cpu().numpy(), lens.cpu().numpy()
 
 
-def test_frontend_vs_reference_fixture(dev, golden_dir):
+def test_frontend_vs_reference_fixture(dev, golden_dir, parity):
     g = np.load(os.path.join(golden_dir, "frontend.npz"))
     ids = [i for i in range(len(g["durs"])) if "wave_%d" % i in g]
     waves = [g["wave_%d" % i] for i in ids]
@@ -47,7 +52,7 @@ def test_frontend_vs_reference_fixture(dev, golden_dir):
     for b, i in enumerate(ids):
         ref = g["fbank_%d" % i]
         assert lens[b] == ref.shape[0]
-        assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3  # fp32 FFT rounding; see test_oracle_golden
+        parity("frontend fbank vs recorded torchaudio output, utt %d (max abs log-mel)" % i, np.abs(out[b, : lens[b]] - ref).max(), FE_TOL)
         assert not out[b, lens[b]:].any()
     # full chain with the reference's recorded mask descriptors: masks identical, values within tolerance
     fms = [[tuple(x) for x in g["fmask_%d" % i]] for i in ids]
@@ -55,14 +60,14 @@ def test_frontend_vs_reference_fixture(dev, golden_dir):
     out, lens = _run_frontend(dev, waves, g["cmvn_mean"], g["cmvn_std"], fms, tms)
     for b, i in enumerate(ids):
         ref = g["final_%d" % i]
-        assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3
+        parity("frontend fbank+CMVN+SpecAugment vs reference, utt %d (max abs)" % i, np.abs(out[b, : lens[b]] - ref).max(), FE_TOL)
         assert not out[b, lens[b]:].any()
     # run twice: the SpecAugment workspace must be left clean by the kernel
     out2, _ = _run_frontend(dev, waves, g["cmvn_mean"], g["cmvn_std"], fms, tms)
     assert np.array_equal(out, out2)
 
 
-def test_frontend_vs_oracle_ragged_and_int16(dev):
+def test_frontend_vs_oracle_ragged_and_int16(dev, parity):
     from oracle import frontend as O
 
     durs = [0.02, 0.025, 1.003, 2.5, 0.7, 4.01]  # includes < 1 frame and exactly 1 frame
@@ -72,13 +77,13 @@ def test_frontend_vs_oracle_ragged_and_int16(dev):
         ref = O.kaldi_fbank(w)
         assert lens[b] == ref.shape[0]
         if ref.shape[0]:
-            assert np.abs(out[b, : lens[b]] - ref).max() < 2e-3
+            parity("frontend vs oracle, %.3f s int16 (max abs)" % durs[b], np.abs(out[b, : lens[b]] - ref).max(), FE_TOL)
         assert not out[b, lens[b]:].any()
     outb, _ = _run_frontend(dev, waves, None, None, None, None, out_dtype=torch.bfloat16)
     assert np.abs(outb - out).max() < 0.1  # bf16 rounding of values ~ 20
 
 
-def test_frontend_full_size_properties(dev):
+def test_frontend_full_size_properties(dev, parity):
     """LibriSpeech-shape batch (24 x up to 35 s): linearity-free properties -- determinism, padding zero,
     per-utterance independence from batch composition."""
     from oracle import frontend as O
@@ -90,7 +95,9 @@ def test_frontend_full_size_properties(dev):
     solo, l1 = _run_frontend(dev, [waves[5]], None, None, None, None)
     assert l1[0] == lens[5] and np.array_equal(solo[0, : l1[0]], out[5, : lens[5]])
     ref = O.kaldi_fbank(waves[5])
-    assert np.abs(out[5, : lens[5]] - ref).max() < 2e-3
+    parity("frontend vs oracle, %.1f s utterance inside a 24-utterance batch (max abs)" % durs[5], np.abs(out[5, : lens[5]] - ref).max(), FE_TOL)
+    k = int(np.argmax(durs))  # the longest utterance of the batch (up to 35 s)
+    parity("frontend vs oracle, longest utterance %.1f s (max abs)" % durs[k], np.abs(out[k, : lens[k]] - O.kaldi_fbank(waves[k])).max(), FE_TOL)
 
 
 # ------------------------------------------------------------------------------------------ CTC
