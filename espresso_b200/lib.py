@@ -59,6 +59,8 @@ SIGNATURES = {
     "esp_qprep_bwd": (C.c_int, [_vp, _vp, _f32, _i64, _i32, _vp, _i64, _vp]),
     "esp_attn_fused_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                      _i64, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
+    "esp_attn_fused_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _u64, _vp,
+                                     _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "esp_attn_softmax_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _f32, _u64, _vp, _vp]),
     "esp_attn_softmax_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _vp, _vp]),
     "esp_glu_dwconv_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -67,6 +67,8 @@ class EncoderEngine:
         # rel-pos attention forward as one fused tcgen05 kernel (csrc/attn_fused.cu); ESP_FUSED_ATTN=0 restores the
         # round-1 chain (BD GEMM -> QK^T+skew GEMM -> softmax -> P V GEMM) for A/B comparisons
         self.fused_attention = os.environ.get("ESP_FUSED_ATTN", "1") != "0"
+        # ... and the score side of its backward (csrc/attn_fused_bwd.cu); ESP_FUSED_ATTN_BWD=0 keeps the unfused chain
+        self.fused_attention_bwd = os.environ.get("ESP_FUSED_ATTN_BWD", "1") != "0"
         self._save_probs = True
         self.key_bounds = None  # (lo, hi) int32 [T] device tensors: per-row visible key range (streaming masks)
 
@@ -214,20 +216,27 @@ class EncoderEngine:
         dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
         self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"), self.G(lp + "self_attn.out_proj.bias"))
         dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
-        dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
-        _ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
-                  sC=(B * T * ldt, T * ldt))
         dqkv = torch.empty(R, 3 * d, device=dev, dtype=torch.bfloat16)
-        # dV = Pd^T dctx
-        _ops.gemm(Pd, dctx, dqkv[:, 2 * d:], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
-                  sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
-        dS, dBD = _ops.attn_softmax_bwd(Pr, dPd, T, ldp, self._drop("attention_dropout"), self._seed(li, 10))
-        # dq_u = dS k ; dK = dS^T q_u
         dqu = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+        if self.fused_attention and hd == 64 and self.fused_attention_bwd:
+            # ONE kernel: dPd = dctx v^T in TMEM, dS in registers (written once, plain and skewed), dV = Pd^T dctx and
+            # dK = dS^T q_u accumulated in TMEM over the query tiles (csrc/attn_fused_bwd.cu)
+            dS, dBD = _ops.attn_fused_bwd(dctx, ctx, qu, v, Pr, Pd, B, T, H, ldp, dqkv[:, d:2 * d], dqkv[:, 2 * d:],
+                                          self._drop("attention_dropout"), self._seed(li, 10))
+        else:
+            dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
+            _ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d),
+                      sC=(B * T * ldt, T * ldt))
+            # dV = Pd^T dctx
+            _ops.gemm(Pd, dctx, dqkv[:, 2 * d:], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+                      sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+            dS, dBD = _ops.attn_softmax_bwd(Pr, dPd, T, ldp, self._drop("attention_dropout"), self._seed(li, 10))
+            # dK = dS^T q_u
+            _ops.gemm(dS, qu, dqkv[:, d:2 * d], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+                      sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+        # dq_u = dS k
         _ops.gemm(dS, k, dqu, T, hd, T, ldt, 3 * d, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
                   sB=(hd, T * 3 * d), sC=(hd, T * d))
-        _ops.gemm(dS, qu, dqkv[:, d:2 * d], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
-                  sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
         # dq_v = dBD P ; dP = sum_b dBD^T q_v
         learned = self.pos_tables is not None
         E = Pp.shape[1]

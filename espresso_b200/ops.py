@@ -282,6 +282,27 @@ def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_pr
     return ctx, p, (pd if pd is not None else p)
 
 
+def attn_fused_bwd(dctx, ctx, qu, v, p, pd, B, T, H, ldp, dk_out, dv_out, drop_p=0.0, seed=0):
+    """Score side of the relative-position attention backward (esp_attn_fused_bwd): dctx, ctx, qu [B*T, d]; v [B*T, d] view;
+    p / pd [H, B, T, ld] as saved by attn_fused_fwd; dk_out / dv_out [B*T, d] views (same row stride) that receive
+    dS^T qu and P_drop^T dctx.  Returns (dS [H,B,T,ld], dBD [H,B,T,ldp] skewed)."""
+    _need_cuda(dctx, ctx, qu, v, p, pd, dk_out, dv_out)
+    _bf(dctx, ctx, qu, v, p, pd, dk_out, dv_out)
+    R, d = dctx.shape
+    hd = d // H
+    assert R == B * T and ctx.shape == dctx.shape and dctx.stride(0) == ctx.stride(0) and dctx.stride(1) == 1
+    assert p.is_contiguous() and pd.is_contiguous() and p.shape == pd.shape and p.shape[:3] == (H, B, T)
+    assert dk_out.stride(0) == dv_out.stride(0) and dk_out.stride(1) == 1 and dv_out.stride(1) == 1 and v.stride(1) == 1
+    ld = p.shape[-1]
+    ds = torch.empty_like(p)
+    dbd = torch.empty(H, B, T, ldp, device=p.device, dtype=torch.bfloat16)
+    ws = torch.empty(H * B * T, device=p.device, dtype=torch.float32)
+    _lib.check(_lib.load().esp_attn_fused_bwd(_ptr(dctx), _ptr(ctx), dctx.stride(0), _ptr(qu), qu.stride(0), _ptr(v), v.stride(0),
+                                              _ptr(p), _ptr(pd), ld, B, T, H, hd, drop_p, seed, _seed_ptr(), _ptr(ws), _ptr(ds),
+                                              _ptr(dbd), ldp, _ptr(dk_out), _ptr(dv_out), dk_out.stride(0), _stream()))
+    return ds, dbd
+
+
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     """Returns (dS [H,B,Tq,ld], dBD [H,B,T,ldp] in skewed relative-position layout or None)."""
     _need_cuda(p, dp_drop)

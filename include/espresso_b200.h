@@ -167,6 +167,19 @@ int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, const void* 
                        int32_t head_dim, const int32_t* lens, const int32_t* key_lo, const int32_t* key_hi, void* ctx,
                        int64_t ldctx, void* p_out, void* pd_out, int32_t ldp, float drop_p, uint64_t seed,
                        const uint64_t* seed_ptr, void* stream);
+/* Fused relative-position self-attention backward, score side (backward of the call above, :788-897): from dctx and the
+ * saved probabilities it produces dS [H,B,T,ldp_probs], its skewed copy dBD[., i, (T-1)-i+j] [H,B,T,ldbd] (zeros elsewhere;
+ * inverse of the shift :824-830), dK = dS^T qu and dV = P_drop^T dctx -- replacing the dPd GEMM, esp_attn_softmax_bwd and
+ * the dV / dK GEMMs of the unfused chain; dPd lives in TMEM only, dK / dV accumulate in TMEM over the query tiles.
+ * dctx, ctx: [B*T, H*64] bf16 (row stride ldctx; ctx = the forward output, for the softmax row term sum_j P dP = dctx.ctx);
+ * qu: as in the forward; v: [B*T, H*64] view with row stride ldkv; p / pd: what the forward saved (pd == p without dropout;
+ * the dropout mask is regenerated from seed / seed_ptr, the forward's stream); rowdot_ws: fp32 [H*B*T] workspace;
+ * dk / dv: [B*T, H*64] views with row stride ld_out (slices of the fused dqkv buffer).  The remaining gradients are plain
+ * GEMMs: dq_u = dS k, dq_v = dBD pos, dpos = dBD^T q_v. */
+int esp_attn_fused_bwd(const void* dctx, const void* ctx, int64_t ldctx, const void* qu, int64_t ldq, const void* v,
+                       int64_t ldkv, const void* p, const void* pd, int32_t ldp_probs, int32_t B, int32_t T, int32_t H,
+                       int32_t head_dim, float drop_p, uint64_t seed, const uint64_t* seed_ptr, float* rowdot_ws, void* ds,
+                       void* dbd, int32_t ldbd, void* dk, void* dv, int64_t ld_out, void* stream);
 /* Conformer convolution module body (fairseq/modules/conformer_layer.py:88-96):
  *   y = depthwise_conv_k(GLU(g)) with 'same' zero padding over the padded length T, g [B,T,2C], w [C,k];
  *   stats (double [2,C], +=): per-channel sum and sum of squares of y for BatchNorm1d batch statistics.

@@ -188,6 +188,25 @@ def attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=0.0, seed=0, save_pr
     return ctx, p, p
 
 
+def attn_fused_bwd(dctx, ctx, qu, v, p, pd, B, T, H, ldp, dk_out, dv_out, drop_p=0.0, seed=0):
+    """The unfused chain in fp32: dPd = dctx v^T, softmax backward (+ skewed copy), dV = P_drop^T dctx, dK = dS^T qu."""
+    assert drop_p == 0.0
+    R, d = dctx.shape
+    hd = d // H
+    dh = dctx.float().view(B, T, H, hd).permute(2, 0, 1, 3)                    # [H, B, T, hd]
+    vh = v.float().reshape(B, T, H, hd).permute(2, 0, 1, 3)
+    quh = qu.float().view(B, T, H, hd).permute(2, 0, 1, 3)
+    ld = p.shape[-1]
+    dpd = torch.zeros(H, B, T, ld)
+    dpd[..., :T] = dh @ vh.transpose(-1, -2)
+    ds, dbd = attn_softmax_bwd(p, dpd, T, ldp)
+    dv = pd.float()[..., :T].transpose(-1, -2) @ dh                            # [H, B, T, hd]
+    dk = ds.float()[..., :T].transpose(-1, -2) @ quh
+    dv_out.copy_(dv.permute(1, 2, 0, 3).reshape(R, d).to(BF))
+    dk_out.copy_(dk.permute(1, 2, 0, 3).reshape(R, d).to(BF))
+    return ds, dbd
+
+
 def attn_softmax_bwd(p, dp_drop, T, ldp, drop_p=0.0, seed=0, want_dbd=True):
     assert drop_p == 0.0
     H, B, Tq, ld = p.shape

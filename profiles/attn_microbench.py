@@ -62,3 +62,25 @@ for drop in (0.0, 0.1):
 c0 = chain(0.0)
 c1, _, _ = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens)
 print("max |ctx_fused - ctx_chain| = %.3e (bf16 scores in the chain, fp32 in the fused kernel)" % (c0.float() - c1.float()).abs().max().item())
+
+# ---- backward, score side: fused kernel (csrc/attn_fused_bwd.cu) vs the unfused chain it replaces ----
+dctx = (torch.randn(R, d, device=dev) * 0.5).bfloat16()
+dqkv = torch.empty(R, 3 * d, device=dev, dtype=torch.bfloat16)
+
+
+def bwd_chain(ctx, p, pd, drop):
+    dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
+    ops.gemm(dctx, v, dPd, T, T, hd, d, 3 * d, ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * 3 * d), sC=(B * T * ldt, T * ldt))
+    ops.gemm(pd, dctx, dqkv[:, 2 * d:], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+             sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+    dS, dBD = ops.attn_softmax_bwd(p, dPd, T, ldp, drop, 11)
+    ops.gemm(dS, qu, dqkv[:, d:2 * d], T, hd, T, ldt, d, 3 * d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B,
+             sA=(B * T * ldt, T * ldt), sB=(hd, T * d), sC=(hd, T * 3 * d))
+    return dS, dBD
+
+
+for drop in (0.0, 0.1):
+    ctx, p, pd = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens, drop_p=drop, seed=11)
+    a = timeit(lambda: bwd_chain(ctx, p, pd, drop))
+    f = timeit(lambda: ops.attn_fused_bwd(dctx, ctx, qu, v, p, pd, B, T, H, ldp, dqkv[:, d:2 * d], dqkv[:, 2 * d:], drop, 11))
+    print("backward (dPd, dS/dBD, dV, dK) B=%d T=%d dropout %.1f: unfused chain %7.1f us | fused %7.1f us" % (B, T, drop, a, f))

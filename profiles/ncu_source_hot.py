@@ -25,10 +25,15 @@ for r in rows:
         continue
     if hdr is None or r[0] in ("Function Name",) or not r[0].isdigit():
         continue
-    n = int(r[i_s] or 0)
+    def num(x):
+        try:
+            return int(x)
+        except ValueError:
+            return 0
+    n = num(r[i_s])
     if n == 0:
         continue
-    st = {h: int(r[i] or 0) for i, h in stall_cols if int(r[i] or 0)}
+    st = {h: num(r[i]) for i, h in stall_cols if num(r[i])}
     k = (fpath, int(r[0]), r[1].strip()[:110])
     a = acc.setdefault(k, [0, {}])
     a[0] += n

@@ -419,3 +419,67 @@ def test_attn_fused_fwd_dropout_stream_matches_softmax_kernels(dev):
     d = H * 64
     ref = torch.einsum("hbij,bjhe->bihe", pd[..., :T].float(), v.float().reshape(B, T, H, 64)).reshape(B * T, d)
     assert (ctx.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def _unfused_attn_bwd(ops, dctx, qu, v, p, pd, B, T, H, ldp, drop_p, seed):
+    """The round-1 chain on the GPU: dPd GEMM -> esp_attn_softmax_bwd -> dV / dK GEMMs (what the fused kernel replaces)."""
+    dev = dctx.device
+    R, d = dctx.shape
+    hd, ldt = 64, p.shape[-1]
+    dPd = torch.empty(H, B, T, ldt, device=dev, dtype=torch.bfloat16)
+    ops.gemm(dctx, v, dPd, T, T, hd, d, v.stride(0), ldt, nb1=H, nb2=B, sA=(hd, T * d), sB=(hd, T * v.stride(0)),
+             sC=(B * T * ldt, T * ldt))
+    dk = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+    dv = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+    ops.gemm(pd, dctx, dv, T, hd, T, ldt, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
+             sB=(hd, T * d), sC=(hd, T * d))
+    dS, dBD = ops.attn_softmax_bwd(p, dPd, T, ldp, drop_p, seed)
+    ops.gemm(dS, qu, dk, T, hd, T, ldt, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldt, T * ldt),
+             sB=(hd, T * d), sC=(hd, T * d))
+    return dS, dBD, dk, dv
+
+
+@pytest.mark.parametrize("B,T,H,lens,drop", [(2, 250, 4, [250, 131], 0.0), (3, 64, 2, None, 0.0), (1, 407, 8, None, 0.0),
+                                             (2, 129, 2, [129, 40], 0.0), (2, 203, 4, [203, 150], 0.25), (2, 300, 8, None, 0.1)])
+def test_attn_fused_bwd(dev, B, T, H, lens, drop):
+    """Score side of the attention backward in one kernel (csrc/attn_fused_bwd.cu): without dropout against the fp32
+    statement of the chain (oracle/ops_ref.py), with dropout against the unfused GPU chain on the same mask stream."""
+    from espresso_b200 import ops
+    from oracle import ops_ref
+
+    d = H * 64
+    qu, qv, k, v, pos = _attn_inputs(B, T, H, 900 + T, dev)
+    lens_t = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=dev)
+    ctx, p, pd = ops.attn_fused_fwd(qu, qv, k, v, pos, B, T, H, lens_t, drop_p=drop, seed=99)
+    g = torch.Generator(device="cpu").manual_seed(T)
+    dctx = (torch.randn(B * T, d, generator=g) * 0.5).to(dev).bfloat16()
+    ldp = (2 * T - 1 + 7) // 8 * 8
+    dqkv = torch.zeros(B * T, 3 * d, device=dev, dtype=torch.bfloat16)
+    vv = torch.empty(B * T, 3 * d, device=dev, dtype=torch.bfloat16)
+    vv[:, 2 * d:] = v
+    dS, dBD = ops.attn_fused_bwd(dctx, ctx, qu, vv[:, 2 * d:], p, pd, B, T, H, ldp, dqkv[:, d:2 * d], dqkv[:, 2 * d:], drop, 99)
+    torch.cuda.synchronize()
+    assert not dqkv[:, :d].any()  # the q slice is not touched
+    if drop == 0.0:
+        dk_r = torch.empty(B * T, d, dtype=torch.bfloat16)
+        dv_r = torch.empty(B * T, d, dtype=torch.bfloat16)
+        dS_r, dBD_r = ops_ref.attn_fused_bwd(dctx.cpu(), ctx.cpu(), qu.cpu(), v.cpu(), p.cpu(), pd.cpu(), B, T, H, ldp, dk_r, dv_r)
+    else:
+        dS_r, dBD_r, dk_r, dv_r = _unfused_attn_bwd(ops, dctx, qu, v.contiguous(), p, pd, B, T, H, ldp, drop, 99)
+        torch.cuda.synchronize()
+    sc = max(dS_r.float().abs().max().item(), 1e-3)
+    e_ds = (dS.float().cpu() - dS_r.float().cpu()).abs().max().item() / sc
+    e_bd = (dBD.float().cpu() - dBD_r.float().cpu()).abs().max().item() / sc
+    e_dk = (dqkv[:, d:2 * d].float().cpu() - dk_r.float().cpu()).abs().max().item() / max(dk_r.float().abs().max().item(), 1e-3)
+    e_dv = (dqkv[:, 2 * d:].float().cpu() - dv_r.float().cpu()).abs().max().item() / max(dv_r.float().abs().max().item(), 1e-3)
+    print("attn fused bwd B=%d T=%d H=%d drop=%.2f: dS %.2e dBD %.2e dK %.2e dV %.2e (max abs / max |ref|)" % (B, T, H, drop, e_ds, e_bd, e_dk, e_dv))
+    # bf16 outputs; the row term comes from dctx.ctx (bf16 ctx) instead of sum_j P dP: a few bf16 ulps of the largest value
+    assert e_ds < 2e-2 and e_bd < 2e-2 and e_dk < 2e-2 and e_dv < 2e-2, (e_ds, e_bd, e_dk, e_dv)
+    # the skewed copy is exactly the plain one moved to columns (T-1)-i+j, zeros elsewhere
+    i = torch.arange(T, device=dev)[:, None]
+    j = torch.arange(T, device=dev)[None, :]
+    idx = ((T - 1) - i + j).expand(H, B, T, T)
+    assert torch.equal(dBD.gather(-1, idx), dS[..., :T])
+    ref_sk = torch.zeros_like(dBD)
+    ref_sk.scatter_(-1, idx, dS[..., :T])
+    assert torch.equal(dBD, ref_sk)
