@@ -150,9 +150,14 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
               const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, const bf16* __restrict__ dres, long R,
               int d, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               const int* __restrict__ lens, int T, float drop_p, uint32_t drop_thresh, unsigned long long seed0,
-              const unsigned long long* __restrict__ seed_ptr) {
+              const unsigned long long* __restrict__ seed_ptr, bf16* __restrict__ dx2, float scale2, uint32_t thresh2,
+              unsigned long long seed2_0) {
   esp_pdl();
   const unsigned long long seed = seed0 + (seed_ptr ? *seed_ptr : 0ull);
+  const unsigned long long seed2 = seed2_0 + (seed_ptr ? *seed_ptr : 0ull);
+  // dx2 = dropout(dx) * scale2 on the SAME counter stream as esp_dropout (index r*d + c): the masked gradient the next
+  // module's backward starts with, produced here instead of by a separate pass over dx
+  const float ds2 = thresh2 > 0 ? scale2 * 65536.f / (65536.f - (float)thresh2) : scale2;
   extern __shared__ float sm_red[];  // [warps][2][NV * 256]: per-warp partial column sums, transposed
   const int lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
@@ -242,6 +247,14 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
           if (dres) o[j] += rr[j];
         }
         store8(dx + r * d + vi * 8, o);
+        if (dx2) {
+          bool keep2[8];
+          if (thresh2 > 0) esp_keep8(seed2, (unsigned long long)r * d + vi * 8, thresh2, keep2);
+          float o2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o2[j] = (thresh2 > 0 && !keep2[j]) ? 0.f : bf2f(f2bf(o[j])) * ds2;  // dropout of the bf16 dx
+          store8(dx2 + r * d + vi * 8, o2);
+        }
       }
     }
   }
@@ -1085,10 +1098,10 @@ extern "C" int esp_layer_norm_fwd(const void* x, const void* gamma, const void* 
   return 0;
 }
 
-extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                                  const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
-                                  const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
-                                  void* stream) {
+extern "C" int esp_layer_norm_bwd2(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                   const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
+                                   const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                                   void* dx2, float drop_p2, uint64_t seed2, float scale2, void* stream) {
   ESP_ST;
   ESP_CHECK(d % 8 == 0 && d <= 256 * kLnMaxVec, "LayerNorm width %d unsupported", d);
   if (R == 0) return 0;
@@ -1101,7 +1114,8 @@ extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* me
     }                                                                                                              \
     esp_launch(ln_bwd_kernel<NV>, grid_for(R, 8, 2), 256, 8 * 2 * NV * 256 * sizeof(float), st,                                           \
       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (const bf16*)dres, R, d, (bf16*)dx, dgamma, \
-      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr);              \
+      dbeta, lens, T, drop_p, esp_dropout_thresh(drop_p), seed, (const unsigned long long*)seed_ptr, (bf16*)dx2, scale2,          \
+      dx2 ? esp_dropout_thresh(drop_p2) : 0u, (unsigned long long)seed2);              \
   }
   if (d <= 512) ESP_LN_BWD(2)
   else if (d <= 1024) ESP_LN_BWD(4)
@@ -1110,6 +1124,14 @@ extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* me
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
+}
+
+extern "C" int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                  const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
+                                  const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                                  void* stream) {
+  return esp_layer_norm_bwd2(dy, x, mean, rstd, gamma, dres, R, d, dx, dgamma, dbeta, lens, T, drop_p, seed, seed_ptr, nullptr, 0.f, 0,
+                             1.f, stream);
 }
 
 extern "C" int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream) {

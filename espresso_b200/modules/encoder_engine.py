@@ -144,18 +144,21 @@ class EncoderEngine:
                         seed=self._seed(li, opbase + 1), alpha=alpha, R=x, ldr=x.stride(0), beta=1.0)
         return y, (x, mean, rstd, ln, U, Hh)
 
-    def ffn_bwd(self, dy, saved, lp, names, act_bwd, alpha, li, opbase):
+    def ffn_bwd(self, dy, saved, lp, names, act_bwd, alpha, li, opbase, dyd=None, next_drop=None):
+        """dyd: dropout(dy) * alpha already formed by the previous module's LayerNorm backward (same mask stream);
+        next_drop: (p, seed, scale) of the module whose backward runs next -- its masked gradient is returned as a
+        second value (written by this module's LayerNorm backward instead of by a separate dropout pass)."""
         ln_n, w1_n, w2_n = names
         x, mean, rstd, ln, U, Hh = saved
         W1, W2 = self.P(lp + w1_n + ".weight"), self.P(lp + w2_n + ".weight")
-        dZ = _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha)
+        dZ = dyd if dyd is not None else _ops.dropout(dy, self._drop("dropout"), self._seed(li, opbase + 1), scale=alpha)
         self._wgrad(dZ, Hh, self.G(lp + w2_n + ".weight"), self.G(lp + w2_n + ".bias"))
         dU = self._dgrad(dZ, W2, act=act_bwd, aux=U, ld_aux=U.stride(0), drop_p=self._drop("activation_dropout"),
                          drop_mode=2, seed=self._seed(li, opbase))
         self._wgrad(dU, ln, self.G(lp + w1_n + ".weight"), self.G(lp + w1_n + ".bias"))
         dln = self._dgrad(dU, W1)
         return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + ln_n + ".weight"), self.G(lp + ln_n + ".weight"),
-                                   self.G(lp + ln_n + ".bias"), dres=dy)
+                                   self.G(lp + ln_n + ".bias"), dres=dy, next_drop=next_drop)
 
     # ---- relative-position multi-head self-attention ---------------------------------------------
     def mha_fwd(self, x, lp, B, T, lens, li):
@@ -206,14 +209,14 @@ class EncoderEngine:
                         drop_p=self._drop("dropout"), drop_mode=1, seed=self._seed(li, 11), R=x, ldr=x.stride(0), beta=1.0)
         return y, (x, mean, rstd, ln, qkv, qu, qv, Pp, Pr, Pd, ctx)
 
-    def mha_bwd(self, dy, saved, lp, B, T, li):
+    def mha_bwd(self, dy, saved, lp, B, T, li, dyd=None, next_drop=None):
         d, H, hd = self.d, self.H, self.hd
         R = B * T
         x, mean, rstd, ln, qkv, qu, qv, Pp, Pr, Pd, ctx = saved
         k, v = qkv[:, d:2 * d], qkv[:, 2 * d:]
         ldt, ldp = _r8(T), _r8(2 * T - 1)
         dev = dy.device
-        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
+        dO = dyd if dyd is not None else _ops.dropout(dy, self._drop("dropout"), self._seed(li, 11))
         self._wgrad(dO, ctx, self.G(lp + "self_attn.out_proj.weight"), self.G(lp + "self_attn.out_proj.bias"))
         dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
         dqkv = torch.empty(R, 3 * d, device=dev, dtype=torch.bfloat16)
@@ -262,7 +265,7 @@ class EncoderEngine:
         dln = self._dgrad(dqkv, Wqkv)
         return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(lp + "self_attn_layer_norm.weight"),
                                    self.G(lp + "self_attn_layer_norm.weight"), self.G(lp + "self_attn_layer_norm.bias"),
-                                   dres=dy)
+                                   dres=dy, next_drop=next_drop)
 
     # ---- convolution module -----------------------------------------------------------------------
     def conv_fwd(self, x, lp, B, T, li):
@@ -281,11 +284,11 @@ class EncoderEngine:
                         drop_p=self._drop("dropout"), drop_mode=1, seed=self._seed(li, 20), R=x, ldr=x.stride(0), beta=1.0)
         return y, (x, mean, rstd, ln, Gg, Y, mr, Z)
 
-    def conv_bwd(self, dy, saved, lp, B, T, li):
+    def conv_bwd(self, dy, saved, lp, B, T, li, dyd=None, next_drop=None):
         d = self.d
         cp = lp + "conv_module."
         x, mean, rstd, ln, Gg, Y, mr, Z = saved
-        dO = _ops.dropout(dy, self._drop("dropout"), self._seed(li, 20))
+        dO = dyd if dyd is not None else _ops.dropout(dy, self._drop("dropout"), self._seed(li, 20))
         W2 = self.P(cp + "pointwise_conv2.weight").view(d, d)
         self._wgrad(dO, Z.view(B * T, d), self.G(cp + "pointwise_conv2.weight"))
         dZ = self._dgrad(dO, W2)
@@ -298,7 +301,7 @@ class EncoderEngine:
         self._wgrad(dG2, ln, self.G(cp + "pointwise_conv1.weight"))
         dln = self._dgrad(dG2, self.P(cp + "pointwise_conv1.weight").view(2 * d, d))
         return _ops.layer_norm_bwd(dln, x, mean, rstd, self.P(cp + "layer_norm.weight"), self.G(cp + "layer_norm.weight"),
-                                   self.G(cp + "layer_norm.bias"), dres=dy)
+                                   self.G(cp + "layer_norm.bias"), dres=dy, next_drop=next_drop)
 
     # ---- layers -----------------------------------------------------------------------------------
     _CONF_FFN1 = ("ffn1.layer_norm", "ffn1.w_1", "ffn1.w_2")
@@ -325,14 +328,19 @@ class EncoderEngine:
         lp = "layers.%d." % li
         if self.cfg["layer_type"] == "conformer":
             x, mean, rstd = st["final"]
-            dx = _ops.layer_norm_bwd(dy, x, mean, rstd, self.P(lp + "final_layer_norm.weight"),
-                                     self.G(lp + "final_layer_norm.weight"), self.G(lp + "final_layer_norm.bias"))
-            dx = self.ffn_bwd(dx, st["ffn2"], lp, self._CONF_FFN2, ACT_SILU_BWD, 0.5, li, 2)
-            dx = self.conv_bwd(dx, st["conv"], lp, B, T, li)
-            dx = self.mha_bwd(dx, st["mha"], lp, B, T, li)
-            return self.ffn_bwd(dx, st["ffn1"], lp, self._CONF_FFN1, ACT_SILU_BWD, 0.5, li, 0)
-        dx = self.ffn_bwd(dy, st["ffn"], lp, self._TR_FFN, ACT_RELU_BWD, 1.0, li, 0)
-        return self.mha_bwd(dx, st["mha"], lp, B, T, li)
+            # every LayerNorm backward also writes the dropout-masked copy of its dx that the next module starts with
+            pd = self._drop("dropout")
+            dx, dxd = _ops.layer_norm_bwd(dy, x, mean, rstd, self.P(lp + "final_layer_norm.weight"),
+                                          self.G(lp + "final_layer_norm.weight"), self.G(lp + "final_layer_norm.bias"),
+                                          next_drop=(pd, self._seed(li, 3), 0.5))
+            dx, dxd = self.ffn_bwd(dx, st["ffn2"], lp, self._CONF_FFN2, ACT_SILU_BWD, 0.5, li, 2, dyd=dxd,
+                                   next_drop=(pd, self._seed(li, 20), 1.0))
+            dx, dxd = self.conv_bwd(dx, st["conv"], lp, B, T, li, dyd=dxd, next_drop=(pd, self._seed(li, 11), 1.0))
+            dx, dxd = self.mha_bwd(dx, st["mha"], lp, B, T, li, dyd=dxd, next_drop=(pd, self._seed(li, 1), 0.5))
+            return self.ffn_bwd(dx, st["ffn1"], lp, self._CONF_FFN1, ACT_SILU_BWD, 0.5, li, 0, dyd=dxd)
+        dx, dxd = self.ffn_bwd(dy, st["ffn"], lp, self._TR_FFN, ACT_RELU_BWD, 1.0, li, 0,
+                               next_drop=(self._drop("dropout"), self._seed(li, 11), 1.0))
+        return self.mha_bwd(dx, st["mha"], lp, B, T, li, dyd=dxd)
 
     # ---- whole encoder ----------------------------------------------------------------------------
     def forward(self, xc, lens, has_pads, save=True):

@@ -176,17 +176,26 @@ def layer_norm_fwd(x, gamma, beta, eps=1e-5, lens=None, T=0, drop_p=0.0, seed=0)
     return y, mean, rstd
 
 
-def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0):
+def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0, next_drop=None):
+    """next_drop = (p, seed, scale): additionally return dropout_p(dx, seed) * scale -- the masked gradient the next module's
+    backward starts with -- as a second tensor (same values as ops.dropout(dx, p, seed, scale))."""
     _need_cuda(dy, x, gamma, dres)
     _bf(dy, x, gamma, dres)
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     assert dgamma_acc.dtype == torch.float32 and dbeta_acc.dtype == torch.float32
     R, d = x.shape
     dx = torch.empty_like(x)
-    _lib.check(_lib.load().esp_layer_norm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), R, d,
-                                              _ptr(dx), _ptr(dgamma_acc), _ptr(dbeta_acc), _ptr(lens), T, drop_p, seed,
-                                              _seed_ptr(), _stream()))
-    return dx
+    if next_drop is None:
+        _lib.check(_lib.load().esp_layer_norm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), R, d,
+                                                  _ptr(dx), _ptr(dgamma_acc), _ptr(dbeta_acc), _ptr(lens), T, drop_p, seed,
+                                                  _seed_ptr(), _stream()))
+        return dx
+    p2, seed2, scale2 = next_drop
+    dx2 = torch.empty_like(x)
+    _lib.check(_lib.load().esp_layer_norm_bwd2(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres), R, d,
+                                               _ptr(dx), _ptr(dgamma_acc), _ptr(dbeta_acc), _ptr(lens), T, drop_p, seed,
+                                               _seed_ptr(), _ptr(dx2), p2, seed2, scale2, _stream()))
+    return dx, dx2
 
 
 def colsum(x, out_acc, scale=1.0):

@@ -128,6 +128,14 @@ int esp_layer_norm_bwd(const void* dy, const void* x, const float* mean, const f
                        const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
                        const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
                        void* stream);
+/* Same, with a second output dx2 = dropout_{drop_p2, seed2}(dx) * scale2 on esp_dropout's counter stream (index r*d + c):
+ * the masked residual-stream gradient the NEXT module's backward starts with (fairseq/modules/conformer_layer.py:232-277
+ * differentiated: every module output passes through dropout before the residual add), written by this pass instead of by a
+ * separate esp_dropout over dx.  dx2 may be NULL. */
+int esp_layer_norm_bwd2(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                        const void* dres, int64_t R, int32_t d, void* dx, float* dgamma, float* dbeta,
+                        const int32_t* lens, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_ptr, void* dx2,
+                        float drop_p2, uint64_t seed2, float scale2, void* stream);
 /* out[n] += scale * sum_r x[r,n]   (bias / pos_bias gradients) */
 int esp_colsum(const void* x, int64_t R, int32_t N, int64_t ld, float scale, float* out, void* stream);
 /* y = dropout(x) * scale, same counter RNG / indexing (r*N+n) as the GEMM epilogue; colsum (fp32 [N] or NULL):

@@ -88,7 +88,7 @@ def layer_norm_fwd(x, gamma, beta, eps=1e-5, lens=None, T=0, drop_p=0.0, seed=0)
     return y.to(BF), mean, rstd
 
 
-def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0):
+def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, lens=None, T=0, drop_p=0.0, seed=0, next_drop=None):
     assert drop_p == 0.0
     dyf = dy.float()
     if lens is not None:
@@ -102,6 +102,8 @@ def layer_norm_bwd(dy, x, mean, rstd, gamma, dgamma_acc, dbeta_acc, dres=None, l
         dx = dx + dres.float()
     dgamma_acc += (dyf * xh).sum(0)
     dbeta_acc += dyf.sum(0)
+    if next_drop is not None:
+        return dx.to(BF), dropout(dx.to(BF), next_drop[0], next_drop[1], scale=next_drop[2])
     return dx.to(BF)
 
 

@@ -483,3 +483,25 @@ def test_attn_fused_bwd(dev, B, T, H, lens, drop):
     ref_sk = torch.zeros_like(dBD)
     ref_sk.scatter_(-1, idx, dS[..., :T])
     assert torch.equal(dBD, ref_sk)
+
+
+@pytest.mark.parametrize("p,scale", [(0.0, 0.5), (0.1, 1.0), (0.3, 0.5)])
+def test_layer_norm_bwd_second_output_is_the_next_dropout(dev, p, scale):
+    """esp_layer_norm_bwd2: the extra output equals esp_dropout(dx, p, seed, scale) bit for bit (the next module's masked
+    gradient comes out of the LayerNorm backward pass instead of a separate pass over dx)."""
+    from espresso_b200 import ops
+
+    R, d = 1000, 512
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(R, d, generator=g).to(dev).bfloat16()
+    dy = torch.randn(R, d, generator=g).to(dev).bfloat16()
+    dres = torch.randn(R, d, generator=g).to(dev).bfloat16()
+    gamma = torch.randn(d, generator=g).to(dev).bfloat16()
+    _, mean, rstd = ops.layer_norm_fwd(x, gamma, gamma, 1e-5)
+    ga, gb = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dx_ref = ops.layer_norm_bwd(dy, x, mean, rstd, gamma, ga, gb, dres=dres)
+    ga2, gb2 = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dx, dxd = ops.layer_norm_bwd(dy, x, mean, rstd, gamma, ga2, gb2, dres=dres, next_drop=(p, 777, scale))
+    assert torch.equal(dx, dx_ref)
+    assert torch.allclose(ga, ga2, rtol=1e-4, atol=1e-3) and torch.allclose(gb, gb2, rtol=1e-4, atol=1e-3)
+    assert torch.equal(dxd, ops.dropout(dx_ref, p, 777, scale=scale))
