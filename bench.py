@@ -88,16 +88,22 @@ def make_batches(n_batches, seed=7, pool=4000):
 
 
 def useful_gemm_flops(frames, d=512, ffn=2048, layers=17, in_dim=2560):
-    """GEMM flops of one update that land on REAL (unpadded) frames (SURVEY.md section 8d accounting; the conv2d
-    front and the depthwise conv are not tcgen05-GEMM launches and are left out).  `frames`: input frames per
-    utterance.  Per encoder frame and layer: FFN 2 x (2 x 2 d ffn), q/k/v/out 8 d^2, point-wise convs 6 d^2; per
-    utterance and layer: scores 2 d T'^2 + 2 d T' (2T'-1) + 2 d T'^2; pos_proj 2 d^2 (2 T'max - 1) once per layer;
-    fc0 and fc_out per frame.  Backward = 2 x forward (dgrad + wgrad); pos_proj has no dgrad."""
+    """Flops of one update that land on REAL (unpadded) frames, split by where they execute (SURVEY.md section 8d accounting;
+    the conv front and the depthwise conv are left out).  `frames`: input frames per utterance.  Returns (gemm, attn_fwd,
+    attn_bwd):
+      gemm      what the tcgen05 GEMM launches execute -- per encoder frame and layer: FFN 2 x (2 x 2 d ffn), q/k/v/out 8 d^2,
+                point-wise convs 6 d^2 (x3: forward, dgrad, wgrad); pos_proj 2 d^2 (2 T'max - 1) per layer (x2: no dgrad);
+                fc0 and fc_out per frame (x3); and the attention-backward products that are still plain GEMMs:
+                dq_u = dS k (2 d T'^2), dq_v = dBD pos and dpos = dBD^T q_v (2 d T'(2T'-1) each) per utterance and layer;
+      attn_fwd  the fused attention forward kernel: scores 2 d T'^2, position logits 2 d T'(2T'-1), P v 2 d T'^2;
+      attn_bwd  the fused attention backward kernel: dPd, dV, dK, 2 d T'^2 each."""
     tp = -(-(-(-np.asarray(frames, dtype=np.float64) // 2)) // 2)   # T' = ceil(ceil(T/2)/2)
     per_frame = layers * (8.0 * d * ffn + 14.0 * d * d) + 2.0 * in_dim * d + 2.0 * d * V
-    attn = layers * 2.0 * d * (4.0 * tp * tp - tp)
     pos = layers * 2.0 * d * d * (2.0 * tp.max() - 1.0)
-    return 3.0 * (per_frame * tp.sum() + attn.sum()) + 2.0 * pos
+    attn_fwd = layers * 2.0 * d * (4.0 * tp * tp - tp)
+    attn_bwd_fused = layers * 2.0 * d * (3.0 * tp * tp)
+    attn_bwd_gemm = layers * 2.0 * d * (tp * tp + 2.0 * tp * (2.0 * tp - 1.0))
+    return 3.0 * per_frame * tp.sum() + 2.0 * pos + attn_bwd_gemm.sum(), attn_fwd.sum(), attn_bwd_fused.sum()
 
 
 def effective_cores():
@@ -708,8 +714,8 @@ def main():
             return e0.elapsed_time(e1) * 1e3 / (reps * len(calls))
 
         # Record every GEMM / CTC call of one eager step (arguments + operand tensors kept alive), then replay them.
-        recs, ctc_recs = [], []
-        orig, orig_ctc = ops.gemm, ops.ctc_loss
+        recs, ctc_recs, af_recs, ab_recs = [], [], [], []
+        orig, orig_ctc, orig_af, orig_ab = ops.gemm, ops.ctc_loss, ops.attn_fused_fwd, ops.attn_fused_bwd
 
         def rec_gemm(A, B, C_out, M, N, K, *a, **kw):
             recs.append(((A, B, C_out, M, N, K) + a, dict(kw), 2.0 * M * N * K * kw.get("nb1", 1) * kw.get("nb2", 1)))
@@ -719,31 +725,52 @@ def main():
             ctc_recs.append((a, dict(kw)))
             return orig_ctc(*a, **kw)
 
-        ops.gemm, ops.ctc_loss = rec_gemm, rec_ctc
+        def rec_af(*a, **kw):
+            af_recs.append((a, dict(kw)))
+            return orig_af(*a, **kw)
+
+        def rec_ab(*a, **kw):
+            ab_recs.append((a, dict(kw)))
+            return orig_ab(*a, **kw)
+
+        ops.gemm, ops.ctc_loss, ops.attn_fused_fwd, ops.attn_fused_bwd = rec_gemm, rec_ctc, rec_af, rec_ab
         trainer.use_cuda_graphs = False
         trainer.world = 1  # rank-0-only pass: no collective (the other ranks are not in this code path)
         try:
             trainer.train_step([sample_of(resident[0], n_cpu[0])])
             torch.cuda.synchronize()
         finally:
-            ops.gemm, ops.ctc_loss = orig, orig_ctc
+            ops.gemm, ops.ctc_loss, ops.attn_fused_fwd, ops.attn_fused_bwd = orig, orig_ctc, orig_af, orig_ab
         us_gemm = replay_us([(lambda a_=a_, kw_=kw_: orig(*a_, **kw_)) for a_, kw_, _ in recs])
         tot_ms = us_gemm * len(recs) * 1e-3
         tot_fl = sum(f_ for _, _, f_ in recs)
-        useful = float(useful_gemm_flops(host[0]["frames"]))
+        useful, fl_af, fl_ab = (float(x_) for x_ in useful_gemm_flops(host[0]["frames"]))
         model.flat.zero_grad()
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = useful / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         roof = {"kernel": "gemm_tcgen05_kernel (all %d launches of one step, replayed back to back)" % len(recs),
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
-                "achieved_is": "useful GEMM flops of the step (padded frames EXCLUDED, SURVEY 8d accounting) / summed device "
-                               "time of the step's GEMM launches",
+                "achieved_is": "useful flops executed by the step's tcgen05 GEMM launches (padded frames EXCLUDED, SURVEY 8d "
+                               "accounting; the fused attention kernels' flops are NOT counted here, see tensor_other) / summed "
+                               "device time of those launches",
                 "achieved_incl_padding": tot_fl / (tot_ms * 1e-3) / 1e12, "useful_tflop_per_step": useful / 1e12,
                 "launched_tflop_per_step": tot_fl / 1e12,
                 "gemm_ms_per_step": tot_ms, "gemm_share_of_step": tot_ms / (ms / args.steps), "traffic": None,
                 "launches": len(recs),
-                "whole_step_frac": useful / ((ms / args.steps) * 1e-3) / 1e12 / peak}
+                "whole_step_frac": (useful + fl_af + fl_ab) / ((ms / args.steps) * 1e-3) / 1e12 / peak}
+        # the other tensor-core kernels of the step: fused attention forward / backward, replayed the same way
+        other = []
+        for nm, rl, fn_, fl_ in (("attn_fused_fwd_kernel", af_recs, orig_af, fl_af),
+                                 ("attn_fused_bwd_kernel (+ row-dot and skew kernels)", ab_recs, orig_ab, fl_ab)):
+            if rl:
+                us_ = replay_us([(lambda a_=a_, kw_=kw_, fn_=fn_: fn_(*a_, **kw_)) for a_, kw_ in rl])
+                t_ms = us_ * len(rl) * 1e-3
+                other.append({"kernel": nm, "launches": len(rl), "ms_per_step": t_ms, "useful_tflop_per_step": fl_ / 1e12,
+                              "achieved": fl_ / (t_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                              "frac": fl_ / (t_ms * 1e-3) / 1e12 / peak,
+                              "bound": "instruction issue of the softmax / dS warps and TMA latency, not the tensor pipe (DESIGN.md 4)"})
+        roof["tensor_other"] = other
         try:  # DRAM bytes per launch from the committed ncu capture of the same command (profiles/)
             tr = _json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
             roof["traffic"] = tr["dram_bytes_per_launch"]
@@ -780,7 +807,7 @@ def main():
                                  "shape": "B=%d T'=%d V=%d valid_frames=%d" % (Bc, Tc, V, cells_valid),
                                  "inputs": "3 rotating logits buffers of %.0f MB" % (a_[0].numel() * 2 / 1e6)})
                 del lg
-        del recs, ctc_recs
+        del recs, ctc_recs, af_recs, ab_recs
 
     if rank == 0:
         val = audio / (ms * 1e-3)
