@@ -362,8 +362,12 @@ struct SmemLayout {
 // producers' TMA transactions signal the LEADER's full barrier (peer bit cleared), which expects the bytes of both
 // CTAs; the MMA thread's commits are multicast to both CTAs' empty / accumulator-full barriers; the epilogue warps of
 // both CTAs arrive on the leader's accumulator-empty barrier.
-template <int BN, bool A_K, bool B_K, int MC, bool TS>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW: epilogue warps, 8 (two per TMEM lane quarter, every fused epilogue) or 16 (four per quarter, 640 threads, <= 102
+// registers): the LIGHT epilogues only -- optional bias, ReLU / SiLU, alpha, bf16 / fp32 store or fp32 accumulate.  With
+// eight warps per SM the per-chunk chain (TMEM load -> convert -> row stores) is not hidden by other warps; sixteen halve
+// each warp's share of the tile.
+template <int BN, bool A_K, bool B_K, int MC, bool TS, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
   constexpr bool CG2 = (MC == 3);
@@ -410,7 +414,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), CG2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(tempty_bar(s), CG2 ? 2 * EW : EW);  // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -669,9 +673,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================ epilogue =========================================
     // 8 warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the tile's columns.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;  // which share of the tile's columns (2 shares with EW = 8, 4 with EW = 16)
+    constexpr bool LIGHT = (EW == 16);
     constexpr int kChunks = BN / 32;          // 32-column chunks per tile
-    constexpr int kChunksPerWarp = kChunks / 2;
+    constexpr int kChunksPerWarp = kChunks / (EW / 4);
+    static_assert(kChunksPerWarp >= 1, "too many epilogue warps for this tile width");
     const EpiParams& e = p.ep;
     const unsigned long long seed = e.seed + (e.seed_ptr ? *e.seed_ptr : 0ull);
     constexpr bool use_slab = TS;
@@ -722,6 +728,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);  // asynchronous
         const int valid = p.N - n0;  // >= 1; >= 32 for a full chunk
+        if constexpr (LIGHT) {
+          // light epilogue (host guarantees: no second output, aux, residual, skew or dropout)
+          Packed32 pkb;
+          const bf16* bp = e.bias ? e.bias + n0 : nullptr;
+          const bool fb = row_ok && valid >= 32 && !e.atomic && bp && al16(bp);
+          if (fb) ldg32(bp, pkb);
+          tmem_ld_wait();
+          if (row_ok && !(p.debug & 1)) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (e.atomic) {
+              float* cp = (float*)e.C + c_off + n0;
+              if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  red_add_v4(cp + j, v[j] * e.alpha, v[j + 1] * e.alpha, v[j + 2] * e.alpha, v[j + 3] * e.alpha);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (j < valid) atomicAdd(cp + j, v[j] * e.alpha);
+              }
+            } else {
+              if (bp) {
+                float bv[32];
+                if (fb) unpack32(pkb, bv);
+                else load32(bp, valid, bv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += bv[j];
+              }
+              if (e.act == ESP_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+              } else if (e.act == ESP_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (e.alpha != 1.f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+              }
+              if (e.c_f32) {
+                float* cp = (float*)e.C + c_off + n0;
+                if (valid >= 32 && ((reinterpret_cast<uintptr_t>(cp) & 31) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 8)
+                    stg256(cp + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                           __float_as_uint(v[j + 3]), __float_as_uint(v[j + 4]), __float_as_uint(v[j + 5]),
+                           __float_as_uint(v[j + 6]), __float_as_uint(v[j + 7]));
+                } else {
+                  for (int j = 0; j < 32; ++j)
+                    if (j < valid) cp[j] = v[j];
+                }
+              } else {
+                store32_bf16((bf16*)e.C + c_off + n0, valid, v);
+              }
+            }
+          }
+          continue;
+        }
         // Put every global operand of this chunk in flight BEFORE waiting for the TMEM load, so the latencies
         // (TMEM, bias from L2, aux / residual from HBM) overlap instead of adding up.
         Packed32 pk_bias, pk_aux, pk_res;
@@ -976,11 +1041,11 @@ bool esp_gemm_cg2_enabled() {
 // co-resident 2-CTA clusters of a kernel variant (clusters sit inside one GPC: with odd SM counts per GPC fewer than
 // SMs/2 pairs fit at once -- ask the runtime instead of assuming)
 template <typename K>
-int cluster_slots(K kfn, int smem_bytes) {
+int cluster_slots(K kfn, int smem_bytes, int threads) {
   int slots = esp_num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(esp_num_sms() / 2 * 2);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -995,12 +1060,13 @@ int cluster_slots(K kfn, int smem_bytes) {
   return slots;
 }
 
-template <int BN, bool A_K, bool B_K, int MC, bool TS = false>
+template <int BN, bool A_K, bool B_K, int MC, bool TS = false, int EW = 8>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KParams& kp, cudaStream_t st) {
   constexpr int CL = MC > 1 ? 2 : 1;
   using L = SmemLayout<BN, A_K, B_K, MC == 3, TS>;
   static bool configured = false;
-  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC, TS>;
+  auto kfn = gemm_tcgen05_kernel<BN, A_K, B_K, MC, TS, EW>;
+  constexpr int kT = 128 + 32 * EW;
   if (!configured) {
     ESP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
@@ -1008,22 +1074,22 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int tiles_m = (((kp.M + BM - 1) / BM) + CL - 1) / CL;
   const int work = tiles_m * ((kp.N + BN - 1) / BN) * kp.nb1 * kp.nb2 * kp.ksplit;
   static int slots = 0;  // persistent grid = what is co-resident
-  if (slots == 0) slots = CL > 1 ? cluster_slots(kfn, L::kTotal) : esp_num_sms();
+  if (slots == 0) slots = CL > 1 ? cluster_slots(kfn, L::kTotal, kT) : esp_num_sms();
   int grid = (work < slots ? work : slots) * CL;
   if (grid < 1) return 0;
-  esp_launch_cluster(kfn, grid, kThreads, L::kTotal, st, CL, ta, tb, tc, kp);
+  esp_launch_cluster(kfn, grid, kT, L::kTotal, st, CL, ta, tb, tc, kp);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
 }
 
-template <int BN, int MC, bool TS = false>
+template <int BN, int MC, bool TS = false, int EW = 8>
 int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const KParams& kp, cudaStream_t st) {
-  if (ak && bk) return launch<BN, true, true, MC, TS>(ta, tb, tc, kp, st);
-  if (ak && !bk) return launch<BN, true, false, MC, TS>(ta, tb, tc, kp, st);
-  if (!ak && bk) return launch<BN, false, true, MC, TS>(ta, tb, tc, kp, st);
-  return launch<BN, false, false, MC, TS>(ta, tb, tc, kp, st);
+  if (ak && bk) return launch<BN, true, true, MC, TS, EW>(ta, tb, tc, kp, st);
+  if (ak && !bk) return launch<BN, true, false, MC, TS, EW>(ta, tb, tc, kp, st);
+  if (!ak && bk) return launch<BN, false, true, MC, TS, EW>(ta, tb, tc, kp, st);
+  return launch<BN, false, false, MC, TS, EW>(ta, tb, tc, kp, st);
 }
 
 }  // namespace
@@ -1154,6 +1220,25 @@ extern "C" int esp_gemm_bf16(const EspGemm* g, void* stream) {
       if (rc) return rc;
       kp.tma_c = 1;
     }
+  }
+  // Experiment switch ESP_GEMM_EPI16=1: sixteen epilogue warps for the light epilogues of the wide tiles.  Measured: no
+  // gain (FFN1 19.6 -> 19.3 us, out_proj 11.6 -> 14.3 us; profiles/r02_gemm_microbench_v6_epi16.txt) -- the epilogue is
+  // bound by the throughput of its row-per-thread stores, not by the latency of each warp's chain.  Off by default.
+  static int epi16 = -1;
+  if (epi16 < 0) {
+    const char* ev = getenv("ESP_GEMM_EPI16");
+    epi16 = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  const bool light = epi16 && bn >= 128 && !kp.tma_c && e.C2 == nullptr && e.R == nullptr && e.drop_mode == 0 &&
+                     e.act < ESP_ACT_RELU_BWD && kp.debug == 0;
+  if (light) {
+    if (bn == 256) {
+      if (mode == 3) return dispatch_major<256, 3, false, 16>(ak, bk, ta, tb, tc, kp, st);
+      return mode == 2 ? dispatch_major<256, 2, false, 16>(ak, bk, ta, tb, tc, kp, st)
+                       : dispatch_major<256, 1, false, 16>(ak, bk, ta, tb, tc, kp, st);
+    }
+    return mode == 2 ? dispatch_major<128, 2, false, 16>(ak, bk, ta, tb, tc, kp, st)
+                     : dispatch_major<128, 1, false, 16>(ak, bk, ta, tb, tc, kp, st);
   }
   if (bn == 64) return dispatch_major<64, 1>(ak, bk, ta, tb, tc, kp, st);
   if (bn == 256) {
