@@ -680,6 +680,16 @@ def main():
                      "unit": "audio-s/s", "from": "pinned host buffers (same path as e2e)"}
     graph_stats = {"graphs": len(trainer._graphs), "distinct_batches": n_distinct, "hits": trainer.graph_hits,
                    "misses": trainer.graph_misses, "bucket_frames": trainer.bucket_frames}
+    if not args.eager and world == 1:
+        # the same step WITHOUT graph replay (every kernel launched from Python): what a batch whose shape bucket has no
+        # captured graph yet costs, on the same resident batches
+        trainer.use_cuda_graphs = False
+        timed(3, False)
+        ms_eager, _ae = timed(10, False)
+        trainer.use_cuda_graphs = True
+        graph_stats["eager_ms_per_step"] = ms_eager / 10
+        graph_stats["note"] = ("a bucket's first occurrence runs eagerly, its second captures; %d buckets cover the %d distinct "
+                               "LibriSpeech-shape batches of this run" % (len(trainer._graphs), n_distinct))
     if os.environ.get("ESP_BENCH_E2E_DEBUG"):
         for name, kw in (("upload+lagged read", {}), ("upload only", dict(read_loss=False)), ("lagged read only", dict(do_upload=False)),
                          ("upload+item()", dict(sync_each=True)), ("item() only", dict(do_upload=False, sync_each=True))):

@@ -221,7 +221,7 @@ class EncoderEngine:
         dctx = self._dgrad(dO, self.P(lp + "self_attn.out_proj.weight"))
         dqkv = torch.empty(R, 3 * d, device=dev, dtype=torch.bfloat16)
         dqu = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        if self.fused_attention and hd == 64 and self.fused_attention_bwd:
+        if self.fused_attention and hd == 64 and self.fused_attention_bwd and T <= 1024:  # skew kernel: rows of <= 1024 keys
             # ONE kernel: dPd = dctx v^T in TMEM, dS in registers (written once, plain and skewed), dV = Pd^T dctx and
             # dK = dS^T q_u accumulated in TMEM over the query tiles (csrc/attn_fused_bwd.cu)
             dS, dBD = _ops.attn_fused_bwd(dctx, ctx, qu, v, Pr, Pd, B, T, H, ldp, dqkv[:, d:2 * d], dqkv[:, 2 * d:],
