@@ -1372,14 +1372,19 @@ extern "C" int esp_bn_act_bwd(const void* dz, const void* y, const void* pre_bia
 namespace {
 
 // x [B, T, F] bf16, w [Cout, 3, 3] bf16, y [B, To, Fo, Cout] bf16.
-// The grid stride is a multiple of Cout/8, so a thread keeps the same 8 output channels: their 72 taps live in registers,
-// an output vector costs 9 cached 2-byte loads + 72 FMAs + one 16-byte store.
+// The grid stride is a multiple of Cout/8, so a thread keeps the same 8 output channels: their 72 taps live in registers.
+// One trip produces kC1Pos ADJACENT output positions along F from one 3 x ((kC1Pos - 1) * SF + 3) window of input samples
+// (4.5 cached 2-byte loads + 72 FMAs + one 16-byte store per output vector); 32-bit position arithmetic.
+constexpr int kC1Pos = 4;
+template <int SF>
 __global__ void __launch_bounds__(256)
 conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int B, int T, int F, int Cout,
-                 int st, int sf, int To, int Fo) {
+                 int st, int To, int Fo) {
   esp_pdl();
+  constexpr int W = (kC1Pos - 1) * SF + 3;
   const int cv = Cout >> 3;
-  const long total = (long)B * To * Fo * cv;
+  const int Fo4 = (Fo + kC1Pos - 1) / kC1Pos;
+  const long total = (long)B * To * Fo4 * cv;
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = (int)(i0 % cv) * 8;
   float wr[9][8];
@@ -1387,24 +1392,35 @@ conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* _
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[k][j] = bf2f(w[(c8 + j) * 9 + k]);
-  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
-    long pos = i / cv;
-    const int fo = (int)(pos % Fo);
-    pos /= Fo;
-    const int to = (int)(pos % To), b = (int)(pos / To);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const unsigned npos = (unsigned)(total / cv), pstep = (unsigned)(((long)gridDim.x * blockDim.x) / cv);
+  for (unsigned pos = (unsigned)(i0 / cv); pos < npos; pos += pstep) {
+    const unsigned bt = pos / (unsigned)Fo4;
+    const int f4 = (int)(pos - bt * (unsigned)Fo4) * kC1Pos;
+    const int b = (int)(bt / (unsigned)To), to = (int)(bt - (unsigned)b * (unsigned)To);
+    float xw[3][W];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int t = to * st + r - 1;
+      const bf16* xr = x + ((long)b * T + t) * F;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int f = fo * sf + c - 1;
-        const float xv = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(x[((long)b * T + t) * F + f]) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[r * 3 + c][j], acc[j]);
+      for (int c = 0; c < W; ++c) {
+        const int f = f4 * SF + c - 1;
+        xw[r][c] = (t >= 0 && t < T && f >= 0 && f < F) ? bf2f(xr[f]) : 0.f;
       }
     }
-    store8(y + i * 8, acc);
+    bf16* yrow = y + (((long)b * To + to) * Fo + f4) * Cout + c8;
+#pragma unroll
+    for (int u = 0; u < kC1Pos; ++u) {
+      if (f4 + u >= Fo) break;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xw[r][u * SF + c], wr[r * 3 + c][j], acc[j]);
+      store8(yrow + (long)u * Cout, acc);
+    }
   }
 }
 
@@ -1412,7 +1428,6 @@ conv1_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* _
 // Same thread mapping (fixed 8 channels per thread, 72 register accumulators).  One trip covers kC1Pos ADJACENT output
 // positions along F: their dy vectors are loaded first (kC1Pos 16-byte loads in flight per thread) and they share one
 // 3 x ((kC1Pos - 1) * SF + 3) window of input samples.
-constexpr int kC1Pos = 4;
 template <int SF>
 __global__ void __launch_bounds__(256, 2)
 conv1_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, float* __restrict__ dw, int B, int T, int F,
@@ -1429,11 +1444,11 @@ conv1_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   const int c8 = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) % cv) * 8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long pos = i / cv;
-    const int f4 = (int)(pos % Fo4) * kC1Pos;
-    pos /= Fo4;
-    const int to = (int)(pos % To), b = (int)(pos / To);
+  const unsigned npos = (unsigned)(total / cv), pstep = (unsigned)(((long)gridDim.x * blockDim.x) / cv);
+  for (unsigned pos = (unsigned)(((long)blockIdx.x * blockDim.x + threadIdx.x) / cv); pos < npos; pos += pstep) {
+    const unsigned bt = pos / (unsigned)Fo4;
+    const int f4 = (int)(pos - bt * (unsigned)Fo4) * kC1Pos;
+    const int b = (int)(bt / (unsigned)To), to = (int)(bt - (unsigned)b * (unsigned)To);
     uint4 dq[kC1Pos];
     const bf16* drow = dy + (((long)b * To + to) * Fo + f4) * Cout + c8;
 #pragma unroll
@@ -1482,14 +1497,17 @@ extern "C" int esp_conv3x3_c1_fwd(const void* x, const void* w, void* y, int32_t
                                   int32_t st, int32_t sf, void* stream) {
   cudaStream_t st_ = (cudaStream_t)stream;
   ESP_CHECK(Cout % 8 == 0 && 256 % (Cout / 8) == 0, "conv3x3 (1 input channel): Cout/8 must divide 256 (got %d)", Cout);
-  ESP_CHECK(st >= 1 && sf >= 1, "bad stride");
+  ESP_CHECK(st >= 1 && (sf == 1 || sf == 2), "conv3x3 (1 input channel): frequency stride 1 or 2 (got %d)", sf);
   const int To = (T + st - 1) / st, Fo = (F + sf - 1) / sf;
-  const long total = (long)B * To * Fo * (Cout / 8);
+  const long total = (long)B * To * ((Fo + kC1Pos - 1) / kC1Pos) * (Cout / 8);
   if (total == 0) return 0;
   long grid = (total + 255) / 256;
-  const long cap = 16L * esp_num_sms();
+  const long cap = 8L * esp_num_sms();
   if (grid > cap) grid = cap;
-  esp_launch(conv1_fwd_kernel, (unsigned)grid, 256, 0, st_, (const bf16*)x, (const bf16*)w, (bf16*)y, B, T, F, Cout, st, sf, To, Fo);
+  if (sf == 1)
+    esp_launch(conv1_fwd_kernel<1>, (unsigned)grid, 256, 0, st_, (const bf16*)x, (const bf16*)w, (bf16*)y, B, T, F, Cout, st, To, Fo);
+  else
+    esp_launch(conv1_fwd_kernel<2>, (unsigned)grid, 256, 0, st_, (const bf16*)x, (const bf16*)w, (bf16*)y, B, T, F, Cout, st, To, Fo);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
   return 0;
