@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "espresso_b200.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 void esp_count_launch(int n);
 
@@ -49,7 +50,22 @@ constexpr int kOffBar = kOffW + kTile * kWRowBytes;
 constexpr int kSmemBytes = kOffBar + 128 + 2 * kTile * 2 * 4 + 1024;   // barriers, (m, l) exchange, alignment slack
 constexpr int kColS = 0, kColW = 128, kColO = 384, kTmemCols = 512;
 
+// optional timeline of CTA (0, 0, 0) (ESP_ATTN_FWD_TIMELINE=1; esp_attn_fwd_timeline reads it): %globaltimer stamps of
+// softmax warp 0 -- per iteration: logits ready (S / W in TMEM), logits in registers, iteration done
+__device__ unsigned long long g_fwd_timeline[128];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TLF(slot)                                                                                                        \
+  do {                                                                                                                   \
+    if (p.timeline && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 128)         \
+      g_fwd_timeline[(slot)] = gtimer();                                                                                 \
+  } while (0)
+
 struct Params {
+  int timeline;
   int B, T, H, d, ld;       // ld: row stride of the probability tensors (multiple of 8, >= T)
   int pos_hstride;          // head stride (elements) inside a projected-position row: hd, or 0 (table shared by heads)
   const int* lens;          // valid keys per utterance or nullptr
@@ -307,7 +323,9 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
       const int jt = it % nkt;
       const bool pass2 = it >= nkt;
       const int j0 = jt * kTile + hf * kHalf;  // first key of this thread's half tile
+      if (it == 0) TLF(0);
       mbar_wait(barS, it & 1);
+      TLF(1 + 3 * it);
       tcgen05_fence_after();
       // ---- stage the row's slice of W in shared memory as bf16: half 0 stages chunks 0-2 (all it reads itself),
       //      half 1 stages chunks 3-4 and additionally needs chunk 2 from its partner warp ----
@@ -369,6 +387,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(barT);
+      TLF(2 + 3 * it);
       if (!pass2) {
         // ---- pass 1: online maximum and normaliser of this thread's half of the row ----
         const float m_new = fmaxf(m_run, tmax);
@@ -437,6 +456,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(barP);
       }
+      TLF(3 + 3 * it);
     }
     // ---- epilogue: O (already normalised) -> ctx; this thread stores 32 of the row's 64 values ----
     mbar_wait(barO, (nkt - 1) & 1);
@@ -500,6 +520,10 @@ extern "C" int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, c
   const long pos_cols = pos_hstride ? (long)H * kHd : kHd;
   if ((rc = esp_make_tmap_bf16(&tp, pos, pos_cols, 2L * T - 1, ldpos, 1, 0, 1, 0, kTile))) return rc;
   Params pr;
+  {
+    const char* tl = getenv("ESP_ATTN_FWD_TIMELINE");
+    pr.timeline = (tl && tl[0] == '1') ? 1 : 0;
+  }
   pr.B = B; pr.T = T; pr.H = H; pr.d = (int)ldctx; pr.ld = ldp; pr.pos_hstride = pos_hstride;
   ESP_CHECK((key_lo == nullptr) == (key_hi == nullptr), "key_lo and key_hi must be given together");
   pr.key_lo = key_lo; pr.key_hi = key_hi;
@@ -515,5 +539,13 @@ extern "C" int esp_attn_fused_fwd(const void* qu, const void* qv, int64_t ldq, c
   esp_launch(attn_fused_fwd_kernel, grid, kThreads, kSmemBytes, st, tqu, tqv, tk, tv, tp, pr);
   ESP_LAUNCH_CHECK();
   esp_count_launch(1);
+  return 0;
+}
+
+// debugging aid: the %globaltimer stamps (ns) of CTA (0, 0, 0) of the last esp_attn_fused_fwd launch with
+// ESP_ATTN_FWD_TIMELINE=1 (profiles/attn_fwd_timeline.py)
+extern "C" int esp_attn_fwd_timeline(unsigned long long* out128) {
+  ESP_CUDA(cudaDeviceSynchronize());
+  ESP_CUDA(cudaMemcpyFromSymbol(out128, g_fwd_timeline, sizeof(unsigned long long) * 128));
   return 0;
 }
