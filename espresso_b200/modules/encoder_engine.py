@@ -245,16 +245,21 @@ class EncoderEngine:
         E = Pp.shape[1]
         ph = hd if E == d else 0
         dqv = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        _ops.gemm(dBD, Pp, dqv, T, hd, 2 * T - 1, ldp, E, d, b_kmajor=False, nb1=H, nb2=B, sA=(B * T * ldp, T * ldp),
-                  sB=(ph, 0), sC=(hd, T * d))
-        dPp = torch.empty(2 * T - 1, d, device=dev, dtype=torch.bfloat16)
-        _ops.gemm(dBD, qv, dPp, 2 * T - 1, hd, B * T, ldp, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=1,
-                  sA=(B * T * ldp, 0), sB=(hd, 0), sC=(hd, 0))
+        # the projected positions are shared by all utterances, so the rows of all utterances form ONE M axis (B*T rows per
+        # head: no partially filled 128-row tile per utterance)
+        _ops.gemm(dBD, Pp, dqv, B * T, hd, 2 * T - 1, ldp, E, d, b_kmajor=False, nb1=H, nb2=1, sA=(B * T * ldp, 0),
+                  sB=(ph, 0), sC=(hd, 0))
+        # dpos = sum over (b, i): 2T-1 output rows per head are too few tiles to fill the machine -> split the B*T-long
+        # reduction across CTAs (fp32 accumulate), then cast
+        dPp32 = torch.zeros(2 * T - 1, d, device=dev, dtype=torch.float32)
+        _ops.gemm(dBD, qv, dPp32, 2 * T - 1, hd, B * T, ldp, d, d, a_kmajor=False, b_kmajor=False, nb1=H, nb2=1,
+                  sA=(B * T * ldp, 0), sB=(hd, 0), sC=(hd, 0), accumulate=True)
+        dPp = dPp32.to(torch.bfloat16)
         _ops.qprep_bwd(dqu, dqv, self.scaling, dqkv[:, :d])
         if learned:
             # scatter-add into the table rows that were read (a width-head_dim table sums its heads first)
             _, idx = self._learned_positions(li, T, dev)
-            dpe = dPp.float() if E == d else dPp.float().view(2 * T - 1, H, hd).sum(1)
+            dpe = dPp32 if E == d else dPp32.view(2 * T - 1, H, hd).sum(1)
             self.flat.grad(self.pos_tables[li]).index_add_(0, idx, dpe)
         else:
             self._wgrad(dPp, self.pe(T, dev), self.G(lp + "self_attn.pos_proj.weight"))
