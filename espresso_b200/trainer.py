@@ -20,7 +20,7 @@ from . import ops as _ops
 class Trainer:
     def __init__(self, model, criterion, lr_scheduler, adam_betas=(0.9, 0.98), adam_eps=1e-8, weight_decay=0.0,
                  clip_norm=2.0, process_group=None, use_cuda_graphs=False, bucket_frames=64, bucket_tokens=16,
-                 max_graphs=96, reduce_dtype="bf16"):
+                 max_graphs=128, reduce_dtype="bf16"):
         self.model = model
         self.criterion = criterion
         self.lr_scheduler = lr_scheduler
