@@ -80,6 +80,10 @@ class SpeechTransformerDecoderBase(nn.Module):
         self.flat = None
         self.dropout_seed = 2
         self.num_updates = 0
+        from ..speech_lstm import ScheduledSamplingRateScheduler
+
+        self.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler(
+            tuple(getattr(cfg, "scheduled_sampling_probs", (1.0,))), getattr(cfg, "start_scheduled_sampling_epoch", 1))
 
     def flat_groups(self, prefix):
         g = []
@@ -211,7 +215,48 @@ class SpeechTransformerModelBase(nn.Module):
             if n_cpu is not None:
                 src_lengths_cpu = torch.where(n_cpu >= 400, 1 + (n_cpu - 400) // 160, torch.zeros_like(n_cpu))
         encoder_out = self.encoder(src_tokens, src_lengths, src_lengths_cpu=src_lengths_cpu)
+        sched = getattr(self.decoder, "scheduled_sampling_rate_scheduler", None)
+        if self.training and sched is not None:
+            prob = sched.step(epoch)
+            if prob < 1.0:
+                eng = self.decoder.engine
+                eng.constant_position = True  # the reference's sampled pass: every step sees the first position (see engine)
+                try:
+                    fed = self._scheduled_sampling_inputs(prev_output_tokens, encoder_out, prob)
+                    return self.decoder(fed, encoder_out=encoder_out, prev_output_tokens_cpu=None)
+                finally:
+                    eng.constant_position = False
         return self.decoder(prev_output_tokens, encoder_out=encoder_out, prev_output_tokens_cpu=prev_output_tokens_cpu)
+
+    @torch.no_grad()
+    def _scheduled_sampling_inputs(self, prev_output_tokens, encoder_out, sampling_prob):
+        """Scheduled sampling (espresso/models/transformer/speech_transformer_decoder.py:254-324): from step 1 on, every
+        sentence feeds the TRUTH token with probability `sampling_prob` (one coin per sentence and step,
+        `torch.rand([bsz, 1]).lt(p)`) and otherwise the arg-max prediction of the previous step given the tokens fed so far.
+        The fed tokens carry no gradient (arg-max), and step t of the reference's incremental pass is exactly position t of a
+        causal teacher-forced pass over the fed sequence (with the reference's constant position embedding, see
+        DecoderEngine.constant_position; pinned against the real reference: tests/golden/scheduled_sampling.npz) -- so the
+        update is: (1) this one-token-per-step pass over the incremental engine (the search kernels, no gradient; dropout
+        off here, whereas the reference's predictions see its training dropout) chooses the inputs, (2) the ordinary
+        forward + hand-written backward runs on them.  Rows of the padded tail are fed whatever the coin says; they only
+        reach positions the loss ignores."""
+        bsz, U = prev_output_tokens.shape
+        dev = prev_output_tokens.device
+        V = len(self.decoder.dictionary)
+        state = self.init_incremental_state(encoder_out, bsz, 1)
+        feed = prev_output_tokens.clone()
+        buf = torch.full((bsz, U + 1), self.decoder.padding_idx, dtype=torch.int32, device=dev)
+        ident = torch.arange(bsz, dtype=torch.int32, device=dev)
+        pred = None
+        for step in range(U):
+            if step > 0:
+                truth = torch.rand([bsz, 1], device=dev).lt(sampling_prob)[:, 0]
+                feed[:, step] = torch.where(truth, prev_output_tokens[:, step], pred)
+            buf[:, step] = feed[:, step].to(torch.int32)
+            logits, _ = self.decode_step(step, buf, state, ident if step > 0 else None)
+            pred = logits[:, :V].float().argmax(-1).to(prev_output_tokens.dtype)
+        self.decoder.engine.training = self.training
+        return feed
 
     def get_normalized_probs(self, net_output, log_probs, sample=None):
         logits = net_output[0].float()

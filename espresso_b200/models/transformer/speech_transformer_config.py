@@ -50,6 +50,10 @@ class SpeechTransformerConfig:
     encoder: SpeechEncoderConfig = field(default_factory=SpeechEncoderConfig)
     decoder: SpeechDecoderConfig = field(default_factory=SpeechDecoderConfig)
     share_decoder_input_output_embed: bool = False
+    # scheduled sampling of the Transformer decoder (espresso/models/transformer/speech_transformer_config.py:260-272):
+    # probability of feeding the TRUTH token per epoch from start_scheduled_sampling_epoch on; the last value persists
+    scheduled_sampling_probs: tuple = (1.0,)
+    start_scheduled_sampling_epoch: int = 1
     no_cross_attention: bool = False
     max_source_positions: Optional[int] = DEFAULT_MAX_SOURCE_POSITIONS
     max_target_positions: Optional[int] = 1024

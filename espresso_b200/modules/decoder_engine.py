@@ -39,11 +39,16 @@ class DecoderEngine(EncoderEngine):
         layernorm_embedding, share_input_output_embed, no_scale_embedding."""
         super().__init__(flat, prefix, dict(cfg, layer_type="decoder"))
         self._pos = {}
+        # Scheduled sampling in the reference feeds a [B, 1] token tensor per step, so its sinusoidal position module
+        # (incremental branch, fairseq/modules/sinusoidal_positional_embedding.py:78-87: pos = seq_len = 1) gives EVERY
+        # step the embedding of the first position; the model sets this flag for such updates to reproduce it.
+        self.constant_position = False
 
     def positions(self, U, device):
-        key = (U, str(device))
+        key = (U, str(device), self.constant_position)
         if key not in self._pos:
-            self._pos[key] = sinusoidal_positions(U, self.d, self.cfg["pad"], device)
+            tab = sinusoidal_positions(U, self.d, self.cfg["pad"], device)
+            self._pos[key] = tab[:1].expand(U, -1).contiguous() if self.constant_position else tab
         return self._pos[key]
 
     def _proj(self, lp, which, names):

@@ -313,6 +313,91 @@ def pin_encdec():
     print("encdec pinned -> tests/golden/encdec_transformer.npz")
 
 
+def pin_scheduled_sampling():
+    """Scheduled sampling of the Transformer decoder (espresso/models/transformer/speech_transformer_decoder.py:254-324): the
+    REAL reference model of the encdec fixture (same weights), sampling probability 0.4, torch seed 77, training mode,
+    dropout 0.  Stores the returned logits and the tokens that were fed (reconstructed from the logits' arg-max and a
+    replay of the coin flips -- the only RNG consumers of that pass)."""
+    from espresso.models.transformer.speech_transformer_base import SpeechTransformerModelBase
+    from espresso.models.transformer.speech_transformer_config import SpeechTransformerConfig
+    from espresso.tools.scheduled_sampling_rate_scheduler import ScheduledSamplingRateScheduler
+
+    gfix = np.load(os.path.join(GOLDEN, "encdec_transformer.npz"))
+    V, pad_idx, eos_idx = 50, 1, 2
+    cfg = SpeechTransformerConfig()
+    cfg.max_source_positions, cfg.max_target_positions, cfg.tpu = 3600, 200, False
+    e = cfg.encoder
+    e.conv_channels = "[64, 64, 128, 128]"
+    e.conv_kernel_sizes = "[(3, 3), (3, 3), (3, 3), (3, 3)]"
+    e.conv_strides = "[(1, 1), (2, 2), (1, 1), (2, 2)]"
+    e.embed_dim, e.ffn_embed_dim, e.layers, e.attention_heads = 64, 128, 2, 4
+    e.normalize_before, e.learned_pos, e.relative_positional_embeddings, e.layer_type = True, False, True, "transformer"
+    d = cfg.decoder
+    d.embed_dim, d.ffn_embed_dim, d.layers, d.attention_heads = 64, 128, 2, 4
+    d.normalize_before, d.learned_pos, d.relative_positional_embeddings = True, False, False
+    d.input_dim, d.output_dim = 64, 64
+    cfg.dropout = cfg.attention_dropout = cfg.activation_dropout = 0.0
+
+    class _Dict:
+        def __len__(self):
+            return V
+
+        def pad(self):
+            return pad_idx
+
+        def eos(self):
+            return eos_idx
+
+    class _Task:
+        feat_dim, feat_in_channels, target_dictionary = 80, 1, _Dict()
+
+    m = SpeechTransformerModelBase.build_model(cfg, _Task())
+    sd = {k[3:]: torch.from_numpy(gfix[k]) for k in gfix.files if k.startswith("sd.")}
+    torch.nn.Module.load_state_dict(m, sd, strict=False)
+    feats, lens, prev = torch.from_numpy(gfix["feats"]), torch.from_numpy(gfix["lens"]), torch.from_numpy(gfix["prev_output_tokens"])
+    out = {}
+    for tag, prob, seed in (("p04", 0.4, 77), ("p00", 0.0, 5)):
+        m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler([prob], 1)
+        m.train()
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            logits, _ = m(feats, lens, prev, epoch=1)
+        B, U = prev.shape
+        torch.manual_seed(seed)
+        feed = prev.clone()
+        for step in range(1, U):
+            coin = torch.rand([B, 1]).lt(prob)[:, 0]
+            feed[:, step] = torch.where(coin, prev[:, step], logits[:, step - 1].argmax(-1))
+        # self-check: a plain teacher-forced pass over the fed tokens reproduces the logits of the sampled pass -- with ONE
+        # quirk of the reference: its sampled pass feeds a [B, 1] token tensor per step, so the sinusoidal position module
+        # (incremental branch, sinusoidal_positional_embedding.py:78-87: pos = seq_len = 1) gives EVERY step the embedding of
+        # the first position
+        m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler([1.0], 1)
+        pe = m.decoder.embed_positions
+        orig_fwd = pe.forward
+
+        def const_pos(input, incremental_state=None, timestep=None, positions=None):
+            full = orig_fwd(input[:, :1], incremental_state={}, timestep=None)   # [B, 1, d]: position padding_idx + 1
+            return full.expand(-1, input.size(1), -1)
+
+        pe.forward = const_pos
+        with torch.no_grad():
+            again, _ = m(feats, lens, feed, epoch=1)
+        pe.forward = orig_fwd
+        # (positions of the padded tail are not comparable: the incremental pass builds its key-padding mask from the ONE
+        # token it is fed, the full pass from the whole row -- they only feed the ignored tail of the loss)
+        valid = prev.ne(pad_idx)
+        top2 = logits.topk(2, dim=-1).values
+        dmax = (again - logits)[valid].abs().max().item()
+        print("scheduled sampling %s: fed != truth at %d of %d valid positions; teacher-forced replay |diff| %.2e; min top-2 margin %.3f"
+              % (tag, int(((feed != prev) & valid).sum()), int(valid.sum()), dmax, (top2[..., 0] - top2[..., 1])[valid].min().item()))
+        assert dmax < 1e-4
+        out.update({tag + "_prob": np.float64(prob), tag + "_seed": np.int64(seed), tag + "_logits": logits.numpy(),
+                    tag + "_feed": feed.numpy(), tag + "_valid": valid.numpy()})
+    np.savez_compressed(os.path.join(GOLDEN, "scheduled_sampling.npz"), **out)
+    print("scheduled sampling pinned -> tests/golden/scheduled_sampling.npz")
+
+
 def pin_transducer():
     """Reference SpeechTransformerTransducerModelBase (Conformer encoder + LSTM predictor + joint) with the criterion's
     torchaudio rnnt_loss call vs oracle/conformer.py + oracle/transducer.py; fixture for the RNN-T path (cfg 4)."""
@@ -1445,7 +1530,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

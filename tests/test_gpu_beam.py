@@ -347,3 +347,63 @@ def test_cuda_generator_matches_reference_generator(golden_dir):
                 assert abs(float(h["score"]) - score) < 1e-4
                 n += 1
     assert n > 50
+
+
+@pytest.mark.parametrize("tag", ["p04", "p00"])
+def test_transformer_decoder_scheduled_sampling_on_gpu(tag, golden_dir):
+    """Scheduled sampling of the Transformer decoder on the CUDA path (incremental search kernels choose the fed tokens, the
+    training forward runs on them) against the REAL reference's outputs (tests/golden/scheduled_sampling.npz), same coin
+    flips: fed tokens equal wherever the reference's arg-max is decided by more than the bf16 error, logits agree there."""
+    from test_host_orchestration import _build_encdec
+    from espresso_b200.models.speech_lstm import ScheduledSamplingRateScheduler
+
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    gs = np.load(os.path.join(golden_dir, "scheduled_sampling.npz"))
+    m = _build_encdec(g).finalize_(dev)
+    prob, seed = float(gs[tag + "_prob"]), int(gs[tag + "_seed"])
+    m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((prob,), 1)
+    feats, lens = torch.from_numpy(g["feats"]).to(dev), torch.from_numpy(g["lens"]).to(dev)
+    prev = torch.from_numpy(g["prev_output_tokens"]).to(dev)
+    B, U = prev.shape
+    # the reference drew its coins on the CPU generator: replay them there and hand them to the model's sampler
+    torch.manual_seed(seed)
+    coins = [torch.rand([B, 1]).lt(prob)[:, 0].to(dev) for _ in range(1, U)]
+    orig_rand = torch.rand
+    state = {"k": 0}
+
+    def _coin():
+        c = coins[state["k"]]
+        state["k"] += 1
+        return torch.where(c, torch.zeros(B, device=dev), torch.ones(B, device=dev)).view(B, 1)  # < p iff the coin said truth
+
+    captured = {}
+    orig = m._scheduled_sampling_inputs
+
+    def spy(*a, **kw):
+        torch.rand = lambda *aa, **kk: _coin()
+        try:
+            captured["feed"] = orig(*a, **kw)
+        finally:
+            torch.rand = orig_rand
+        return captured["feed"]
+
+    m._scheduled_sampling_inputs = spy
+    m.train()
+    with torch.no_grad():
+        logits, _ = m(feats, lens, prev, epoch=1)
+    ref_logits, ref_feed, valid = gs[tag + "_logits"], gs[tag + "_feed"], gs[tag + "_valid"]
+    feed = captured["feed"].cpu().numpy()
+    top2 = np.sort(ref_logits, axis=-1)[..., -2:]
+    margin = top2[..., 1] - top2[..., 0]
+    same = np.ones((B, U), dtype=bool)
+    for b in range(B):
+        for t in range(1, U):
+            if feed[b, t] != ref_feed[b, t]:
+                assert margin[b, t - 1] < 0.15, (tag, b, t, margin[b, t - 1])
+                same[b, t:] = False
+                break
+    cmp = same & valid
+    assert cmp.sum() >= 0.5 * valid.sum(), (tag, int(cmp.sum()), int(valid.sum()))
+    err = np.abs(logits.float().cpu().numpy() - ref_logits)[cmp].max()
+    assert err < 0.06 * np.abs(ref_logits).max(), (tag, err)

@@ -769,3 +769,59 @@ def test_full_size_encoder_host_path_vs_reference(golden_dir, cpu_ops):
     from fullsize_util import run_and_check
 
     run_and_check("cpu", golden_dir)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scheduled sampling of the Transformer decoder vs the REAL reference (tests/golden/scheduled_sampling.npz)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["p04", "p00"])
+def test_transformer_decoder_scheduled_sampling_vs_reference(tag, golden_dir, cpu_ops):
+    """espresso/models/transformer/speech_transformer_decoder.py:254-324: with the reference's coin flips (same torch seed),
+    the tokens we feed equal the tokens the reference fed wherever its arg-max is decided by more than the bf16 error, and
+    the training logits over those tokens equal the reference's (which include its constant-position quirk)."""
+    from espresso_b200.models.speech_lstm import ScheduledSamplingRateScheduler
+
+    g = np.load(os.path.join(golden_dir, "encdec_transformer.npz"))
+    gs = np.load(os.path.join(golden_dir, "scheduled_sampling.npz"))
+    m = _build_encdec(g).finalize_(torch.device("cpu"))
+    prob, seed = float(gs[tag + "_prob"]), int(gs[tag + "_seed"])
+    m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((prob,), 1)
+    feats, lens, prev = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"]), torch.from_numpy(g["prev_output_tokens"])
+    m.train()
+    captured = {}
+    orig = m._scheduled_sampling_inputs
+
+    def spy(*a, **kw):
+        captured["feed"] = orig(*a, **kw)
+        return captured["feed"]
+
+    m._scheduled_sampling_inputs = spy
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        logits, _ = m(feats, lens, prev, epoch=1)
+    assert not m.decoder.engine.constant_position  # the mode is left again
+    ref_logits, ref_feed, valid = gs[tag + "_logits"], gs[tag + "_feed"], gs[tag + "_valid"]
+    feed = captured["feed"].numpy()
+    # a fed token can only differ where the reference's previous-step arg-max was a near-tie; once a row diverges its later
+    # positions are not comparable
+    top2 = np.sort(ref_logits, axis=-1)[..., -2:]
+    margin = top2[..., 1] - top2[..., 0]
+    B, U = feed.shape
+    same = np.ones((B, U), dtype=bool)
+    for b in range(B):
+        for t in range(1, U):
+            if not same[b, t - 1] or feed[b, t] != ref_feed[b, t]:
+                if same[b, t - 1] and feed[b, t] != ref_feed[b, t]:
+                    assert margin[b, t - 1] < 0.15, (tag, b, t, margin[b, t - 1])
+                same[b, t:] = False
+                break
+    cmp = same & valid
+    assert cmp.sum() >= 0.6 * valid.sum(), (tag, int(cmp.sum()), int(valid.sum()))
+    assert (feed != prev.numpy())[cmp].any() or prob == 1.0  # predictions really were fed
+    err = np.abs(logits.float().numpy() - ref_logits)[cmp].max()
+    assert err < 0.06 * np.abs(ref_logits).max(), (tag, err)
+    # probability 1 is plain teacher forcing
+    m.decoder.scheduled_sampling_rate_scheduler = ScheduledSamplingRateScheduler((1.0,), 1)
+    with torch.no_grad():
+        tf, _ = m(feats, lens, prev, epoch=1)
+    assert np.abs(tf.float().numpy() - g["logits"]).max() < 0.06 * np.abs(g["logits"]).max()
