@@ -7,7 +7,6 @@ bounded number of steps ahead are enough; the consumer gets pinned tensors it ca
 previous step computes.  Same epoch semantics as the reference: batches are frozen once (batch_by_size over the dataset's
 ordered_indices), shuffled per epoch under numpy_seed(seed + epoch), sharded round-robin over ranks with dummy padding
 batches so every rank does the same number of updates, resumable from (epoch, iterations_in_epoch)."""
-import queue
 import threading
 
 import numpy as np
