@@ -1,1 +1,2 @@
-from .lr_scheduler import NoamLRScheduler, TriStageLRScheduler  # noqa: F401
+from .lr_scheduler import (NoamLRScheduler, PolynomialDecayV2LRScheduler, ReduceLROnPlateauV2LRScheduler,  # noqa: F401
+                           TriStageLRScheduler)

@@ -801,6 +801,83 @@ def pin_optimizer():
     print("optimizer + schedules pinned -> tests/golden/optimizer.npz")
 
 
+def pin_lr_schedules_v2():
+    """The schedules of the speech_lstm recipes -- reduce_lr_on_plateau_v2 (espresso/optim/lr_scheduler/
+    reduce_lr_on_plateau_v2.py over fairseq's reduce_lr_on_plateau and torch's ReduceLROnPlateau) and polynomial_decay_v2 --
+    run with the REAL reference classes on recorded validation curves / update counts; espresso_b200.optim must replay them."""
+    from argparse import Namespace
+
+    import fairseq.optim.lr_scheduler.fairseq_lr_scheduler as _fl
+    from espresso.optim.lr_scheduler.polynomial_decay_schedule import PolynomialDecayV2LRSchedule
+    from espresso.optim.lr_scheduler.reduce_lr_on_plateau_v2 import ReduceLROnPlateauLRScheduleV2
+
+    from espresso_b200.optim.lr_scheduler import PolynomialDecayV2LRScheduler, ReduceLROnPlateauV2LRScheduler
+
+    class _Opt:  # what the schedules need from a FairseqOptimizer: one param group with an lr
+        def __init__(self, lr):
+            self.optimizer = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+
+        def set_lr(self, lr):
+            for gp in self.optimizer.param_groups:
+                gp["lr"] = lr
+
+        def get_lr(self):
+            return self.optimizer.param_groups[0]["lr"]
+
+    _orig = _fl.FairseqLRScheduler.__init__
+    _fl.FairseqLRScheduler.__init__ = lambda self, cfg, optimizer: (setattr(self, "cfg", cfg), setattr(self, "optimizer", optimizer),
+                                                                    setattr(self, "best", None)) and None
+    out = {}
+    try:
+        rs = np.random.RandomState(4)
+        cases = [dict(lr=1e-3, lr_shrink=0.5, lr_threshold=1e-4, lr_patience=0, warmup_updates=0, warmup_init_lr=-1.0,
+                      start_reduce_lr_epoch=4, final_lr_scale=0.01, maximize_best_checkpoint_metric=False),
+                 dict(lr=2e-3, lr_shrink=0.1, lr_threshold=1e-2, lr_patience=1, warmup_updates=50, warmup_init_lr=1e-5,
+                      start_reduce_lr_epoch=0, final_lr_scale=0.05, maximize_best_checkpoint_metric=True),
+                 dict(lr=5e-4, lr_shrink=0.5, lr_threshold=1e-4, lr_patience=0, warmup_updates=0, warmup_init_lr=-1.0,
+                      start_reduce_lr_epoch=11, final_lr_scale=1e-4, maximize_best_checkpoint_metric=False)]  # asr_wsj run.sh
+        for ci, c in enumerate(cases):
+            cfg = Namespace(lr=[c["lr"]], **{k: v for k, v in c.items() if k != "lr"})
+            ref = ReduceLROnPlateauLRScheduleV2(cfg, _Opt(c["lr"]))
+            ours = ReduceLROnPlateauV2LRScheduler(**c)
+            E = 30
+            base = np.linspace(5.0, 3.0, E) if not c["maximize_best_checkpoint_metric"] else np.linspace(0.5, 0.8, E)
+            vals = base + rs.randn(E) * 0.05
+            vals[12:18] = vals[12]  # a plateau
+            lrs, n = [], 0
+            for ep in range(1, E + 1):
+                for _ in range(20):  # updates of the epoch
+                    n += 1
+                    a, b = ref.step_update(n), ours.step_update(n)
+                    assert abs(a - b) <= 1e-12 * max(abs(a), 1e-12), (ci, ep, n, a, b)
+                a, b = ref.step(ep, float(vals[ep - 1])), ours.step(ep, float(vals[ep - 1]))
+                assert abs(a - b) <= 1e-12 * max(abs(a), 1e-12), (ci, ep, a, b)
+                lrs.append(a)
+            sd = ref.state_dict()
+            assert abs(sd["best"] - ours.state_dict()["best"]) < 1e-12 and sd["last_epoch"] == ours.state_dict()["last_epoch"]
+            out["plateau%d_cfg" % ci] = np.array([c["lr"], c["lr_shrink"], c["lr_threshold"], c["lr_patience"], c["warmup_updates"],
+                                                  c["warmup_init_lr"], c["start_reduce_lr_epoch"], c["final_lr_scale"],
+                                                  float(c["maximize_best_checkpoint_metric"])])
+            out["plateau%d_vals" % ci] = vals
+            out["plateau%d_lr" % ci] = np.array(lrs)
+            print("reduce_lr_on_plateau_v2 case %d: %d distinct rates over %d epochs, identical to the reference" % (ci, len(set(lrs)), E))
+        pcfg = Namespace(lr=[3e-4], warmup_updates=100, end_learning_rate=1e-6, total_num_update=2000, power=2.0, force_anneal=None)
+        pref = PolynomialDecayV2LRSchedule(pcfg, _Opt(3e-4))
+        pours = PolynomialDecayV2LRScheduler(3e-4, 2000, warmup_updates=100, end_learning_rate=1e-6, power=2.0)
+        psteps = [0, 1, 50, 100, 101, 500, 1999, 2000, 2001, 9999]
+        plr = []
+        for s_ in psteps:
+            a, b = pref.step_update(s_), pours.step_update(s_)
+            assert abs(a - b) <= 1e-12 * max(abs(a), 1e-12), (s_, a, b)
+            plr.append(a)
+        out.update(poly_steps=np.array(psteps), poly_lr=np.array(plr))
+        print("polynomial_decay_v2: identical to the reference at %d update counts" % len(psteps))
+    finally:
+        _fl.FairseqLRScheduler.__init__ = _orig
+    np.savez_compressed(os.path.join(GOLDEN, "lr_schedules_v2.npz"), **out)
+    print("schedules pinned -> tests/golden/lr_schedules_v2.npz")
+
+
 def pin_batching():
     """The reference's native batch packer (fairseq/data/data_utils_fast.pyx, compiled from /root/reference into
     oracle/_ref/ by oracle/build_ref.sh) vs espresso_b200.data.batching.batch_by_size (esp_batch_by_size in the C ABI)
@@ -1530,7 +1607,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"lr_schedules_v2": pin_lr_schedules_v2, "scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

@@ -825,3 +825,35 @@ def test_transformer_decoder_scheduled_sampling_vs_reference(tag, golden_dir, cp
     with torch.no_grad():
         tf, _ = m(feats, lens, prev, epoch=1)
     assert np.abs(tf.float().numpy() - g["logits"]).max() < 0.06 * np.abs(g["logits"]).max()
+
+
+def test_plateau_and_polynomial_schedules_replay_the_reference(golden_dir):
+    """reduce_lr_on_plateau_v2 (the speech_lstm recipes' schedule) and polynomial_decay_v2: learning rates recorded from the
+    REAL reference classes on validation curves with a plateau, warm-up, max-mode and the asr_wsj settings
+    (tests/golden/lr_schedules_v2.npz, made by oracle/pin_against_reference.py lr_schedules_v2)."""
+    from espresso_b200.optim import PolynomialDecayV2LRScheduler, ReduceLROnPlateauV2LRScheduler
+
+    g = np.load(os.path.join(golden_dir, "lr_schedules_v2.npz"))
+    ci = 0
+    while "plateau%d_cfg" % ci in g.files:
+        c = g["plateau%d_cfg" % ci]
+        s = ReduceLROnPlateauV2LRScheduler(lr=float(c[0]), lr_shrink=float(c[1]), lr_threshold=float(c[2]), lr_patience=int(c[3]),
+                                           warmup_updates=int(c[4]), warmup_init_lr=float(c[5]), start_reduce_lr_epoch=int(c[6]),
+                                           final_lr_scale=float(c[7]), maximize_best_checkpoint_metric=bool(c[8]))
+        n = 0
+        for ep, (v, want) in enumerate(zip(g["plateau%d_vals" % ci], g["plateau%d_lr" % ci]), start=1):
+            for _ in range(20):
+                n += 1
+                s.step_update(n)
+            got = s.step(ep, float(v))
+            assert abs(got - want) <= 1e-12 * max(abs(want), 1e-12), (ci, ep, got, want)
+        assert len(set(g["plateau%d_lr" % ci].tolist())) >= 3  # the rate really moved
+        # resumption: best / last_epoch round-trip
+        t = ReduceLROnPlateauV2LRScheduler(lr=float(c[0]))
+        t.load_state_dict(s.state_dict())
+        assert t.best == s.best and t.last_epoch == s.last_epoch
+        ci += 1
+    assert ci == 3
+    p = PolynomialDecayV2LRScheduler(3e-4, 2000, warmup_updates=100, end_learning_rate=1e-6, power=2.0)
+    for n, want in zip(g["poly_steps"], g["poly_lr"]):
+        assert abs(p.step_update(int(n)) - want) <= 1e-12 * max(abs(want), 1e-12)
