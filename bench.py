@@ -784,7 +784,8 @@ def main():
         try:  # DRAM bytes per launch from the committed ncu capture of the same command (profiles/)
             tr = _json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
             roof["traffic"] = tr["dram_bytes_per_launch"]
-            roof["traffic_unit"] = "bytes per launch (dram read+write, mean over %d launches, ncu)" % tr["launches"]
+            roof["traffic_unit"] = ("bytes per launch (dram read+write, mean over the %d GEMM launches of a step, ncu capture "
+                                    "profiles/r02_gemm_traffic.json taken before the attention-backward fusion removed 51 of them)" % tr["launches"])
             roof["algorithmic_bytes_per_launch"] = sum(
                 2.0 * (a_[3] * a_[5] + a_[4] * a_[5] + a_[3] * a_[4]) * kw_.get("nb1", 1) * kw_.get("nb2", 1)
                 for a_, kw_, _ in recs) / max(len(recs), 1)
