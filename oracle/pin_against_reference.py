@@ -878,6 +878,69 @@ def pin_lr_schedules_v2():
     print("schedules pinned -> tests/golden/lr_schedules_v2.npz")
 
 
+def pin_wer_scorer():
+    """espresso/tools/wer.py Scorer (+ edit_distance / aligned_print of espresso/tools/utils.py) on random token strings with
+    non-linguistic symbols and a word filter file: edit counts, rates and the printed blocks, recorded for
+    espresso_b200.tools.wer.Scorer (tests/golden/wer_scorer.json)."""
+    import json
+    import tempfile
+
+    from espresso.tools.wer import Scorer as RefScorer
+
+    from espresso_b200.tools.wer import Scorer as OurScorer
+
+    class _D:
+        non_lang_syms = ["<noise>", "<laugh>"]
+
+        @staticmethod
+        def wordpiece_decode(x):
+            return x.replace(" ", "").replace("\u2581", " ").strip()
+
+    rs = np.random.RandomState(17)
+    pieces = ["\u2581the", "\u2581a", "\u2581cat", "\u2581sat", "s", "ing", "\u2581on", "\u2581mat", "ter", "\u2581uh", "\u2581um", "\u2581it's",
+              "\u2581dog", "\u2581ran", "<noise>", "<laugh>", "\u2581far", "ther", "\u2581", "\u2581x"]
+    filt = tempfile.NamedTemporaryFile("w", suffix=".filt", delete=False, encoding="utf-8")
+    filt.write("#!/bin/sed -f\ns/\\buh\\b//g\ns:\\bum\\b::g\nthis line is ignored\n")
+    filt.close()
+    ref, ours = RefScorer(_D(), wer_output_filter=filt.name), OurScorer(_D(), wer_output_filter=filt.name)
+    utts = []
+    for u in range(60):
+        n = int(rs.randint(0, 14))
+        r = [pieces[i] for i in rs.randint(0, len(pieces), size=n)]
+        h = list(r)
+        for _ in range(int(rs.randint(0, 5))):  # corrupt: substitute / insert / delete
+            k = rs.randint(0, 3)
+            if k == 0 and h:
+                h[int(rs.randint(0, len(h)))] = pieces[int(rs.randint(0, len(pieces)))]
+            elif k == 1:
+                h.insert(int(rs.randint(0, len(h) + 1)), pieces[int(rs.randint(0, len(pieces)))])
+            elif h:
+                del h[int(rs.randint(0, len(h)))]
+        uid = "utt%03d" % u
+        rstr, hstr = " ".join(r), " ".join(h)
+        for sc in (ref, ours):
+            sc.add_prediction(uid, hstr)
+            sc.add_evaluation(uid, rstr, hstr)
+        utts.append([uid, rstr, hstr])
+    order = [u[0] for u in utts][::-1]
+    for sc in (ref, ours):
+        sc.add_ordered_utt_list(order)
+    exp = {"utts": utts, "order": order, "filter": open(filt.name, encoding="utf-8").read(),
+           "char_counter": dict(ref.char_counter), "word_counter": dict(ref.word_counter), "cer": list(ref.cer()), "wer": list(ref.wer()),
+           "print_char_results": ref.print_char_results(), "print_results": ref.print_results(),
+           "print_aligned_results": ref.print_aligned_results()}
+    assert dict(ours.char_counter) == exp["char_counter"] and dict(ours.word_counter) == exp["word_counter"]
+    assert list(ours.cer()) == exp["cer"] and list(ours.wer()) == exp["wer"]
+    assert ours.print_char_results() == exp["print_char_results"] and ours.print_results() == exp["print_results"]
+    assert ours.print_aligned_results() == exp["print_aligned_results"]
+    assert ours.tot_word_error() == ref.tot_word_error() and ours.tot_char_count() == ref.tot_char_count()
+    os.unlink(filt.name)
+    with open(os.path.join(GOLDEN, "wer_scorer.json"), "w", encoding="utf-8") as f:
+        json.dump(exp, f, ensure_ascii=False, indent=0)
+    print("wer scorer: %d utterances, WER %.2f%% CER %.2f%%, counters / rates / printed blocks identical to the reference -> tests/golden/wer_scorer.json"
+          % (len(utts), exp["wer"][0], exp["cer"][0]))
+
+
 def pin_batching():
     """The reference's native batch packer (fairseq/data/data_utils_fast.pyx, compiled from /root/reference into
     oracle/_ref/ by oracle/build_ref.sh) vs espresso_b200.data.batching.batch_by_size (esp_batch_by_size in the C ABI)
@@ -1607,7 +1670,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"lr_schedules_v2": pin_lr_schedules_v2, "scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"wer_scorer": pin_wer_scorer, "lr_schedules_v2": pin_lr_schedules_v2, "scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

@@ -5,6 +5,9 @@ this repository's implementations:
   tests/test_label_smoothing.py:62-127          label-smoothed CE: nll == plain CE, padding ignored, per-row reduction,
                                                 zero smoothing == CE
 (the beam-search tables of tests/test_sequence_generator.py are in tests/test_beam_search.py)."""
+import os
+
+import pytest
 import torch
 
 from oracle import ops_ref as O
@@ -53,3 +56,42 @@ def test_label_smoothing_properties_of_the_reference_tests():
     assert abs(float(loss.sum()) - float(l_a.sum() + l_b.sum())) < 1e-5
     # test_reduction: the reduced loss is the sum of the per-token losses, padding contributes zero
     assert float(loss.view(2, 4)[1, 2:].abs().sum()) == 0.0
+
+
+def test_wer_scorer_replays_the_reference(golden_dir, tmp_path):
+    """espresso_b200.tools.wer.Scorer on 60 recorded utterances (non-linguistic symbols, sed-style word filters, reversed print
+    order): edit counters, CER / WER with their shares and the aligned REF / HYP / STP blocks equal what the REAL reference
+    Scorer produced (tests/golden/wer_scorer.json, made by oracle/pin_against_reference.py wer_scorer)."""
+    import json
+
+    from espresso_b200.tools.wer import Scorer, align
+
+    g = json.load(open(os.path.join(golden_dir, "wer_scorer.json"), encoding="utf-8"))
+
+    class _D:
+        non_lang_syms = ["<noise>", "<laugh>"]
+
+        @staticmethod
+        def wordpiece_decode(x):
+            return x.replace(" ", "").replace("▁", " ").strip()
+
+    filt = tmp_path / "words.filt"
+    filt.write_text(g["filter"], encoding="utf-8")
+    sc = Scorer(_D(), wer_output_filter=str(filt))
+    for uid, ref, hyp in g["utts"]:
+        sc.add_prediction(uid, hyp)
+        sc.add_evaluation(uid, ref, hyp)
+    sc.add_ordered_utt_list(g["order"])
+    assert dict(sc.char_counter) == g["char_counter"] and dict(sc.word_counter) == g["word_counter"]
+    assert list(sc.cer()) == g["cer"] and list(sc.wer()) == g["wer"]
+    assert sc.print_char_results() == g["print_char_results"]
+    assert sc.print_results() == g["print_results"]
+    assert sc.print_aligned_results() == g["print_aligned_results"]
+    assert sc.tot_word_error() == sum(g["word_counter"][k] for k in ("sub", "ins", "del")) and sc.tot_word_count() == g["word_counter"]["words"]
+    with pytest.raises(AssertionError):
+        sc.add_prediction(g["utts"][0][0], "x")  # duplicated utterance id
+    with pytest.raises(TypeError):
+        sc.add_evaluation(3, "a", "b")
+    # edge cases of the alignment itself
+    assert align([], []) == [] and align(["a"], []) == ["del"] and align([], ["a", "b"]) == ["ins", "ins"]
+    assert align(["a", "b", "c"], ["a", "x", "c"]) == ["corr", "sub", "corr"]
