@@ -941,6 +941,35 @@ def pin_wer_scorer():
           % (len(utts), exp["wer"][0], exp["cer"][0]))
 
 
+def pin_global_cmvn():
+    """Global CMVN statistics as espresso/tools/compute_global_cmvn_stats.py computes them: the reference's fbank per utterance
+    (get_torchaudio_fbank_or_mfcc) and its pooling of per-utterance sums / unnormalised variances (:93-116, restated here
+    because the script's own main() reads files through libsndfile); the seeds of the synthetic int16 utterances are
+    stored so the test regenerates them."""
+    from espresso.tools.utils import get_torchaudio_fbank_or_mfcc
+
+    from oracle import frontend as OF
+
+    durs = [1.3, 0.03, 4.0, 2.25, 0.6, 7.1]
+    total_sum, total_var, total_frames = np.zeros(80), np.zeros(80), 0
+    for i, dsec in enumerate(durs):
+        w = OF.synth_waveform(300 + i, dsec)
+        feat = get_torchaudio_fbank_or_mfcc(w[None, :], 16000, n_bins=80)
+        if feat.shape[0] == 0:
+            continue
+        cur_sum, cur_frames = feat.sum(axis=0), feat.shape[0]
+        cur_var = np.var(feat, axis=0) * cur_frames
+        if total_frames > 0:
+            ratio = total_frames / cur_frames
+            total_var = total_var + cur_var + ratio / (total_frames + cur_frames) * (total_sum / ratio - cur_sum) ** 2
+        else:
+            total_var = cur_var
+        total_sum, total_frames = total_sum + cur_sum, total_frames + cur_frames
+    np.savez_compressed(os.path.join(GOLDEN, "global_cmvn.npz"), durs=np.array(durs), seed0=np.int64(300),
+                        mean=total_sum / total_frames, std=np.sqrt(total_var / total_frames), frames=np.int64(total_frames))
+    print("global CMVN: %d frames of %d utterances pinned -> tests/golden/global_cmvn.npz" % (total_frames, len(durs)))
+
+
 def pin_batching():
     """The reference's native batch packer (fairseq/data/data_utils_fast.pyx, compiled from /root/reference into
     oracle/_ref/ by oracle/build_ref.sh) vs espresso_b200.data.batching.batch_by_size (esp_batch_by_size in the C ABI)
@@ -1670,7 +1699,7 @@ def pin_fullsize():
     print("full-size encoder pinned -> tests/golden/fullsize_conformer.npz")
 
 
-SECTIONS = {"wer_scorer": pin_wer_scorer, "lr_schedules_v2": pin_lr_schedules_v2, "scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
+SECTIONS = {"global_cmvn": pin_global_cmvn, "wer_scorer": pin_wer_scorer, "lr_schedules_v2": pin_lr_schedules_v2, "scheduled_sampling": pin_scheduled_sampling, "multilevel": pin_multilevel, "lookahead": pin_lookahead, "streaming": pin_streaming, "fullsize": pin_fullsize, "text": pin_text, "lstm_lm": pin_lstm_lm, "speech_lstm": pin_speech_lstm, "dictionary": pin_dictionary, "sharding": pin_sharding, "collate": pin_collate, "batching": pin_batching, "optimizer": pin_optimizer, "beam": pin_beam, "label_smoothing": pin_label_smoothing, "frontend": pin_frontend, "ctc": pin_ctc, "conformer": pin_conformer, "encdec": pin_encdec,
             "transducer": pin_transducer}
 
 

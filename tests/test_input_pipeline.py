@@ -260,3 +260,33 @@ def test_task_load_dataset_and_batch_iterator(tmp_path):
     assert sorted(seen) == sorted(man)
     with pytest.raises(KeyError):
         task.dataset("valid")
+
+
+def test_global_cmvn_stats_match_the_reference_tool(monkeypatch, tmp_path):
+    """espresso_b200.tools.compute_global_cmvn_stats (device front end + float64 sums) against the statistics the reference's
+    tool produces with its own fbank and pooling formula (tests/golden/global_cmvn.npz); host path over oracle/ops_ref, incl.
+    the command-line entry reading WAVE files."""
+    from espresso_b200 import ops
+    from espresso_b200.tools import compute_global_cmvn_stats as G
+    from oracle import frontend as OF
+    from oracle import ops_ref
+
+    monkeypatch.setattr(ops, "frontend_fbank", ops_ref.frontend_fbank)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "global_cmvn.npz"))
+    waves = [OF.synth_waveform(int(g["seed0"]) + i, float(d)) for i, d in enumerate(g["durs"])]
+    mean, std, n = G.global_cmvn_stats(waves, torch.device("cpu"), batch_seconds=5.0)  # several batches
+    assert n == int(g["frames"])
+    assert np.abs(mean - g["mean"]).max() < 2e-4 and np.abs(std - g["std"]).max() < 2e-4
+    # the command-line entry: wav.scp -> gcmvn.npz readable by the on-the-fly front end
+    lines = []
+    for i, w in enumerate(waves):
+        p = str(tmp_path / ("u%d.wav" % i))
+        _write_wav16(p, w.astype(np.int16))
+        lines.append("utt%d %s\n" % (i, p))
+    (tmp_path / "wav.scp").write_text("".join(lines))
+    G.main([str(tmp_path / "wav.scp"), str(tmp_path / "out"), "--device", "cpu", "--max-num-utts", "6"])
+    st = np.load(str(tmp_path / "out" / "gcmvn.npz"))
+    assert np.abs(st["mean"] - g["mean"]).max() < 2e-4 and np.abs(st["std"] - g["std"]).max() < 2e-4
+    from espresso_b200.data.frontend import OnTheFlyFbank
+
+    assert OnTheFlyFbank.from_npz(str(tmp_path / "out" / "gcmvn.npz")) is not None
