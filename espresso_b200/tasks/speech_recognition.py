@@ -167,11 +167,15 @@ class SpeechRecognitionEspressoTask:
             return (seq_gen_cls or CTCDecoder)(self.target_dictionary, blank_idx=self.target_dictionary.index(self.blank_symbol), **extra)
         from ..sequence_generator import SequenceGenerator
 
+        # the decode script hands lm_model / lm_weight / eos_factor through extra_gen_cls_kwargs (speech_recognize.py:206-216);
+        # stand-alone callers may leave them on `args`
+        lm_weight = extra.pop("lm_weight", g("lm_weight", 0.0))
+        eos_factor = extra.pop("eos_factor", g("eos_factor", None))
         return (seq_gen_cls or SequenceGenerator)(
             models, self.target_dictionary, beam_size=g("beam", 5), max_len_a=g("max_len_a", 0), max_len_b=g("max_len_b", 200),
             min_len=g("min_len", 1), normalize_scores=not g("unnormalized", False), len_penalty=g("lenpen", 1.0),
             unk_penalty=g("unkpen", 0.0), temperature=g("temperature", 1.0), lm_model=extra.pop("lm_model", None),
-            lm_weight=g("lm_weight", 0.0) or 1.0, eos_factor=g("eos_factor", None), **extra)
+            lm_weight=lm_weight or 1.0, eos_factor=eos_factor, **extra)
 
     def build_decoder_for_validation(self, model):
         """Greedy decoders used for validation WER (speech_recognition.py:451-489)."""

@@ -290,3 +290,54 @@ def test_global_cmvn_stats_match_the_reference_tool(monkeypatch, tmp_path):
     from espresso_b200.data.frontend import OnTheFlyFbank
 
     assert OnTheFlyFbank.from_npz(str(tmp_path / "out" / "gcmvn.npz")) is not None
+
+
+def test_recognize_loop_from_manifest_to_wer(tmp_path, monkeypatch):
+    """espresso_b200.speech_recognize.recognize (the reference's decode-and-score loop, espresso/speech_recognize.py:60-400) end
+    to end on the host path: WAVE files + JSON manifest -> dataset -> batch iterator -> on-the-fly front end -> encoder-decoder
+    beam search -> T- / H- lines -> Scorer."""
+    from argparse import Namespace
+
+    from espresso_b200 import ops
+    from espresso_b200.data.frontend import OnTheFlyFbank
+    from espresso_b200.models import SpeechTransformerConfig, SpeechTransformerModelBase
+    from espresso_b200.speech_recognize import recognize
+    from espresso_b200.tasks.speech_recognition import SpeechRecognitionEspressoConfig, SpeechRecognitionEspressoTask
+    from oracle import ops_ref
+
+    for name in dir(ops_ref):   # host orchestration over the oracle's statement of every kernel
+        if not name.startswith("_") and callable(getattr(ops_ref, name)) and hasattr(ops, name):
+            monkeypatch.setattr(ops, name, getattr(ops_ref, name))
+    d, man = _corpus(tmp_path, n=7, fmt="wave")
+    os.rename(str(tmp_path / "train.json"), str(tmp_path / "test.json"))
+    cfg = SpeechRecognitionEspressoConfig(criterion_name="label_smoothed_cross_entropy_v2", data=str(tmp_path), autoregressive=True)
+    task = SpeechRecognitionEspressoTask(cfg, d, feat_dim=80)
+    torch.manual_seed(3)
+    mcfg = SpeechTransformerConfig.from_dict(dict(
+        dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layernorm_embedding=False, max_target_positions=64,
+        encoder=dict(embed_dim=64, ffn_embed_dim=128, layers=1, attention_heads=4, normalize_before=True, learned_pos=False,
+                     relative_positional_embeddings=True, layer_type="transformer"),
+        decoder=dict(embed_dim=64, ffn_embed_dim=128, layers=1, attention_heads=4, normalize_before=True, learned_pos=False,
+                     relative_positional_embeddings=False, input_dim=64, output_dim=64)))
+    m = SpeechTransformerModelBase.build_model(mcfg, task).finalize_(torch.device("cpu"))
+    m.frontend = OnTheFlyFbank(None, None)
+    args = Namespace(beam=2, max_len_a=0.0, max_len_b=6, lm_weight=0.0)
+    out = recognize(task, [m], subset="test", gen_args=args, max_tokens=None, max_sentences=3, device="cpu", quiet=True)
+    sc = out["scorer"]
+    assert out["num_sentences"] == len(man) == len(sc.results) == len(sc.aligned_results)
+    t_lines = [l for l in out["lines"] if l.startswith("T-")]
+    h_lines = [l for l in out["lines"] if l.startswith("H-")]
+    assert len(t_lines) == len(h_lines) == len(man)
+    assert {l.split("\t")[0][2:]: l.split("\t")[1] for l in t_lines} == {u: v["text"] for u, v in man.items()}
+    for l in h_lines:   # the printed hypothesis is the word-level decoding of what the scorer stored; scores are base-2 logs
+        uid, hyp, score = l.split("\t")
+        assert sc.results[uid[2:]].rstrip("\n") == hyp and float(score) <= 0.0
+    wer, sub, ins, dele = sc.wer()
+    assert wer >= 0 and abs(wer - (sub + ins + dele)) < 1e-9 and sc.tot_word_count() == sum(len(v["text"].split()) for v in man.values())
+    # the loop is deterministic and independent of how the subset is sharded
+    again = recognize(task, [m], subset="test", gen_args=args, max_tokens=None, max_sentences=3, device="cpu")
+    assert again["scorer"].print_results() == sc.print_results()
+    parts = [recognize(task, [m], subset="test", gen_args=args, max_sentences=3, max_tokens=None, device="cpu", num_shards=2, shard_id=r)
+             for r in range(2)]
+    assert sum(p["num_sentences"] for p in parts) == len(man)
+    assert set(parts[0]["scorer"].results) | set(parts[1]["scorer"].results) == set(man)
